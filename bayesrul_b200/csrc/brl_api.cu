@@ -1,0 +1,712 @@
+// C ABI (include/bayesrul_b200.h) + host-side tape executor of the fp32 SIMT engine.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/bayesrul_b200.h"
+#include "brl_kernels.cuh"
+#include "brl_nets.h"
+#include "brl_philox.cuh"
+#include "brl_tc.cuh"
+
+using namespace brl;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define BRL_REQUIRE(cond, msg) \
+  do {                         \
+    if (!(cond)) return fail(BRL_ERR_INVALID, std::string("bayesrul_b200: ") + msg); \
+  } while (0)
+#define BRL_CUDA(expr)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t e__ = (expr);                                                                            \
+    if (e__ != cudaSuccess)                                                                              \
+      return fail(BRL_ERR_CUDA, std::string("bayesrul_b200: CUDA error: ") + cudaGetErrorString(e__) + " at " #expr); \
+  } while (0)
+
+// per-conv-op device tables
+struct OpTables {
+  int *koff = nullptr, *kdhw = nullptr, *kci = nullptr;          // forward / dW gather
+  int *koff_dx = nullptr, *kdhw_dx = nullptr, *kB_dx = nullptr;  // dX gather + transposed weight offsets
+};
+
+struct brl_ctx {
+  int net_id = 0, device = 0;
+  const NetSpec* net = nullptr;
+  std::vector<OpTables> tabs;
+  long long* site_off_dev = nullptr;
+  int max_site = 0;
+  int* table_pool = nullptr;
+  TcState* tc = nullptr;
+};
+
+// bump allocator over the caller's workspace (256-byte aligned); base == nullptr only measures
+struct Carve {
+  char* base;
+  size_t cap, used = 0;
+  bool ok = true;
+  Carve(void* b, size_t c) : base((char*)b), cap(c) {}
+  template <typename T>
+  T* take(long long n) {
+    const size_t bytes = ((size_t)(n < 0 ? 0 : n) * sizeof(T) + 255) & ~(size_t)255;
+    T* p = base ? reinterpret_cast<T*>(base + used) : nullptr;
+    used += bytes;
+    if (base && used > cap) ok = false;
+    return p;
+  }
+};
+
+struct ActBufs {
+  std::vector<float*> act, grad, sd;  // per buffer / per buffer / per op
+  float *dpre = nullptr, *dsec = nullptr;
+  float *g0 = nullptr, *g1 = nullptr, *wsamp = nullptr, *delta = nullptr, *norms = nullptr;
+  std::vector<float*> sgn_in, sgn_out;  // per layer
+  double* acc = nullptr;
+};
+
+static void carve_forward(const NetSpec& n, Carve& c, long long B, long long S, ActBufs& ab) {
+  ab.act.resize(n.bufs.size());
+  for (size_t i = 0; i < n.bufs.size(); ++i) ab.act[i] = c.take<float>((n.bufs[i].shared ? B : S * B) * n.bufs[i].elems());
+}
+static void carve_train(const NetSpec& n, Carve& c, long long B, ActBufs& ab) {
+  ab.grad.resize(n.bufs.size());
+  for (size_t i = 0; i < n.bufs.size(); ++i) ab.grad[i] = n.bufs[i].shared ? nullptr : c.take<float>(B * n.bufs[i].elems());
+  ab.sd.assign(n.ops.size(), nullptr);
+  long long mx = 0;
+  for (size_t i = 0; i < n.ops.size(); ++i)
+    if (n.ops[i].kind == OP_CONV) {
+      const long long e = n.layers[n.ops[i].layer].out_elems;
+      ab.sd[i] = c.take<float>(B * e);
+      mx = std::max(mx, e);
+    }
+  ab.dpre = c.take<float>(B * mx);
+  ab.dsec = c.take<float>(B * mx);
+  ab.g0 = c.take<float>(n.P);
+  ab.g1 = c.take<float>(n.P);
+  ab.wsamp = c.take<float>(n.P);
+  ab.delta = c.take<float>(n.P);
+  ab.norms = c.take<float>(2 * n.layers.size());
+  ab.sgn_in.resize(n.layers.size());
+  ab.sgn_out.resize(n.layers.size());
+  for (size_t l = 0; l < n.layers.size(); ++l) {
+    ab.sgn_in[l] = c.take<float>(B * n.layers[l].cin);
+    ab.sgn_out[l] = c.take<float>(B * n.layers[l].cout);
+  }
+  ab.acc = c.take<double>(8);
+}
+
+static NoiseRef nref(const brl_noise* nz, const float* ptr, unsigned kind, unsigned site) {
+  NoiseRef r;
+  r.ptr = ptr;
+  r.seed = nz ? nz->seed : 0ull;
+  r.kind = kind;
+  r.site = site;
+  r.sample0 = nz ? (unsigned)nz->sample0 : 0u;
+  r.window0 = nz ? (unsigned)nz->window0 : 0u;
+  return r;
+}
+
+// shift every injected pointer to MC sample `s` of a call over B windows
+static brl_noise noise_at_sample(const NetSpec& n, const brl_noise* nz, long long s, long long B) {
+  brl_noise o;
+  memset(&o, 0, sizeof(o));
+  if (!nz) return o;
+  o = *nz;
+  o.sample0 = nz->sample0 + s;
+  if (o.weight_eps) o.weight_eps += s * n.P;
+  if (o.radial_r) o.radial_r += s * (long long)(2 * n.layers.size());
+  for (size_t l = 0; l < n.layers.size(); ++l) {
+    const LayerSpec& L = n.layers[l];
+    if (o.lrt_eps[l]) o.lrt_eps[l] += s * B * L.out_elems;
+    if (o.drop_mask[l]) o.drop_mask[l] += s * B * L.out_elems;
+    if (o.flip_in[l]) o.flip_in[l] += s * B * L.cin;
+    if (o.flip_out[l]) o.flip_out[l] += s * B * L.cout;
+  }
+  return o;
+}
+
+struct FwdArgs {
+  const float* x;
+  long long B, S;
+  int mode;
+  const float *theta, *sigma, *wsamp;
+  float p_dropout;
+  const brl_noise* noise;
+  const float* const* sgn_in;   // per layer (flipout), resolved pointers
+  const float* const* sgn_out;
+  float* out;  // [S,B,2] or nullptr (leave in the net's output buffer)
+  bool save_sd;
+};
+
+static Gather fwd_gather(const brl_ctx* ctx, const OpSpec& op, size_t oi, const ActBufs& ab, const float* x) {
+  const NetSpec& n = *ctx->net;
+  Gather g{};
+  if (op.in.buf < 0) {
+    g.base0 = x; g.img_stride = 540; g.per_sample = 0;
+    g.sH = n.xsH; g.sW = n.xsW;
+  } else {
+    g.base0 = ab.act[op.in.buf]; g.img_stride = n.bufs[op.in.buf].elems(); g.per_sample = n.bufs[op.in.buf].shared ? 0 : 1;
+    g.sH = op.in.W; g.sW = 1;
+  }
+  g.base1 = g.base0;
+  g.Hin = op.in.H; g.Win = op.in.W;
+  g.koff = ctx->tabs[oi].koff; g.kdhw = ctx->tabs[oi].kdhw; g.kci = ctx->tabs[oi].kci;
+  return g;
+}
+
+static PoolParams pool_params(const NetSpec& n, const OpSpec& op, const ActBufs& ab, const float* x, long long B, long long S) {
+  PoolParams p{};
+  if (op.in.buf < 0) {
+    p.in = x; p.in_img_stride = 540; p.sC = n.xsC; p.sH = n.xsH; p.sW = n.xsW; p.n_img = B;
+  } else {
+    p.in = ab.act[op.in.buf]; p.in_img_stride = n.bufs[op.in.buf].elems();
+    p.sC = op.in.H * op.in.W; p.sH = op.in.W; p.sW = 1;
+    p.n_img = n.bufs[op.in.buf].shared ? B : S * B;
+  }
+  p.out = ab.act[op.out_buf]; p.out_img_stride = n.bufs[op.out_buf].elems();
+  p.C = op.in.C; p.Hin = op.in.H; p.Win = op.in.W; p.Hout = op.Hout;
+  return p;
+}
+
+static void run_forward(const brl_ctx* ctx, const ActBufs& ab, const FwdArgs& a, cudaStream_t st) {
+  const NetSpec& n = *ctx->net;
+  for (size_t oi = 0; oi < n.ops.size(); ++oi) {
+    const OpSpec& op = n.ops[oi];
+    if (op.kind == OP_MAXPOOL3) { launch_maxpool3(pool_params(n, op, ab, a.x, a.B, a.S), st); continue; }
+    if (op.kind == OP_AVGPOOL2) { launch_avgpool2(pool_params(n, op, ab, a.x, a.B, a.S), st); continue; }
+    const LayerSpec& L = n.layers[op.layer];
+    ConvGemm p{};
+    p.B = (int)a.B; p.P = op.Hout * op.Wout; p.Wrow = op.Wout; p.N = L.cout; p.K = L.cin * L.kh * L.kw; p.S = (int)a.S;
+    p.a = fwd_gather(ctx, op, oi, ab, a.x);
+    p.kB = nullptr; p.nB = p.K;
+    int epi = EPI_FWD_PLAIN;
+    switch (a.mode) {
+      case BRL_MODE_DET:
+        p.W0 = a.theta + L.w_off; p.bias0 = a.theta + L.b_off; break;
+      case BRL_MODE_WS:
+        p.W0 = a.wsamp + L.w_off; p.ws0 = n.P; p.bias0 = a.wsamp + L.b_off; p.bs0 = n.P; break;
+      case BRL_MODE_LRT:
+        epi = EPI_FWD_LRT;
+        p.W0 = a.theta + L.w_off; p.W1 = a.sigma + L.w_off; p.trA = TRA_SQUARE; p.trB = TRB_SQUARE;
+        p.bias0 = a.theta + L.b_off; p.bias1 = a.sigma + L.b_off;
+        p.eps = nref(a.noise, a.noise ? a.noise->lrt_eps[op.layer] : nullptr, KIND_LRT_EPS, op.layer);
+        p.sd_out = a.save_sd ? ab.sd[oi] : nullptr;
+        break;
+      case BRL_MODE_FLIPOUT:
+        epi = EPI_FWD_FLIPOUT;
+        p.W0 = a.theta + L.w_off; p.W1 = a.wsamp + L.w_off; p.ws1 = n.P; p.trA = TRA_SIGN; p.trB = TRB_MINUS_W0;
+        p.sign_in = a.sgn_in[op.layer]; p.sign_C = L.cin; p.sign_out = a.sgn_out[op.layer];
+        p.bias1 = a.wsamp + L.b_off; p.bs1 = n.P;
+        break;
+    }
+    const bool is_last = op.out_buf == n.out_buf;
+    p.out = (is_last && a.out) ? a.out : ab.act[op.out_buf];
+    p.out_img_stride = n.bufs[op.out_buf].elems();
+    p.out_P = n.bufs[op.out_buf].H * n.bufs[op.out_buf].W;
+    p.co_off = op.co_off; p.relu = op.relu; p.head = op.head;
+    p.keep = (a.p_dropout > 0.f && L.drop_factor > 0.f) ? 1.0f - a.p_dropout * L.drop_factor : 1.0f;
+    p.drop = nref(a.noise, a.noise ? a.noise->drop_mask[op.layer] : nullptr, KIND_DROPOUT, op.layer);
+    launch_conv_gemm(p, epi, st);
+  }
+}
+
+struct BwdArgs {
+  const float* x;
+  long long B;
+  int mode;  // DET/WS: plain weights `w`; LRT/FLIPOUT: mu (+ sigma / wsamp)
+  const float *w, *sigma, *wsamp;
+  float p_dropout;
+  const brl_noise* noise;
+  const float* const* sgn_in;
+  const float* const* sgn_out;
+  const float* out;  // [B,2] forward output (the head's buffer)
+  float *g0, *g1;    // flat gradient accumulators
+};
+
+// expects grad[out_buf] to hold dLoss/d(out) and every other grad buffer zeroed
+static void run_backward(const brl_ctx* ctx, const ActBufs& ab, const BwdArgs& a, cudaStream_t st) {
+  const NetSpec& n = *ctx->net;
+  for (int oi = (int)n.ops.size() - 1; oi >= 0; --oi) {
+    const OpSpec& op = n.ops[oi];
+    if (op.kind != OP_CONV) {
+      if (op.in.buf < 0) continue;  // pooled raw input: no gradient needed
+      PoolParams pp = pool_params(n, op, ab, a.x, a.B, 1);
+      if (op.kind == OP_MAXPOOL3) launch_maxpool3_bwd(pp, ab.grad[op.out_buf], ab.grad[op.in.buf], st);
+      else launch_avgpool2_bwd(pp, ab.grad[op.out_buf], ab.grad[op.in.buf], st);
+      continue;
+    }
+    const LayerSpec& L = n.layers[op.layer];
+    const int Pout = op.Hout * op.Wout;
+    const bool is_last = op.out_buf == n.out_buf;
+    const float keep = (a.p_dropout > 0.f && L.drop_factor > 0.f) ? 1.0f - a.p_dropout * L.drop_factor : 1.0f;
+    BwdAct ba{};
+    ba.gout = ab.grad[op.out_buf];
+    ba.outv = (is_last && a.out) ? a.out : ab.act[op.out_buf];
+    ba.img_stride = n.bufs[op.out_buf].elems();
+    ba.out_P = n.bufs[op.out_buf].H * n.bufs[op.out_buf].W;
+    ba.co_off = op.co_off; ba.N = L.cout; ba.P = Pout; ba.n_img = a.B; ba.B = (int)a.B;
+    ba.relu = op.relu; ba.head = op.head; ba.inv_keep = 1.0f / keep;
+    ba.dpre = ab.dpre;
+    if (a.mode == BRL_MODE_LRT) {
+      ba.dvar = ab.dsec; ba.sd = ab.sd[oi];
+      ba.eps = nref(a.noise, a.noise ? a.noise->lrt_eps[op.layer] : nullptr, KIND_LRT_EPS, op.layer);
+    } else if (a.mode == BRL_MODE_FLIPOUT) {
+      ba.dpert = ab.dsec; ba.sign_out = a.sgn_out[op.layer];
+    }
+    launch_bwd_act(ba, st);
+
+    // weight gradients
+    ConvDw dw{};
+    dw.B = (int)a.B; dw.P = Pout; dw.Wrow = op.Wout; dw.N = L.cout; dw.K = L.cin * L.kh * L.kw;
+    dw.a = fwd_gather(ctx, op, oi, ab, a.x);
+    dw.G = ab.dpre; dw.gw = a.g0 + L.w_off; dw.gb = a.g0 + L.b_off;
+    dw.gb2 = a.mode == BRL_MODE_FLIPOUT ? a.g1 + L.b_off : nullptr;
+    launch_conv_dw(dw, st);
+    if (a.mode == BRL_MODE_LRT) {
+      dw.G = ab.dsec; dw.trA = TRA_SQUARE; dw.gw = a.g1 + L.w_off; dw.gb = a.g1 + L.b_off; dw.gb2 = nullptr;
+      launch_conv_dw(dw, st);
+    } else if (a.mode == BRL_MODE_FLIPOUT) {
+      dw.G = ab.dsec; dw.trA = TRA_SIGN; dw.sign_in = a.sgn_in[op.layer]; dw.sign_C = L.cin;
+      dw.gw = a.g1 + L.w_off; dw.gb = nullptr; dw.gb2 = nullptr;
+      launch_conv_dw(dw, st);
+    }
+
+    // input gradient
+    if (op.in.buf < 0 || n.bufs[op.in.buf].shared) continue;
+    ConvGemm p{};
+    p.B = (int)a.B; p.P = op.in.H * op.in.W; p.Wrow = op.in.W; p.N = L.cin; p.K = L.cout * L.kh * L.kw; p.S = 1;
+    p.a.base0 = ab.dpre; p.a.base1 = ab.dsec; p.a.img_stride = (long long)L.cout * Pout; p.a.per_sample = 1;
+    p.a.Hin = op.Hout; p.a.Win = op.Wout; p.a.sH = op.Wout; p.a.sW = 1;
+    p.a.koff = ctx->tabs[oi].koff_dx; p.a.kdhw = ctx->tabs[oi].kdhw_dx; p.a.kci = nullptr;
+    p.kB = ctx->tabs[oi].kB_dx; p.nB = L.kh * L.kw;
+    p.W0 = a.w + L.w_off;
+    p.out = ab.grad[op.in.buf];
+    p.out_img_stride = n.bufs[op.in.buf].elems();
+    p.out_P = op.in.H * op.in.W; p.co_off = 0;
+    int epi = EPI_DX_PLAIN;
+    if (a.mode == BRL_MODE_LRT) {
+      epi = EPI_DX_LRT; p.W1 = a.sigma + L.w_off; p.trB = TRB_SQUARE; p.xin = ab.act[op.in.buf];
+    } else if (a.mode == BRL_MODE_FLIPOUT) {
+      epi = EPI_DX_FLIPOUT; p.W1 = a.wsamp + L.w_off; p.trB = TRB_MINUS_W0; p.sign_in = a.sgn_in[op.layer]; p.sign_C = L.cin;
+    }
+    launch_conv_gemm(p, epi, st);
+  }
+}
+
+static int zero_grads(const NetSpec& n, const ActBufs& ab, long long B, cudaStream_t st) {
+  for (size_t i = 0; i < n.bufs.size(); ++i)
+    if (ab.grad[i]) BRL_CUDA(cudaMemsetAsync(ab.grad[i], 0, sizeof(float) * B * n.bufs[i].elems(), st));
+  return BRL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int brl_version(void) { return 100; }
+const char* brl_last_error(void) { return g_err.c_str(); }
+
+int brl_net_num_params(int net) { try { return (int)get_net(net).P; } catch (...) { return BRL_ERR_INVALID; } }
+int brl_net_num_layers(int net) { try { return (int)get_net(net).layers.size(); } catch (...) { return BRL_ERR_INVALID; } }
+int brl_net_num_sites(int net) { try { return 2 * (int)get_net(net).layers.size(); } catch (...) { return BRL_ERR_INVALID; } }
+int64_t brl_net_flops_fwd(int net) { try { return get_net(net).flops_fwd; } catch (...) { return BRL_ERR_INVALID; } }
+
+int brl_net_site(int net, int site, int64_t* offset, int* ndim, int64_t shape[4]) {
+  try {
+    const NetSpec& n = get_net(net);
+    BRL_REQUIRE(site >= 0 && site < 2 * (int)n.layers.size(), "site out of range");
+    const LayerSpec& L = n.layers[site / 2];
+    for (int i = 0; i < 4; ++i) shape[i] = 1;
+    if (site % 2 == 0) {
+      *offset = L.w_off; *ndim = L.wndim;
+      for (int i = 0; i < L.wndim; ++i) shape[i] = L.wshape[i];
+    } else {
+      *offset = L.b_off; *ndim = 1; shape[0] = L.cout;
+    }
+    return BRL_OK;
+  } catch (...) { return fail(BRL_ERR_INVALID, "unknown net"); }
+}
+
+int brl_net_layer(int net, int layer, int* cout, int* cin, int* out_elems, float* dropout_factor) {
+  try {
+    const NetSpec& n = get_net(net);
+    BRL_REQUIRE(layer >= 0 && layer < (int)n.layers.size(), "layer out of range");
+    const LayerSpec& L = n.layers[layer];
+    *cout = L.cout; *cin = L.cin; *out_elems = L.out_elems; *dropout_factor = L.drop_factor;
+    return BRL_OK;
+  } catch (...) { return fail(BRL_ERR_INVALID, "unknown net"); }
+}
+
+int brl_create(brl_ctx** out, int net, int device) {
+  BRL_REQUIRE(out != nullptr, "ctx pointer is NULL");
+  const NetSpec* ns;
+  try { ns = &get_net(net); } catch (...) { return fail(BRL_ERR_INVALID, "unknown net"); }
+  int ndev = 0;
+  BRL_CUDA(cudaGetDeviceCount(&ndev));
+  BRL_REQUIRE(device >= 0 && device < ndev, "device index out of range");
+  cudaDeviceProp prop;
+  BRL_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(BRL_ERR_UNSUPPORTED, "bayesrul_b200: built for sm_100a (B200) only; device is sm_" +
+                                         std::to_string(prop.major) + std::to_string(prop.minor) + " -- no fallback by design");
+  BRL_CUDA(cudaSetDevice(device));
+  brl_ctx* c = new brl_ctx();
+  c->net_id = net; c->device = device; c->net = ns;
+  // build gather tables
+  std::vector<int> pool;
+  struct Loc { size_t koff, kdhw, kci, koff_dx, kdhw_dx, kB_dx; };
+  std::vector<Loc> locs(ns->ops.size());
+  for (size_t oi = 0; oi < ns->ops.size(); ++oi) {
+    const OpSpec& op = ns->ops[oi];
+    if (op.kind != OP_CONV) continue;
+    const LayerSpec& L = ns->layers[op.layer];
+    int sC, sH, sW;
+    if (op.in.buf < 0) { sC = ns->xsC; sH = ns->xsH; sW = ns->xsW; }
+    else { sC = op.in.H * op.in.W; sH = op.in.W; sW = 1; }
+    const int KK = L.kh * L.kw, K = L.cin * KK, Kdx = L.cout * KK, Pout = op.Hout * op.Wout;
+    Loc lc;
+    lc.koff = pool.size();
+    for (int k = 0; k < K; ++k) { int ci = k / KK, r = k % KK, kh = r / L.kw, kw = r % L.kw; pool.push_back(ci * sC + (kh - L.ph) * sH + (kw - L.pw) * sW); }
+    lc.kdhw = pool.size();
+    for (int k = 0; k < K; ++k) { int r = k % KK, kh = r / L.kw, kw = r % L.kw; pool.push_back(((kh - L.ph) & 0xffff) | ((kw - L.pw) << 16)); }
+    lc.kci = pool.size();
+    for (int k = 0; k < K; ++k) pool.push_back(k / KK);
+    lc.koff_dx = pool.size();
+    for (int k = 0; k < Kdx; ++k) { int co = k / KK, r = k % KK, kh = r / L.kw, kw = r % L.kw; pool.push_back(co * Pout + (L.ph - kh) * op.Wout + (L.pw - kw)); }
+    lc.kdhw_dx = pool.size();
+    for (int k = 0; k < Kdx; ++k) { int r = k % KK, kh = r / L.kw, kw = r % L.kw; pool.push_back(((L.ph - kh) & 0xffff) | ((L.pw - kw) << 16)); }
+    lc.kB_dx = pool.size();
+    for (int k = 0; k < Kdx; ++k) { int co = k / KK, r = k % KK; pool.push_back(co * L.cin * KK + r); }
+    locs[oi] = lc;
+  }
+  BRL_CUDA(cudaMalloc(&c->table_pool, pool.size() * sizeof(int)));
+  BRL_CUDA(cudaMemcpy(c->table_pool, pool.data(), pool.size() * sizeof(int), cudaMemcpyHostToDevice));
+  c->tabs.resize(ns->ops.size());
+  for (size_t oi = 0; oi < ns->ops.size(); ++oi) {
+    if (ns->ops[oi].kind != OP_CONV) continue;
+    OpTables& t = c->tabs[oi];
+    t.koff = c->table_pool + locs[oi].koff; t.kdhw = c->table_pool + locs[oi].kdhw; t.kci = c->table_pool + locs[oi].kci;
+    t.koff_dx = c->table_pool + locs[oi].koff_dx; t.kdhw_dx = c->table_pool + locs[oi].kdhw_dx; t.kB_dx = c->table_pool + locs[oi].kB_dx;
+  }
+  BRL_CUDA(cudaMalloc(&c->site_off_dev, ns->site_off.size() * sizeof(long long)));
+  BRL_CUDA(cudaMemcpy(c->site_off_dev, ns->site_off.data(), ns->site_off.size() * sizeof(long long), cudaMemcpyHostToDevice));
+  for (size_t j = 0; j + 1 < ns->site_off.size(); ++j) c->max_site = std::max(c->max_site, (int)(ns->site_off[j + 1] - ns->site_off[j]));
+  c->tc = tc_create(net);
+  *out = c;
+  return BRL_OK;
+}
+
+int brl_destroy(brl_ctx* ctx) {
+  if (!ctx) return BRL_OK;
+  cudaFree(ctx->table_pool);
+  cudaFree(ctx->site_off_dev);
+  tc_destroy(ctx->tc);
+  delete ctx;
+  return BRL_OK;
+}
+
+int64_t brl_workspace_bytes(const brl_ctx* ctx, int64_t B, int64_t S, int train, int engine) {
+  if (!ctx || B <= 0 || S <= 0) return BRL_ERR_INVALID;
+  const NetSpec& n = *ctx->net;
+  Carve c(nullptr, 0);
+  ActBufs ab;
+  c.take<float>(4 * B);          // moment state
+  c.take<float>(S * n.P);        // weight samples
+  c.take<float>(S * 2 * (long long)n.layers.size());
+  c.take<float>(S * B * 2);      // chunk outputs
+  if (engine == BRL_ENGINE_TC_FP16) c.used += tc_workspace_bytes(ctx->tc, B, S);
+  else carve_forward(n, c, B, S, ab);
+  if (train) carve_train(n, c, B, ab);
+  return (int64_t)c.used + 4096;
+}
+
+int brl_sample_weights(brl_ctx* ctx, const float* mu, const float* sigma, int guide, int64_t S, const brl_noise* noise,
+                       float* w_out, float* delta_out, void* workspace, size_t workspace_bytes, void* stream) {
+  BRL_REQUIRE(ctx && mu && sigma && w_out && S > 0, "brl_sample_weights: NULL argument or S <= 0");
+  const NetSpec& n = *ctx->net;
+  cudaStream_t st = (cudaStream_t)stream;
+  NoiseRef eps = nref(noise, noise ? noise->weight_eps : nullptr, KIND_WEIGHT_EPS, 0);
+  if (guide == BRL_GUIDE_NORMAL) {
+    launch_sample_normal(mu, sigma, n.P, S, eps, w_out, delta_out, st);
+  } else if (guide == BRL_GUIDE_RADIAL) {
+    const int ns = 2 * (int)n.layers.size();
+    Carve c(workspace, workspace_bytes);
+    float* norms = c.take<float>(S * ns);
+    if (!workspace || !c.ok) return fail(BRL_ERR_WORKSPACE, "brl_sample_weights: workspace too small for radial norms");
+    NoiseRef r = nref(noise, noise ? noise->radial_r : nullptr, KIND_RADIAL_R, 0);
+    launch_sample_radial(mu, sigma, n.P, S, ctx->site_off_dev, ns, ctx->max_site, eps, r, norms, w_out, delta_out, st);
+  } else {
+    return fail(BRL_ERR_INVALID, "Guide unknown. Choose from 'normal', 'radial'.");
+  }
+  BRL_CUDA(cudaGetLastError());
+  return BRL_OK;
+}
+
+static int resolve_signs(const brl_ctx* ctx, const brl_noise* nz, long long S, long long B, Carve& c,
+                         std::vector<const float*>& sin_, std::vector<const float*>& sout_, cudaStream_t st) {
+  const NetSpec& n = *ctx->net;
+  sin_.assign(n.layers.size(), nullptr);
+  sout_.assign(n.layers.size(), nullptr);
+  for (size_t l = 0; l < n.layers.size(); ++l) {
+    const LayerSpec& L = n.layers[l];
+    if (nz && nz->flip_in[l]) sin_[l] = nz->flip_in[l];
+    else {
+      float* d = c.take<float>(S * B * L.cin);
+      if (!c.ok) return fail(BRL_ERR_WORKSPACE, "workspace too small (flipout signs)");
+      launch_gen_signs(d, S, B, L.cin, nref(nz, nullptr, KIND_FLIP_IN, (unsigned)l), st);
+      sin_[l] = d;
+    }
+    if (nz && nz->flip_out[l]) sout_[l] = nz->flip_out[l];
+    else {
+      float* d = c.take<float>(S * B * L.cout);
+      if (!c.ok) return fail(BRL_ERR_WORKSPACE, "workspace too small (flipout signs)");
+      launch_gen_signs(d, S, B, L.cout, nref(nz, nullptr, KIND_FLIP_OUT, (unsigned)l), st);
+      sout_[l] = d;
+    }
+  }
+  return BRL_OK;
+}
+
+int brl_forward(brl_ctx* ctx, const float* x, int64_t B, int64_t S, int mode, const float* theta, const float* sigma,
+                const float* wsamp, float p_dropout, const brl_noise* noise, float* out, int engine, void* workspace,
+                size_t workspace_bytes, void* stream) {
+  BRL_REQUIRE(ctx && x && out && workspace, "brl_forward: NULL argument");
+  BRL_REQUIRE(B > 0 && S > 0 && B * 30 < (1ll << 31) / 512, "brl_forward: bad B or S");
+  BRL_REQUIRE(mode >= BRL_MODE_DET && mode <= BRL_MODE_FLIPOUT, "brl_forward: unknown mode");
+  BRL_REQUIRE(mode == BRL_MODE_WS || theta, "brl_forward: theta is NULL");
+  BRL_REQUIRE(mode != BRL_MODE_LRT || sigma, "brl_forward: LRT needs sigma");
+  BRL_REQUIRE((mode != BRL_MODE_WS && mode != BRL_MODE_FLIPOUT) || wsamp, "brl_forward: WS/FLIPOUT need wsamp [S,P]");
+  BRL_REQUIRE(p_dropout >= 0.f && p_dropout < 1.f, "brl_forward: p_dropout must be in [0,1)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const NetSpec& n = *ctx->net;
+  if (engine == BRL_ENGINE_TC_FP16) {
+    BRL_REQUIRE(mode == BRL_MODE_DET || mode == BRL_MODE_WS, "tensor-core engine supports DET / WS forward only");
+    const char* err = tc_forward(ctx->tc, x, B, S, mode == BRL_MODE_WS ? wsamp : theta, mode == BRL_MODE_WS ? n.P : 0,
+                                 p_dropout, noise, out, workspace, workspace_bytes, st);
+    if (err) return fail(BRL_ERR_UNSUPPORTED, err);
+    BRL_CUDA(cudaGetLastError());
+    return BRL_OK;
+  }
+  BRL_REQUIRE(engine == BRL_ENGINE_SIMT_FP32, "unknown engine");
+  Carve c(workspace, workspace_bytes);
+  ActBufs ab;
+  carve_forward(n, c, B, S, ab);
+  if (!c.ok) return fail(BRL_ERR_WORKSPACE, "brl_forward: workspace too small");
+  std::vector<const float*> sin_, sout_;
+  if (mode == BRL_MODE_FLIPOUT) {
+    int rc = resolve_signs(ctx, noise, S, B, c, sin_, sout_, st);
+    if (rc) return rc;
+  }
+  FwdArgs fa{x, B, S, mode, theta, sigma, wsamp, p_dropout, noise, sin_.data(), sout_.data(), out, false};
+  run_forward(ctx, ab, fa, st);
+  BRL_CUDA(cudaGetLastError());
+  return BRL_OK;
+}
+
+int brl_predict_moments(brl_ctx* ctx, const float* x, int64_t B, int64_t S, int guide, const float* mu,
+                        const float* sigma, float p_dropout, const brl_noise* noise, float* pred, float* std,
+                        float* ep_var, float* al_var, int engine, void* workspace, size_t workspace_bytes, void* stream) {
+  BRL_REQUIRE(ctx && x && mu && pred && std && workspace, "brl_predict_moments: NULL argument");
+  BRL_REQUIRE(B > 0 && S > 0 && B * 30 < (1ll << 31) / 512, "brl_predict_moments: bad B or S");
+  BRL_REQUIRE(guide < 0 || sigma, "brl_predict_moments: sigma is NULL");
+  BRL_REQUIRE(guide <= BRL_GUIDE_RADIAL, "Guide unknown. Choose from 'normal', 'radial'.");
+  cudaStream_t st = (cudaStream_t)stream;
+  const NetSpec& n = *ctx->net;
+  const int nsites = 2 * (int)n.layers.size();
+  // largest chunk of samples that fits
+  long long Sc = std::min<long long>(S, 16);
+  for (; Sc >= 1; --Sc)
+    if ((size_t)brl_workspace_bytes(ctx, B, Sc, 0, engine) <= workspace_bytes) break;
+  if (Sc < 1) return fail(BRL_ERR_WORKSPACE, "brl_predict_moments: workspace too small for one MC sample; need " +
+                                                 std::to_string(brl_workspace_bytes(ctx, B, 1, 0, engine)) + " bytes");
+  Carve c(workspace, workspace_bytes);
+  float* state = c.take<float>(4 * B);
+  float* wsamp = c.take<float>(Sc * n.P);
+  float* norms = c.take<float>(Sc * nsites);
+  float* outc = c.take<float>(Sc * B * 2);
+  ActBufs ab;
+  void* tc_ws = nullptr;
+  size_t tc_bytes = 0;
+  if (engine == BRL_ENGINE_TC_FP16) {
+    tc_bytes = tc_workspace_bytes(ctx->tc, B, Sc);
+    tc_ws = c.take<char>((long long)tc_bytes);
+  } else {
+    carve_forward(n, c, B, Sc, ab);
+  }
+  if (!c.ok) return fail(BRL_ERR_WORKSPACE, "brl_predict_moments: workspace carve failed");
+  for (long long s0 = 0; s0 < S; s0 += Sc) {
+    const long long sc = std::min(Sc, S - s0);
+    brl_noise nz = noise_at_sample(n, noise, s0, B);
+    const float* w = mu;
+    int mode = BRL_MODE_DET;
+    if (guide >= 0) {
+      NoiseRef eps = nref(&nz, nz.weight_eps, KIND_WEIGHT_EPS, 0);
+      if (guide == BRL_GUIDE_NORMAL) launch_sample_normal(mu, sigma, n.P, sc, eps, wsamp, nullptr, st);
+      else launch_sample_radial(mu, sigma, n.P, sc, ctx->site_off_dev, nsites, ctx->max_site, eps,
+                                nref(&nz, nz.radial_r, KIND_RADIAL_R, 0), norms, wsamp, nullptr, st);
+      w = wsamp;
+      mode = BRL_MODE_WS;
+    }
+    if (engine == BRL_ENGINE_TC_FP16) {
+      const char* err = tc_forward(ctx->tc, x, B, sc, w, mode == BRL_MODE_WS ? n.P : 0, p_dropout, &nz, outc, tc_ws, tc_bytes, st);
+      if (err) return fail(BRL_ERR_UNSUPPORTED, err);
+    } else {
+      FwdArgs fa{x, B, sc, mode, w, nullptr, w, p_dropout, &nz, nullptr, nullptr, outc, false};
+      run_forward(ctx, ab, fa, st);
+    }
+    launch_moments_update(outc, sc, B, state, s0 == 0, st);
+  }
+  launch_moments_final(state, B, pred, std, ep_var, al_var, st);
+  BRL_CUDA(cudaGetLastError());
+  return BRL_OK;
+}
+
+int brl_moments(const float* out, int64_t S, int64_t B, float* pred, float* std, float* ep_var, float* al_var, void* stream) {
+  BRL_REQUIRE(out && pred && std && S > 0 && B > 0, "brl_moments: bad argument");
+  BRL_REQUIRE(ep_var && al_var, "brl_moments: ep_var / al_var must be given");
+  cudaStream_t st = (cudaStream_t)stream;
+  launch_moments_direct(out, S, B, pred, std, ep_var, al_var, st);
+  BRL_CUDA(cudaGetLastError());
+  return BRL_OK;
+}
+
+int brl_aggregate_predictions(const float* out, int64_t S, int64_t B, float* agg, void* stream) {
+  BRL_REQUIRE(out && agg && S > 0 && B > 0, "brl_aggregate_predictions: bad argument");
+  launch_aggregate(out, S, B, agg, (cudaStream_t)stream);
+  BRL_CUDA(cudaGetLastError());
+  return BRL_OK;
+}
+
+int brl_elbo_step(brl_ctx* ctx, const float* x, const float* y, int64_t B, const float* mu, const float* sigma, int mode,
+                  int guide, int particles, float prior_loc, float prior_scale, int64_t dataset_size,
+                  const brl_noise* noise, int compute_grads, double* scalars, float* grad_mu, float* grad_sigma,
+                  float* grad_log_sigma, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  BRL_REQUIRE(ctx && x && y && mu && sigma && scalars && out && workspace, "brl_elbo_step: NULL argument");
+  BRL_REQUIRE(B > 0 && particles > 0 && dataset_size > 0 && prior_scale > 0.f, "brl_elbo_step: bad sizes");
+  BRL_REQUIRE(guide == BRL_GUIDE_NORMAL || guide == BRL_GUIDE_RADIAL, "Guide unknown. Choose from 'normal', 'radial'.");
+  BRL_REQUIRE(mode == BRL_MODE_WS || mode == BRL_MODE_LRT || mode == BRL_MODE_FLIPOUT, "brl_elbo_step: mode must be WS, LRT or FLIPOUT");
+  BRL_REQUIRE(!compute_grads || (grad_mu && grad_sigma), "brl_elbo_step: gradient buffers are NULL");
+  if (guide == BRL_GUIDE_RADIAL) mode = BRL_MODE_WS;  // bayesian.py:81-83: radial forces nullcontext
+  cudaStream_t st = (cudaStream_t)stream;
+  const NetSpec& n = *ctx->net;
+  Carve c(workspace, workspace_bytes);
+  ActBufs ab;
+  carve_forward(n, c, B, 1, ab);
+  carve_train(n, c, B, ab);
+  if (!c.ok) return fail(BRL_ERR_WORKSPACE, "brl_elbo_step: workspace too small; need " +
+                                                std::to_string(brl_workspace_bytes(ctx, B, 1, 1, 0)) + " bytes");
+  const double cc = 1.0 / ((double)dataset_size * 30.0 * 18.0);
+  const double c_nll = cc * (double)dataset_size / (double)B;
+  BRL_CUDA(cudaMemsetAsync(ab.acc, 0, 8 * sizeof(double), st));
+  const int nsites = 2 * (int)n.layers.size();
+  for (int pt = 0; pt < particles; ++pt) {
+    brl_noise nz = noise_at_sample(n, noise, pt, B);
+    const bool need_w = mode != BRL_MODE_LRT;
+    if (need_w) {
+      NoiseRef eps = nref(&nz, nz.weight_eps, KIND_WEIGHT_EPS, 0);
+      if (guide == BRL_GUIDE_NORMAL) launch_sample_normal(mu, sigma, n.P, 1, eps, ab.wsamp, ab.delta, st);
+      else launch_sample_radial(mu, sigma, n.P, 1, ctx->site_off_dev, nsites, ctx->max_site, eps,
+                                nref(&nz, nz.radial_r, KIND_RADIAL_R, 0), ab.norms, ab.wsamp, ab.delta, st);
+    }
+    std::vector<const float*> sin_(n.layers.size(), nullptr), sout_(n.layers.size(), nullptr);
+    if (mode == BRL_MODE_FLIPOUT) {
+      for (size_t l = 0; l < n.layers.size(); ++l) {
+        if (nz.flip_in[l]) sin_[l] = nz.flip_in[l];
+        else { launch_gen_signs(ab.sgn_in[l], 1, B, n.layers[l].cin, nref(&nz, nullptr, KIND_FLIP_IN, (unsigned)l), st); sin_[l] = ab.sgn_in[l]; }
+        if (nz.flip_out[l]) sout_[l] = nz.flip_out[l];
+        else { launch_gen_signs(ab.sgn_out[l], 1, B, n.layers[l].cout, nref(&nz, nullptr, KIND_FLIP_OUT, (unsigned)l), st); sout_[l] = ab.sgn_out[l]; }
+      }
+    }
+    float* outp = out + (long long)pt * B * 2;
+    FwdArgs fa{x, B, 1, mode, mu, sigma, ab.wsamp, 0.f, &nz, sin_.data(), sout_.data(), outp, compute_grads != 0};
+    run_forward(ctx, ab, fa, st);
+    if (compute_grads) {
+      int rc = zero_grads(n, ab, B, st);
+      if (rc) return rc;
+      BRL_CUDA(cudaMemsetAsync(ab.g0, 0, sizeof(float) * n.P, st));
+      BRL_CUDA(cudaMemsetAsync(ab.g1, 0, sizeof(float) * n.P, st));
+    }
+    launch_nll_elbo(outp, y, B, (float)(c_nll / particles), ab.acc, compute_grads ? ab.grad[n.out_buf] : nullptr, st);
+    if (compute_grads) {
+      BwdArgs ba{x, B, mode, mode == BRL_MODE_WS ? ab.wsamp : mu, sigma, ab.wsamp, 0.f, &nz, sin_.data(), sout_.data(), outp, ab.g0, ab.g1};
+      run_backward(ctx, ab, ba, st);
+    }
+    Finalize f{};
+    f.P = n.P; f.mode = mode; f.guide = guide; f.first = pt == 0;
+    f.mu = mu; f.sigma = sigma; f.w = ab.wsamp; f.delta = ab.delta;
+    f.g0 = compute_grads ? ab.g0 : nullptr; f.g1 = compute_grads ? ab.g1 : nullptr;
+    f.prior_loc = prior_loc; f.prior_scale = prior_scale; f.c_kl = (float)(cc / particles);
+    f.grad_mu = compute_grads ? grad_mu : nullptr; f.grad_sigma = compute_grads ? grad_sigma : nullptr;
+    f.kl_acc = ab.acc + 2;
+    launch_finalize(f, st);
+  }
+  launch_post_scalars(scalars, ab.acc, c_nll, cc, particles, B, st);
+  if (compute_grads && grad_log_sigma) launch_log_sigma_grad(grad_sigma, sigma, grad_log_sigma, n.P, st);
+  BRL_CUDA(cudaGetLastError());
+  return BRL_OK;
+}
+
+int brl_hnn_step(brl_ctx* ctx, const float* x, const float* y, int64_t B, const float* theta, float p_dropout,
+                 const brl_noise* noise, int compute_grads, double* scalars, float* grad_theta, float* out,
+                 void* workspace, size_t workspace_bytes, void* stream) {
+  BRL_REQUIRE(ctx && x && y && theta && scalars && out && workspace, "brl_hnn_step: NULL argument");
+  BRL_REQUIRE(B > 0 && p_dropout >= 0.f && p_dropout < 1.f, "brl_hnn_step: bad B or p_dropout");
+  BRL_REQUIRE(!compute_grads || grad_theta, "brl_hnn_step: grad_theta is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  const NetSpec& n = *ctx->net;
+  Carve c(workspace, workspace_bytes);
+  ActBufs ab;
+  carve_forward(n, c, B, 1, ab);
+  carve_train(n, c, B, ab);
+  if (!c.ok) return fail(BRL_ERR_WORKSPACE, "brl_hnn_step: workspace too small");
+  brl_noise nz = noise_at_sample(n, noise, 0, B);
+  FwdArgs fa{x, B, 1, BRL_MODE_DET, theta, nullptr, nullptr, p_dropout, &nz, nullptr, nullptr, out, false};
+  run_forward(ctx, ab, fa, st);
+  BRL_CUDA(cudaMemsetAsync(scalars, 0, 2 * sizeof(double), st));
+  if (compute_grads) {
+    int rc = zero_grads(n, ab, B, st);
+    if (rc) return rc;
+    BRL_CUDA(cudaMemsetAsync(grad_theta, 0, sizeof(float) * n.P, st));
+  }
+  launch_nll_hnn(out, y, B, scalars, compute_grads ? ab.grad[n.out_buf] : nullptr, st);
+  if (compute_grads) {
+    BwdArgs ba{x, B, BRL_MODE_DET, theta, nullptr, nullptr, p_dropout, &nz, nullptr, nullptr, out, grad_theta, nullptr};
+    run_backward(ctx, ab, ba, st);
+  }
+  BRL_CUDA(cudaGetLastError());
+  return BRL_OK;
+}
+
+int brl_mixture_moments(const float* mu_m, const float* sigma_m, int64_t M, int64_t nn, float* mu, float* sigma, void* stream) {
+  BRL_REQUIRE(mu_m && sigma_m && mu && sigma && M > 0 && nn > 0, "brl_mixture_moments: bad argument");
+  launch_mixture(mu_m, sigma_m, M, nn, mu, sigma, (cudaStream_t)stream);
+  BRL_CUDA(cudaGetLastError());
+  return BRL_OK;
+}
+
+int brl_test_metrics(const float* pred, const float* std, const float* y, int64_t nn, double* scalars, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  BRL_REQUIRE(pred && std && y && scalars && workspace && nn > 0, "brl_test_metrics: bad argument");
+  if (workspace_bytes < 1024) return fail(BRL_ERR_WORKSPACE, "brl_test_metrics: workspace must be >= 1024 bytes");
+  launch_test_metrics(pred, std, y, nn, scalars, (unsigned int*)workspace, (cudaStream_t)stream);
+  BRL_CUDA(cudaGetLastError());
+  return BRL_OK;
+}
+
+int brl_clipped_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t nn, int64_t step, float lr,
+                     float beta1, float beta2, float eps, float clip_norm, float lrd, float weight_decay, void* stream) {
+  BRL_REQUIRE(param && grad && exp_avg && exp_avg_sq && nn > 0 && step >= 1, "brl_clipped_adam: bad argument");
+  const double lr_t = (double)lr * std::pow((double)lrd, (double)step);
+  const double bc1 = 1.0 - std::pow((double)beta1, (double)step), bc2 = 1.0 - std::pow((double)beta2, (double)step);
+  launch_clipped_adam(param, grad, exp_avg, exp_avg_sq, nn, (float)(lr_t * std::sqrt(bc2) / bc1), beta1, beta2, eps,
+                      clip_norm, weight_decay, (cudaStream_t)stream);
+  BRL_CUDA(cudaGetLastError());
+  return BRL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,779 @@
+// fp32 SIMT engine: implicit-GEMM conv / linear layers with the variational rules fused in the
+// gather prologue and the epilogue, plus the small reductions of the ELBO / predictive path.
+// This is the parity engine (rtol 1e-3 vs the oracle); the tcgen05 engine lives in brl_tc.cu.
+#include "brl_kernels.cuh"
+#include "brl_philox.cuh"
+
+namespace brl {
+
+// ------------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float noise_normal(const NoiseRef& nz, int s, int b, int B, int per_window, int e) {
+  if (nz.ptr) return nz.ptr[((long long)s * B + b) * per_window + e];
+  return philox_normal(nz.seed, nz.kind, nz.site, nz.sample0 + s, nz.window0 + b, e);
+}
+__device__ __forceinline__ bool noise_keep(const NoiseRef& nz, int s, int b, int B, int per_window, int e, float keep) {
+  if (nz.ptr) return nz.ptr[((long long)s * B + b) * per_window + e] != 0.0f;
+  return philox_uniform(nz.seed, nz.kind, nz.site, nz.sample0 + s, nz.window0 + b, e) < keep;
+}
+__device__ __forceinline__ float softplusf(float x) { return x > 20.0f ? x : log1pf(expf(x)); }
+
+__device__ __forceinline__ double block_sum(double v) {
+  __shared__ double red[32];
+  __syncthreads();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    v = threadIdx.x < (blockDim.x + 31) / 32 ? red[threadIdx.x] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  }
+  return v;  // valid in thread 0
+}
+
+// ------------------------------------------------------------------------------------------------
+// implicit-GEMM conv: C[m,n] = sum_k A(m,k) * B(k,n)   (forward and input-gradient passes)
+// tile 128x32x16, 256 threads, 4x4 micro-tile; DUAL carries the second product of LRT / Flipout
+// ------------------------------------------------------------------------------------------------
+constexpr int BM = 128, BN = 32, BK = 16;
+
+template <bool DUAL, int EPI>
+__global__ void __launch_bounds__(256) conv_gemm_kernel(const ConvGemm p) {
+  __shared__ __align__(16) float As0[BK][BM];
+  __shared__ __align__(16) float Bs0[BK][BN];
+  __shared__ __align__(16) float As1[DUAL ? BK : 1][BM];
+  __shared__ __align__(16) float Bs1[DUAL ? BK : 1][BN];
+
+  const int s = blockIdx.z;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int tid = threadIdx.x;
+  const int Mtot = p.B * p.P;
+
+  // A-load mapping: one row per thread, 8 k's
+  const int ar = tid & (BM - 1), ak0 = tid >> 7;
+  const int am = m0 + ar;
+  const bool arv = am < Mtot;
+  const int ab = arv ? am / p.P : 0;
+  const int app = arv ? am - ab * p.P : 0;
+  const int aoh = app / p.Wrow, aow = app - aoh * p.Wrow;
+  const long long aimg = p.a.per_sample ? (long long)s * p.B + ab : ab;
+  const long long rowbase = aimg * p.a.img_stride + (long long)aoh * p.a.sH + (long long)aow * p.a.sW;
+  const long long signrow = ((long long)s * p.B + ab) * p.sign_C;
+  // B-load mapping
+  const int bn = tid & (BN - 1), bk0 = tid >> 5;
+  const int tx = tid & 7, ty = tid >> 3;
+
+  float acc0[4][4], acc1[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc0[i][j] = acc1[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < p.K; k0 += BK) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int kk = ak0 + 2 * j, k = k0 + kk;
+      float v0 = 0.f, v1 = 0.f;
+      if (arv && k < p.K) {
+        const int dhw = p.a.kdhw[k];
+        const int ih = aoh + (int)(short)(dhw & 0xffff), iw = aow + (dhw >> 16);
+        if ((unsigned)ih < (unsigned)p.a.Hin && (unsigned)iw < (unsigned)p.a.Win) {
+          const long long off = rowbase + p.a.koff[k];
+          v0 = __ldg(p.a.base0 + off);
+          if (DUAL) {
+            v1 = (p.a.base1 == p.a.base0) ? v0 : __ldg(p.a.base1 + off);
+            if (p.trA == TRA_SQUARE) v1 = v1 * v1;
+            else if (p.trA == TRA_SIGN) v1 *= __ldg(p.sign_in + signrow + p.a.kci[k]);
+          }
+        }
+      }
+      As0[kk][ar] = v0;
+      if (DUAL) As1[kk][ar] = v1;
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int kk = bk0 + 8 * j, k = k0 + kk, n = n0 + bn;
+      float v0 = 0.f, v1 = 0.f;
+      if (k < p.K && n < p.N) {
+        const long long off = (p.kB ? p.kB[k] : k) + (long long)n * p.nB;
+        v0 = __ldg(p.W0 + (long long)s * p.ws0 + off);
+        if (DUAL) {
+          v1 = __ldg(p.W1 + (long long)s * p.ws1 + off);
+          if (p.trB == TRB_SQUARE) v1 = v1 * v1;
+          else if (p.trB == TRB_MINUS_W0) v1 -= v0;
+        }
+      }
+      Bs0[kk][bn] = v0;
+      if (DUAL) Bs1[kk][bn] = v1;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&As0[kk][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs0[kk][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc0[i][j] = fmaf(av[i], bv[j], acc0[i][j]);
+      if (DUAL) {
+        const float4 a1 = *reinterpret_cast<const float4*>(&As1[kk][ty * 4]);
+        const float4 b1 = *reinterpret_cast<const float4*>(&Bs1[kk][tx * 4]);
+        const float av1[4] = {a1.x, a1.y, a1.z, a1.w}, bv1[4] = {b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc1[i][j] = fmaf(av1[i], bv1[j], acc1[i][j]);
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---------------- epilogue
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= Mtot) continue;
+    const int b = m / p.P, pp = m - b * p.P;
+    const long long img = (long long)s * p.B + b;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= p.N) continue;
+      const long long oidx = img * p.out_img_stride + (long long)(p.co_off + n) * p.out_P + pp;
+      if (EPI >= EPI_DX_PLAIN) {
+        float g = acc0[i][j];
+        if (EPI == EPI_DX_LRT) g = fmaf(2.0f * p.xin[oidx], acc1[i][j], g);
+        if (EPI == EPI_DX_FLIPOUT) g = fmaf(p.sign_in[img * p.sign_C + n], acc1[i][j], g);
+        p.out[oidx] += g;
+      } else {
+        float v = acc0[i][j];
+        if (EPI == EPI_FWD_PLAIN) {
+          v += p.bias0[(long long)s * p.bs0 + n];
+        } else if (EPI == EPI_FWD_LRT) {
+          const float mean = v + p.bias0[n];
+          const float sb = p.bias1[n];
+          float var = fmaf(sb, sb, acc1[i][j]);
+          if (var < 0.f) var += fabsf(var) + 1e-6f;
+          const float sd = sqrtf(var);
+          const float e = noise_normal(p.eps, s, b, p.B, p.N * p.P, n * p.P + pp);
+          v = fmaf(sd, e, mean);
+          if (p.sd_out) p.sd_out[(img * p.N + n) * p.P + pp] = sd;
+        } else {  // flipout
+          v = v + acc1[i][j] * p.sign_out[img * p.N + n] + p.bias1[(long long)s * p.bs1 + n];
+        }
+        if (p.relu) v = fmaxf(v, 0.f);
+        if (p.keep < 1.0f) v = noise_keep(p.drop, s, b, p.B, p.N * p.P, n * p.P + pp, p.keep) ? v / p.keep : 0.f;
+        if (p.head) {
+          v = softplusf(v);
+          v = v > 1e-9f ? v : 1e-9f;
+        }
+        p.out[oidx] = v;
+      }
+    }
+  }
+}
+
+void launch_conv_gemm(const ConvGemm& p, int epi, cudaStream_t st) {
+  dim3 grid((p.B * p.P + BM - 1) / BM, (p.N + BN - 1) / BN, p.S);
+  switch (epi) {
+    case EPI_FWD_PLAIN: conv_gemm_kernel<false, EPI_FWD_PLAIN><<<grid, 256, 0, st>>>(p); break;
+    case EPI_FWD_LRT: conv_gemm_kernel<true, EPI_FWD_LRT><<<grid, 256, 0, st>>>(p); break;
+    case EPI_FWD_FLIPOUT: conv_gemm_kernel<true, EPI_FWD_FLIPOUT><<<grid, 256, 0, st>>>(p); break;
+    case EPI_DX_PLAIN: conv_gemm_kernel<false, EPI_DX_PLAIN><<<grid, 256, 0, st>>>(p); break;
+    case EPI_DX_LRT: conv_gemm_kernel<true, EPI_DX_LRT><<<grid, 256, 0, st>>>(p); break;
+    case EPI_DX_FLIPOUT: conv_gemm_kernel<true, EPI_DX_FLIPOUT><<<grid, 256, 0, st>>>(p); break;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight gradient: C[co][k] += sum_m G[m][co] * tr(A[m][k]); split over row ranges, fp32 atomics
+// ------------------------------------------------------------------------------------------------
+constexpr int DW_CO = 32, DW_K = 128, DW_M = 16, DW_PAD = 4;
+
+__global__ void __launch_bounds__(256) conv_dw_kernel(const ConvDw p, int rows_per_split) {
+  __shared__ __align__(16) float Gs[DW_M][DW_CO];
+  __shared__ __align__(16) float As[DW_M][DW_K + DW_PAD];
+  const int tid = threadIdx.x;
+  const int kt0 = blockIdx.x * DW_K, co0 = blockIdx.y * DW_CO;
+  const int Mtot = p.B * p.P;
+  const int mbeg = blockIdx.z * rows_per_split;
+  const int mend = min(Mtot, mbeg + rows_per_split);
+  const int r = tid & 15, c0 = tid >> 4;
+  const int tx = tid & 31, ty = tid >> 5;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int mb = mbeg; mb < mend; mb += DW_M) {
+    const int m = mb + r;
+    const bool rv = m < mend;
+    const int b = rv ? m / p.P : 0;
+    const int pp = rv ? m - b * p.P : 0;
+    const int oh = pp / p.Wrow, ow = pp - oh * p.Wrow;
+    const long long img = b;  // training passes are single-sample
+    const long long rowbase = img * p.a.img_stride + (long long)oh * p.a.sH + (long long)ow * p.a.sW;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int c = c0 + 16 * j, co = co0 + c;
+      Gs[r][c] = (rv && co < p.N) ? __ldg(p.G + ((long long)b * p.N + co) * p.P + pp) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int kc = c0 + 16 * j, k = kt0 + kc;
+      float v = 0.f;
+      if (rv) {
+        if (k < p.K) {
+          const int dhw = p.a.kdhw[k];
+          const int ih = oh + (int)(short)(dhw & 0xffff), iw = ow + (dhw >> 16);
+          if ((unsigned)ih < (unsigned)p.a.Hin && (unsigned)iw < (unsigned)p.a.Win) {
+            v = __ldg(p.a.base0 + rowbase + p.a.koff[k]);
+            if (p.trA == TRA_SQUARE) v = v * v;
+            else if (p.trA == TRA_SIGN) v *= __ldg(p.sign_in + (long long)b * p.sign_C + p.a.kci[k]);
+          }
+        } else if (k == p.K) {
+          v = 1.0f;  // bias column
+        }
+      }
+      As[r][kc] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int mm = 0; mm < DW_M; ++mm) {
+      const float4 g = *reinterpret_cast<const float4*>(&Gs[mm][ty * 4]);
+      const float4 a = *reinterpret_cast<const float4*>(&As[mm][tx * 4]);
+      const float gv[4] = {g.x, g.y, g.z, g.w}, av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(gv[i], av[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int co = co0 + ty * 4 + i;
+    if (co >= p.N) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = kt0 + tx * 4 + j;
+      if (k < p.K) {
+        atomicAdd(p.gw + (long long)co * p.K + k, acc[i][j]);
+      } else if (k == p.K) {
+        if (p.gb) atomicAdd(p.gb + co, acc[i][j]);
+        if (p.gb2) atomicAdd(p.gb2 + co, acc[i][j]);
+      }
+    }
+  }
+}
+
+void launch_conv_dw(const ConvDw& p, cudaStream_t st) {
+  const int Mtot = p.B * p.P;
+  const int gx = (p.K + 1 + DW_K - 1) / DW_K, gy = (p.N + DW_CO - 1) / DW_CO;
+  int split = max(1, min((Mtot + 63) / 64, (296 + gx * gy - 1) / (gx * gy)));
+  int rows = (Mtot + split - 1) / split;
+  rows = (rows + DW_M - 1) / DW_M * DW_M;
+  split = (Mtot + rows - 1) / rows;
+  conv_dw_kernel<<<dim3(gx, gy, split), 256, 0, st>>>(p, rows);
+}
+
+// ------------------------------------------------------------------------------------------------
+// pooling
+// ------------------------------------------------------------------------------------------------
+__global__ void maxpool3_kernel(const PoolParams p) {
+  const long long total = p.n_img * p.C * p.Hin * p.Win;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int w = i % p.Win;
+    const int h = (i / p.Win) % p.Hin;
+    const int c = (i / ((long long)p.Win * p.Hin)) % p.C;
+    const long long img = i / ((long long)p.Win * p.Hin * p.C);
+    const float* src = p.in + img * p.in_img_stride + (long long)c * p.sC + (long long)w * p.sW;
+    float v = src[(long long)h * p.sH];
+    if (h > 0) v = fmaxf(v, src[(long long)(h - 1) * p.sH]);
+    if (h + 1 < p.Hin) v = fmaxf(v, src[(long long)(h + 1) * p.sH]);
+    p.out[img * p.out_img_stride + ((long long)c * p.Hin + h) * p.Win + w] = v;
+  }
+}
+void launch_maxpool3(const PoolParams& p, cudaStream_t st) {
+  const long long total = p.n_img * p.C * p.Hin * p.Win;
+  maxpool3_kernel<<<(unsigned)min((total + 255) / 256, (long long)148 * 16), 256, 0, st>>>(p);
+}
+
+__device__ __forceinline__ int argmax3_first(const float* src, int o, int H, long long sH) {
+  int best = o > 0 ? o - 1 : o;
+  float bv = src[(long long)best * sH];
+  for (int t = best + 1; t <= min(o + 1, H - 1); ++t) {
+    const float v = src[(long long)t * sH];
+    if (v > bv) { bv = v; best = t; }
+  }
+  return best;
+}
+__global__ void maxpool3_bwd_kernel(const PoolParams p, const float* gout, float* gin) {
+  const long long total = p.n_img * p.C * p.Hin * p.Win;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int w = i % p.Win;
+    const int h = (i / p.Win) % p.Hin;
+    const int c = (i / ((long long)p.Win * p.Hin)) % p.C;
+    const long long img = i / ((long long)p.Win * p.Hin * p.C);
+    const float* src = p.in + img * p.in_img_stride + (long long)c * p.sC + (long long)w * p.sW;
+    const float* go = gout + img * p.out_img_stride + (long long)c * p.Hin * p.Win + w;
+    float g = 0.f;
+    for (int o = max(h - 1, 0); o <= min(h + 1, p.Hin - 1); ++o)
+      if (argmax3_first(src, o, p.Hin, p.sH) == h) g += go[(long long)o * p.Win];
+    gin[img * p.in_img_stride + (long long)c * p.sC + (long long)h * p.sH + (long long)w * p.sW] += g;
+  }
+}
+void launch_maxpool3_bwd(const PoolParams& p, const float* gout, float* gin, cudaStream_t st) {
+  const long long total = p.n_img * p.C * p.Hin * p.Win;
+  maxpool3_bwd_kernel<<<(unsigned)min((total + 255) / 256, (long long)148 * 16), 256, 0, st>>>(p, gout, gin);
+}
+
+__global__ void avgpool2_kernel(const PoolParams p) {
+  const long long total = p.n_img * p.C * p.Hout * p.Win;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int w = i % p.Win;
+    const int h = (i / p.Win) % p.Hout;
+    const int c = (i / ((long long)p.Win * p.Hout)) % p.C;
+    const long long img = i / ((long long)p.Win * p.Hout * p.C);
+    const float* src = p.in + img * p.in_img_stride + (long long)c * p.sC + (long long)w * p.sW;
+    p.out[img * p.out_img_stride + ((long long)c * p.Hout + h) * p.Win + w] =
+        0.5f * (src[(long long)(2 * h) * p.sH] + src[(long long)(2 * h + 1) * p.sH]);
+  }
+}
+void launch_avgpool2(const PoolParams& p, cudaStream_t st) {
+  const long long total = p.n_img * p.C * p.Hout * p.Win;
+  avgpool2_kernel<<<(unsigned)min((total + 255) / 256, (long long)148 * 16), 256, 0, st>>>(p);
+}
+__global__ void avgpool2_bwd_kernel(const PoolParams p, const float* gout, float* gin) {
+  const long long total = p.n_img * p.C * p.Hin * p.Win;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int w = i % p.Win;
+    const int h = (i / p.Win) % p.Hin;
+    const int c = (i / ((long long)p.Win * p.Hin)) % p.C;
+    const long long img = i / ((long long)p.Win * p.Hin * p.C);
+    if (h < 2 * p.Hout)
+      gin[img * p.in_img_stride + (long long)c * p.sC + (long long)h * p.sH + (long long)w * p.sW] +=
+          0.5f * gout[img * p.out_img_stride + ((long long)c * p.Hout + (h >> 1)) * p.Win + w];
+  }
+}
+void launch_avgpool2_bwd(const PoolParams& p, const float* gout, float* gin, cudaStream_t st) {
+  const long long total = p.n_img * p.C * p.Hin * p.Win;
+  avgpool2_bwd_kernel<<<(unsigned)min((total + 255) / 256, (long long)148 * 16), 256, 0, st>>>(p, gout, gin);
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward through activation / dropout / head
+// ------------------------------------------------------------------------------------------------
+__global__ void bwd_act_kernel(const BwdAct p) {
+  const long long per = (long long)p.N * p.P, total = p.n_img * per;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long img = i / per;
+    const int e = (int)(i - img * per);
+    const int n = e / p.P, pp = e - n * p.P;
+    const long long oidx = img * p.img_stride + (long long)(p.co_off + n) * p.out_P + pp;
+    const float g = p.gout[oidx], o = p.outv[oidx];
+    float d;
+    if (p.head) d = o > 1e-9f ? g * (1.0f - expf(-o)) : 0.f;
+    else if (p.relu) d = o > 0.f ? g * p.inv_keep : 0.f;
+    else d = g * p.inv_keep;
+    p.dpre[i] = d;
+    const int s = (int)(img / p.B), b = (int)(img - (long long)s * p.B);
+    if (p.dvar) {
+      const float sd = p.sd[i];
+      const float eps = noise_normal(p.eps, s, b, p.B, (int)per, e);
+      p.dvar[i] = sd > 0.f ? d * eps / (2.0f * sd) : 0.f;
+    }
+    if (p.dpert) p.dpert[i] = d * p.sign_out[img * p.N + n];
+  }
+}
+void launch_bwd_act(const BwdAct& p, cudaStream_t st) {
+  const long long total = p.n_img * p.N * p.P;
+  bwd_act_kernel<<<(unsigned)min((total + 255) / 256, (long long)148 * 16), 256, 0, st>>>(p);
+}
+
+// ------------------------------------------------------------------------------------------------
+// guide samplers
+// ------------------------------------------------------------------------------------------------
+__global__ void sample_normal_kernel(const float* __restrict__ mu, const float* __restrict__ sigma, long long P,
+                                     NoiseRef eps, float* __restrict__ w, float* __restrict__ delta) {
+  const long long nblk = (P + 3) >> 2;
+  const int s = blockIdx.y;
+  for (long long blk = blockIdx.x * (long long)blockDim.x + threadIdx.x; blk < nblk; blk += (long long)gridDim.x * blockDim.x) {
+    float z[4];
+    const long long e0 = blk << 2;
+    if (eps.ptr) {
+#pragma unroll
+      for (int l = 0; l < 4; ++l) z[l] = e0 + l < P ? eps.ptr[(long long)s * P + e0 + l] : 0.f;
+    } else {
+      const float4 n4 = normal4(philox_block(eps.seed, KIND_WEIGHT_EPS, 0, eps.sample0 + s, 0, (uint32_t)blk));
+      z[0] = n4.x; z[1] = n4.y; z[2] = n4.z; z[3] = n4.w;
+    }
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      const long long e = e0 + l;
+      if (e < P) {
+        w[(long long)s * P + e] = fmaf(sigma[e], z[l], mu[e]);
+        if (delta) delta[(long long)s * P + e] = z[l];
+      }
+    }
+  }
+}
+void launch_sample_normal(const float* mu, const float* sigma, long long P, long long S, NoiseRef eps, float* w,
+                          float* delta, cudaStream_t st) {
+  const long long nblk = (P + 3) >> 2;
+  dim3 grid((unsigned)min((nblk + 255) / 256, (long long)148 * 8), (unsigned)S);
+  sample_normal_kernel<<<grid, 256, 0, st>>>(mu, sigma, P, eps, w, delta);
+}
+
+__device__ __forceinline__ float weight_eps_at(const NoiseRef& eps, int s, long long P, long long e) {
+  if (eps.ptr) return eps.ptr[(long long)s * P + e];
+  return philox_normal(eps.seed, KIND_WEIGHT_EPS, 0, eps.sample0 + s, 0, (uint32_t)e);
+}
+__global__ void radial_norm_kernel(long long P, const long long* __restrict__ site_off, int n_sites, NoiseRef eps,
+                                   float* __restrict__ norms) {
+  const int j = blockIdx.x, s = blockIdx.y;
+  const long long beg = site_off[j], end = site_off[j + 1];
+  double acc = 0.0;
+  for (long long e = beg + threadIdx.x; e < end; e += blockDim.x) {
+    const float z = weight_eps_at(eps, s, P, e);
+    acc += (double)z * z;
+  }
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) norms[(long long)s * n_sites + j] = (float)sqrt(acc);
+}
+__global__ void radial_apply_kernel(const float* __restrict__ mu, const float* __restrict__ sigma, long long P,
+                                    const long long* __restrict__ site_off, int n_sites, NoiseRef eps, NoiseRef r,
+                                    const float* __restrict__ norms, float* __restrict__ w, float* __restrict__ delta) {
+  const int j = blockIdx.y, s = blockIdx.z;
+  const long long beg = site_off[j], end = site_off[j + 1];
+  const long long e = beg + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (e >= end) return;
+  const float rr = r.ptr ? r.ptr[(long long)s * n_sites + j]
+                         : philox_normal(r.seed, KIND_RADIAL_R, 0, r.sample0 + s, 0, (uint32_t)j);
+  const float d = weight_eps_at(eps, s, P, e) / norms[(long long)s * n_sites + j] * rr;
+  w[(long long)s * P + e] = fmaf(d, sigma[e], mu[e]);
+  if (delta) delta[(long long)s * P + e] = d;
+}
+void launch_sample_radial(const float* mu, const float* sigma, long long P, long long S, const long long* site_off,
+                          int n_sites, int max_site, NoiseRef eps, NoiseRef r, float* norms, float* w, float* delta,
+                          cudaStream_t st) {
+  radial_norm_kernel<<<dim3(n_sites, (unsigned)S), 256, 0, st>>>(P, site_off, n_sites, eps, norms);
+  radial_apply_kernel<<<dim3((max_site + 255) / 256, n_sites, (unsigned)S), 256, 0, st>>>(mu, sigma, P, site_off, n_sites,
+                                                                                        eps, r, norms, w, delta);
+}
+
+__global__ void gen_signs_kernel(float* dst, long long S, long long B, int C, NoiseRef nz) {
+  const long long total = S * B * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = i % C;
+    const long long sb = i / C;
+    const int b = sb % B, s = sb / B;
+    dst[i] = philox_sign(nz.seed, nz.kind, nz.site, nz.sample0 + s, nz.window0 + b, c);
+  }
+}
+void launch_gen_signs(float* dst, long long S, long long B, int C, NoiseRef nz, cudaStream_t st) {
+  const long long total = S * B * C;
+  gen_signs_kernel<<<(unsigned)min((total + 255) / 256, (long long)148 * 8), 256, 0, st>>>(dst, S, B, C, nz);
+}
+
+// ------------------------------------------------------------------------------------------------
+// likelihoods
+// ------------------------------------------------------------------------------------------------
+__global__ void nll_elbo_kernel(const float* __restrict__ out, const float* __restrict__ y, long long B, float gscale,
+                                double* acc, float* __restrict__ gout) {
+  double nll = 0.0, se = 0.0;
+  for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
+    const float loc = out[2 * b], sc = out[2 * b + 1];
+    const float s = softplusf(sc);  // second softplus: positive_scale=False (bayesian.py:73-76)
+    const float d = y[b] - loc, r = d / s;
+    nll += 0.5 * (double)r * r + (double)logf(s) + 0.9189385332046727;
+    se += (double)d * d;
+    if (gout) {
+      const float sig = sc > 20.0f ? 1.0f : 1.0f / (1.0f + expf(-sc));
+      gout[2 * b] = -r / s * gscale;
+      gout[2 * b + 1] = (1.0f - r * r) / s * sig * gscale;
+    }
+  }
+  nll = block_sum(nll);
+  se = block_sum(se);
+  if (threadIdx.x == 0) {
+    atomicAdd(acc + 0, nll);
+    atomicAdd(acc + 1, se);
+  }
+}
+void launch_nll_elbo(const float* out, const float* y, long long B, float gscale, double* acc, float* gout,
+                     cudaStream_t st) {
+  nll_elbo_kernel<<<(unsigned)min((B + 255) / 256, (long long)148), 256, 0, st>>>(out, y, B, gscale, acc, gout);
+}
+
+__global__ void nll_hnn_kernel(const float* __restrict__ out, const float* __restrict__ y, long long B, double* acc,
+                               float* __restrict__ gout) {
+  double loss = 0.0, se = 0.0;
+  const float invB = 1.0f / (float)B;
+  for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
+    const float loc = out[2 * b], sc = out[2 * b + 1];
+    const float var0 = sc * sc, var = fmaxf(var0, 1e-6f);  // F.gaussian_nll_loss eps clamp
+    const float d = loc - y[b];
+    loss += 0.5 * ((double)logf(var) + (double)d * d / var);
+    se += (double)d * d;
+    if (gout) {
+      gout[2 * b] = d / var * invB;
+      gout[2 * b + 1] = var0 > 1e-6f ? 0.5f * (1.0f / var - d * d / (var * var)) * 2.0f * sc * invB : 0.f;
+    }
+  }
+  loss = block_sum(loss);
+  se = block_sum(se);
+  if (threadIdx.x == 0) {
+    atomicAdd(acc + 0, loss / (double)B);
+    atomicAdd(acc + 1, se / (double)B);
+  }
+}
+void launch_nll_hnn(const float* out, const float* y, long long B, double* acc, float* gout, cudaStream_t st) {
+  nll_hnn_kernel<<<(unsigned)min((B + 255) / 256, (long long)148), 256, 0, st>>>(out, y, B, acc, gout);
+}
+
+// ------------------------------------------------------------------------------------------------
+// KL + gradient finalisation
+// ------------------------------------------------------------------------------------------------
+__global__ void finalize_kernel(const Finalize p) {
+  double kl = 0.0;
+  const float isp2 = 1.0f / (p.prior_scale * p.prior_scale);
+  const float lsp = logf(p.prior_scale);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < p.P; i += (long long)gridDim.x * blockDim.x) {
+    const float mu = p.mu[i], sg = p.sigma[i];
+    float gmu = 0.f, gsg = 0.f, dmu_kl, dsg_kl;
+    if (p.guide == 1) {  // radial: sampled log q - log p (Trace_ELBO)
+      const float w = p.w[i], d = p.delta[i];
+      const float zp = (w - p.prior_loc) / p.prior_scale;
+      kl += (double)(-logf(sg) - 0.5f * d * d) - (double)(-lsp - 0.5f * zp * zp);
+      dmu_kl = (w - p.prior_loc) * isp2;
+      dsg_kl = -1.0f / sg + (w - p.prior_loc) * isp2 * d;
+      if (p.g0) { gmu = p.g0[i]; gsg = p.g0[i] * d; }
+    } else {
+      const float dm = mu - p.prior_loc;
+      kl += (double)(lsp - logf(sg)) + (double)((sg * sg + dm * dm) * 0.5f * isp2) - 0.5;
+      dmu_kl = dm * isp2;
+      dsg_kl = -1.0f / sg + sg * isp2;
+      if (p.g0) {
+        gmu = p.g0[i];
+        if (p.mode == 2) gsg = 2.0f * sg * p.g1[i];       // LRT: d/dsigma through sigma^2
+        else if (p.mode == 3) gsg = p.g1[i] * p.delta[i]; // flipout: dDeltaW * eps
+        else gsg = p.g0[i] * p.delta[i];                   // weight sampling
+      }
+    }
+    if (p.grad_mu) {
+      gmu = fmaf(p.c_kl, dmu_kl, gmu);
+      gsg = fmaf(p.c_kl, dsg_kl, gsg);
+      if (p.first) { p.grad_mu[i] = gmu; p.grad_sigma[i] = gsg; }
+      else { p.grad_mu[i] += gmu; p.grad_sigma[i] += gsg; }
+    }
+  }
+  kl = block_sum(kl);
+  if (threadIdx.x == 0) atomicAdd(p.kl_acc, kl);
+}
+void launch_finalize(const Finalize& p, cudaStream_t st) {
+  finalize_kernel<<<(unsigned)min((p.P + 255) / 256, (long long)148 * 4), 256, 0, st>>>(p);
+}
+
+__global__ void post_scalars_kernel(double* scalars, const double* acc, double c_nll, double c, int particles,
+                                    long long B) {
+  // acc = {nll_sum over particles, squared error sum over particles, kl sum over particles}
+  scalars[0] = (c_nll * acc[0] + c * acc[2]) / particles;
+  scalars[1] = acc[0] / particles;
+  scalars[2] = acc[2] / particles;
+  scalars[3] = acc[1] / ((double)particles * (double)B);
+}
+void launch_post_scalars(double* scalars, const double* acc, double c_nll, double c, int particles, long long B,
+                         cudaStream_t st) {
+  post_scalars_kernel<<<1, 1, 0, st>>>(scalars, acc, c_nll, c, particles, B);
+}
+
+__global__ void log_sigma_grad_kernel(const float* gs, const float* sigma, float* gls, long long P) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < P; i += (long long)gridDim.x * blockDim.x)
+    gls[i] = gs[i] * sigma[i];
+}
+void launch_log_sigma_grad(const float* gs, const float* sigma, float* gls, long long P, cudaStream_t st) {
+  log_sigma_grad_kernel<<<(unsigned)min((P + 255) / 256, (long long)148 * 4), 256, 0, st>>>(gs, sigma, gls, P);
+}
+
+// ------------------------------------------------------------------------------------------------
+// predictive moments (Welford over MC samples; chunks merge through `state`)
+// ------------------------------------------------------------------------------------------------
+__global__ void moments_update_kernel(const float* __restrict__ out, long long S, long long B, float* state, int first) {
+  for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
+    float n = 0.f, mean = 0.f, m2 = 0.f, s2 = 0.f;
+    if (!first) { n = state[b]; mean = state[B + b]; m2 = state[2 * B + b]; s2 = state[3 * B + b]; }
+    for (long long s = 0; s < S; ++s) {
+      const float2 o = *reinterpret_cast<const float2*>(out + (s * B + b) * 2);
+      n += 1.f;
+      const float d = o.x - mean;
+      mean += d / n;
+      m2 = fmaf(d, o.x - mean, m2);
+      s2 = fmaf(o.y, o.y, s2);
+    }
+    state[b] = n; state[B + b] = mean; state[2 * B + b] = m2; state[3 * B + b] = s2;
+  }
+}
+void launch_moments_update(const float* out, long long S, long long B, float* state, int first, cudaStream_t st) {
+  moments_update_kernel<<<(unsigned)min((B + 127) / 128, (long long)148 * 8), 128, 0, st>>>(out, S, B, state, first);
+}
+__global__ void moments_final_kernel(const float* __restrict__ state, long long B, float* pred, float* std, float* ep,
+                                     float* al) {
+  for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
+    const float n = state[b];
+    const float e = state[2 * B + b] / (n - 1.f);  // unbiased: loc.var(0) (bayesian.py:212)
+    const float a = state[3 * B + b] / n;
+    pred[b] = state[B + b];
+    if (ep) ep[b] = e;
+    if (al) al[b] = a;
+    std[b] = sqrtf(a + e);
+  }
+}
+void launch_moments_final(const float* state, long long B, float* pred, float* std, float* ep, float* al,
+                          cudaStream_t st) {
+  moments_final_kernel<<<(unsigned)min((B + 255) / 256, (long long)148 * 8), 256, 0, st>>>(state, B, pred, std, ep, al);
+}
+
+__global__ void moments_direct_kernel(const float* __restrict__ out, long long S, long long B, float* pred, float* std,
+                                      float* ep, float* al) {
+  for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
+    float n = 0.f, mean = 0.f, m2 = 0.f, s2 = 0.f;
+    for (long long s = 0; s < S; ++s) {
+      const float2 o = *reinterpret_cast<const float2*>(out + (s * B + b) * 2);
+      n += 1.f;
+      const float d = o.x - mean;
+      mean += d / n;
+      m2 = fmaf(d, o.x - mean, m2);
+      s2 = fmaf(o.y, o.y, s2);
+    }
+    const float e = m2 / (n - 1.f), a = s2 / n;
+    pred[b] = mean; ep[b] = e; al[b] = a; std[b] = sqrtf(a + e);
+  }
+}
+void launch_moments_direct(const float* out, long long S, long long B, float* pred, float* std, float* ep, float* al,
+                           cudaStream_t st) {
+  moments_direct_kernel<<<(unsigned)min((B + 127) / 128, (long long)148 * 8), 128, 0, st>>>(out, S, B, pred, std, ep, al);
+}
+
+__global__ void aggregate_kernel(const float* __restrict__ out, long long S, long long B, float* agg) {
+  for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
+    float n = 0.f, mean = 0.f, m2 = 0.f, s2 = 0.f, wl = 0.f, wp = 0.f;
+    for (long long s = 0; s < S; ++s) {
+      const float2 o = *reinterpret_cast<const float2*>(out + (s * B + b) * 2);
+      n += 1.f;
+      const float d = o.x - mean;
+      mean += d / n;
+      m2 = fmaf(d, o.x - mean, m2);
+      s2 = fmaf(o.y, o.y, s2);
+      const float prec = 1.0f / (o.y * o.y);
+      wl = fmaf(o.x, prec, wl);
+      wp += prec;
+    }
+    const float sc = sqrtf(s2 / n + m2 / (n - 1.f));
+    agg[2 * b] = wl / wp;
+    agg[2 * b + 1] = sc + logf(-expm1f(-sc));  // inverse softplus (positive_scale=False)
+  }
+}
+void launch_aggregate(const float* out, long long S, long long B, float* agg, cudaStream_t st) {
+  aggregate_kernel<<<(unsigned)min((B + 127) / 128, (long long)148 * 8), 128, 0, st>>>(out, S, B, agg);
+}
+
+__global__ void mixture_kernel(const float* __restrict__ mu_m, const float* __restrict__ sd_m, long long M, long long n,
+                               float* mu, float* sd) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double a = 0.0, q = 0.0;
+    for (long long m = 0; m < M; ++m) {
+      const double u = mu_m[m * n + i], s = sd_m[m * n + i];
+      a += u;
+      q += u * u + s * s;
+    }
+    a /= (double)M;
+    mu[i] = (float)a;
+    sd[i] = (float)sqrt(q / (double)M - a * a);  // biased mixture variance (deepens.py:24)
+  }
+}
+void launch_mixture(const float* mu_m, const float* sd_m, long long M, long long n, float* mu, float* sd,
+                    cudaStream_t st) {
+  mixture_kernel<<<(unsigned)min((n + 255) / 256, (long long)148 * 8), 256, 0, st>>>(mu_m, sd_m, M, n, mu, sd);
+}
+
+// ------------------------------------------------------------------------------------------------
+// test-time scalar metrics (bayesian.py:217-224; results/metrics.py:210-274)
+// ------------------------------------------------------------------------------------------------
+__global__ void test_metrics_acc_kernel(const float* __restrict__ pred, const float* __restrict__ std,
+                                        const float* __restrict__ y, long long n, double* acc, unsigned int* hist) {
+  __shared__ unsigned int sh[100];
+  for (int i = threadIdx.x; i < 100; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  double nll = 0.0, se = 0.0, s2 = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float sd = std[i], d = pred[i] - y[i];
+    const float var = fmaxf(sd * sd, 1e-6f);
+    nll += 0.5 * ((double)logf(var) + (double)d * d / var);
+    se += (double)d * d;
+    s2 += (double)sd * sd;
+    // interval coverage: |z| <= icdf(0.5 + p/2)  <=>  erf(|z|/sqrt2) <= p ; first bin j with p_j >= q
+    const float q = erff(fabsf(d / sd) * 0.70710678f);
+    int j = (int)ceilf(q * 99.0f - 1e-6f);
+    j = max(0, min(99, j));
+    atomicAdd(&sh[j], 1u);
+  }
+  nll = block_sum(nll);
+  se = block_sum(se);
+  s2 = block_sum(s2);
+  if (threadIdx.x == 0) { atomicAdd(acc + 0, nll); atomicAdd(acc + 1, se); atomicAdd(acc + 2, s2); }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 100; i += blockDim.x)
+    if (sh[i]) atomicAdd(hist + i, sh[i]);
+}
+__global__ void test_metrics_final_kernel(const double* acc, const unsigned int* hist, long long n, double* scalars) {
+  if (threadIdx.x != 0) return;
+  scalars[0] = acc[0] / (double)n;
+  scalars[1] = acc[1] / (double)n;
+  scalars[2] = sqrt(acc[2] / (double)n);
+  double cum = 0.0, sq = 0.0;
+  for (int j = 0; j < 100; ++j) {
+    cum += hist[j];
+    const double e = (double)j / 99.0 - cum / (double)n;
+    sq += e * e;
+  }
+  scalars[3] = sqrt(sq / 100.0);
+}
+void launch_test_metrics(const float* pred, const float* std, const float* y, long long n, double* scalars,
+                         unsigned int* hist, cudaStream_t st) {
+  // workspace layout: hist[100] u32 followed (at +512 B) by acc[3] doubles
+  double* acc = reinterpret_cast<double*>(reinterpret_cast<char*>(hist) + 512);
+  cudaMemsetAsync(hist, 0, 512 + 3 * sizeof(double), st);
+  test_metrics_acc_kernel<<<(unsigned)min((n + 255) / 256, (long long)148 * 4), 256, 0, st>>>(pred, std, y, n, acc, hist);
+  test_metrics_final_kernel<<<1, 32, 0, st>>>(acc, hist, n, scalars);
+}
+
+// ------------------------------------------------------------------------------------------------
+// ClippedAdam
+// ------------------------------------------------------------------------------------------------
+__global__ void clipped_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                    float* __restrict__ v, long long n, float step_size, float b1, float b2, float eps,
+                                    float clip, float wd) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float gr = fminf(fmaxf(g[i], -clip), clip);
+    const float pi = p[i];
+    if (wd != 0.f) gr = fmaf(wd, pi, gr);
+    const float mi = b1 * m[i] + (1.f - b1) * gr;
+    const float vi = b2 * v[i] + (1.f - b2) * gr * gr;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = pi - step_size * mi / (sqrtf(vi) + eps);
+  }
+}
+void launch_clipped_adam(float* p, const float* g, float* m, float* v, long long n, float step_size, float b1,
+                         float b2, float eps, float clip, float wd, cudaStream_t st) {
+  clipped_adam_kernel<<<(unsigned)min((n + 255) / 256, (long long)148 * 8), 256, 0, st>>>(p, g, m, v, n, step_size, b1, b2,
+                                                                                         eps, clip, wd);
+}
+
+}  // namespace brl

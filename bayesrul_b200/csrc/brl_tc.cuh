@@ -1,0 +1,16 @@
+// tcgen05 / TMEM engine (fp16 operands, fp32 accumulate) -- interface used by brl_api.cu.
+#pragma once
+#include <cstddef>
+#include <cuda_runtime.h>
+
+struct brl_noise;
+
+namespace brl {
+struct TcState;
+TcState* tc_create(int net);
+void tc_destroy(TcState*);
+size_t tc_workspace_bytes(const TcState*, long long B, long long S);
+// returns nullptr on success, else a static error string
+const char* tc_forward(TcState*, const float* x, long long B, long long S, const float* weights, long long w_sample_stride,
+                       float p_dropout, const brl_noise* noise, float* out, void* ws, size_t ws_bytes, cudaStream_t st);
+}  // namespace brl

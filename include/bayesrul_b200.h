@@ -1,0 +1,165 @@
+/*
+ * bayesrul_b200 -- C ABI of the B200-native Monte-Carlo variational-BNN hot path.
+ *
+ * This is the drop-in boundary for ONE path of lbasora/bayesrul: the weight-sampled forward,
+ * ELBO backward and S-sample predictive-moment reduction of its N-CMAPSS regressors.
+ * The reference has no FFI (it is pure Python on top of TyXe/Pyro/torch), so each
+ * entry point below names the Python call sequence it replaces (file:line under
+ * /root/reference/bayesrul unless prefixed); INTEGRATION.md shows the ctypes stubs a bayesrul
+ * maintainer would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer to contiguous fp32 unless stated otherwise; tensors are
+ *    allocated and owned by the caller (PyTorch caching allocator on the Python side);
+ *  - `stream` is a cudaStream_t passed as void*; no entry point synchronises the host;
+ *  - every function returns BRL_OK (0) or a negative error code; brl_last_error() gives the text;
+ *  - variational parameters are two flat [P] buffers (mu, sigma) in named_parameters() order
+ *    (weight then bias per layer) -- brl_net_site() gives per-site offsets so the host can expose
+ *    `{site}.loc` / `{site}.scale` views compatible with pyro.get_param_store() (bayesian.py:255-264);
+ *  - noise is counter-based Philox4x32-10 keyed by (seed, kind, layer, MC sample, global window,
+ *    element), or injected tensors (brl_noise), see csrc/brl_philox.cuh.
+ */
+#ifndef BAYESRUL_B200_H
+#define BAYESRUL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BRL_OK 0
+#define BRL_ERR_INVALID (-1)   /* bad argument (shape, enum, NULL) */
+#define BRL_ERR_CUDA (-2)      /* CUDA runtime error */
+#define BRL_ERR_WORKSPACE (-3) /* workspace too small */
+#define BRL_ERR_UNSUPPORTED (-4)
+
+/* nets: models/nets/inception.py:142-217, conv.py:14-79, linear.py:10-72 */
+#define BRL_NET_INCEPTION 0
+#define BRL_NET_CONV 1
+#define BRL_NET_LINEAR 2
+
+/* per-layer rule */
+#define BRL_MODE_DET 0     /* plain weights `theta` shared by all S passes (HNN, MC-dropout) */
+#define BRL_MODE_WS 1      /* one full weight draw per MC sample: `wsamp` [S,P] (tyxe VariationalBNN.predict) */
+#define BRL_MODE_LRT 2     /* tyxe.poutine.local_reparameterization (bayesian.py:66-67) */
+#define BRL_MODE_FLIPOUT 3 /* tyxe.poutine.flipout (bayesian.py:68-69) */
+
+#define BRL_GUIDE_NORMAL 0 /* tyxe.guides.AutoNormal (bayesian.py:79-80) */
+#define BRL_GUIDE_RADIAL 1 /* AutoRadial / RadialNormal.rsample (guides/radial.py:31-41) */
+
+/* arithmetic back-ends of the forward pass */
+#define BRL_ENGINE_SIMT_FP32 0 /* fp32 FFMA implicit-GEMM kernels: the parity engine (rtol 1e-3 vs oracle) */
+#define BRL_ENGINE_TC_FP16 1   /* tcgen05 / TMEM kernels, fp16 operands (10-bit mantissa) + fp32 accumulate */
+
+#define BRL_MAX_LAYERS 16
+
+typedef struct brl_ctx brl_ctx;
+
+/* Noise specification.  NULL injected pointers => in-kernel Philox keyed by `seed`.
+ * Injected layouts (S = MC samples / particles of this call, B = windows of this call):
+ *   weight_eps [S,P]        standard normals for the guide draw                      (A7)
+ *   radial_r   [S,n_sites]  radial distance, one scalar per site per draw            (A8)
+ *   lrt_eps[l]  [S,B,out_elems(l)]  eps of layer l's output                          (A5)
+ *   flip_in[l]  [S,B,Cin(l)], flip_out[l] [S,B,Cout(l)]  +-1 sign tensors            (A6)
+ *   drop_mask[l] [S,B,out_elems(l)] 0/1 keep masks of the dropout site after layer l (A4)   */
+typedef struct brl_noise {
+  uint64_t seed;
+  int64_t sample0; /* global index of the first MC sample / particle of this call */
+  int64_t window0; /* global index of the first window of this call (multi-GPU sharding) */
+  const float* weight_eps;
+  const float* radial_r;
+  const float* lrt_eps[BRL_MAX_LAYERS];
+  const float* flip_in[BRL_MAX_LAYERS];
+  const float* flip_out[BRL_MAX_LAYERS];
+  const float* drop_mask[BRL_MAX_LAYERS];
+} brl_noise;
+
+/* ---- library / static net description ------------------------------------------------ */
+int brl_version(void);
+const char* brl_last_error(void);
+int brl_net_num_params(int net);
+int brl_net_num_layers(int net);
+int brl_net_num_sites(int net);
+/* site j of named_parameters(): flat offset, rank and shape (nets/*.py parameter order) */
+int brl_net_site(int net, int site, int64_t* offset, int* ndim, int64_t shape[4]);
+/* layer l: Cout, C_in seen by flipout, elements of its per-window output, dropout factor
+ * (fraction of p applied at the site after this layer: inception.py:48-52,119-123,204-206) */
+int brl_net_layer(int net, int layer, int* cout, int* cin, int* out_elems, float* dropout_factor);
+/* algorithmic GEMM FLOPs of one forward pass of one window */
+int64_t brl_net_flops_fwd(int net);
+
+/* ---- context ------------------------------------------------------------------------- */
+int brl_create(brl_ctx** ctx, int net, int device);
+int brl_destroy(brl_ctx* ctx);
+/* bytes of scratch needed by the calls below for B windows x S concurrently-resident samples;
+ * train != 0 adds the saved activations / gradient buffers of brl_elbo_step / brl_hnn_step */
+int64_t brl_workspace_bytes(const brl_ctx* ctx, int64_t B, int64_t S, int train, int engine);
+
+/* ---- guide: weight sampler (replaces AutoNormal.forward / AutoRadial.forward,
+ *      guides/radial.py:31-41,124-144; 24 pyro.sample sites per draw) ------------------- */
+int brl_sample_weights(brl_ctx* ctx, const float* mu, const float* sigma, int guide, int64_t S,
+                       const brl_noise* noise, float* w_out /*[S,P]*/, float* delta_out /*[S,P] or NULL*/,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- forward of S passes over B windows (replaces net.forward under the TyXe messengers,
+ *      inception.py:211-215 + tyxe reparameterization_messengers) -------------
+ * x [B,30,18]; theta [P] (DET: weights, LRT/FLIPOUT: mu); sigma [P] (LRT); wsamp [S,P] (WS, FLIPOUT);
+ * out [S,B,2] = (loc, scale) after softplus + Threshold(1e-9). */
+int brl_forward(brl_ctx* ctx, const float* x, int64_t B, int64_t S, int mode, const float* theta,
+                const float* sigma, const float* wsamp, float p_dropout, const brl_noise* noise,
+                float* out, int engine, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- S-sample predictive moments (replaces bnn.predict(aggregate=False) + bayesian.py:242-249,
+ *      and HNN.mc_sampling + frequentist.py:141-146).  guide < 0 => MC-dropout/deterministic with
+ *      weights `mu`.  Samples are generated and consumed in chunks that fit the workspace; the
+ *      [S,B,2] tensor is never materialised.  Outputs [B] each. */
+int brl_predict_moments(brl_ctx* ctx, const float* x, int64_t B, int64_t S, int guide, const float* mu,
+                        const float* sigma, float p_dropout, const brl_noise* noise, float* pred,
+                        float* std, float* ep_var, float* al_var, int engine, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
+/* moment reduction of an explicit [S,B,2] tensor (bayesian.py:212-215) */
+int brl_moments(const float* out, int64_t S, int64_t B, float* pred, float* std, float* ep_var,
+                float* al_var, void* stream);
+/* tyxe HeteroskedasticGaussian.aggregate_predictions, positive_scale=False (bayesian.py:149-153) */
+int brl_aggregate_predictions(const float* out, int64_t S, int64_t B, float* agg /*[B,2]*/, void* stream);
+
+/* ---- one ELBO step: forward + backward (replaces svi.step: bayesian.py:111-132,147) -----
+ * loss = mean_particles c*[(N/B)*NLL_sum + KL], c = 1/(N*win_length*n_features).
+ * guide RADIAL uses the sampled KL of Trace_ELBO (bayesian.py:105-109) and mode WS.
+ * scalars (device, double[4]) = {loss, nll_sum (mean over particles), kl (unscaled), mse(loc,y)}.
+ * grad_mu/grad_sigma/grad_log_sigma [P] (any may be NULL when compute_grads == 0).
+ * out [particles,B,2]. */
+int brl_elbo_step(brl_ctx* ctx, const float* x, const float* y, int64_t B, const float* mu,
+                  const float* sigma, int mode, int guide, int particles, float prior_loc,
+                  float prior_scale, int64_t dataset_size, const brl_noise* noise, int compute_grads,
+                  double* scalars, float* grad_mu, float* grad_sigma, float* grad_log_sigma, float* out,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- heteroscedastic NN step (replaces HNN.step + backward: frequentist.py:39-48) ------
+ * loss = F.gaussian_nll_loss(loc, y, scale^2); scalars (device double[2]) = {loss, mse}. */
+int brl_hnn_step(brl_ctx* ctx, const float* x, const float* y, int64_t B, const float* theta,
+                 float p_dropout, const brl_noise* noise, int compute_grads, double* scalars,
+                 float* grad_theta, float* out /*[B,2]*/, void* workspace, size_t workspace_bytes,
+                 void* stream);
+
+/* ---- deep-ensemble mixture moments (models/deepens.py:21-24), [M,n] -> [n] ------------- */
+int brl_mixture_moments(const float* mu_m, const float* sigma_m, int64_t M, int64_t n, float* mu,
+                        float* sigma, void* stream);
+
+/* ---- test-time scalar metrics (bayesian.py:217-224): device double[4] =
+ *      {gaussian_nll_loss(pred,y,std^2), mse, sharpness, rms_calibration_error(100 bins)} */
+int brl_test_metrics(const float* pred, const float* std, const float* y, int64_t n, double* scalars,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- fused ClippedAdam over a flat buffer (pyro.optim.ClippedAdam, conf/model/bnn.yaml:6-10) */
+int brl_clipped_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                     int64_t step, float lr, float beta1, float beta2, float eps, float clip_norm,
+                     float lrd, float weight_decay, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BAYESRUL_B200_H */
