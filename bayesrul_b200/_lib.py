@@ -42,6 +42,7 @@ _np = C.POINTER(BrlNoise)
 SIGNATURES = {
     "brl_version": (_i, []),
     "brl_last_error": (C.c_char_p, []),
+    "brl_launch_count": (_i64, []),
     "brl_net_num_params": (_i, [_i]),
     "brl_net_num_layers": (_i, [_i]),
     "brl_net_num_sites": (_i, [_i]),
@@ -50,6 +51,7 @@ SIGNATURES = {
     "brl_net_flops_fwd": (_i64, [_i]),
     "brl_create": (_i, [C.POINTER(_vp), _i, _i]),
     "brl_destroy": (_i, [_vp]),
+    "brl_engine_available": (_i, [_vp, _i]),
     "brl_workspace_bytes": (_i64, [_vp, _i64, _i64, _i, _i]),
     "brl_sample_weights": (_i, [_vp, _vp, _vp, _i, _i64, _np, _vp, _vp, _vp, _sz, _vp]),
     "brl_forward": (_i, [_vp, _vp, _i64, _i64, _i, _vp, _vp, _vp, _f, _np, _vp, _i, _vp, _sz, _vp]),

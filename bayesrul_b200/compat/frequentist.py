@@ -1,0 +1,128 @@
+"""`HNN`: mirror of bayesrul.models.frequentist.HNN (frequentist.py:9-154) -- heteroscedastic NN /
+MC-dropout wrapper.  `step` runs the fused CUDA forward (+ backward when training); `mc_sampling`
+is ONE batched launch sequence over all S dropout masks instead of a Python loop of S net calls."""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from ..engine import Noise
+from .bayesian import _Base
+from .metrics import rms_calibration_error, sharpness
+from .nets import enable_dropout, weights_init
+
+
+class HNN(_Base):
+    def __init__(self, net, optimizer, mc_samples: int, p_dropout, device=None, engine: str = "simt"):
+        super().__init__()
+        self.save_hyperparameters(logger=False, ignore=["net", "device", "engine"])
+        self.net = net
+        self.net.apply(weights_init)
+        self._engine_kind = engine
+        self._it = 0
+        if device is not None:
+            self._device = torch.device(device)
+            self.net.to(self._device)
+
+    def forward(self, x):
+        return self.net(x)
+
+    def get_device(self):
+        return next(self.net.parameters()).device
+
+    def to_device(self, device: torch.device):
+        self.net.to(device)
+
+    def _noise(self):
+        self._it += 1
+        return Noise(seed=(torch.initial_seed() + 0x9E3779B97F4A7C15 * self._it) & 0xFFFFFFFFFFFFFFFF)
+
+    def step(self, batch, phase):  # frequentist.py:39-48
+        (x, y) = batch
+        if phase == "predict":
+            output = self.net(x)
+            return output[:, 0], output[:, 1]
+        train = phase == "train"
+        p = float(self.net.dropout) if (train or getattr(self.net, "mc_dropout", False)) else 0.0
+        res = self.net.engine().hnn_step(x.contiguous(), y.contiguous(), self.net.flat(), p, self._noise(), compute_grads=train)
+        if train:  # hand the flat gradient to the per-site parameters (views of the same buffer)
+            for prm, (off, shape) in zip(self.net._params, self.net._sites):
+                prm.grad = res["grad"][off: off + prm.numel()].view(shape)
+        loss = res["scalars"][0].float()
+        self.log(f"nll/{phase}", loss, on_step=False, on_epoch=True)
+        return loss, res["out"][:, 0], res["out"][:, 1]
+
+    def training_step(self, batch, batch_idx):
+        loss, loc, scale = self.step(batch, "train")
+        self.log("mse/train", F.mse_loss(loc, batch[1]), on_step=False, on_epoch=True)
+        self.log("rmsce/train", rms_calibration_error(loc, scale, batch[1]), on_step=False, on_epoch=True)
+        self.log("sharp/train", sharpness(scale), on_step=False, on_epoch=True)
+        return loss
+
+    def mc_sampling(self, batch, mc_samples: int, phase: str, agg: bool = True):  # frequentist.py:60-81
+        (x, y) = batch
+        eng = self.net.engine()
+        out = eng.forward(x.contiguous(), "det", theta=self.net.flat(), S=mc_samples, p_dropout=float(self.net.dropout),
+                          noise=self._noise(), engine=self._engine_kind)
+        locs, scales = out[:, :, 0], out[:, :, 1]
+        if phase == "predict":
+            return locs, scales
+        loss = F.gaussian_nll_loss(locs, y.expand_as(locs), scales**2, reduction="none").mean(1).mean(0)
+        if agg:
+            pred, std, _, _ = eng.moments(out)
+            return loss, pred, std
+        return loss, locs, scales
+
+    def validation_step(self, batch, batch_idx):
+        phase = "val"
+        if self.net.dropout > 0:
+            enable_dropout(self.net)
+            loss, loc, scale = self.mc_sampling(batch, self.hparams.mc_samples, phase=phase)
+        else:
+            loss, loc, scale = self.step(batch, phase)
+        return {"loss": loss, "label": batch[1], "pred": loc, "std": scale}
+
+    def validation_epoch_end(self, outputs) -> None:
+        preds = torch.cat([o["pred"].detach() for o in outputs])
+        labels = torch.cat([o["label"].detach() for o in outputs])
+        stds = torch.cat([o["std"].detach() for o in outputs])
+        self.log("mse/val", F.mse_loss(preds, labels))
+        self.log("rmsce/val", rms_calibration_error(preds, stds, labels))
+        self.log("sharp/val", sharpness(stds))
+
+    def _mc_moments(self, batch):
+        x = batch[0]
+        return self.net.engine().predict_moments(x.contiguous(), self.net.flat(), None, S=self.hparams.mc_samples, guide=None,
+                                                 p_dropout=float(self.net.dropout), noise=self._noise(),
+                                                 engine=self._engine_kind)
+
+    def test_step(self, batch, batch_idx):  # frequentist.py:112-130
+        y = batch[1]
+        if self.net.dropout > 0:
+            enable_dropout(self.net)
+            loss, locs, scales = self.mc_sampling(batch, self.hparams.mc_samples, phase="test", agg=False)
+            loc, scale, _, _ = self.net.engine().moments(torch.stack([locs, scales], -1).contiguous())
+        else:
+            loss, loc, scale = self.step(batch, "test")
+        self.log("nll/test", loss)
+        self.log("mse/test", F.mse_loss(loc, y))
+        self.log("rmsce/test", rms_calibration_error(loc, scale, y))
+        self.log("sharp/test", sharpness(scale))
+
+    def predict_step(self, batch, batch_idx, dataloader_idx=0):  # frequentist.py:132-151
+        batch = (batch[0].to(self.get_device(), non_blocking=True), batch[1])
+        pred = dict()
+        pred["labels"] = batch[1].cpu().numpy()
+        if self.net.dropout > 0:
+            enable_dropout(self.net)
+            loc, scale, ep_var, al_var = self._mc_moments(batch)
+            pred["ep_vars"] = ep_var.cpu().numpy()
+            pred["al_vars"] = al_var.cpu().numpy()
+        else:
+            loc, scale = self.step(batch, "predict")
+        pred["preds"] = loc.cpu().numpy()
+        pred["stds"] = scale.cpu().numpy()
+        return pred
+
+    def configure_optimizers(self):
+        return self.hparams.optimizer(params=self.parameters())

@@ -309,6 +309,7 @@ static int zero_grads(const NetSpec& n, const ActBufs& ab, long long B, cudaStre
 extern "C" {
 
 int brl_version(void) { return 100; }
+int64_t brl_launch_count(void) { return (int64_t)launch_count(); }
 const char* brl_last_error(void) { return g_err.c_str(); }
 
 int brl_net_num_params(int net) { try { return (int)get_net(net).P; } catch (...) { return BRL_ERR_INVALID; } }
@@ -408,6 +409,13 @@ int brl_destroy(brl_ctx* ctx) {
   tc_destroy(ctx->tc);
   delete ctx;
   return BRL_OK;
+}
+
+int brl_engine_available(const brl_ctx* ctx, int engine) {
+  if (!ctx) return 0;
+  if (engine == BRL_ENGINE_SIMT_FP32) return 1;
+  if (engine == BRL_ENGINE_TC_FP16) return tc_available(ctx->tc) ? 1 : 0;
+  return 0;
 }
 
 int64_t brl_workspace_bytes(const brl_ctx* ctx, int64_t B, int64_t S, int train, int engine) {

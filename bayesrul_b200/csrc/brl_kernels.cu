@@ -1,10 +1,16 @@
 // fp32 SIMT engine: implicit-GEMM conv / linear layers with the variational rules fused in the
 // gather prologue and the epilogue, plus the small reductions of the ELBO / predictive path.
 // This is the parity engine (rtol 1e-3 vs the oracle); the tcgen05 engine lives in brl_tc.cu.
+#include <atomic>
+
 #include "brl_kernels.cuh"
 #include "brl_philox.cuh"
 
 namespace brl {
+
+std::atomic<long long> g_launch_count{0};
+long long launch_count() { return g_launch_count.load(); }
+void count_launch(int n) { g_launch_count.fetch_add(n); }
 
 // ------------------------------------------------------------------------------------------------
 // helpers
@@ -180,12 +186,12 @@ __global__ void __launch_bounds__(256) conv_gemm_kernel(const ConvGemm p) {
 void launch_conv_gemm(const ConvGemm& p, int epi, cudaStream_t st) {
   dim3 grid((p.B * p.P + BM - 1) / BM, (p.N + BN - 1) / BN, p.S);
   switch (epi) {
-    case EPI_FWD_PLAIN: conv_gemm_kernel<false, EPI_FWD_PLAIN><<<grid, 256, 0, st>>>(p); break;
-    case EPI_FWD_LRT: conv_gemm_kernel<true, EPI_FWD_LRT><<<grid, 256, 0, st>>>(p); break;
-    case EPI_FWD_FLIPOUT: conv_gemm_kernel<true, EPI_FWD_FLIPOUT><<<grid, 256, 0, st>>>(p); break;
-    case EPI_DX_PLAIN: conv_gemm_kernel<false, EPI_DX_PLAIN><<<grid, 256, 0, st>>>(p); break;
-    case EPI_DX_LRT: conv_gemm_kernel<true, EPI_DX_LRT><<<grid, 256, 0, st>>>(p); break;
-    case EPI_DX_FLIPOUT: conv_gemm_kernel<true, EPI_DX_FLIPOUT><<<grid, 256, 0, st>>>(p); break;
+    case EPI_FWD_PLAIN: ++g_launch_count; conv_gemm_kernel<false, EPI_FWD_PLAIN><<<grid, 256, 0, st>>>(p); break;
+    case EPI_FWD_LRT: ++g_launch_count; conv_gemm_kernel<true, EPI_FWD_LRT><<<grid, 256, 0, st>>>(p); break;
+    case EPI_FWD_FLIPOUT: ++g_launch_count; conv_gemm_kernel<true, EPI_FWD_FLIPOUT><<<grid, 256, 0, st>>>(p); break;
+    case EPI_DX_PLAIN: ++g_launch_count; conv_gemm_kernel<false, EPI_DX_PLAIN><<<grid, 256, 0, st>>>(p); break;
+    case EPI_DX_LRT: ++g_launch_count; conv_gemm_kernel<true, EPI_DX_LRT><<<grid, 256, 0, st>>>(p); break;
+    case EPI_DX_FLIPOUT: ++g_launch_count; conv_gemm_kernel<true, EPI_DX_FLIPOUT><<<grid, 256, 0, st>>>(p); break;
   }
 }
 
@@ -279,6 +285,7 @@ void launch_conv_dw(const ConvDw& p, cudaStream_t st) {
   int rows = (Mtot + split - 1) / split;
   rows = (rows + DW_M - 1) / DW_M * DW_M;
   split = (Mtot + rows - 1) / rows;
+  ++g_launch_count;
   conv_dw_kernel<<<dim3(gx, gy, split), 256, 0, st>>>(p, rows);
 }
 
@@ -301,6 +308,7 @@ __global__ void maxpool3_kernel(const PoolParams p) {
 }
 void launch_maxpool3(const PoolParams& p, cudaStream_t st) {
   const long long total = p.n_img * p.C * p.Hin * p.Win;
+  ++g_launch_count;
   maxpool3_kernel<<<(unsigned)min((total + 255) / 256, (long long)148 * 16), 256, 0, st>>>(p);
 }
 
@@ -330,6 +338,7 @@ __global__ void maxpool3_bwd_kernel(const PoolParams p, const float* gout, float
 }
 void launch_maxpool3_bwd(const PoolParams& p, const float* gout, float* gin, cudaStream_t st) {
   const long long total = p.n_img * p.C * p.Hin * p.Win;
+  ++g_launch_count;
   maxpool3_bwd_kernel<<<(unsigned)min((total + 255) / 256, (long long)148 * 16), 256, 0, st>>>(p, gout, gin);
 }
 
@@ -347,6 +356,7 @@ __global__ void avgpool2_kernel(const PoolParams p) {
 }
 void launch_avgpool2(const PoolParams& p, cudaStream_t st) {
   const long long total = p.n_img * p.C * p.Hout * p.Win;
+  ++g_launch_count;
   avgpool2_kernel<<<(unsigned)min((total + 255) / 256, (long long)148 * 16), 256, 0, st>>>(p);
 }
 __global__ void avgpool2_bwd_kernel(const PoolParams p, const float* gout, float* gin) {
@@ -363,6 +373,7 @@ __global__ void avgpool2_bwd_kernel(const PoolParams p, const float* gout, float
 }
 void launch_avgpool2_bwd(const PoolParams& p, const float* gout, float* gin, cudaStream_t st) {
   const long long total = p.n_img * p.C * p.Hin * p.Win;
+  ++g_launch_count;
   avgpool2_bwd_kernel<<<(unsigned)min((total + 255) / 256, (long long)148 * 16), 256, 0, st>>>(p, gout, gin);
 }
 
@@ -393,6 +404,7 @@ __global__ void bwd_act_kernel(const BwdAct p) {
 }
 void launch_bwd_act(const BwdAct& p, cudaStream_t st) {
   const long long total = p.n_img * p.N * p.P;
+  ++g_launch_count;
   bwd_act_kernel<<<(unsigned)min((total + 255) / 256, (long long)148 * 16), 256, 0, st>>>(p);
 }
 
@@ -427,6 +439,7 @@ void launch_sample_normal(const float* mu, const float* sigma, long long P, long
                           float* delta, cudaStream_t st) {
   const long long nblk = (P + 3) >> 2;
   dim3 grid((unsigned)min((nblk + 255) / 256, (long long)148 * 8), (unsigned)S);
+  ++g_launch_count;
   sample_normal_kernel<<<grid, 256, 0, st>>>(mu, sigma, P, eps, w, delta);
 }
 
@@ -462,7 +475,9 @@ __global__ void radial_apply_kernel(const float* __restrict__ mu, const float* _
 void launch_sample_radial(const float* mu, const float* sigma, long long P, long long S, const long long* site_off,
                           int n_sites, int max_site, NoiseRef eps, NoiseRef r, float* norms, float* w, float* delta,
                           cudaStream_t st) {
+  ++g_launch_count;
   radial_norm_kernel<<<dim3(n_sites, (unsigned)S), 256, 0, st>>>(P, site_off, n_sites, eps, norms);
+  ++g_launch_count;
   radial_apply_kernel<<<dim3((max_site + 255) / 256, n_sites, (unsigned)S), 256, 0, st>>>(mu, sigma, P, site_off, n_sites,
                                                                                         eps, r, norms, w, delta);
 }
@@ -478,6 +493,7 @@ __global__ void gen_signs_kernel(float* dst, long long S, long long B, int C, No
 }
 void launch_gen_signs(float* dst, long long S, long long B, int C, NoiseRef nz, cudaStream_t st) {
   const long long total = S * B * C;
+  ++g_launch_count;
   gen_signs_kernel<<<(unsigned)min((total + 255) / 256, (long long)148 * 8), 256, 0, st>>>(dst, S, B, C, nz);
 }
 
@@ -508,6 +524,7 @@ __global__ void nll_elbo_kernel(const float* __restrict__ out, const float* __re
 }
 void launch_nll_elbo(const float* out, const float* y, long long B, float gscale, double* acc, float* gout,
                      cudaStream_t st) {
+  ++g_launch_count;
   nll_elbo_kernel<<<(unsigned)min((B + 255) / 256, (long long)148), 256, 0, st>>>(out, y, B, gscale, acc, gout);
 }
 
@@ -534,6 +551,7 @@ __global__ void nll_hnn_kernel(const float* __restrict__ out, const float* __res
   }
 }
 void launch_nll_hnn(const float* out, const float* y, long long B, double* acc, float* gout, cudaStream_t st) {
+  ++g_launch_count;
   nll_hnn_kernel<<<(unsigned)min((B + 255) / 256, (long long)148), 256, 0, st>>>(out, y, B, acc, gout);
 }
 
@@ -577,6 +595,7 @@ __global__ void finalize_kernel(const Finalize p) {
   if (threadIdx.x == 0) atomicAdd(p.kl_acc, kl);
 }
 void launch_finalize(const Finalize& p, cudaStream_t st) {
+  ++g_launch_count;
   finalize_kernel<<<(unsigned)min((p.P + 255) / 256, (long long)148 * 4), 256, 0, st>>>(p);
 }
 
@@ -590,6 +609,7 @@ __global__ void post_scalars_kernel(double* scalars, const double* acc, double c
 }
 void launch_post_scalars(double* scalars, const double* acc, double c_nll, double c, int particles, long long B,
                          cudaStream_t st) {
+  ++g_launch_count;
   post_scalars_kernel<<<1, 1, 0, st>>>(scalars, acc, c_nll, c, particles, B);
 }
 
@@ -598,6 +618,7 @@ __global__ void log_sigma_grad_kernel(const float* gs, const float* sigma, float
     gls[i] = gs[i] * sigma[i];
 }
 void launch_log_sigma_grad(const float* gs, const float* sigma, float* gls, long long P, cudaStream_t st) {
+  ++g_launch_count;
   log_sigma_grad_kernel<<<(unsigned)min((P + 255) / 256, (long long)148 * 4), 256, 0, st>>>(gs, sigma, gls, P);
 }
 
@@ -620,6 +641,7 @@ __global__ void moments_update_kernel(const float* __restrict__ out, long long S
   }
 }
 void launch_moments_update(const float* out, long long S, long long B, float* state, int first, cudaStream_t st) {
+  ++g_launch_count;
   moments_update_kernel<<<(unsigned)min((B + 127) / 128, (long long)148 * 8), 128, 0, st>>>(out, S, B, state, first);
 }
 __global__ void moments_final_kernel(const float* __restrict__ state, long long B, float* pred, float* std, float* ep,
@@ -636,6 +658,7 @@ __global__ void moments_final_kernel(const float* __restrict__ state, long long 
 }
 void launch_moments_final(const float* state, long long B, float* pred, float* std, float* ep, float* al,
                           cudaStream_t st) {
+  ++g_launch_count;
   moments_final_kernel<<<(unsigned)min((B + 255) / 256, (long long)148 * 8), 256, 0, st>>>(state, B, pred, std, ep, al);
 }
 
@@ -657,6 +680,7 @@ __global__ void moments_direct_kernel(const float* __restrict__ out, long long S
 }
 void launch_moments_direct(const float* out, long long S, long long B, float* pred, float* std, float* ep, float* al,
                            cudaStream_t st) {
+  ++g_launch_count;
   moments_direct_kernel<<<(unsigned)min((B + 127) / 128, (long long)148 * 8), 128, 0, st>>>(out, S, B, pred, std, ep, al);
 }
 
@@ -680,6 +704,7 @@ __global__ void aggregate_kernel(const float* __restrict__ out, long long S, lon
   }
 }
 void launch_aggregate(const float* out, long long S, long long B, float* agg, cudaStream_t st) {
+  ++g_launch_count;
   aggregate_kernel<<<(unsigned)min((B + 127) / 128, (long long)148 * 8), 128, 0, st>>>(out, S, B, agg);
 }
 
@@ -699,6 +724,7 @@ __global__ void mixture_kernel(const float* __restrict__ mu_m, const float* __re
 }
 void launch_mixture(const float* mu_m, const float* sd_m, long long M, long long n, float* mu, float* sd,
                     cudaStream_t st) {
+  ++g_launch_count;
   mixture_kernel<<<(unsigned)min((n + 255) / 256, (long long)148 * 8), 256, 0, st>>>(mu_m, sd_m, M, n, mu, sd);
 }
 
@@ -749,7 +775,9 @@ void launch_test_metrics(const float* pred, const float* std, const float* y, lo
   // workspace layout: hist[100] u32 followed (at +512 B) by acc[3] doubles
   double* acc = reinterpret_cast<double*>(reinterpret_cast<char*>(hist) + 512);
   cudaMemsetAsync(hist, 0, 512 + 3 * sizeof(double), st);
+  ++g_launch_count;
   test_metrics_acc_kernel<<<(unsigned)min((n + 255) / 256, (long long)148 * 4), 256, 0, st>>>(pred, std, y, n, acc, hist);
+  ++g_launch_count;
   test_metrics_final_kernel<<<1, 32, 0, st>>>(acc, hist, n, scalars);
 }
 
@@ -772,6 +800,7 @@ __global__ void clipped_adam_kernel(float* __restrict__ p, const float* __restri
 }
 void launch_clipped_adam(float* p, const float* g, float* m, float* v, long long n, float step_size, float b1,
                          float b2, float eps, float clip, float wd, cudaStream_t st) {
+  ++g_launch_count;
   clipped_adam_kernel<<<(unsigned)min((n + 255) / 256, (long long)148 * 8), 256, 0, st>>>(p, g, m, v, n, step_size, b1, b2,
                                                                                          eps, clip, wd);
 }

@@ -5,6 +5,9 @@
 
 namespace brl {
 
+long long launch_count();  // kernels launched by this library since load
+void count_launch(int n);
+
 // How the A operand (activations / gradients) of an implicit GEMM is gathered:
 //   row m  -> (b = m / P, oh = (m % P) / Wrow, ow = (m % P) % Wrow), image = s*B + b (or b when shared)
 //   col k  -> element offset koff[k] and tap displacement (dh, dw) packed in kdhw[k]

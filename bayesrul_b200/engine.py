@@ -109,6 +109,10 @@ class Engine:
         except Exception:
             pass
 
+    def has_tc(self) -> bool:
+        """True when the tcgen05 (fp16 operand / fp32 accumulate) engine supports this net."""
+        return bool(self.lib.brl_engine_available(self.ctx, ENGINE_IDS["tc"]))
+
     # -- helpers ------------------------------------------------------------------------------
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream

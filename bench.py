@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""Benchmark of the MC variational-BNN hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--engine tc|simt]
+
+Headline workload (config.workload): the LRT experiment's Inception BNN (experiment=ncmapss_lrt,
+q_scale 1.351e-3, prior 0.138793) predicting B=10 000 synthetic N-CMAPSS windows [30x18] with S=100
+Monte-Carlo weight samples per step (reference semantics: bnn.predict draws one full weight sample
+per MC sample, bayesian.py:235-249) + the predictive-moment reduction.
+A "step" = one such batch; `value` = window x samples / s with inputs resident in HBM; `e2e` = the
+same through BNN.predict_step with pinned HOST inputs and host results.  The ELBO-train throughput
+(LRT and Flipout, B=256) rides along under "train".  One process per GPU; windows are sharded
+across ranks, no data-path collective (weak scaling).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+NET = "inception"
+B_PRED, S_PRED = 10000, 100
+B_TRAIN = 256
+N_DATASET = 238150
+CFG = dict(q_scale=1.351e-3, prior_scale=0.138793, prior_loc=0.0)
+F_FWD = 2_289_376  # GEMM FLOPs / window / weight sample
+F_TRAIN_LRT = 13_036_416
+METRIC = "mc_predictive_window_samples_per_s"
+UNIT = "window*samples/s"
+
+
+def synth(n, seed=12345):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, 30, 18, generator=g)
+    y = torch.rand(n, generator=g) * 100.0
+    return x, y
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.p is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, smax, reasons, power = [], 0.0, set(), 0.0
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                smax = max(smax, float(r[2]))
+                power = max(power, float(r[3]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        busy = [c for c in sm if c > 0.5 * smax] or sm
+        return dict(sm_mhz=statistics.median(busy) if busy else None, sm_max_mhz=smax or None, reasons=sorted(reasons),
+                    power_w_max=power, samples=len(sm))
+
+
+def flush_l2(buf):
+    buf.add_(1.0)  # 256 MiB read+write > 126 MB L2
+
+
+def timed_steps(fn, steps, warmup, flush_buf, dist):
+    """W warm-ups, then K steps each bracketed by its own CUDA events (L2 flushed in between, outside the
+    timed regions); barrier + synchronize on both sides; returns per-rank total seconds."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    evs = []
+    for i in range(steps):
+        flush_l2(flush_buf)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn(i)
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    return sum(a.elapsed_time(b) for a, b in evs) / 1e3
+
+
+def max_over_ranks(t, dist, device):
+    if dist is None:
+        return t
+    v = torch.tensor([t], dtype=torch.float64, device=device)
+    dist.all_reduce(v, op=dist.ReduceOp.MAX)
+    return v.item()
+
+
+def cpu_predict_rate(n_windows, n_samples, threads):
+    """Oracle port of the same workload on the host cores (bounded sample)."""
+    from oracle import bnn_oracle as O
+
+    torch.set_num_threads(threads)
+    x, _ = synth(n_windows)
+    mu = O.init_params(NET, 12345)
+    sg = torch.full_like(mu, CFG["q_scale"])
+    g = torch.Generator().manual_seed(1)
+
+    def run():
+        nz = [O.InjectedNoise({"weight_eps": torch.randn(mu.numel(), generator=g)}) for _ in range(n_samples)]
+        return O.predictive_moments(O.predict(NET, x, mu, sg, "normal", nz))
+
+    run_small = n_samples
+    t0 = time.perf_counter()
+    run()
+    dt = time.perf_counter() - t0
+    return n_windows * run_small / dt, dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path = the plain-PyTorch restatement
+    (oracle port; pyro/tyxe are not installable) on all host threads; bounded sample per step."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    nb, ns = B_PRED, 2
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_predict_rate(nb // 4, 1, threads)
+    t = 0.0
+    units = 0
+    for _ in range(args.steps):
+        r, dt = cpu_predict_rate(nb, ns, threads)
+        t += dt
+        units += nb * ns
+    v = units / t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"ncmapss_lrt Inception BNN predict, B={B_PRED} windows x S={S_PRED} weight samples + moments",
+                   "net": NET, "windows_per_step": nb, "samples_per_step": ns},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"each step = {nb} windows x {ns} of the {S_PRED} MC samples (plain-PyTorch restatement, "
+                                   f"torch {torch.__version__} CPU, {threads} threads)"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--engine", default=os.environ.get("BRL_ENGINE", "auto"))
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-train", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist_mod.init_process_group("nccl", device_id=device)
+        dist = dist_mod
+
+    from bayesrul_b200 import Engine, Noise, _lib
+    from bayesrul_b200.compat import BNN, Inception
+
+    lib = _lib.load()
+    eng = Engine(NET, device)
+    engine = args.engine
+    if engine == "auto":
+        engine = "tc" if eng.has_tc() else "simt"
+
+    # ---- synthetic workload: each rank owns its own shard of windows (global window index offset)
+    n_rot = 8  # rotate 8 distinct batches (8 x 21.6 MB of windows > L2 together with the flush)
+    xs = [synth(B_PRED, seed=12345 + 17 * rank + i)[0].to(device) for i in range(n_rot)]
+    from oracle.bnn_oracle import init_params  # parameter initialisation only (weights_init statistics)
+    mu = init_params(NET, 12345).to(device)
+    sigma = torch.full_like(mu, CFG["q_scale"])
+    flush_buf = torch.zeros(64 * 1024 * 1024, device=device)
+    outs = {}
+
+    def pred_step(i=0):
+        outs["m"] = eng.predict_moments(xs[i % n_rot], mu, sigma, S=S_PRED, guide="normal",
+                                        noise=Noise(seed=2024, window0=rank * B_PRED), engine=engine)
+
+    sampler = ClockSampler(local)
+    l0 = lib.brl_launch_count()
+    t_local = timed_steps(pred_step, args.steps, args.warmup, flush_buf, dist)
+    launches = lib.brl_launch_count() - l0
+    clocks = sampler.stop()
+    launches_timed = launches * args.steps // (args.steps + args.warmup)
+    t = max_over_ranks(t_local, dist, device)
+    units_per_step = B_PRED * S_PRED
+    value = world * units_per_step * args.steps / t
+    pk = peaks()
+    flops_step = units_per_step * F_FWD
+    achieved_tf = flops_step * args.steps / t_local / 1e12
+
+    # ---- e2e: BNN.predict_step through the reference-facing class, pinned host inputs, host results
+    net = Inception(30, 18)
+    model = BNN(net, optimizer=None, pretrain_epochs=0, mc_samples_train=1, mc_samples_eval=S_PRED, dataset_size=N_DATASET,
+                fit_context="lrt", prior_loc=CFG["prior_loc"], prior_scale=CFG["prior_scale"], guide="normal",
+                q_scale=CFG["q_scale"], device=device, engine=engine)
+    model.on_predict_start()
+    hx = [synth(B_PRED, seed=999 + i) for i in range(2)]
+    hx = [(x.pin_memory(), y.pin_memory()) for x, y in hx]
+    res = {}
+
+    def e2e_step(i=0):
+        x, y = hx[i % 2]
+        res["p"] = model.predict_step((x, y), i)  # H2D of the batch + D2H of 5 result vectors inside
+
+    t_e2e_local = timed_steps(e2e_step, args.steps, args.warmup, flush_buf, dist)
+    t_e2e = max_over_ranks(t_e2e_local, dist, device)
+    e2e_value = world * units_per_step * args.steps / t_e2e
+    h2d = B_PRED * (30 * 18 + 1) * 4
+    d2h = B_PRED * 4 * 4
+
+    # ---- ELBO-train throughput (second half of the BASELINE metric), B=256
+    train = {}
+    if not args.no_train:
+        xt, yt = synth(B_TRAIN, seed=777 + rank)
+        xt, yt = xt.to(device), yt.to(device)
+        for mode, particles, q, ps in (("lrt", 1, 1.351e-3, 0.138793), ("flipout", 2, 2.14e-4, 0.198768)):
+            sg = torch.full_like(mu, q)
+            st = {"i": 0}
+
+            def train_step(i=0):
+                st["i"] += 1
+                eng.elbo_step(xt, yt, mu, sg, mode=mode, guide="normal", particles=particles, prior_loc=0.0,
+                              prior_scale=ps, dataset_size=N_DATASET, noise=Noise(seed=5000 + st["i"], window0=rank * B_TRAIN))
+
+            tt = max_over_ranks(timed_steps(train_step, 20, 5, flush_buf, dist), dist, device)
+            train[mode] = {"windows_per_s": world * B_TRAIN * 20 / tt, "ms_per_step": 1e3 * tt / 20, "batch": B_TRAIN,
+                           "particles": particles, "includes": "forward + backward + KL + gradient finalisation (no optimiser)"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16 operands / f32 accumulate" if engine == "tc" else "f32", "data": "synthetic",
+        "config": {"workload": f"ncmapss_lrt Inception BNN predict (configs[0]), B={B_PRED} windows x S={S_PRED} weight samples "
+                               "+ predictive moments per step per GPU", "net": NET, "engine": engine,
+                   "windows_per_step_per_gpu": B_PRED, "mc_samples": S_PRED, "q_scale": CFG["q_scale"],
+                   "l2": "256 MiB flush between timed steps + 8 rotating input batches", "parallelism": f"windows sharded x{world}"},
+        "clocks": clocks, "gpu_launches": int(launches_timed),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "bayesrul_b200.compat.BNN.predict_step (pinned host batch -> numpy results)"},
+        "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": pk["tf_sust"], "unit": "TFLOP/s",
+                     "frac": achieved_tf / pk["tf_sust"], "traffic": None,
+                     "note": f"algorithmic GEMM FLOPs of the whole step ({F_FWD} per window-sample) / step time on rank 0; "
+                             f"peak = sustained bf16 cuBLAS of {pk['src']} MEASURED_PEAKS.json"},
+        "train": train,
+    }
+    if world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        cpu_predict_rate(1000, 1, threads)  # warm-up
+        v, dt = cpu_predict_rate(B_PRED, 10, threads)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"{B_PRED} windows x 10 of the {S_PRED} MC samples ({dt:.1f} s), plain-PyTorch "
+                                          f"restatement on torch {torch.__version__} CPU"}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

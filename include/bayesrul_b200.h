@@ -79,6 +79,8 @@ typedef struct brl_noise {
 /* ---- library / static net description ------------------------------------------------ */
 int brl_version(void);
 const char* brl_last_error(void);
+/* number of CUDA kernels this library has launched since it was loaded (bench.py gpu_launches) */
+int64_t brl_launch_count(void);
 int brl_net_num_params(int net);
 int brl_net_num_layers(int net);
 int brl_net_num_sites(int net);
@@ -95,6 +97,8 @@ int brl_create(brl_ctx** ctx, int net, int device);
 int brl_destroy(brl_ctx* ctx);
 /* bytes of scratch needed by the calls below for B windows x S concurrently-resident samples;
  * train != 0 adds the saved activations / gradient buffers of brl_elbo_step / brl_hnn_step */
+/* 1 when `engine` can run this net's forward on this build, else 0 */
+int brl_engine_available(const brl_ctx* ctx, int engine);
 int64_t brl_workspace_bytes(const brl_ctx* ctx, int64_t B, int64_t S, int train, int engine);
 
 /* ---- guide: weight sampler (replaces AutoNormal.forward / AutoRadial.forward,

@@ -1,0 +1,63 @@
+"""CPU tests of the host-side mirrors: parameter naming, flat-buffer views, param-store state."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+
+@pytest.mark.parametrize("kind", ["inception", "conv", "linear"])
+def test_state_dict_keys_match_reference(golden_dir, kind):
+    from bayesrul_b200.compat import Conv, Inception, Linear
+    cls = {"inception": Inception, "conv": Conv, "linear": Linear}[kind]
+    z = np.load(os.path.join(golden_dir, f"{kind}.npz"))
+    net = cls(30, 18)
+    assert list(net.state_dict().keys()) == list(z["names"])
+    assert [str(tuple(v.shape)) for v in net.state_dict().values()] == list(z["shapes"])
+    netd = cls(30, 18, dropout=0.2)
+    assert list(netd.state_dict().keys()) == list(z["names_dropout_variant"])
+    # parameters are views of one flat buffer in named_parameters() order
+    sd = {k: torch.from_numpy(np.ascontiguousarray(z["theta"][off: off + int(np.prod(shape))].reshape(shape)))
+          for k, (off, shape) in zip(net.state_dict().keys(), net._sites)}
+    net.load_state_dict(sd)
+    np.testing.assert_array_equal(net.flat().numpy(), z["theta"])
+    assert net.win_length == 30 and net.n_features == 18 and net.dropout == 0  # attributes the wrappers read (F5)
+
+
+def test_weights_init_statistics(golden_dir):
+    from bayesrul_b200.compat import Inception, weights_init
+    ref = np.load(os.path.join(golden_dir, "weights_init_std.npz"))["inception"]
+    torch.manual_seed(0)
+    net = Inception(30, 18)
+    net.apply(weights_init)
+    for (name, p), r in zip(net.named_parameters(), ref):
+        if p.numel() >= 512 and name.endswith("weight"):
+            assert abs(p.std().item() / r - 1) < 0.15, name
+
+
+def test_unsupported_configurations_raise():
+    from bayesrul_b200.compat import BNN, Inception
+    with pytest.raises(ValueError):
+        Inception(30, 18, activation="tanh")
+    with pytest.raises(ValueError):
+        Inception(50, 18)
+    m = BNN(Inception(30, 18), None, 0, 1, 20, 1000, "lrt", 0.0, 1.0, "laplace", 1.0)
+    with pytest.raises(RuntimeError, match="Guide unknown"):
+        m.define_bnn()
+
+
+def test_param_store_roundtrip_cpu():
+    from bayesrul_b200.compat import Inception, pyro_shim, tyxe_shim
+    pyro_shim.clear_param_store()
+    net = Inception(30, 18)
+    g = tyxe_shim.AutoNormal(net, init_scale=0.01, init_loc_fn=tyxe_shim.PretrainedInitializer.from_net(net))
+    st = pyro_shim.get_param_store().get_state()
+    assert len(st["params"]) == 48
+    k = "net_guide.net.last.bias"
+    assert torch.allclose(st["params"][k + ".scale"], torch.full((2,), 0.01).log())
+    assert torch.allclose(pyro_shim.get_param_store()[k + ".scale"], torch.full((2,), 0.01))
+    new = {n: v.clone() + 1.0 for n, v in st["params"].items()}
+    pyro_shim.get_param_store().set_state({"params": new, "constraints": st["constraints"]})
+    assert torch.allclose(g.loc, net.flat() + 1.0)
+    pyro_shim.clear_param_store()
+    assert pyro_shim.get_param_store().get_state()["params"] == {}
