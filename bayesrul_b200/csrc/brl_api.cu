@@ -411,6 +411,8 @@ int brl_destroy(brl_ctx* ctx) {
   return BRL_OK;
 }
 
+int brl_tc_status(const brl_ctx* ctx) { return ctx ? tc_status(ctx->tc) : -1; }
+
 int brl_engine_available(const brl_ctx* ctx, int engine) {
   if (!ctx) return 0;
   if (engine == BRL_ENGINE_SIMT_FP32) return 1;

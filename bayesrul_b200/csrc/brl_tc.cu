@@ -1,12 +1,715 @@
+// tcgen05 / TMEM engine for the Inception regressor (fp16 operands, fp32 accumulation in TMEM).
+//
+// Three kernels per chunk of MC samples:
+//   tc_pack_kernel  fp32 weight draws [S,P] -> per-sample fp16 images in the UMMA canonical K-major
+//                   (no-swizzle) layout, i.e. exactly the bytes the MMA descriptors address
+//   tc_conv_kernel  persistent, one CTA per SM: the whole conv stack (both inception modules) of a
+//                   128-row tile (4 windows x 32 rows) stays in SMEM/TMEM; weights of the current MC
+//                   sample are staged once per sample by cp.async.bulk (1-D TMA) and stay resident;
+//                   'same' padding = shifted A descriptors over zero pad rows; epilogues (bias, ReLU,
+//                   dropout, fp16 pack, max-pool) run TMEM -> registers -> SMEM (next layer's A operand)
+//   tc_fc_kernel    warp-specialised GEMM [128 windows x 2400] x [2400 x 64] per (sample, window tile):
+//                   bulk-copy producer warp / single-thread tcgen05.mma issuer / 4 epilogue warps with a
+//                   double-buffered TMEM accumulator; epilogue fuses bias, ReLU, dropout, the 64->2
+//                   head, softplus and Threshold(1e-9).
+// Reference semantics: nets/inception.py:54-61,125-132,211-215.
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/bayesrul_b200.h"
+#include "brl_kernels.cuh"
+#include "brl_nets.h"
+#include "brl_philox.cuh"
 #include "brl_tc.cuh"
+
 namespace brl {
-struct TcState { int net; };
-TcState* tc_create(int net) { return new TcState{net}; }
-void tc_destroy(TcState* s) { delete s; }
-bool tc_available(const TcState*) { return false; }
-size_t tc_workspace_bytes(const TcState*, long long, long long) { return 0; }
-const char* tc_forward(TcState*, const float*, long long, long long, const float*, long long, float, const brl_noise*, float*,
-                       void*, size_t, cudaStream_t) {
-  return "bayesrul_b200: tensor-core engine not available for this net";
+
+// ------------------------------------------------------------------------------------------------
+// geometry
+// ------------------------------------------------------------------------------------------------
+constexpr int ROWS = 132;            // 2 zero rows + 128 tile rows + 2 slack rows
+constexpr int CS = ROWS * 16;        // bytes of one 8-channel chunk (K-major, 16 B per row)
+constexpr int ROW0 = 2;              // buffer row of tile row 0
+constexpr int OFF_X = 0;             // 4 chunks: 18 features padded to 32
+constexpr int OFF_XP = OFF_X + 4 * CS;
+constexpr int OFF_M1 = OFF_XP + 4 * CS;     // 16 chunks: 4 branches x (27 padded to 32)
+constexpr int OFF_M1P = OFF_M1 + 16 * CS;
+constexpr int OFF_T2 = OFF_M1P + 16 * CS;   // 8 chunks
+constexpr int OFF_T3 = OFF_T2 + 8 * CS;
+constexpr int OFF_W = OFF_T3 + 8 * CS;      // weight image
+// weight image (identical in the global blob)
+constexpr int WA_TAP = 4 * 32 * 16;         // [4 chunks][32 n][16 B]
+constexpr int WI_A = 0;                     // 12 taps
+constexpr int WI_B1 = WI_A + 12 * WA_TAP;   // [16 chunks][144 n][16 B]
+constexpr int WI_B4 = WI_B1 + 16 * 144 * 16;  // [16 chunks][32 n][16 B]
+constexpr int WC_TAP = 8 * 16 * 16;         // [8 chunks][16 n][16 B]
+constexpr int WI_B2B = WI_B4 + 16 * 32 * 16;  // 3 taps
+constexpr int WI_B3B = WI_B2B + 3 * WC_TAP;   // 5 taps
+constexpr int WI_BIAS = WI_B3B + 5 * WC_TAP;  // fp32: A 4x32, B1 144, B4 32, b2b 16, b3b 16
+constexpr int NBIAS = 128 + 144 + 32 + 16 + 16;
+constexpr int CONV_IMG = WI_BIAS + NBIAS * 4;
+static_assert(CONV_IMG % 16 == 0, "bulk copies need 16-byte multiples");
+constexpr int OFF_BAR = OFF_W + CONV_IMG;
+constexpr int CONV_SMEM = OFF_BAR + 64;
+// blob = conv image + fc image + fp32 tail (fc bias 64, last W 128, last b 2)
+constexpr int FC_IMG = 300 * 64 * 16;
+constexpr int BLOB_FC = CONV_IMG;
+constexpr int BLOB_TAIL = BLOB_FC + FC_IMG;
+constexpr int BLOB_BYTES = ((BLOB_TAIL + 194 * 4) + 255) / 256 * 256;
+constexpr int FEAT_TILE_BYTES = 300 * 2048;  // [300 k-chunks][128 windows][16 B]
+// fc kernel
+constexpr int FC_KCH = 10;                   // k-chunks per pipeline stage (K = 80)
+constexpr int FC_STAGES = 4;
+constexpr int FC_A_BYTES = FC_KCH * 2048, FC_W_BYTES = FC_KCH * 1024;
+constexpr int FC_STAGE_BYTES = FC_A_BYTES + FC_W_BYTES;
+constexpr int FC_SMEM = FC_STAGES * FC_STAGE_BYTES + 256;
+constexpr uint32_t SPIN_LIMIT = 1u << 22;
+
+struct TcState {
+  int net;
+  int* status;  // device: 0 ok, else first mbarrier time-out code
+  int sm_count;
+  long long loff[12][2];  // w_off, b_off per layer
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug must end the kernel, not hang the GPU
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* status, int code) {
+  for (uint32_t i = 0; i < SPIN_LIMIT; ++i)
+    if (mbar_try(bar, parity)) return true;
+  atomicCAS(status, 0, code);
+  return false;
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start >> 4 | [16,30) LBO >> 4 (between the two 8-element K chunks) | [32,46) SBO >> 4 (between 8-row groups)
+//   [46,48) version = 1 | [61,64) layout = 0
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// kind::f16 instruction descriptor: fp16 A/B (format 0), fp32 D, both K-major, M=128
+__host__ __device__ constexpr uint32_t umma_idesc(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24); }
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint4 hmax4(uint4 a, uint4 b) {
+  uint4 r;
+  const __half2* pa = reinterpret_cast<const __half2*>(&a);
+  const __half2* pb = reinterpret_cast<const __half2*>(&b);
+  __half2* pr = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) pr[i] = __hmax2(pa[i], pb[i]);
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing: fp32 [S,P] -> fp16 images
+// ------------------------------------------------------------------------------------------------
+struct PackArgs {
+  const float* w;
+  long long w_stride;  // P, or 0 when the weights are shared by all samples
+  unsigned char* blob;
+  long long off[12][2];
+};
+
+__device__ __forceinline__ void put_h(unsigned char* img, int byte_off, float v) {
+  *reinterpret_cast<__half*>(img + byte_off) = __float2half_rn(v);
+}
+
+__global__ void tc_pack_kernel(const PackArgs a) {
+  const int s = blockIdx.y;
+  const float* w = a.w + (long long)s * a.w_stride;
+  unsigned char* blob = a.blob + (long long)s * BLOB_BYTES;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr int N_A = 12 * 32 * 32, N_B1 = 144 * 128, N_B4 = 32 * 128, N_C2 = 3 * 16 * 64, N_C3 = 5 * 16 * 64;
+  constexpr int N_FC = 64 * 2400;
+  int j = i;
+  if (j < N_A) {  // module 1: tap-major [tap][k/8][n][k%8]
+    const int tap = j / 1024, r = j % 1024, n = r / 32, k = r % 32;
+    const int layer = tap == 0 ? 0 : tap < 4 ? 1 : tap < 9 ? 2 : 3;
+    const int t0 = layer == 0 ? 0 : layer == 1 ? 1 : layer == 2 ? 4 : 9;
+    const int ntap = layer == 0 ? 1 : layer == 2 ? 5 : 3;
+    float v = 0.f;
+    if (n < 27 && k < 18) v = w[a.off[layer][0] + ((long long)n * 18 + k) * ntap + (tap - t0)];
+    put_h(blob, WI_A + tap * WA_TAP + (k >> 3) * 512 + n * 16 + (k & 7) * 2, v);
+    return;
+  }
+  j -= N_A;
+  if (j < N_B1) {  // module-2 1x1 convs of b1 | b2a | b3a over the padded M1 channels
+    const int n = j / 128, k = j % 128;
+    const int layer = n < 16 ? 4 : n < 80 ? 5 : 7;
+    const int co = n < 16 ? n : n < 80 ? n - 16 : n - 80;
+    const int grp = k >> 5, c = k & 31;
+    float v = 0.f;
+    if (c < 27) v = w[a.off[layer][0] + (long long)co * 108 + grp * 27 + c];
+    put_h(blob, WI_B1 + (k >> 3) * (144 * 16) + n * 16 + (k & 7) * 2, v);
+    return;
+  }
+  j -= N_B1;
+  if (j < N_B4) {
+    const int n = j / 128, k = j % 128, grp = k >> 5, c = k & 31;
+    float v = 0.f;
+    if (c < 27) v = w[a.off[9][0] + (long long)n * 108 + grp * 27 + c];
+    put_h(blob, WI_B4 + (k >> 3) * 512 + n * 16 + (k & 7) * 2, v);
+    return;
+  }
+  j -= N_B4;
+  if (j < N_C2) {
+    const int tap = j / 1024, r = j % 1024, n = r / 64, k = r % 64;
+    put_h(blob, WI_B2B + tap * WC_TAP + (k >> 3) * 256 + n * 16 + (k & 7) * 2, w[a.off[6][0] + ((long long)n * 64 + k) * 3 + tap]);
+    return;
+  }
+  j -= N_C2;
+  if (j < N_C3) {
+    const int tap = j / 1024, r = j % 1024, n = r / 64, k = r % 64;
+    put_h(blob, WI_B3B + tap * WC_TAP + (k >> 3) * 256 + n * 16 + (k & 7) * 2, w[a.off[8][0] + ((long long)n * 64 + k) * 5 + tap]);
+    return;
+  }
+  j -= N_C3;
+  if (j < NBIAS) {
+    float v = 0.f;
+    if (j < 128) { const int br = j >> 5, c = j & 31; if (c < 27) v = w[a.off[br][1] + c]; }
+    else if (j < 272) { const int n = j - 128; v = n < 16 ? w[a.off[4][1] + n] : n < 80 ? w[a.off[5][1] + n - 16] : w[a.off[7][1] + n - 80]; }
+    else if (j < 304) v = w[a.off[9][1] + j - 272];
+    else if (j < 320) v = w[a.off[6][1] + j - 304];
+    else v = w[a.off[8][1] + j - 320];
+    *reinterpret_cast<float*>(blob + WI_BIAS + j * 4) = v;
+    return;
+  }
+  j -= NBIAS;
+  if (j < N_FC) {  // fc: k' = t*80 + c  <-  original column c*30 + t
+    const int n = j / 2400, kp = j % 2400, t = kp / 80, c = kp % 80;
+    put_h(blob, BLOB_FC + (kp >> 3) * 1024 + n * 16 + (kp & 7) * 2, w[a.off[10][0] + (long long)n * 2400 + c * 30 + t]);
+    return;
+  }
+  j -= N_FC;
+  if (j < 194) {
+    float v = j < 64 ? w[a.off[10][1] + j] : j < 192 ? w[a.off[11][0] + j - 64] : w[a.off[11][1] + j - 192];
+    *reinterpret_cast<float*>(blob + BLOB_TAIL + j * 4) = v;
+  }
+}
+constexpr int PACK_THREADS_TOTAL = 12 * 1024 + 144 * 128 + 32 * 128 + 3 * 1024 + 5 * 1024 + NBIAS + 64 * 2400 + 194;
+
+// ------------------------------------------------------------------------------------------------
+// conv stack kernel
+// ------------------------------------------------------------------------------------------------
+struct ConvArgs {
+  const float* x;             // [B,30,18]
+  const unsigned char* blob;  // [S or 1][BLOB_BYTES]
+  long long blob_stride;      // BLOB_BYTES or 0
+  unsigned char* feat;        // [S][NT128][300][128][16 B]
+  int B, S, ntile4, ntile128;
+  float keep4;                // dropout keep of the branch sites (1 = off)
+  NoiseRef drop[12];
+  int* status;
+};
+
+// epilogue helper: 16 accumulator columns -> bias, ReLU, (dropout), fp16, zero for pad rows
+template <bool DROP>
+__device__ __forceinline__ void epi16(const float (&acc)[16], const float* bias, bool live, uint4& lo, uint4& hi,
+                                      const ConvArgs& a, int layer, int s, int gw, int t, int ch0, int nvalid) {
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float u = fmaxf(acc[j] + bias[j], 0.f);
+    if (DROP) {
+      if (ch0 + j < nvalid && live) {
+        const NoiseRef& nz = a.drop[layer];
+        const int e = (ch0 + j) * 30 + t;
+        const bool keep = nz.ptr ? nz.ptr[((long long)s * a.B + gw) * (nvalid * 30) + e] != 0.f
+                                 : philox_uniform(nz.seed, nz.kind, nz.site, nz.sample0 + s, nz.window0 + gw, e) < a.keep4;
+        u = keep ? u / a.keep4 : 0.f;
+      }
+    }
+    v[j] = live ? u : 0.f;
+  }
+  lo = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+  hi = make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
+}
+
+template <bool DROP>
+__global__ void __launch_bounds__(256, 1) tc_conv_kernel(const ConvArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t bar0 = sbase + OFF_BAR;  // [0..2] phase barriers, [3] weight barrier
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 40);
+  const float* sbias = reinterpret_cast<const float*>(smem + OFF_W + WI_BIAS);
+
+  // zero all activation buffers once: pad rows / pad features stay zero for the kernel's lifetime
+  for (int i = tid; i < OFF_W / 16; i += 256) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(bar0 + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  const long long total = (long long)a.S * a.ntile4;
+  const long long per = (total + gridDim.x - 1) / gridDim.x;
+  const long long beg = per * blockIdx.x, end = min(total, beg + per);
+  const int row = tid & 127, half = tid >> 7;
+  const int wq = row >> 5, t = row & 31;  // window inside the tile, time step
+  const uint32_t lane_addr = tmem + ((uint32_t)(row & ~31) << 16);
+  const uint32_t rowoff = (uint32_t)(ROW0 + row) * 16;
+  int cur_s = -1;
+  uint32_t ph = 0, wph = 0;
+  bool ok = true;
+
+  for (long long it = beg; it < end && ok; ++it) {
+    const int s = (int)(it / a.ntile4), tile = (int)(it % a.ntile4);
+    if (s != cur_s) {  // stage this sample's conv weights (all MMAs of the previous tile have completed)
+      cur_s = s;
+      if (tid == 0) {
+        const unsigned char* src = a.blob + (long long)s * a.blob_stride;
+        mbar_expect_tx(bar0 + 24, CONV_IMG);
+        for (int o = 0; o < CONV_IMG; o += 16384)
+          bulk_g2s(sbase + OFF_W + o, src + o, min(16384, CONV_IMG - o), bar0 + 24);
+      }
+      ok = mbar_wait(bar0 + 24, wph, a.status, 1);
+      wph ^= 1;
+    }
+    // ---- stage the 4 windows: fp32 [t][18] -> fp16 chunks of 8 features, K-major
+    for (int u = tid; u < 384; u += 256) {
+      const int r = u & 127, c = u >> 7, w4 = r >> 5, tt = r & 31;
+      const int gw = tile * 4 + w4;
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = 0.f;
+      if (tt < 30 && gw < a.B) {
+        const float* px = a.x + (long long)gw * 540 + tt * 18 + c * 8;
+        const int nf = c < 2 ? 8 : 2;
+        for (int j = 0; j < nf; j += 2) {
+          const float2 p2 = __ldg(reinterpret_cast<const float2*>(px + j));
+          f[j] = p2.x; f[j + 1] = p2.y;
+        }
+      }
+      *reinterpret_cast<uint4*>(smem + OFF_X + c * CS + (ROW0 + r) * 16) =
+          make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
+    }
+    __syncthreads();
+    // ---- MaxPool1d(3,1,1) of the raw window (-inf padding: only in-window neighbours take part)
+    for (int u = tid; u < 384; u += 256) {
+      const int r = u & 127, c = u >> 7, tt = r & 31;
+      const unsigned char* p = smem + OFF_X + c * CS + (ROW0 + r) * 16;
+      uint4 v = *reinterpret_cast<const uint4*>(p);
+      if (tt < 30) {
+        if (tt > 0) v = hmax4(v, *reinterpret_cast<const uint4*>(p - 16));
+        if (tt < 29) v = hmax4(v, *reinterpret_cast<const uint4*>(p + 16));
+      }
+      *reinterpret_cast<uint4*>(smem + OFF_XP + c * CS + (ROW0 + r) * 16) = v;
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    // ---- phase A: module 1 (4 branches, N = 32 each) ------------------------------------------------
+    if (tid == 0) {
+      tc_fence_after();
+      constexpr uint32_t idA = umma_idesc(32);
+      const int ntap[4] = {1, 3, 5, 3}, tap0[4] = {0, 1, 4, 9}, pad[4] = {0, 1, 2, 1};
+      for (int br = 0; br < 4; ++br) {
+        const uint32_t abase = sbase + (br == 3 ? OFF_XP : OFF_X);
+        uint32_t acc = 0;
+        for (int tp = 0; tp < ntap[br]; ++tp)
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint64_t ad = umma_desc(abase + 2 * ks * CS + (ROW0 + tp - pad[br]) * 16, CS, 128);
+            const uint64_t bd = umma_desc(sbase + OFF_W + WI_A + (tap0[br] + tp) * WA_TAP + 2 * ks * 512, 512, 128);
+            umma(tmem + br * 32, ad, bd, idA, acc);
+            acc = 1;
+          }
+      }
+      umma_commit(bar0);
+    }
+    ok = mbar_wait(bar0, ph, a.status, 2);
+    tc_fence_after();
+    {
+      const int gw = tile * 4 + wq;
+      const bool live = t < 30 && gw < a.B;
+      float acc[4][16];
+#pragma unroll
+      for (int br = 0; br < 4; ++br) tmem_ld16(lane_addr + br * 32 + half * 16, acc[br]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int br = 0; br < 4; ++br) {
+        uint4 lo, hi;
+        epi16<DROP>(acc[br], sbias + br * 32 + half * 16, live, lo, hi, a, br, s, gw, t, half * 16, 27);
+        unsigned char* dst = smem + OFF_M1 + (br * 4 + half * 2) * CS + rowoff;
+        *reinterpret_cast<uint4*>(dst) = lo;
+        *reinterpret_cast<uint4*>(dst + CS) = hi;
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+    // ---- MaxPool1d(3,1,1) of module-1 output (post-ReLU >= 0, zero pad rows act as -inf)
+    for (int u = tid; u < 2048; u += 256) {
+      const int r = u & 127, c = u >> 7;
+      const unsigned char* p = smem + OFF_M1 + c * CS + (ROW0 + r) * 16;
+      const uint4 v = hmax4(hmax4(*reinterpret_cast<const uint4*>(p - 16), *reinterpret_cast<const uint4*>(p)),
+                            *reinterpret_cast<const uint4*>(p + 16));
+      *reinterpret_cast<uint4*>(smem + OFF_M1P + c * CS + (ROW0 + r) * 16) = v;
+    }
+    fence_async_smem();
+    __syncthreads();
+    // ---- phase B: module-2 1x1 convs: [b1 | b2a | b3a] (N = 144) on M1, b4 (N = 32) on pooled M1 ------
+    if (tid == 0) {
+      tc_fence_after();
+      constexpr uint32_t idB1 = umma_idesc(144), idB4 = umma_idesc(32);
+      for (int ks = 0; ks < 8; ++ks)
+        umma(tmem + 128, umma_desc(sbase + OFF_M1 + 2 * ks * CS + ROW0 * 16, CS, 128),
+             umma_desc(sbase + OFF_W + WI_B1 + 2 * ks * 2304, 2304, 128), idB1, ks > 0);
+      for (int ks = 0; ks < 8; ++ks)
+        umma(tmem + 272, umma_desc(sbase + OFF_M1P + 2 * ks * CS + ROW0 * 16, CS, 128),
+             umma_desc(sbase + OFF_W + WI_B4 + 2 * ks * 512, 512, 128), idB4, ks > 0);
+      umma_commit(bar0 + 8);
+    }
+    ok = ok && mbar_wait(bar0 + 8, ph, a.status, 3);
+    tc_fence_after();
+    const int gw = tile * 4 + wq;
+    const bool live = t < 30 && gw < a.B;
+    unsigned char* frow = a.feat + ((long long)s * a.ntile128 + (gw >> 7)) * FEAT_TILE_BYTES + (long long)(gw & 127) * 16 +
+                          (long long)t * 10 * 2048;
+    {
+      // 11 groups of 16 columns: g0 = b1 -> feat ch 0..15 | g1..4 = b2a -> T2 | g5..8 = b3a -> T3 | g9,10 = b4 -> feat ch 48..79
+      for (int g = half; g < 11; g += 2) {
+        float acc[16];
+        tmem_ld16(lane_addr + 128 + g * 16, acc);
+        tmem_ld_wait();
+        uint4 lo, hi;
+        if (g == 0) {
+          epi16<DROP>(acc, sbias + 128, live, lo, hi, a, 4, s, gw, t, 0, 16);
+          if (live) { *reinterpret_cast<uint4*>(frow) = lo; *reinterpret_cast<uint4*>(frow + 2048) = hi; }
+        } else if (g < 9) {
+          epi16<false>(acc, sbias + 128 + g * 16, live, lo, hi, a, 0, s, gw, t, 0, 16);
+          unsigned char* dst = smem + (g < 5 ? OFF_T2 + (g - 1) * 2 * CS : OFF_T3 + (g - 5) * 2 * CS) + rowoff;
+          *reinterpret_cast<uint4*>(dst) = lo;
+          *reinterpret_cast<uint4*>(dst + CS) = hi;
+        } else {
+          epi16<DROP>(acc, sbias + 272 + (g - 9) * 16, live, lo, hi, a, 9, s, gw, t, (g - 9) * 16, 32);
+          if (live) {
+            *reinterpret_cast<uint4*>(frow + (6 + (g - 9) * 2) * 2048) = lo;
+            *reinterpret_cast<uint4*>(frow + (7 + (g - 9) * 2) * 2048) = hi;
+          }
+        }
+      }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    // ---- phase C: b2b (k3 over T2) and b3b (k5 over T3), N = 16 each -----------------------------------
+    if (tid == 0) {
+      tc_fence_after();
+      constexpr uint32_t idC = umma_idesc(16);
+      uint32_t acc = 0;
+      for (int tp = 0; tp < 3; ++tp)
+        for (int ks = 0; ks < 4; ++ks) {
+          umma(tmem + 304, umma_desc(sbase + OFF_T2 + 2 * ks * CS + (ROW0 + tp - 1) * 16, CS, 128),
+               umma_desc(sbase + OFF_W + WI_B2B + tp * WC_TAP + 2 * ks * 256, 256, 128), idC, acc);
+          acc = 1;
+        }
+      acc = 0;
+      for (int tp = 0; tp < 5; ++tp)
+        for (int ks = 0; ks < 4; ++ks) {
+          umma(tmem + 320, umma_desc(sbase + OFF_T3 + 2 * ks * CS + (ROW0 + tp - 2) * 16, CS, 128),
+               umma_desc(sbase + OFF_W + WI_B3B + tp * WC_TAP + 2 * ks * 256, 256, 128), idC, acc);
+          acc = 1;
+        }
+      umma_commit(bar0 + 16);
+    }
+    ok = ok && mbar_wait(bar0 + 16, ph, a.status, 4);
+    tc_fence_after();
+    {
+      float acc[16];
+      tmem_ld16(lane_addr + 304 + half * 16, acc);
+      tmem_ld_wait();
+      uint4 lo, hi;
+      epi16<DROP>(acc, sbias + 304 + half * 16, live, lo, hi, a, half ? 8 : 6, s, gw, t, 0, 16);
+      if (live) {
+        *reinterpret_cast<uint4*>(frow + (2 + half * 2) * 2048) = lo;
+        *reinterpret_cast<uint4*>(frow + (3 + half * 2) * 2048) = hi;
+      }
+    }
+    tc_fence_before();
+    ph ^= 1;
+    __syncthreads();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fc + head kernel
+// ------------------------------------------------------------------------------------------------
+struct FcArgs {
+  const unsigned char* feat;
+  const unsigned char* blob;
+  long long blob_stride;
+  float* out;  // [S,B,2]
+  int B, S, ntile128;
+  float keep;  // dropout keep of the fc site
+  NoiseRef drop;
+  int* status;
+};
+
+template <bool DROP>
+__global__ void __launch_bounds__(192, 1) tc_fc_kernel(const FcArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bars = sbase + FC_STAGES * FC_STAGE_BYTES;
+  // full[4] @0, empty[4] @32, tmem_full[2] @64, tmem_empty[2] @80, tmem slot @96
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + FC_STAGES * FC_STAGE_BYTES + 96);
+  if (tid == 0) {
+    for (int i = 0; i < FC_STAGES; ++i) { mbar_init(bars + 8 * i, 1); mbar_init(bars + 32 + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bars + 64 + 8 * i, 1); mbar_init(bars + 80 + 8 * i, 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const long long total = (long long)a.S * a.ntile128;
+  constexpr int NKB = 300 / FC_KCH;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== producer: bulk copies of the A (features) and B (fc weights) k-blocks
+      uint32_t stage = 0, ph = 1;
+      bool ok = true;
+      for (long long it = blockIdx.x; it < total && ok; it += gridDim.x) {
+        const int s = (int)(it / a.ntile128);
+        const unsigned char* ga = a.feat + it * (long long)FEAT_TILE_BYTES;
+        const unsigned char* gb = a.blob + (long long)s * a.blob_stride + BLOB_FC;
+        for (int kb = 0; kb < NKB && ok; ++kb) {
+          ok = mbar_wait(bars + 32 + 8 * stage, ph, a.status, 10);
+          const uint32_t dst = sbase + stage * FC_STAGE_BYTES;
+          mbar_expect_tx(bars + 8 * stage, FC_STAGE_BYTES);
+          bulk_g2s(dst, ga + (long long)kb * FC_A_BYTES, FC_A_BYTES, bars + 8 * stage);
+          bulk_g2s(dst + FC_A_BYTES, gb + (long long)kb * FC_W_BYTES, FC_W_BYTES, bars + 8 * stage);
+          if (++stage == FC_STAGES) { stage = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== single-thread MMA issuer
+      constexpr uint32_t idesc = umma_idesc(64);
+      uint32_t stage = 0, ph = 0, acc_i = 0, aph = 1;
+      bool ok = true;
+      for (long long it = blockIdx.x; it < total && ok; it += gridDim.x) {
+        ok = mbar_wait(bars + 80 + 8 * acc_i, aph, a.status, 11);
+        tc_fence_after();
+        for (int kb = 0; kb < NKB && ok; ++kb) {
+          ok = mbar_wait(bars + 8 * stage, ph, a.status, 12);
+          tc_fence_after();
+          const uint32_t sa = sbase + stage * FC_STAGE_BYTES, sb = sa + FC_A_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < FC_KCH / 2; ++ks)
+            umma(tmem + acc_i * 64, umma_desc(sa + 2 * ks * 2048, 2048, 128), umma_desc(sb + 2 * ks * 1024, 1024, 128), idesc,
+                 (kb | ks) != 0);
+          umma_commit(bars + 32 + 8 * stage);
+          if (++stage == FC_STAGES) { stage = 0; ph ^= 1; }
+        }
+        umma_commit(bars + 64 + 8 * acc_i);
+        if (++acc_i == 2) { acc_i = 0; aph ^= 1; }
+      }
+    }
+  } else {  // ===== epilogue warps 2..5: TMEM lane quadrant = warp % 4
+    const int q = warp & 3, row = q * 32 + lane;
+    uint32_t acc_i = 0, aph = 0;
+    bool ok = true;
+    for (long long it = blockIdx.x; it < total && ok; it += gridDim.x) {
+      const int s = (int)(it / a.ntile128), tile = (int)(it % a.ntile128);
+      const float* tail = reinterpret_cast<const float*>(a.blob + (long long)s * a.blob_stride + BLOB_TAIL);
+      ok = mbar_wait(bars + 64 + 8 * acc_i, aph, a.status, 13);
+      tc_fence_after();
+      float acc[4][16];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + acc_i * 64 + g * 16, acc[g]);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(bars + 80 + 8 * acc_i);  // accumulator drained: the issuer may reuse it
+      const int gw = tile * 128 + row;
+      float o0 = __ldg(tail + 192), o1 = __ldg(tail + 193);
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int n = g * 16 + j;
+          float h = fmaxf(acc[g][j] + __ldg(tail + n), 0.f);
+          if (DROP) {
+            if (gw < a.B) {
+              const bool keep = a.drop.ptr ? a.drop.ptr[((long long)s * a.B + gw) * 64 + n] != 0.f
+                                           : philox_uniform(a.drop.seed, a.drop.kind, a.drop.site, a.drop.sample0 + s,
+                                                            a.drop.window0 + gw, n) < a.keep;
+              h = keep ? h / a.keep : 0.f;
+            }
+          }
+          o0 = fmaf(h, __ldg(tail + 64 + n), o0);
+          o1 = fmaf(h, __ldg(tail + 128 + n), o1);
+        }
+      if (gw < a.B) {
+        o0 = o0 > 20.f ? o0 : log1pf(expf(o0));
+        o1 = o1 > 20.f ? o1 : log1pf(expf(o1));
+        float2 r = make_float2(o0 > 1e-9f ? o0 : 1e-9f, o1 > 1e-9f ? o1 : 1e-9f);
+        *reinterpret_cast<float2*>(a.out + ((long long)s * a.B + gw) * 2) = r;
+      }
+      if (++acc_i == 2) { acc_i = 0; aph ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 128);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+TcState* tc_create(int net) {
+  TcState* st = new TcState();
+  st->net = net;
+  st->status = nullptr;
+  st->sm_count = 148;
+  if (net != BRL_NET_INCEPTION) return st;
+  const NetSpec& n = get_net(net);
+  for (int l = 0; l < 12; ++l) { st->loff[l][0] = n.layers[l].w_off; st->loff[l][1] = n.layers[l].b_off; }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&st->sm_count, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaMalloc(&st->status, sizeof(int)) != cudaSuccess) { st->status = nullptr; return st; }
+  cudaMemset(st->status, 0, sizeof(int));
+  cudaFuncSetAttribute(tc_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM);
+  cudaFuncSetAttribute(tc_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM);
+  cudaFuncSetAttribute(tc_fc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM);
+  cudaFuncSetAttribute(tc_fc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM);
+  return st;
+}
+void tc_destroy(TcState* s) {
+  if (!s) return;
+  if (s->status) cudaFree(s->status);
+  delete s;
+}
+bool tc_available(const TcState* s) { return s && s->net == BRL_NET_INCEPTION && s->status != nullptr; }
+int tc_status(const TcState* s) {
+  int v = -1;
+  if (s && s->status) cudaMemcpy(&v, s->status, sizeof(int), cudaMemcpyDeviceToHost);
+  return v;
+}
+size_t tc_workspace_bytes(const TcState* s, long long B, long long S) {
+  const long long nt128 = (B + 127) / 128;
+  return (size_t)(S * (long long)BLOB_BYTES + S * nt128 * FEAT_TILE_BYTES + 1024);
+}
+
+const char* tc_forward(TcState* st, const float* x, long long B, long long S, const float* weights, long long w_sample_stride,
+                       float p_dropout, const brl_noise* noise, float* out, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  if (!tc_available(st)) return "bayesrul_b200: tensor-core engine is implemented for the Inception net only";
+  if (ws_bytes < tc_workspace_bytes(st, B, S)) return "bayesrul_b200: workspace too small for the tensor-core engine";
+  const long long nt128 = (B + 127) / 128, nt4 = (B + 3) / 4;
+  unsigned char* blob = reinterpret_cast<unsigned char*>(ws);
+  const long long nblob = w_sample_stride ? S : 1;
+  unsigned char* feat = blob + ((S * (long long)BLOB_BYTES + 255) / 256) * 256;
+  PackArgs pa;
+  pa.w = weights; pa.w_stride = w_sample_stride; pa.blob = blob;
+  for (int l = 0; l < 12; ++l) { pa.off[l][0] = st->loff[l][0]; pa.off[l][1] = st->loff[l][1]; }
+  tc_pack_kernel<<<dim3((PACK_THREADS_TOTAL + 255) / 256, (unsigned)nblob), 256, 0, stream>>>(pa);
+  const bool drop = p_dropout > 0.f;
+  auto nr = [&](int layer) {
+    NoiseRef r;
+    r.ptr = noise ? noise->drop_mask[layer] : nullptr;
+    r.seed = noise ? noise->seed : 0ull;
+    r.kind = KIND_DROPOUT; r.site = layer;
+    r.sample0 = noise ? (unsigned)noise->sample0 : 0u;
+    r.window0 = noise ? (unsigned)noise->window0 : 0u;
+    return r;
+  };
+  ConvArgs ca;
+  ca.x = x; ca.blob = blob; ca.blob_stride = w_sample_stride ? BLOB_BYTES : 0; ca.feat = feat;
+  ca.B = (int)B; ca.S = (int)S; ca.ntile4 = (int)nt4; ca.ntile128 = (int)nt128;
+  ca.keep4 = drop ? 1.0f - p_dropout * 0.25f : 1.0f;
+  for (int l = 0; l < 12; ++l) ca.drop[l] = nr(l);
+  ca.status = st->status;
+  const long long items = S * nt4;
+  const int grid = (int)std::min<long long>(st->sm_count, items);
+  if (drop) tc_conv_kernel<true><<<grid, 256, CONV_SMEM, stream>>>(ca);
+  else tc_conv_kernel<false><<<grid, 256, CONV_SMEM, stream>>>(ca);
+  FcArgs fa;
+  fa.feat = feat; fa.blob = blob; fa.blob_stride = ca.blob_stride; fa.out = out;
+  fa.B = (int)B; fa.S = (int)S; fa.ntile128 = (int)nt128;
+  fa.keep = drop ? 1.0f - p_dropout : 1.0f;
+  fa.drop = nr(10);
+  fa.status = st->status;
+  const int gridf = (int)std::min<long long>(st->sm_count, S * nt128);
+  if (drop) tc_fc_kernel<true><<<gridf, 192, FC_SMEM, stream>>>(fa);
+  else tc_fc_kernel<false><<<gridf, 192, FC_SMEM, stream>>>(fa);
+  count_launch(3);
+  return nullptr;
+}
+
 }  // namespace brl

@@ -10,6 +10,7 @@ struct TcState;
 TcState* tc_create(int net);
 void tc_destroy(TcState*);
 bool tc_available(const TcState*);
+int tc_status(const TcState*);  // 0 ok; else the code of the first mbarrier wait that timed out (synchronises)
 size_t tc_workspace_bytes(const TcState*, long long B, long long S);
 // returns nullptr on success, else a static error string
 const char* tc_forward(TcState*, const float* x, long long B, long long S, const float* weights, long long w_sample_stride,

@@ -112,6 +112,10 @@ class Engine:
     def has_tc(self) -> bool:
         """True when the tcgen05 (fp16 operand / fp32 accumulate) engine supports this net."""
         return bool(self.lib.brl_engine_available(self.ctx, ENGINE_IDS["tc"]))
+    def tc_status(self) -> int:
+        """0 = ok; >0 = an mbarrier wait inside a tcgen05 kernel timed out (synchronises)."""
+        return int(self.lib.brl_tc_status(self.ctx))
+
 
     # -- helpers ------------------------------------------------------------------------------
     def _stream(self) -> int:

@@ -155,7 +155,7 @@ def run_reference(args, rank, world):
     threads = os.cpu_count() or 1
     nb, ns = B_PRED, 2
     for _ in range(max(1, min(args.warmup, 1))):
-        cpu_predict_rate(nb // 4, 1, threads)
+        cpu_predict_rate(nb // 4, 2, threads)
     t = 0.0
     units = 0
     for _ in range(args.steps):
@@ -300,7 +300,7 @@ def main():
     }
     if world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
-        cpu_predict_rate(1000, 1, threads)  # warm-up
+        cpu_predict_rate(1000, 2, threads)  # warm-up
         v, dt = cpu_predict_rate(B_PRED, 10, threads)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": f"{B_PRED} windows x 10 of the {S_PRED} MC samples ({dt:.1f} s), plain-PyTorch "

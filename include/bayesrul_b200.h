@@ -100,6 +100,10 @@ int brl_destroy(brl_ctx* ctx);
 /* 1 when `engine` can run this net's forward on this build, else 0 */
 int brl_engine_available(const brl_ctx* ctx, int engine);
 int64_t brl_workspace_bytes(const brl_ctx* ctx, int64_t B, int64_t S, int train, int engine);
+/* tensor-core engine health: 0 = ok, > 0 = code of the first mbarrier wait that timed out inside a
+ * tcgen05 kernel (waits are bounded so a protocol bug ends the kernel instead of hanging the GPU),
+ * < 0 = engine unavailable.  Synchronises the device. */
+int brl_tc_status(const brl_ctx* ctx);
 
 /* ---- guide: weight sampler (replaces AutoNormal.forward / AutoRadial.forward,
  *      guides/radial.py:31-41,124-144; 24 pyro.sample sites per draw) ------------------- */

@@ -21,6 +21,8 @@ def test_bnn_training_loop_and_checkpoint(fit_context, guide, particles):
     from bayesrul_b200.compat import BNN, Inception, pyro_shim
     torch.manual_seed(12345)
     net = Inception(30, 18)
+    with torch.no_grad():
+        net.last.bias.fill_(3.0)  # keep the aggregated scale above ln 2 so that inverse_softplus stays positive (A.5)
     opt = pyro_shim.ClippedAdam({"lr": 0.000857, "betas": [0.95, 0.999], "clip_norm": 15})
     m = BNN(net, opt, pretrain_epochs=5, mc_samples_train=particles, mc_samples_eval=8, dataset_size=238150,
             fit_context=fit_context, prior_loc=0.0, prior_scale=0.138793, guide=guide, q_scale=1.351e-3, device=DEV)
