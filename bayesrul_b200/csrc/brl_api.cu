@@ -64,7 +64,7 @@ struct Carve {
 
 struct ActBufs {
   std::vector<float*> act, grad, sd;  // per buffer / per buffer / per op
-  float *dpre = nullptr, *dsec = nullptr;
+  float *dpre = nullptr, *dsec = nullptr, *part = nullptr;
   float *g0 = nullptr, *g1 = nullptr, *wsamp = nullptr, *delta = nullptr, *norms = nullptr;
   std::vector<float*> sgn_in, sgn_out;  // per layer
   double* acc = nullptr;
@@ -99,6 +99,7 @@ static void carve_train(const NetSpec& n, Carve& c, long long B, ActBufs& ab) {
     ab.sgn_out[l] = c.take<float>(B * n.layers[l].cout);
   }
   ab.acc = c.take<double>(8);
+  ab.part = c.take<float>(SPLITK_SCRATCH_FLOATS);
 }
 
 static NoiseRef nref(const brl_noise* nz, const float* ptr, unsigned kind, unsigned site) {
@@ -212,6 +213,7 @@ static void run_forward(const brl_ctx* ctx, const ActBufs& ab, const FwdArgs& a,
     p.co_off = op.co_off; p.relu = op.relu; p.head = op.head;
     p.keep = (a.p_dropout > 0.f && L.drop_factor > 0.f) ? 1.0f - a.p_dropout * L.drop_factor : 1.0f;
     p.drop = nref(a.noise, a.noise ? a.noise->drop_mask[op.layer] : nullptr, KIND_DROPOUT, op.layer);
+    p.part = ab.part;
     launch_conv_gemm(p, epi, st);
   }
 }
@@ -295,6 +297,7 @@ static void run_backward(const brl_ctx* ctx, const ActBufs& ab, const BwdArgs& a
     } else if (a.mode == BRL_MODE_FLIPOUT) {
       epi = EPI_DX_FLIPOUT; p.W1 = a.wsamp + L.w_off; p.trB = TRB_MINUS_W0; p.sign_in = a.sgn_in[op.layer]; p.sign_C = L.cin;
     }
+    p.part = ab.part;
     launch_conv_gemm(p, epi, st);
   }
 }

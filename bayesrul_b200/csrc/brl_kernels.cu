@@ -41,255 +41,6 @@ __device__ __forceinline__ double block_sum(double v) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// implicit-GEMM conv: C[m,n] = sum_k A(m,k) * B(k,n)   (forward and input-gradient passes)
-// tile 128x32x16, 256 threads, 4x4 micro-tile; DUAL carries the second product of LRT / Flipout
-// ------------------------------------------------------------------------------------------------
-constexpr int BM = 128, BN = 32, BK = 16;
-
-template <bool DUAL, int EPI>
-__global__ void __launch_bounds__(256) conv_gemm_kernel(const ConvGemm p) {
-  __shared__ __align__(16) float As0[BK][BM];
-  __shared__ __align__(16) float Bs0[BK][BN];
-  __shared__ __align__(16) float As1[DUAL ? BK : 1][BM];
-  __shared__ __align__(16) float Bs1[DUAL ? BK : 1][BN];
-
-  const int s = blockIdx.z;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-  const int tid = threadIdx.x;
-  const int Mtot = p.B * p.P;
-
-  // A-load mapping: one row per thread, 8 k's
-  const int ar = tid & (BM - 1), ak0 = tid >> 7;
-  const int am = m0 + ar;
-  const bool arv = am < Mtot;
-  const int ab = arv ? am / p.P : 0;
-  const int app = arv ? am - ab * p.P : 0;
-  const int aoh = app / p.Wrow, aow = app - aoh * p.Wrow;
-  const long long aimg = p.a.per_sample ? (long long)s * p.B + ab : ab;
-  const long long rowbase = aimg * p.a.img_stride + (long long)aoh * p.a.sH + (long long)aow * p.a.sW;
-  const long long signrow = ((long long)s * p.B + ab) * p.sign_C;
-  // B-load mapping
-  const int bn = tid & (BN - 1), bk0 = tid >> 5;
-  const int tx = tid & 7, ty = tid >> 3;
-
-  float acc0[4][4], acc1[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc0[i][j] = acc1[i][j] = 0.f;
-
-  for (int k0 = 0; k0 < p.K; k0 += BK) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int kk = ak0 + 2 * j, k = k0 + kk;
-      float v0 = 0.f, v1 = 0.f;
-      if (arv && k < p.K) {
-        const int dhw = p.a.kdhw[k];
-        const int ih = aoh + (int)(short)(dhw & 0xffff), iw = aow + (dhw >> 16);
-        if ((unsigned)ih < (unsigned)p.a.Hin && (unsigned)iw < (unsigned)p.a.Win) {
-          const long long off = rowbase + p.a.koff[k];
-          v0 = __ldg(p.a.base0 + off);
-          if (DUAL) {
-            v1 = (p.a.base1 == p.a.base0) ? v0 : __ldg(p.a.base1 + off);
-            if (p.trA == TRA_SQUARE) v1 = v1 * v1;
-            else if (p.trA == TRA_SIGN) v1 *= __ldg(p.sign_in + signrow + p.a.kci[k]);
-          }
-        }
-      }
-      As0[kk][ar] = v0;
-      if (DUAL) As1[kk][ar] = v1;
-    }
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int kk = bk0 + 8 * j, k = k0 + kk, n = n0 + bn;
-      float v0 = 0.f, v1 = 0.f;
-      if (k < p.K && n < p.N) {
-        const long long off = (p.kB ? p.kB[k] : k) + (long long)n * p.nB;
-        v0 = __ldg(p.W0 + (long long)s * p.ws0 + off);
-        if (DUAL) {
-          v1 = __ldg(p.W1 + (long long)s * p.ws1 + off);
-          if (p.trB == TRB_SQUARE) v1 = v1 * v1;
-          else if (p.trB == TRB_MINUS_W0) v1 -= v0;
-        }
-      }
-      Bs0[kk][bn] = v0;
-      if (DUAL) Bs1[kk][bn] = v1;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < BK; ++kk) {
-      const float4 a = *reinterpret_cast<const float4*>(&As0[kk][ty * 4]);
-      const float4 b = *reinterpret_cast<const float4*>(&Bs0[kk][tx * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc0[i][j] = fmaf(av[i], bv[j], acc0[i][j]);
-      if (DUAL) {
-        const float4 a1 = *reinterpret_cast<const float4*>(&As1[kk][ty * 4]);
-        const float4 b1 = *reinterpret_cast<const float4*>(&Bs1[kk][tx * 4]);
-        const float av1[4] = {a1.x, a1.y, a1.z, a1.w}, bv1[4] = {b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc1[i][j] = fmaf(av1[i], bv1[j], acc1[i][j]);
-      }
-    }
-    __syncthreads();
-  }
-
-  // ---------------- epilogue
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
-    if (m >= Mtot) continue;
-    const int b = m / p.P, pp = m - b * p.P;
-    const long long img = (long long)s * p.B + b;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
-      if (n >= p.N) continue;
-      const long long oidx = img * p.out_img_stride + (long long)(p.co_off + n) * p.out_P + pp;
-      if (EPI >= EPI_DX_PLAIN) {
-        float g = acc0[i][j];
-        if (EPI == EPI_DX_LRT) g = fmaf(2.0f * p.xin[oidx], acc1[i][j], g);
-        if (EPI == EPI_DX_FLIPOUT) g = fmaf(p.sign_in[img * p.sign_C + n], acc1[i][j], g);
-        p.out[oidx] += g;
-      } else {
-        float v = acc0[i][j];
-        if (EPI == EPI_FWD_PLAIN) {
-          v += p.bias0[(long long)s * p.bs0 + n];
-        } else if (EPI == EPI_FWD_LRT) {
-          const float mean = v + p.bias0[n];
-          const float sb = p.bias1[n];
-          float var = fmaf(sb, sb, acc1[i][j]);
-          if (var < 0.f) var += fabsf(var) + 1e-6f;
-          const float sd = sqrtf(var);
-          const float e = noise_normal(p.eps, s, b, p.B, p.N * p.P, n * p.P + pp);
-          v = fmaf(sd, e, mean);
-          if (p.sd_out) p.sd_out[(img * p.N + n) * p.P + pp] = sd;
-        } else {  // flipout
-          v = v + acc1[i][j] * p.sign_out[img * p.N + n] + p.bias1[(long long)s * p.bs1 + n];
-        }
-        if (p.relu) v = fmaxf(v, 0.f);
-        if (p.keep < 1.0f) v = noise_keep(p.drop, s, b, p.B, p.N * p.P, n * p.P + pp, p.keep) ? v / p.keep : 0.f;
-        if (p.head) {
-          v = softplusf(v);
-          v = v > 1e-9f ? v : 1e-9f;
-        }
-        p.out[oidx] = v;
-      }
-    }
-  }
-}
-
-void launch_conv_gemm(const ConvGemm& p, int epi, cudaStream_t st) {
-  dim3 grid((p.B * p.P + BM - 1) / BM, (p.N + BN - 1) / BN, p.S);
-  switch (epi) {
-    case EPI_FWD_PLAIN: ++g_launch_count; conv_gemm_kernel<false, EPI_FWD_PLAIN><<<grid, 256, 0, st>>>(p); break;
-    case EPI_FWD_LRT: ++g_launch_count; conv_gemm_kernel<true, EPI_FWD_LRT><<<grid, 256, 0, st>>>(p); break;
-    case EPI_FWD_FLIPOUT: ++g_launch_count; conv_gemm_kernel<true, EPI_FWD_FLIPOUT><<<grid, 256, 0, st>>>(p); break;
-    case EPI_DX_PLAIN: ++g_launch_count; conv_gemm_kernel<false, EPI_DX_PLAIN><<<grid, 256, 0, st>>>(p); break;
-    case EPI_DX_LRT: ++g_launch_count; conv_gemm_kernel<true, EPI_DX_LRT><<<grid, 256, 0, st>>>(p); break;
-    case EPI_DX_FLIPOUT: ++g_launch_count; conv_gemm_kernel<true, EPI_DX_FLIPOUT><<<grid, 256, 0, st>>>(p); break;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// weight gradient: C[co][k] += sum_m G[m][co] * tr(A[m][k]); split over row ranges, fp32 atomics
-// ------------------------------------------------------------------------------------------------
-constexpr int DW_CO = 32, DW_K = 128, DW_M = 16, DW_PAD = 4;
-
-__global__ void __launch_bounds__(256) conv_dw_kernel(const ConvDw p, int rows_per_split) {
-  __shared__ __align__(16) float Gs[DW_M][DW_CO];
-  __shared__ __align__(16) float As[DW_M][DW_K + DW_PAD];
-  const int tid = threadIdx.x;
-  const int kt0 = blockIdx.x * DW_K, co0 = blockIdx.y * DW_CO;
-  const int Mtot = p.B * p.P;
-  const int mbeg = blockIdx.z * rows_per_split;
-  const int mend = min(Mtot, mbeg + rows_per_split);
-  const int r = tid & 15, c0 = tid >> 4;
-  const int tx = tid & 31, ty = tid >> 5;
-  float acc[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-
-  for (int mb = mbeg; mb < mend; mb += DW_M) {
-    const int m = mb + r;
-    const bool rv = m < mend;
-    const int b = rv ? m / p.P : 0;
-    const int pp = rv ? m - b * p.P : 0;
-    const int oh = pp / p.Wrow, ow = pp - oh * p.Wrow;
-    const long long img = b;  // training passes are single-sample
-    const long long rowbase = img * p.a.img_stride + (long long)oh * p.a.sH + (long long)ow * p.a.sW;
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int c = c0 + 16 * j, co = co0 + c;
-      Gs[r][c] = (rv && co < p.N) ? __ldg(p.G + ((long long)b * p.N + co) * p.P + pp) : 0.f;
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int kc = c0 + 16 * j, k = kt0 + kc;
-      float v = 0.f;
-      if (rv) {
-        if (k < p.K) {
-          const int dhw = p.a.kdhw[k];
-          const int ih = oh + (int)(short)(dhw & 0xffff), iw = ow + (dhw >> 16);
-          if ((unsigned)ih < (unsigned)p.a.Hin && (unsigned)iw < (unsigned)p.a.Win) {
-            v = __ldg(p.a.base0 + rowbase + p.a.koff[k]);
-            if (p.trA == TRA_SQUARE) v = v * v;
-            else if (p.trA == TRA_SIGN) v *= __ldg(p.sign_in + (long long)b * p.sign_C + p.a.kci[k]);
-          }
-        } else if (k == p.K) {
-          v = 1.0f;  // bias column
-        }
-      }
-      As[r][kc] = v;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int mm = 0; mm < DW_M; ++mm) {
-      const float4 g = *reinterpret_cast<const float4*>(&Gs[mm][ty * 4]);
-      const float4 a = *reinterpret_cast<const float4*>(&As[mm][tx * 4]);
-      const float gv[4] = {g.x, g.y, g.z, g.w}, av[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(gv[i], av[j], acc[i][j]);
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int co = co0 + ty * 4 + i;
-    if (co >= p.N) continue;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int k = kt0 + tx * 4 + j;
-      if (k < p.K) {
-        atomicAdd(p.gw + (long long)co * p.K + k, acc[i][j]);
-      } else if (k == p.K) {
-        if (p.gb) atomicAdd(p.gb + co, acc[i][j]);
-        if (p.gb2) atomicAdd(p.gb2 + co, acc[i][j]);
-      }
-    }
-  }
-}
-
-void launch_conv_dw(const ConvDw& p, cudaStream_t st) {
-  const int Mtot = p.B * p.P;
-  const int gx = (p.K + 1 + DW_K - 1) / DW_K, gy = (p.N + DW_CO - 1) / DW_CO;
-  int split = max(1, min((Mtot + 63) / 64, (296 + gx * gy - 1) / (gx * gy)));
-  int rows = (Mtot + split - 1) / split;
-  rows = (rows + DW_M - 1) / DW_M * DW_M;
-  split = (Mtot + rows - 1) / rows;
-  ++g_launch_count;
-  conv_dw_kernel<<<dim3(gx, gy, split), 256, 0, st>>>(p, rows);
-}
-
-// ------------------------------------------------------------------------------------------------
 // pooling
 // ------------------------------------------------------------------------------------------------
 __global__ void maxpool3_kernel(const PoolParams p) {

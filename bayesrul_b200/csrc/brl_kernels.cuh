@@ -62,7 +62,10 @@ struct ConvGemm {
   const float* sign_out;  // [S,B,N] flip_out signs
   float* sd_out;          // LRT: sqrt(var) saved for backward, compact [img][N][P] (nullable)
   const float* xin;       // EPI_DX_LRT: the layer input (same indexing as out)
+  float* part;            // split-K scratch [2][B*P][N] (nullable: no split)
+  int ksplit;             // filled by launch_conv_gemm
 };
+constexpr long long SPLITK_SCRATCH_FLOATS = 2ll * 74 * 128 * 32;
 
 void launch_conv_gemm(const ConvGemm& p, int epi, cudaStream_t st);
 

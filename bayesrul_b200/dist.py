@@ -1,0 +1,86 @@
+"""Multi-GPU plumbing (one process per GPU, torch.distributed: NCCL on GPUs, gloo in the CPU tests).
+
+The path shards without a data-path collective:
+  * predict: contiguous blocks of windows per rank, every rank runs all S samples with the same Philox
+    key -> identical weight draws everywhere, results are concatenated in rank order;
+  * MC-sample / ensemble-member sharding: each rank reduces its own samples to (n, mean, M2, sum sigma^2)
+    per window; one all-gather + Chan's parallel-variance merge gives the global moments;
+  * training: data-parallel minibatches, ONE flat all-reduce(avg) of [grad_mu | grad_log_sigma | scalars].
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, order-preserving block of `n` items for `rank` (first n % world ranks get one more)."""
+    base, rem = divmod(n, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def merge_moments(parts: Sequence[Tuple[int, torch.Tensor, torch.Tensor, torch.Tensor]]):
+    """Chan merge of per-shard predictive moments.  parts = [(n_r, pred_r, ep_var_r (unbiased), al_var_r)].
+    Returns (pred, std, ep_var, al_var) identical to reducing all samples at once (bayesian.py:212-215)."""
+    n = sum(p[0] for p in parts)
+    mean = sum(p[0] * p[1].double() for p in parts) / n
+    m2 = sum((p[2].double() * (p[0] - 1) if p[0] > 1 else torch.zeros_like(mean)) + p[0] * (p[1].double() - mean) ** 2
+             for p in parts)
+    al = sum(p[0] * p[3].double() for p in parts) / n
+    ep = m2 / (n - 1) if n > 1 else torch.full_like(mean, float("nan"))
+    dt = parts[0][1].dtype
+    return mean.to(dt), (al + ep).sqrt().to(dt), ep.to(dt), al.to(dt)
+
+
+def all_gather_moments(n_local: int, pred, ep_var, al_var, group=None):
+    """Moment merge across ranks that each hold a different subset of MC samples of the SAME windows."""
+    world = dist.get_world_size(group)
+    packed = torch.stack([torch.full_like(pred, float(n_local)), pred, ep_var.nan_to_num(0.0), al_var])
+    bufs = [torch.empty_like(packed) for _ in range(world)]
+    dist.all_gather(bufs, packed, group=group)
+    return merge_moments([(int(b[0, 0].item()), b[1], b[2], b[3]) for b in bufs])
+
+
+def mixture_across_ranks(mu_local: torch.Tensor, sigma_local: torch.Tensor, group=None):
+    """Deep-ensemble mixture (deepens.py:21-24, biased variance) when members are spread over ranks:
+    mu_local / sigma_local are [M_r, n]."""
+    s = torch.stack([mu_local.double().sum(0), (mu_local.double() ** 2 + sigma_local.double() ** 2).sum(0),
+                     torch.full((mu_local.shape[1],), float(mu_local.shape[0]), dtype=torch.float64, device=mu_local.device)])
+    dist.all_reduce(s, group=group)
+    mu = s[0] / s[2]
+    return mu.to(mu_local.dtype), (s[1] / s[2] - mu**2).sqrt().to(mu_local.dtype)
+
+
+def allreduce_elbo_grads(res: dict, group=None) -> dict:
+    """Average the ELBO step outputs of data-parallel ranks with one flat all-reduce.  Each rank computed its
+    loss with plate scale N/B_r, so the mean over ranks is the global-batch gradient (KL is rank-replicated)."""
+    world = dist.get_world_size(group)
+    gm, gl, gs = res["grad_mu"], res["grad_log_sigma"], res["grad_sigma"]
+    flat = torch.cat([gm, gl, gs, res["scalars"].to(gm.dtype)])
+    dist.all_reduce(flat, group=group)
+    flat /= world
+    P = gm.numel()
+    out = dict(res)
+    out["grad_mu"], out["grad_log_sigma"], out["grad_sigma"] = flat[:P], flat[P:2 * P], flat[2 * P:3 * P]
+    out["scalars"] = flat[3 * P:].double()
+    return out
+
+
+def gather_predictions(local: Sequence[torch.Tensor], group=None) -> List[torch.Tensor]:
+    """Concatenate per-rank window blocks in rank order (blocks may differ by one window)."""
+    world = dist.get_world_size(group)
+    n_loc = torch.tensor([local[0].shape[0]], device=local[0].device)
+    sizes = [torch.zeros_like(n_loc) for _ in range(world)]
+    dist.all_gather(sizes, n_loc, group=group)
+    mx = int(max(s.item() for s in sizes))
+    out = []
+    for t in local:
+        pad = torch.zeros(mx, dtype=t.dtype, device=t.device)
+        pad[: t.shape[0]] = t
+        bufs = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(bufs, pad, group=group)
+        out.append(torch.cat([b[: int(s.item())] for b, s in zip(bufs, sizes)]))
+    return out

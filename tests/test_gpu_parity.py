@@ -213,7 +213,7 @@ def test_elbo_step_vs_oracle(engines, net, mode, guide, particles, sigma):
     assert_close(got["grad_log_sigma"], ref["grad_log_sigma"], rtol=1e-3, atol_scale=2e-5, what="grad_log_sigma")
     ev = e.elbo_step(x.to(DEV), y.to(DEV), mu.to(DEV), sg.to(DEV), particles=particles,
                      noise=injected_to_engine(net, nzs, B, DEV), compute_grads=False, **kw)
-    assert abs(ev["scalars"][0].item() - sc[0].item()) < 1e-9 * abs(sc[0].item()) + 1e-12
+    assert abs(ev["scalars"][0].item() - sc[0].item()) < 1e-6 * abs(sc[0].item())  # split-K atomics: summation order varies
 
 
 @pytest.mark.parametrize("net", NETS)
