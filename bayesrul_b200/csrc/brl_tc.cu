@@ -33,13 +33,13 @@ namespace brl {
 constexpr int ROWS = 132;            // 2 zero rows + 128 tile rows + 2 slack rows
 constexpr int CS = ROWS * 16;        // bytes of one 8-channel chunk (K-major, 16 B per row)
 constexpr int ROW0 = 2;              // buffer row of tile row 0
-constexpr int OFF_X = 0;             // 4 chunks: 18 features padded to 32
-constexpr int OFF_XP = OFF_X + 4 * CS;
-constexpr int OFF_M1 = OFF_XP + 4 * CS;     // 16 chunks: 4 branches x (27 padded to 32)
-constexpr int OFF_M1P = OFF_M1 + 16 * CS;
-constexpr int OFF_T2 = OFF_M1P + 16 * CS;   // 8 chunks
-constexpr int OFF_T3 = OFF_T2 + 8 * CS;
-constexpr int OFF_W = OFF_T3 + 8 * CS;      // weight image
+// per-group activation region: 32 chunks; M1 | M1P, with T2/T3 aliasing M1 and X/XP aliasing M1P
+constexpr int R_M1 = 0;                     // 16 chunks: 4 branches x (27 real + const-1 + zero pad = 32)
+constexpr int R_M1P = 16 * CS;              // 16 chunks
+constexpr int R_T2 = R_M1, R_T3 = R_M1 + 8 * CS;   // 8 + 8 chunks (live after the M1 readers have completed)
+constexpr int R_X = R_M1P, R_XP = R_M1P + 4 * CS;  // 4 + 4 chunks (live before M1P is produced)
+constexpr int G_BYTES = 32 * CS;
+constexpr int OFF_W = 2 * G_BYTES;          // weight image, shared by the two groups
 // weight image (identical in the global blob)
 constexpr int WA_TAP = 4 * 32 * 16;         // [4 chunks][32 n][16 B]
 constexpr int WI_A = 0;                     // 12 taps
@@ -53,7 +53,8 @@ constexpr int NBIAS = 128 + 144 + 32 + 16 + 16;
 constexpr int CONV_IMG = WI_BIAS + NBIAS * 4;
 static_assert(CONV_IMG % 16 == 0, "bulk copies need 16-byte multiples");
 constexpr int OFF_BAR = OFF_W + CONV_IMG;
-constexpr int CONV_SMEM = OFF_BAR + 64;
+constexpr int CONV_SMEM = OFF_BAR + 128;
+static_assert(CONV_SMEM <= 232448, "conv kernel shared memory exceeds the 227 KB opt-in limit");
 // blob = conv image + fc image + fp32 tail (fc bias 64, last W 128, last b 2)
 constexpr int FC_IMG = 300 * 64 * 16;
 constexpr int BLOB_FC = CONV_IMG;
@@ -99,11 +100,14 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// bounded wait: a protocol bug must end the kernel, not hang the GPU
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* status, int code) {
+// bounded wait: a protocol bug must end the kernel, not hang the GPU.  After the first time-out (recorded in
+// *status and in the CTA's shared abort word) every later wait returns immediately, so control flow stays uniform.
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* status, int code, volatile int* abort_flag = nullptr) {
+  if (abort_flag && *abort_flag) return false;
   for (uint32_t i = 0; i < SPIN_LIMIT; ++i)
     if (mbar_try(bar, parity)) return true;
   atomicCAS(status, 0, code);
+  if (abort_flag) *abort_flag = 1;
   return false;
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -195,7 +199,10 @@ __global__ void tc_pack_kernel(const PackArgs a) {
     const int t0 = layer == 0 ? 0 : layer == 1 ? 1 : layer == 2 ? 4 : 9;
     const int ntap = layer == 0 ? 1 : layer == 2 ? 5 : 3;
     float v = 0.f;
+    const bool centre = (tap - t0) == (ntap >> 1);
     if (n < 27 && k < 18) v = w[a.off[layer][0] + ((long long)n * 18 + k) * ntap + (tap - t0)];
+    else if (k == 18 && centre && n < 27) v = w[a.off[layer][1] + n];  // bias rides on the constant-1 feature
+    else if (k == 18 && layer == 0 && n == 27) v = 1.0f;               // conv1 column 27 re-emits the constant into M1
     put_h(blob, WI_A + tap * WA_TAP + (k >> 3) * 512 + n * 16 + (k & 7) * 2, v);
     return;
   }
@@ -207,6 +214,7 @@ __global__ void tc_pack_kernel(const PackArgs a) {
     const int grp = k >> 5, c = k & 31;
     float v = 0.f;
     if (c < 27) v = w[a.off[layer][0] + (long long)co * 108 + grp * 27 + c];
+    else if (k == 27) v = w[a.off[layer][1] + co];  // bias on M1's constant channel
     put_h(blob, WI_B1 + (k >> 3) * (144 * 16) + n * 16 + (k & 7) * 2, v);
     return;
   }
@@ -215,6 +223,7 @@ __global__ void tc_pack_kernel(const PackArgs a) {
     const int n = j / 128, k = j % 128, grp = k >> 5, c = k & 31;
     float v = 0.f;
     if (c < 27) v = w[a.off[9][0] + (long long)n * 108 + grp * 27 + c];
+    else if (k == 27) v = w[a.off[9][1] + n];
     put_h(blob, WI_B4 + (k >> 3) * 512 + n * 16 + (k & 7) * 2, v);
     return;
   }
@@ -255,255 +264,7 @@ __global__ void tc_pack_kernel(const PackArgs a) {
 }
 constexpr int PACK_THREADS_TOTAL = 12 * 1024 + 144 * 128 + 32 * 128 + 3 * 1024 + 5 * 1024 + NBIAS + 64 * 2400 + 194;
 
-// ------------------------------------------------------------------------------------------------
-// conv stack kernel
-// ------------------------------------------------------------------------------------------------
-struct ConvArgs {
-  const float* x;             // [B,30,18]
-  const unsigned char* blob;  // [S or 1][BLOB_BYTES]
-  long long blob_stride;      // BLOB_BYTES or 0
-  unsigned char* feat;        // [S][NT128][300][128][16 B]
-  int B, S, ntile4, ntile128;
-  float keep4;                // dropout keep of the branch sites (1 = off)
-  NoiseRef drop[12];
-  int* status;
-};
-
-// epilogue helper: 16 accumulator columns -> bias, ReLU, (dropout), fp16, zero for pad rows
-template <bool DROP>
-__device__ __forceinline__ void epi16(const float (&acc)[16], const float* bias, bool live, uint4& lo, uint4& hi,
-                                      const ConvArgs& a, int layer, int s, int gw, int t, int ch0, int nvalid) {
-  float v[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    float u = fmaxf(acc[j] + bias[j], 0.f);
-    if (DROP) {
-      if (ch0 + j < nvalid && live) {
-        const NoiseRef& nz = a.drop[layer];
-        const int e = (ch0 + j) * 30 + t;
-        const bool keep = nz.ptr ? nz.ptr[((long long)s * a.B + gw) * (nvalid * 30) + e] != 0.f
-                                 : philox_uniform(nz.seed, nz.kind, nz.site, nz.sample0 + s, nz.window0 + gw, e) < a.keep4;
-        u = keep ? u / a.keep4 : 0.f;
-      }
-    }
-    v[j] = live ? u : 0.f;
-  }
-  lo = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
-  hi = make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
-}
-
-template <bool DROP>
-__global__ void __launch_bounds__(256, 1) tc_conv_kernel(const ConvArgs a) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  const uint32_t sbase = smem_u32(smem);
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const uint32_t bar0 = sbase + OFF_BAR;  // [0..2] phase barriers, [3] weight barrier
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 40);
-  const float* sbias = reinterpret_cast<const float*>(smem + OFF_W + WI_BIAS);
-
-  // zero all activation buffers once: pad rows / pad features stay zero for the kernel's lifetime
-  for (int i = tid; i < OFF_W / 16; i += 256) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-  if (tid == 0) {
-    for (int i = 0; i < 4; ++i) mbar_init(bar0 + 8 * i, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-
-  const long long total = (long long)a.S * a.ntile4;
-  const long long per = (total + gridDim.x - 1) / gridDim.x;
-  const long long beg = per * blockIdx.x, end = min(total, beg + per);
-  const int row = tid & 127, half = tid >> 7;
-  const int wq = row >> 5, t = row & 31;  // window inside the tile, time step
-  const uint32_t lane_addr = tmem + ((uint32_t)(row & ~31) << 16);
-  const uint32_t rowoff = (uint32_t)(ROW0 + row) * 16;
-  int cur_s = -1;
-  uint32_t ph = 0, wph = 0;
-  bool ok = true;
-
-  for (long long it = beg; it < end && ok; ++it) {
-    const int s = (int)(it / a.ntile4), tile = (int)(it % a.ntile4);
-    if (s != cur_s) {  // stage this sample's conv weights (all MMAs of the previous tile have completed)
-      cur_s = s;
-      if (tid == 0) {
-        const unsigned char* src = a.blob + (long long)s * a.blob_stride;
-        mbar_expect_tx(bar0 + 24, CONV_IMG);
-        for (int o = 0; o < CONV_IMG; o += 16384)
-          bulk_g2s(sbase + OFF_W + o, src + o, min(16384, CONV_IMG - o), bar0 + 24);
-      }
-      ok = mbar_wait(bar0 + 24, wph, a.status, 1);
-      wph ^= 1;
-    }
-    // ---- stage the 4 windows: fp32 [t][18] -> fp16 chunks of 8 features, K-major
-    for (int u = tid; u < 384; u += 256) {
-      const int r = u & 127, c = u >> 7, w4 = r >> 5, tt = r & 31;
-      const int gw = tile * 4 + w4;
-      float f[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = 0.f;
-      if (tt < 30 && gw < a.B) {
-        const float* px = a.x + (long long)gw * 540 + tt * 18 + c * 8;
-        const int nf = c < 2 ? 8 : 2;
-        for (int j = 0; j < nf; j += 2) {
-          const float2 p2 = __ldg(reinterpret_cast<const float2*>(px + j));
-          f[j] = p2.x; f[j + 1] = p2.y;
-        }
-      }
-      *reinterpret_cast<uint4*>(smem + OFF_X + c * CS + (ROW0 + r) * 16) =
-          make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
-    }
-    __syncthreads();
-    // ---- MaxPool1d(3,1,1) of the raw window (-inf padding: only in-window neighbours take part)
-    for (int u = tid; u < 384; u += 256) {
-      const int r = u & 127, c = u >> 7, tt = r & 31;
-      const unsigned char* p = smem + OFF_X + c * CS + (ROW0 + r) * 16;
-      uint4 v = *reinterpret_cast<const uint4*>(p);
-      if (tt < 30) {
-        if (tt > 0) v = hmax4(v, *reinterpret_cast<const uint4*>(p - 16));
-        if (tt < 29) v = hmax4(v, *reinterpret_cast<const uint4*>(p + 16));
-      }
-      *reinterpret_cast<uint4*>(smem + OFF_XP + c * CS + (ROW0 + r) * 16) = v;
-    }
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    // ---- phase A: module 1 (4 branches, N = 32 each) ------------------------------------------------
-    if (tid == 0) {
-      tc_fence_after();
-      constexpr uint32_t idA = umma_idesc(32);
-      const int ntap[4] = {1, 3, 5, 3}, tap0[4] = {0, 1, 4, 9}, pad[4] = {0, 1, 2, 1};
-      for (int br = 0; br < 4; ++br) {
-        const uint32_t abase = sbase + (br == 3 ? OFF_XP : OFF_X);
-        uint32_t acc = 0;
-        for (int tp = 0; tp < ntap[br]; ++tp)
-          for (int ks = 0; ks < 2; ++ks) {
-            const uint64_t ad = umma_desc(abase + 2 * ks * CS + (ROW0 + tp - pad[br]) * 16, CS, 128);
-            const uint64_t bd = umma_desc(sbase + OFF_W + WI_A + (tap0[br] + tp) * WA_TAP + 2 * ks * 512, 512, 128);
-            umma(tmem + br * 32, ad, bd, idA, acc);
-            acc = 1;
-          }
-      }
-      umma_commit(bar0);
-    }
-    ok = mbar_wait(bar0, ph, a.status, 2);
-    tc_fence_after();
-    {
-      const int gw = tile * 4 + wq;
-      const bool live = t < 30 && gw < a.B;
-      float acc[4][16];
-#pragma unroll
-      for (int br = 0; br < 4; ++br) tmem_ld16(lane_addr + br * 32 + half * 16, acc[br]);
-      tmem_ld_wait();
-#pragma unroll
-      for (int br = 0; br < 4; ++br) {
-        uint4 lo, hi;
-        epi16<DROP>(acc[br], sbias + br * 32 + half * 16, live, lo, hi, a, br, s, gw, t, half * 16, 27);
-        unsigned char* dst = smem + OFF_M1 + (br * 4 + half * 2) * CS + rowoff;
-        *reinterpret_cast<uint4*>(dst) = lo;
-        *reinterpret_cast<uint4*>(dst + CS) = hi;
-      }
-    }
-    tc_fence_before();
-    __syncthreads();
-    // ---- MaxPool1d(3,1,1) of module-1 output (post-ReLU >= 0, zero pad rows act as -inf)
-    for (int u = tid; u < 2048; u += 256) {
-      const int r = u & 127, c = u >> 7;
-      const unsigned char* p = smem + OFF_M1 + c * CS + (ROW0 + r) * 16;
-      const uint4 v = hmax4(hmax4(*reinterpret_cast<const uint4*>(p - 16), *reinterpret_cast<const uint4*>(p)),
-                            *reinterpret_cast<const uint4*>(p + 16));
-      *reinterpret_cast<uint4*>(smem + OFF_M1P + c * CS + (ROW0 + r) * 16) = v;
-    }
-    fence_async_smem();
-    __syncthreads();
-    // ---- phase B: module-2 1x1 convs: [b1 | b2a | b3a] (N = 144) on M1, b4 (N = 32) on pooled M1 ------
-    if (tid == 0) {
-      tc_fence_after();
-      constexpr uint32_t idB1 = umma_idesc(144), idB4 = umma_idesc(32);
-      for (int ks = 0; ks < 8; ++ks)
-        umma(tmem + 128, umma_desc(sbase + OFF_M1 + 2 * ks * CS + ROW0 * 16, CS, 128),
-             umma_desc(sbase + OFF_W + WI_B1 + 2 * ks * 2304, 2304, 128), idB1, ks > 0);
-      for (int ks = 0; ks < 8; ++ks)
-        umma(tmem + 272, umma_desc(sbase + OFF_M1P + 2 * ks * CS + ROW0 * 16, CS, 128),
-             umma_desc(sbase + OFF_W + WI_B4 + 2 * ks * 512, 512, 128), idB4, ks > 0);
-      umma_commit(bar0 + 8);
-    }
-    ok = ok && mbar_wait(bar0 + 8, ph, a.status, 3);
-    tc_fence_after();
-    const int gw = tile * 4 + wq;
-    const bool live = t < 30 && gw < a.B;
-    unsigned char* frow = a.feat + ((long long)s * a.ntile128 + (gw >> 7)) * FEAT_TILE_BYTES + (long long)(gw & 127) * 16 +
-                          (long long)t * 10 * 2048;
-    {
-      // 11 groups of 16 columns: g0 = b1 -> feat ch 0..15 | g1..4 = b2a -> T2 | g5..8 = b3a -> T3 | g9,10 = b4 -> feat ch 48..79
-      for (int g = half; g < 11; g += 2) {
-        float acc[16];
-        tmem_ld16(lane_addr + 128 + g * 16, acc);
-        tmem_ld_wait();
-        uint4 lo, hi;
-        if (g == 0) {
-          epi16<DROP>(acc, sbias + 128, live, lo, hi, a, 4, s, gw, t, 0, 16);
-          if (live) { *reinterpret_cast<uint4*>(frow) = lo; *reinterpret_cast<uint4*>(frow + 2048) = hi; }
-        } else if (g < 9) {
-          epi16<false>(acc, sbias + 128 + g * 16, live, lo, hi, a, 0, s, gw, t, 0, 16);
-          unsigned char* dst = smem + (g < 5 ? OFF_T2 + (g - 1) * 2 * CS : OFF_T3 + (g - 5) * 2 * CS) + rowoff;
-          *reinterpret_cast<uint4*>(dst) = lo;
-          *reinterpret_cast<uint4*>(dst + CS) = hi;
-        } else {
-          epi16<DROP>(acc, sbias + 272 + (g - 9) * 16, live, lo, hi, a, 9, s, gw, t, (g - 9) * 16, 32);
-          if (live) {
-            *reinterpret_cast<uint4*>(frow + (6 + (g - 9) * 2) * 2048) = lo;
-            *reinterpret_cast<uint4*>(frow + (7 + (g - 9) * 2) * 2048) = hi;
-          }
-        }
-      }
-    }
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    // ---- phase C: b2b (k3 over T2) and b3b (k5 over T3), N = 16 each -----------------------------------
-    if (tid == 0) {
-      tc_fence_after();
-      constexpr uint32_t idC = umma_idesc(16);
-      uint32_t acc = 0;
-      for (int tp = 0; tp < 3; ++tp)
-        for (int ks = 0; ks < 4; ++ks) {
-          umma(tmem + 304, umma_desc(sbase + OFF_T2 + 2 * ks * CS + (ROW0 + tp - 1) * 16, CS, 128),
-               umma_desc(sbase + OFF_W + WI_B2B + tp * WC_TAP + 2 * ks * 256, 256, 128), idC, acc);
-          acc = 1;
-        }
-      acc = 0;
-      for (int tp = 0; tp < 5; ++tp)
-        for (int ks = 0; ks < 4; ++ks) {
-          umma(tmem + 320, umma_desc(sbase + OFF_T3 + 2 * ks * CS + (ROW0 + tp - 2) * 16, CS, 128),
-               umma_desc(sbase + OFF_W + WI_B3B + tp * WC_TAP + 2 * ks * 256, 256, 128), idC, acc);
-          acc = 1;
-        }
-      umma_commit(bar0 + 16);
-    }
-    ok = ok && mbar_wait(bar0 + 16, ph, a.status, 4);
-    tc_fence_after();
-    {
-      float acc[16];
-      tmem_ld16(lane_addr + 304 + half * 16, acc);
-      tmem_ld_wait();
-      uint4 lo, hi;
-      epi16<DROP>(acc, sbias + 304 + half * 16, live, lo, hi, a, half ? 8 : 6, s, gw, t, 0, 16);
-      if (live) {
-        *reinterpret_cast<uint4*>(frow + (2 + half * 2) * 2048) = lo;
-        *reinterpret_cast<uint4*>(frow + (3 + half * 2) * 2048) = hi;
-      }
-    }
-    tc_fence_before();
-    ph ^= 1;
-    __syncthreads();
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 512);
-}
+#include "brl_tc_conv.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // fc + head kernel
@@ -695,10 +456,10 @@ const char* tc_forward(TcState* st, const float* x, long long B, long long S, co
   ca.keep4 = drop ? 1.0f - p_dropout * 0.25f : 1.0f;
   for (int l = 0; l < 12; ++l) ca.drop[l] = nr(l);
   ca.status = st->status;
-  const long long items = S * nt4;
+  const long long items = S * ((nt4 + 1) / 2);
   const int grid = (int)std::min<long long>(st->sm_count, items);
-  if (drop) tc_conv_kernel<true><<<grid, 256, CONV_SMEM, stream>>>(ca);
-  else tc_conv_kernel<false><<<grid, 256, CONV_SMEM, stream>>>(ca);
+  if (drop) tc_conv_kernel<true><<<grid, 512, CONV_SMEM, stream>>>(ca);
+  else tc_conv_kernel<false><<<grid, 512, CONV_SMEM, stream>>>(ca);
   FcArgs fa;
   fa.feat = feat; fa.blob = blob; fa.blob_stride = ca.blob_stride; fa.out = out;
   fa.B = (int)B; fa.S = (int)S; fa.ntile128 = (int)nt128;
