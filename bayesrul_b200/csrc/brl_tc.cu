@@ -52,7 +52,9 @@ constexpr int WI_BIAS = WI_B3B + 5 * WC_TAP;  // fp32: A 4x32, B1 144, B4 32, b2
 constexpr int NBIAS = 128 + 144 + 32 + 16 + 16;
 constexpr int CONV_IMG = WI_BIAS + NBIAS * 4;
 static_assert(CONV_IMG % 16 == 0, "bulk copies need 16-byte multiples");
-constexpr int OFF_BAR = OFF_W + CONV_IMG;
+constexpr int OFF_RAW = OFF_W + CONV_IMG;     // raw fp16 windows of the next tile, one buffer per group
+constexpr int RAW_BYTES = 4352;               // 4 x 540 halves, padded
+constexpr int OFF_BAR = OFF_RAW + 2 * RAW_BYTES;
 constexpr int CONV_SMEM = OFF_BAR + 128;
 static_assert(CONV_SMEM <= 232448, "conv kernel shared memory exceeds the 227 KB opt-in limit");
 // blob = conv image + fc image + fp32 tail (fc bias 64, last W 128, last b 2)
@@ -198,12 +200,23 @@ __global__ void tc_pack_kernel(const PackArgs a) {
     const int layer = tap == 0 ? 0 : tap < 4 ? 1 : tap < 9 ? 2 : 3;
     const int t0 = layer == 0 ? 0 : layer == 1 ? 1 : layer == 2 ? 4 : 9;
     const int ntap = layer == 0 ? 1 : layer == 2 ? 5 : 3;
+    const int tl = tap - t0, padl = ntap >> 1;
     float v = 0.f;
-    const bool centre = (tap - t0) == (ntap >> 1);
-    if (n < 27 && k < 18) v = w[a.off[layer][0] + ((long long)n * 18 + k) * ntap + (tap - t0)];
-    else if (k == 18 && centre && n < 27) v = w[a.off[layer][1] + n];  // bias rides on the constant-1 feature
-    else if (k == 18 && layer == 0 && n == 27) v = 1.0f;               // conv1 column 27 re-emits the constant into M1
-    put_h(blob, WI_A + tap * WA_TAP + (k >> 3) * 512 + n * 16 + (k & 7) * 2, v);
+    if (n < 27 && k < 18) v = w[a.off[layer][0] + ((long long)n * 18 + k) * ntap + tl];
+    else if (k == 18 && tl == padl && n < 27) v = w[a.off[layer][1] + n];  // bias rides on the constant-1 feature
+    else if (k == 18 && layer == 0 && n == 27) v = 1.0f;                  // conv1 column 27 re-emits the constant into M1
+    int dst;
+    if (layer == 3) {  // pooled branch: one [4 chunks][32][16 B] tile per tap
+      dst = WI_A + 18432 + tl * 2048 + (k >> 3) * 512 + n * 16 + (k & 7) * 2;
+    } else {           // x branches: one tile per input shift, rows = conv5 | conv3 | conv1
+      const int sh = tl - padl;
+      const int q = sh == 0 ? 0 : sh == -1 ? 1 : sh == 1 ? 2 : sh == -2 ? 3 : 4;
+      const int nsh = q == 0 ? 96 : q < 3 ? 64 : 32;
+      const int osh = q == 0 ? 0 : q == 1 ? 6144 : q == 2 ? 10240 : q == 3 ? 14336 : 16384;
+      const int nrow = (layer == 2 ? 0 : layer == 1 ? 32 : 64) + n;
+      dst = WI_A + osh + (k >> 3) * (nsh * 16) + nrow * 16 + (k & 7) * 2;
+    }
+    put_h(blob, dst, v);
     return;
   }
   j -= N_A;
@@ -230,13 +243,13 @@ __global__ void tc_pack_kernel(const PackArgs a) {
   j -= N_B4;
   if (j < N_C2) {
     const int tap = j / 1024, r = j % 1024, n = r / 64, k = r % 64;
-    put_h(blob, WI_B2B + tap * WC_TAP + (k >> 3) * 256 + n * 16 + (k & 7) * 2, w[a.off[6][0] + ((long long)n * 64 + k) * 3 + tap]);
+    put_h(blob, WI_B2B + (k >> 3) * 768 + (tap * 16 + n) * 16 + (k & 7) * 2, w[a.off[6][0] + ((long long)n * 64 + k) * 3 + tap]);
     return;
   }
   j -= N_C2;
   if (j < N_C3) {
     const int tap = j / 1024, r = j % 1024, n = r / 64, k = r % 64;
-    put_h(blob, WI_B3B + tap * WC_TAP + (k >> 3) * 256 + n * 16 + (k & 7) * 2, w[a.off[8][0] + ((long long)n * 64 + k) * 5 + tap]);
+    put_h(blob, WI_B3B + (k >> 3) * 1280 + (tap * 16 + n) * 16 + (k & 7) * 2, w[a.off[8][0] + ((long long)n * 64 + k) * 5 + tap]);
     return;
   }
   j -= N_C3;

@@ -1,17 +1,23 @@
 // tcgen05 conv-stack kernel (included by brl_tc.cu after the PTX wrappers and geometry constants).
 //
 // One persistent CTA per SM, 512 threads = two independent 256-thread groups.  Each group owns one 128-row tile
-// (4 windows x 32 rows) at a time, its own 66 KB activation region, 256 TMEM columns, three mbarriers and one
-// named barrier, so while one group sits in an MMA wait / barrier the other runs its epilogue: the tensor pipe and
-// the issue slots see two tiles in flight.  The fp16 weights of the current MC sample (86 KB) are shared.
+// (4 windows x 32 rows; a warp = one window) at a time, its own 66 KB activation region, 256 TMEM columns, three
+// mbarriers and one named barrier, so while one group waits for its MMAs the other runs its epilogue.  The fp16
+// weights of the current MC sample (86 KB) are shared by both groups and stay resident.
 //
 // Activation region of a group (K-major, no swizzle: [8-channel chunk][132 rows][16 B]):
 //   M1  16 chunks  module-1 output, 4 branches x 32 channels (27 real + const-1 channel + zeros)
-//   M1P 16 chunks  MaxPool1d(3,1,1)(M1)
+//   M1P 16 chunks  MaxPool1d(3,1,1)(M1)  -- produced in the phase-A epilogue with warp shuffles (row = lane)
 //   T2 / T3 (8 + 8 chunks) alias M1   (written after the MMAs reading M1 have completed)
-//   X / XP  (4 + 4 chunks) alias M1P  (read by phase A only, M1P is written after phase A completed)
+//   X / XP  (4 + 4 chunks) alias M1P  (read by phase A only; M1P is written after phase A completed)
+// MMA count per tile is kept low because every M=128 MMA re-reads its 4 KB A slice from shared memory whatever N is:
+//   phase A  convs that share an input shift share one MMA (N = 96 / 64 / 32 for |shift| = 0 / 1 / 2)      -> 16 MMAs
+//   phase B  [b1 | b2a | b3a] as one N = 144 GEMM over M1, b4 (N = 32) over pooled M1                          -> 16 MMAs
+//   phase C  all taps of a k3 / k5 conv are concatenated along N (N = 48 / 80, un-shifted A) and the tap shift is
+//            applied afterwards in registers: out[t] = sum_tap P_tap[t + tap - pad] via __shfl_up / __shfl_down   ->  8 MMAs
 // Biases ride in the MMAs: input feature 18 is a constant 1 whose weight row (centre tap only) holds the bias;
 // conv1's column 27 reproduces the constant into M1 (and, pooled, into M1P) for the module-2 1x1 convs.
+// The next tile's windows are prefetched into registers while the current tile is in flight (raw fp16 staging buffer).
 #pragma once
 
 struct ConvArgs {
@@ -27,14 +33,13 @@ struct ConvArgs {
 
 __device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory"); }
 
-// 16 accumulator columns -> (+bias), ReLU, (dropout), fp16; zeros for dead rows
+// ReLU (+bias) (+dropout) on 16 fp32 accumulator columns
 template <bool DROP, bool BIAS>
-__device__ __forceinline__ void epi16(const float (&acc)[16], const float* bias, bool live, uint4& lo, uint4& hi,
-                                      const ConvArgs& a, int layer, int s, int gw, int t, int ch0, int nvalid) {
-  float v[16];
+__device__ __forceinline__ void act16(float (&v)[16], const float* bias, bool live, const ConvArgs& a, int layer, int s,
+                                      int gw, int t, int ch0, int nvalid) {
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
-    float u = fmaxf(BIAS ? acc[j] + bias[j] : acc[j], 0.f);
+    float u = fmaxf(BIAS ? v[j] + bias[j] : v[j], 0.f);
     if (DROP) {
       if (ch0 + j < nvalid && live) {
         const NoiseRef& nz = a.drop[layer];
@@ -46,23 +51,39 @@ __device__ __forceinline__ void epi16(const float (&acc)[16], const float* bias,
     }
     v[j] = u;
   }
+}
+__device__ __forceinline__ void pack16(const float (&v)[16], bool live, uint4& lo, uint4& hi) {
   lo = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
   hi = make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
   if (!live) { lo = make_uint4(0, 0, 0, 0); hi = lo; }
 }
-
-__device__ __forceinline__ void fmax8(float (&d)[8], const float (&s)[8]) {
-#pragma unroll
-  for (int j = 0; j < 8; ++j) d[j] = fmaxf(d[j], s[j]);
+__device__ __forceinline__ uint32_t hmax2u(uint32_t a, uint32_t b) {
+  __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+// MaxPool1d(3,1,1) across rows of a window = across lanes of the warp (values >= 0, dead rows are 0)
+__device__ __forceinline__ uint32_t pool3(uint32_t v, int lane) {
+  uint32_t up = __shfl_up_sync(0xffffffffu, v, 1), dn = __shfl_down_sync(0xffffffffu, v, 1);
+  if (lane == 0) up = 0u;
+  if (lane == 31) dn = 0u;
+  return hmax2u(v, hmax2u(up, dn));
+}
+__device__ __forceinline__ uint4 pool3x4(uint4 v, int lane) {
+  return make_uint4(pool3(v.x, lane), pool3(v.y, lane), pool3(v.z, lane), pool3(v.w, lane));
+}
+__device__ __forceinline__ float shf(float v, int d, int lane) {  // value of row (lane + d) of the window, 0 outside
+  const float r = d < 0 ? __shfl_up_sync(0xffffffffu, v, -d) : __shfl_down_sync(0xffffffffu, v, d);
+  return (lane + d < 0 || lane + d > 31) ? 0.f : r;
 }
 
 template <bool DROP>
 __global__ void __launch_bounds__(512, 1) tc_conv_kernel(const ConvArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int grp = tid >> 8, gt = tid & 255;
   unsigned char* reg = smem + grp * G_BYTES;          // this group's activation region
+  __half* raw = reinterpret_cast<__half*>(smem + OFF_RAW + grp * RAW_BYTES);  // raw fp16 copy of the tile's 4 windows
   const uint32_t rbase = sbase + grp * G_BYTES;
   const uint32_t gbar = sbase + OFF_BAR + grp * 24;   // phase barriers A, B, C of the group
   const uint32_t wbar = sbase + OFF_BAR + 48;         // weight barrier (CTA-wide)
@@ -87,27 +108,53 @@ __global__ void __launch_bounds__(512, 1) tc_conv_kernel(const ConvArgs a) {
   const long long per = (total + gridDim.x - 1) / gridDim.x;
   const long long beg = per * blockIdx.x, end = min(total, beg + per);
   const int row = gt & 127, half = gt >> 7;
-  const int wq = row >> 5, t = row & 31;
+  const int wq = row >> 5, t = row & 31;  // t == lane
   const uint32_t lane_addr = tmem + ((uint32_t)(row & ~31) << 16);
   const uint32_t rowoff = (uint32_t)(ROW0 + row) * 16;
 
-  // descriptor bases (all operand addresses are compile-time offsets from these)
   const uint64_t dX = umma_desc(rbase + R_X + ROW0 * 16, CS, 128);
   const uint64_t dXP = umma_desc(rbase + R_XP + ROW0 * 16, CS, 128);
   const uint64_t dM1 = umma_desc(rbase + R_M1 + ROW0 * 16, CS, 128);
   const uint64_t dM1P = umma_desc(rbase + R_M1P + ROW0 * 16, CS, 128);
   const uint64_t dT2 = umma_desc(rbase + R_T2 + ROW0 * 16, CS, 128);
   const uint64_t dT3 = umma_desc(rbase + R_T3 + ROW0 * 16, CS, 128);
-  const uint64_t dWA = umma_desc(sbase + OFF_W + WI_A, 512, 128);
   const uint64_t dWB1 = umma_desc(sbase + OFF_W + WI_B1, 2304, 128);
   const uint64_t dWB4 = umma_desc(sbase + OFF_W + WI_B4, 512, 128);
-  const uint64_t dWC2 = umma_desc(sbase + OFF_W + WI_B2B, 256, 128);
-  const uint64_t dWC3 = umma_desc(sbase + OFF_W + WI_B3B, 256, 128);
+  const uint64_t dWC2 = umma_desc(sbase + OFF_W + WI_B2B, 48 * 16, 128);
+  const uint64_t dWC3 = umma_desc(sbase + OFF_W + WI_B3B, 80 * 16, 128);
+
+  // wait for an MMA phase: one warp polls the mbarrier, the others block on the group's named barrier
+  auto phase_wait = [&](uint32_t bar, uint32_t parity, int code) {
+    if ((gt >> 5) == 0) mbar_wait(bar, parity, a.status, code, abort_flag);
+    group_sync(grp);
+    tc_fence_after();
+  };
+  // raw windows of a tile: global fp32 -> registers (9 floats / thread, coalesced) -> fp16 staging buffer
+  float pre[9];
+  auto prefetch = [&](long long item) {
+    const bool valid = item < end;
+    const int ptile = valid ? (int)(item % npair) * 2 + grp : 0;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      const int idx = gt + 256 * j;
+      const int gw = ptile * 4 + idx / 540;
+      const bool okx = valid && idx < 2160 && ptile < a.ntile4 && gw < a.B;
+      pre[j] = okx ? __ldg(a.x + (long long)ptile * 2160 + idx) : 0.f;
+    }
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      const int idx = gt + 256 * j;
+      if (idx < 2160) raw[idx] = __float2half_rn(pre[j]);
+    }
+  };
 
   int cur_s = -1;
   uint32_t ph = 0, wph = 0;
-  bool ok = true;
-  (void)ok;
+  prefetch(beg);
+  stash();
+  group_sync(grp);
 
   for (long long it = beg; it < end; ++it) {
     const int s = (int)(it / npair);
@@ -120,59 +167,58 @@ __global__ void __launch_bounds__(512, 1) tc_conv_kernel(const ConvArgs a) {
         mbar_expect_tx(wbar, CONV_IMG);
         for (int o = 0; o < CONV_IMG; o += 16384) bulk_g2s(sbase + OFF_W + o, src + o, min(16384, CONV_IMG - o), wbar);
       }
-      ok = mbar_wait(wbar, wph, a.status, 1, abort_flag);
+      mbar_wait(wbar, wph, a.status, 1, abort_flag);
       wph ^= 1;
     }
-    // ---- stage the 4 windows (fp32 -> fp16, 8-feature chunks) and their MaxPool1d(3,1,1) (-inf padding) ----
+    // ---- X / XP: 8-feature fp16 chunks of the windows and of their MaxPool1d(3,1,1) (-inf padding) ----
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int u = gt + 256 * i, r = u & 127, c = u >> 7;  // i = 0: chunks 0,1; i = 1: chunks 2,3
-      const int tt = r & 31, gw = tile * 4 + (r >> 5);
+      const int tt = r & 31, w4 = r >> 5, gw = tile * 4 + w4;
       const bool lv = tt < 30 && gw < a.B && tile < a.ntile4;
-      float f[8], pm[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = pm[j] = 0.f;
+      uint32_t f[4] = {0u, 0u, 0u, 0u}, pm[4] = {0u, 0u, 0u, 0u};
       if (lv && c < 3) {
-        const float* px = a.x + (long long)gw * 540 + tt * 18 + c * 8;
-        const int nf = c < 2 ? 8 : 2;
-        float lo[8], hi[8];
+        const uint32_t* pr = reinterpret_cast<const uint32_t*>(raw + w4 * 540 + tt * 18 + c * 8);  // 4-byte aligned
+        const int nw = c < 2 ? 4 : 1;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) lo[j] = hi[j] = -INFINITY;
-        for (int j = 0; j < nf; j += 2) {
-          const float2 p2 = __ldg(reinterpret_cast<const float2*>(px + j));
-          f[j] = p2.x; f[j + 1] = p2.y;
-          if (tt > 0) { const float2 q = __ldg(reinterpret_cast<const float2*>(px - 18 + j)); lo[j] = q.x; lo[j + 1] = q.y; }
-          if (tt < 29) { const float2 q = __ldg(reinterpret_cast<const float2*>(px + 18 + j)); hi[j] = q.x; hi[j + 1] = q.y; }
+        for (int j = 0; j < 4; ++j) {
+          if (j < nw) {
+            const uint32_t v = pr[j];
+            uint32_t m = v;
+            if (tt > 0) m = hmax2u(m, pr[j - 9]);
+            if (tt < 29) m = hmax2u(m, pr[j + 9]);
+            f[j] = v;
+            pm[j] = m;
+          }
         }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) pm[j] = j < nf ? fmaxf(f[j], fmaxf(lo[j], hi[j])) : 0.f;
-        if (c == 2) f[2] = pm[2] = 1.0f;  // constant-1 feature carrying the biases
+        if (c == 2) f[1] = pm[1] = 0x00003C00u;  // feature 18 = 1.0 (fp16), feature 19 = 0: carries the biases
       }
-      *reinterpret_cast<uint4*>(reg + R_X + c * CS + (ROW0 + r) * 16) =
-          make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
-      *reinterpret_cast<uint4*>(reg + R_XP + c * CS + (ROW0 + r) * 16) =
-          make_uint4(pack_h2(pm[0], pm[1]), pack_h2(pm[2], pm[3]), pack_h2(pm[4], pm[5]), pack_h2(pm[6], pm[7]));
+      *reinterpret_cast<uint4*>(reg + R_X + c * CS + (ROW0 + r) * 16) = make_uint4(f[0], f[1], f[2], f[3]);
+      *reinterpret_cast<uint4*>(reg + R_XP + c * CS + (ROW0 + r) * 16) = make_uint4(pm[0], pm[1], pm[2], pm[3]);
     }
     fence_async_smem();
     tc_fence_before();
     group_sync(grp);
-    // ---- phase A: module 1, 4 branches x (N = 32), taps = row-shifted A descriptors ----
+    // ---- phase A: module 1.  TMEM cols: conv5 0..31 | conv3 32..63 | conv1 64..95 | convpool 96..127 ----
     if (gt == 0) {
       tc_fence_after();
-      constexpr uint32_t idA = umma_idesc(32);
-      constexpr int ntap[4] = {1, 3, 5, 3}, tap0[4] = {0, 1, 4, 9}, pad[4] = {0, 1, 2, 1};
+      constexpr int shs[5] = {0, -1, 1, -2, 2}, nsh[5] = {96, 64, 64, 32, 32}, osh[5] = {0, 6144, 10240, 14336, 16384};
 #pragma unroll
-      for (int br = 0; br < 4; ++br)
+      for (int q = 0; q < 5; ++q)
 #pragma unroll
-        for (int tp = 0; tp < ntap[br]; ++tp)
+        for (int ks = 0; ks < 2; ++ks)
+          umma(tmem, dX + (uint64_t)((2 * ks * CS + shs[q] * 16) >> 4),
+               umma_desc(sbase + OFF_W + WI_A + osh[q] + 2 * ks * nsh[q] * 16, nsh[q] * 16, 128), umma_idesc(nsh[q]), (q | ks) != 0);
 #pragma unroll
-          for (int ks = 0; ks < 2; ++ks)
-            umma(tmem + br * 32, (br == 3 ? dXP : dX) + (uint64_t)((2 * ks * CS + (tp - pad[br]) * 16) >> 4),
-                 dWA + (uint64_t)(((tap0[br] + tp) * WA_TAP + 2 * ks * 512) >> 4), idA, (tp | ks) != 0);
+      for (int tp = 0; tp < 3; ++tp)
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+          umma(tmem + 96, dXP + (uint64_t)((2 * ks * CS + (tp - 1) * 16) >> 4),
+               umma_desc(sbase + OFF_W + WI_A + 18432 + tp * 2048 + 2 * ks * 512, 512, 128), umma_idesc(32), (tp | ks) != 0);
       umma_commit(gbar);
     }
-    ok = mbar_wait(gbar, ph, a.status, 2, abort_flag);
-    tc_fence_after();
+    prefetch(it + 1);  // next tile's windows: global loads stay in flight for the rest of this tile
+    phase_wait(gbar, ph, 2);
     const int gw = tile * 4 + wq;
     const bool live = t < 30 && gw < a.B && tile < a.ntile4;
 #pragma unroll
@@ -183,41 +229,33 @@ __global__ void __launch_bounds__(512, 1) tc_conv_kernel(const ConvArgs a) {
       tmem_ld_wait();
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
-        const int br = 2 * bp + q;
+        const int cb = 2 * bp + q;                         // TMEM column block
+        const int br = cb == 0 ? 2 : cb == 1 ? 1 : cb == 2 ? 0 : 3;  // -> M1 channel group / dropout layer
+        act16<DROP, false>(acc[q], nullptr, live, a, br, s, gw, t, half * 16, 27);
         uint4 lo, hi;
-        epi16<DROP, false>(acc[q], nullptr, live, lo, hi, a, br, s, gw, t, half * 16, 27);
+        pack16(acc[q], live, lo, hi);
         unsigned char* dst = reg + R_M1 + (br * 4 + half * 2) * CS + rowoff;
         *reinterpret_cast<uint4*>(dst) = lo;
         *reinterpret_cast<uint4*>(dst + CS) = hi;
+        *reinterpret_cast<uint4*>(dst + R_M1P) = pool3x4(lo, lane);  // R_M1P - R_M1 == 16 chunks
+        *reinterpret_cast<uint4*>(dst + R_M1P + CS) = pool3x4(hi, lane);
       }
     }
-    tc_fence_before();
-    group_sync(grp);
-    // ---- MaxPool1d(3,1,1) of module-1 output (post-ReLU >= 0, zero pad rows act as -inf) ----
-#pragma unroll 2
-    for (int u = gt; u < 2048; u += 256) {
-      const int r = u & 127, c = u >> 7;
-      const unsigned char* p = reg + R_M1 + c * CS + (ROW0 + r) * 16;
-      const uint4 v = hmax4(hmax4(*reinterpret_cast<const uint4*>(p - 16), *reinterpret_cast<const uint4*>(p)),
-                            *reinterpret_cast<const uint4*>(p + 16));
-      *reinterpret_cast<uint4*>(reg + R_M1P + c * CS + (ROW0 + r) * 16) = v;
-    }
     fence_async_smem();
+    tc_fence_before();
     group_sync(grp);
     // ---- phase B: module-2 1x1 convs: [b1 | b2a | b3a] (N = 144) on M1, b4 (N = 32) on pooled M1 ----
     if (gt == 0) {
       tc_fence_after();
-      constexpr uint32_t idB1 = umma_idesc(144), idB4 = umma_idesc(32);
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks)
-        umma(tmem, dM1 + (uint64_t)((2 * ks * CS) >> 4), dWB1 + (uint64_t)((2 * ks * 2304) >> 4), idB1, ks != 0);
+        umma(tmem, dM1 + (uint64_t)((2 * ks * CS) >> 4), dWB1 + (uint64_t)((2 * ks * 2304) >> 4), umma_idesc(144), ks != 0);
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks)
-        umma(tmem + 144, dM1P + (uint64_t)((2 * ks * CS) >> 4), dWB4 + (uint64_t)((2 * ks * 512) >> 4), idB4, ks != 0);
+        umma(tmem + 144, dM1P + (uint64_t)((2 * ks * CS) >> 4), dWB4 + (uint64_t)((2 * ks * 512) >> 4), umma_idesc(32), ks != 0);
       umma_commit(gbar + 8);
     }
-    ok = mbar_wait(gbar + 8, ph, a.status, 3, abort_flag);
-    tc_fence_after();
+    phase_wait(gbar + 8, ph, 3);
     unsigned char* frow = a.feat + ((long long)s * a.ntile128 + (gw >> 7)) * FEAT_TILE_BYTES + (long long)(gw & 127) * 16 +
                           (long long)t * 10 * 2048;
     // 11 groups of 16 columns: g0 = b1 -> feat ch 0..15 | g1..4 = b2a -> T2 | g5..8 = b3a -> T3 | g9,10 = b4 -> feat ch 48..79
@@ -235,15 +273,18 @@ __global__ void __launch_bounds__(512, 1) tc_conv_kernel(const ConvArgs a) {
         if (q && !two) break;
         uint4 lo, hi;
         if (g == 0) {
-          epi16<DROP, false>(acc[q], nullptr, live, lo, hi, a, 4, s, gw, t, 0, 16);
+          act16<DROP, false>(acc[q], nullptr, live, a, 4, s, gw, t, 0, 16);
+          pack16(acc[q], live, lo, hi);
           if (live) { *reinterpret_cast<uint4*>(frow) = lo; *reinterpret_cast<uint4*>(frow + 2048) = hi; }
         } else if (g < 9) {
-          epi16<false, false>(acc[q], nullptr, live, lo, hi, a, 0, s, gw, t, 0, 16);
+          act16<false, false>(acc[q], nullptr, live, a, 0, s, gw, t, 0, 16);
+          pack16(acc[q], live, lo, hi);
           unsigned char* dst = reg + (g < 5 ? R_T2 + (g - 1) * 2 * CS : R_T3 + (g - 5) * 2 * CS) + rowoff;
           *reinterpret_cast<uint4*>(dst) = lo;
           *reinterpret_cast<uint4*>(dst + CS) = hi;
         } else {
-          epi16<DROP, false>(acc[q], nullptr, live, lo, hi, a, 9, s, gw, t, (g - 9) * 16, 32);
+          act16<DROP, false>(acc[q], nullptr, live, a, 9, s, gw, t, (g - 9) * 16, 32);
+          pack16(acc[q], live, lo, hi);
           if (live) {
             *reinterpret_cast<uint4*>(frow + (6 + (g - 9) * 2) * 2048) = lo;
             *reinterpret_cast<uint4*>(frow + (7 + (g - 9) * 2) * 2048) = hi;
@@ -254,32 +295,44 @@ __global__ void __launch_bounds__(512, 1) tc_conv_kernel(const ConvArgs a) {
     fence_async_smem();
     tc_fence_before();
     group_sync(grp);
-    // ---- phase C: b2b (k3 over T2) and b3b (k5 over T3), N = 16 each ----
+    // ---- phase C: b2b (k3 over T2) / b3b (k5 over T3): taps concatenated along N, shifts applied in the epilogue ----
     if (gt == 0) {
       tc_fence_after();
-      constexpr uint32_t idC = umma_idesc(16);
 #pragma unroll
-      for (int tp = 0; tp < 3; ++tp)
+      for (int ks = 0; ks < 4; ++ks)
+        umma(tmem, dT2 + (uint64_t)((2 * ks * CS) >> 4), dWC2 + (uint64_t)((2 * ks * 48 * 16) >> 4), umma_idesc(48), ks != 0);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          umma(tmem + 176, dT2 + (uint64_t)((2 * ks * CS + (tp - 1) * 16) >> 4), dWC2 + (uint64_t)((tp * WC_TAP + 2 * ks * 256) >> 4),
-               idC, (tp | ks) != 0);
-#pragma unroll
-      for (int tp = 0; tp < 5; ++tp)
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          umma(tmem + 192, dT3 + (uint64_t)((2 * ks * CS + (tp - 2) * 16) >> 4), dWC3 + (uint64_t)((tp * WC_TAP + 2 * ks * 256) >> 4),
-               idC, (tp | ks) != 0);
+      for (int ks = 0; ks < 4; ++ks)
+        umma(tmem + 48, dT3 + (uint64_t)((2 * ks * CS) >> 4), dWC3 + (uint64_t)((2 * ks * 80 * 16) >> 4), umma_idesc(80), ks != 0);
       umma_commit(gbar + 16);
     }
-    ok = mbar_wait(gbar + 16, ph, a.status, 4, abort_flag);
-    tc_fence_after();
+    stash();  // the prefetched windows have landed long ago; the barrier inside phase_wait publishes them
+    phase_wait(gbar + 16, ph, 4);
     {
-      float acc[16];
-      tmem_ld16(lane_addr + 176 + half * 16, acc);
-      tmem_ld_wait();
+      float out[16];
+      if (half == 0) {  // b2b: out[t] = P0[t-1] + P1[t] + P2[t+1]
+        float p[3][16];
+#pragma unroll
+        for (int tp = 0; tp < 3; ++tp) tmem_ld16(lane_addr + tp * 16, p[tp]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) out[j] = shf(p[0][j], -1, lane) + p[1][j] + shf(p[2][j], 1, lane);
+      } else {  // b3b: out[t] = sum_tap P_tap[t + tap - 2]
+        float p[3][16];
+#pragma unroll
+        for (int tp = 0; tp < 3; ++tp) tmem_ld16(lane_addr + 48 + tp * 16, p[tp]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) out[j] = shf(p[0][j], -2, lane) + shf(p[1][j], -1, lane) + p[2][j];
+        tmem_ld16(lane_addr + 48 + 48, p[0]);
+        tmem_ld16(lane_addr + 48 + 64, p[1]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) out[j] += shf(p[0][j], 1, lane) + shf(p[1][j], 2, lane);
+      }
+      act16<DROP, true>(out, sbias + 304 + half * 16, live, a, half ? 8 : 6, s, gw, t, 0, 16);
       uint4 lo, hi;
-      epi16<DROP, true>(acc, sbias + 304 + half * 16, live, lo, hi, a, half ? 8 : 6, s, gw, t, 0, 16);
+      pack16(out, live, lo, hi);
       if (live) {
         *reinterpret_cast<uint4*>(frow + (2 + half * 2) * 2048) = lo;
         *reinterpret_cast<uint4*>(frow + (3 + half * 2) * 2048) = hi;
