@@ -61,19 +61,23 @@ __device__ __forceinline__ uint32_t hmax2u(uint32_t a, uint32_t b) {
   __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
   return *reinterpret_cast<uint32_t*>(&r);
 }
-// MaxPool1d(3,1,1) across rows of a window = across lanes of the warp (values >= 0, dead rows are 0)
+// Rows of a window are the lanes of a warp and lanes 30 / 31 are dead rows that hold exact zeros, so a ROTATING
+// shuffle implements both the zero padding of the tap shifts and the -inf padding of the max-pool (values >= 0).
 __device__ __forceinline__ uint32_t pool3(uint32_t v, int lane) {
-  uint32_t up = __shfl_up_sync(0xffffffffu, v, 1), dn = __shfl_down_sync(0xffffffffu, v, 1);
-  if (lane == 0) up = 0u;
-  if (lane == 31) dn = 0u;
+  const uint32_t up = __shfl_sync(0xffffffffu, v, (lane + 31) & 31), dn = __shfl_sync(0xffffffffu, v, (lane + 1) & 31);
   return hmax2u(v, hmax2u(up, dn));
 }
 __device__ __forceinline__ uint4 pool3x4(uint4 v, int lane) {
   return make_uint4(pool3(v.x, lane), pool3(v.y, lane), pool3(v.z, lane), pool3(v.w, lane));
 }
-__device__ __forceinline__ float shf(float v, int d, int lane) {  // value of row (lane + d) of the window, 0 outside
-  const float r = d < 0 ? __shfl_up_sync(0xffffffffu, v, -d) : __shfl_down_sync(0xffffffffu, v, d);
-  return (lane + d < 0 || lane + d > 31) ? 0.f : r;
+__device__ __forceinline__ float shf(float v, int src_lane) { return __shfl_sync(0xffffffffu, v, src_lane); }
+// ReLU + fp16 pack of 16 accumulator columns without bias / dropout: convert first, clamp on packed halves
+__device__ __forceinline__ void relu_pack16(const float (&v)[16], bool live, uint4& lo, uint4& hi) {
+  uint32_t r[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = live ? hmax2u(pack_h2(v[2 * j], v[2 * j + 1]), 0u) : 0u;
+  lo = make_uint4(r[0], r[1], r[2], r[3]);
+  hi = make_uint4(r[4], r[5], r[6], r[7]);
 }
 
 template <bool DROP>
@@ -231,9 +235,13 @@ __global__ void __launch_bounds__(512, 1) tc_conv_kernel(const ConvArgs a) {
       for (int q = 0; q < 2; ++q) {
         const int cb = 2 * bp + q;                         // TMEM column block
         const int br = cb == 0 ? 2 : cb == 1 ? 1 : cb == 2 ? 0 : 3;  // -> M1 channel group / dropout layer
-        act16<DROP, false>(acc[q], nullptr, live, a, br, s, gw, t, half * 16, 27);
         uint4 lo, hi;
-        pack16(acc[q], live, lo, hi);
+        if (DROP) {
+          act16<DROP, false>(acc[q], nullptr, live, a, br, s, gw, t, half * 16, 27);
+          pack16(acc[q], live, lo, hi);
+        } else {
+          relu_pack16(acc[q], live, lo, hi);
+        }
         unsigned char* dst = reg + R_M1 + (br * 4 + half * 2) * CS + rowoff;
         *reinterpret_cast<uint4*>(dst) = lo;
         *reinterpret_cast<uint4*>(dst + CS) = hi;
@@ -273,18 +281,17 @@ __global__ void __launch_bounds__(512, 1) tc_conv_kernel(const ConvArgs a) {
         if (q && !two) break;
         uint4 lo, hi;
         if (g == 0) {
-          act16<DROP, false>(acc[q], nullptr, live, a, 4, s, gw, t, 0, 16);
-          pack16(acc[q], live, lo, hi);
+          if (DROP) { act16<DROP, false>(acc[q], nullptr, live, a, 4, s, gw, t, 0, 16); pack16(acc[q], live, lo, hi); }
+          else relu_pack16(acc[q], live, lo, hi);
           if (live) { *reinterpret_cast<uint4*>(frow) = lo; *reinterpret_cast<uint4*>(frow + 2048) = hi; }
         } else if (g < 9) {
-          act16<false, false>(acc[q], nullptr, live, a, 0, s, gw, t, 0, 16);
-          pack16(acc[q], live, lo, hi);
+          relu_pack16(acc[q], live, lo, hi);
           unsigned char* dst = reg + (g < 5 ? R_T2 + (g - 1) * 2 * CS : R_T3 + (g - 5) * 2 * CS) + rowoff;
           *reinterpret_cast<uint4*>(dst) = lo;
           *reinterpret_cast<uint4*>(dst + CS) = hi;
         } else {
-          act16<DROP, false>(acc[q], nullptr, live, a, 9, s, gw, t, (g - 9) * 16, 32);
-          pack16(acc[q], live, lo, hi);
+          if (DROP) { act16<DROP, false>(acc[q], nullptr, live, a, 9, s, gw, t, (g - 9) * 16, 32); pack16(acc[q], live, lo, hi); }
+          else relu_pack16(acc[q], live, lo, hi);
           if (live) {
             *reinterpret_cast<uint4*>(frow + (6 + (g - 9) * 2) * 2048) = lo;
             *reinterpret_cast<uint4*>(frow + (7 + (g - 9) * 2) * 2048) = hi;
@@ -309,6 +316,7 @@ __global__ void __launch_bounds__(512, 1) tc_conv_kernel(const ConvArgs a) {
     stash();  // the prefetched windows have landed long ago; the barrier inside phase_wait publishes them
     phase_wait(gbar + 16, ph, 4);
     {
+      const int lm1 = (lane + 31) & 31, lm2 = (lane + 30) & 31, lp1 = (lane + 1) & 31, lp2 = (lane + 2) & 31;
       float out[16];
       if (half == 0) {  // b2b: out[t] = P0[t-1] + P1[t] + P2[t+1]
         float p[3][16];
@@ -316,19 +324,19 @@ __global__ void __launch_bounds__(512, 1) tc_conv_kernel(const ConvArgs a) {
         for (int tp = 0; tp < 3; ++tp) tmem_ld16(lane_addr + tp * 16, p[tp]);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) out[j] = shf(p[0][j], -1, lane) + p[1][j] + shf(p[2][j], 1, lane);
+        for (int j = 0; j < 16; ++j) out[j] = shf(p[0][j], lm1) + p[1][j] + shf(p[2][j], lp1);
       } else {  // b3b: out[t] = sum_tap P_tap[t + tap - 2]
         float p[3][16];
 #pragma unroll
         for (int tp = 0; tp < 3; ++tp) tmem_ld16(lane_addr + 48 + tp * 16, p[tp]);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) out[j] = shf(p[0][j], -2, lane) + shf(p[1][j], -1, lane) + p[2][j];
+        for (int j = 0; j < 16; ++j) out[j] = shf(p[0][j], lm2) + shf(p[1][j], lm1) + p[2][j];
         tmem_ld16(lane_addr + 48 + 48, p[0]);
         tmem_ld16(lane_addr + 48 + 64, p[1]);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) out[j] += shf(p[0][j], 1, lane) + shf(p[1][j], 2, lane);
+        for (int j = 0; j < 16; ++j) out[j] += shf(p[0][j], lp1) + shf(p[1][j], lp2);
       }
       act16<DROP, true>(out, sbias + 304 + half * 16, live, a, half ? 8 : 6, s, gw, t, 0, 16);
       uint4 lo, hi;
