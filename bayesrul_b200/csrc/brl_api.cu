@@ -415,6 +415,23 @@ int brl_destroy(brl_ctx* ctx) {
 }
 
 int brl_tc_status(const brl_ctx* ctx) { return ctx ? tc_status(ctx->tc) : -1; }
+int brl_tc_timing(brl_ctx* ctx, int enable) {
+  BRL_REQUIRE(ctx && tc_available(ctx->tc), "brl_tc_timing: tensor-core engine unavailable");
+  tc_timing(ctx->tc, enable != 0);
+  return BRL_OK;
+}
+int brl_tc_timing_read(brl_ctx* ctx, double* kernel_ms, int64_t* launches) {
+  BRL_REQUIRE(ctx && kernel_ms && launches && tc_available(ctx->tc), "brl_tc_timing_read: bad argument");
+  long long n = 0;
+  tc_timing_read(ctx->tc, kernel_ms, &n);
+  *launches = n;
+  return BRL_OK;
+}
+int brl_tc_trace(brl_ctx* ctx, int64_t* device_buf) {
+  BRL_REQUIRE(ctx && tc_available(ctx->tc), "brl_tc_trace: tensor-core engine unavailable");
+  tc_trace(ctx->tc, reinterpret_cast<long long*>(device_buf));
+  return BRL_OK;
+}
 
 int brl_engine_available(const brl_ctx* ctx, int engine) {
   if (!ctx) return 0;
@@ -500,7 +517,7 @@ int brl_forward(brl_ctx* ctx, const float* x, int64_t B, int64_t S, int mode, co
   if (engine == BRL_ENGINE_TC_FP16) {
     BRL_REQUIRE(mode == BRL_MODE_DET || mode == BRL_MODE_WS, "tensor-core engine supports DET / WS forward only");
     const char* err = tc_forward(ctx->tc, x, B, S, mode == BRL_MODE_WS ? wsamp : theta, mode == BRL_MODE_WS ? n.P : 0,
-                                 p_dropout, noise, out, workspace, workspace_bytes, st);
+                                 p_dropout, noise, out, workspace, workspace_bytes, true, st);
     if (err) return fail(BRL_ERR_UNSUPPORTED, err);
     BRL_CUDA(cudaGetLastError());
     return BRL_OK;
@@ -566,7 +583,7 @@ int brl_predict_moments(brl_ctx* ctx, const float* x, int64_t B, int64_t S, int 
       mode = BRL_MODE_WS;
     }
     if (engine == BRL_ENGINE_TC_FP16) {
-      const char* err = tc_forward(ctx->tc, x, B, sc, w, mode == BRL_MODE_WS ? n.P : 0, p_dropout, &nz, outc, tc_ws, tc_bytes, st);
+      const char* err = tc_forward(ctx->tc, x, B, sc, w, mode == BRL_MODE_WS ? n.P : 0, p_dropout, &nz, outc, tc_ws, tc_bytes, s0 == 0, st);
       if (err) return fail(BRL_ERR_UNSUPPORTED, err);
     } else {
       FwdArgs fa{x, B, sc, mode, w, nullptr, w, p_dropout, &nz, nullptr, nullptr, outc, false};

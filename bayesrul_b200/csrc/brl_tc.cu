@@ -18,6 +18,8 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
+#include <utility>
+#include <vector>
 
 #include "../../include/bayesrul_b200.h"
 #include "brl_kernels.cuh"
@@ -33,11 +35,11 @@ namespace brl {
 constexpr int ROWS = 132;            // 2 zero rows + 128 tile rows + 2 slack rows
 constexpr int CS = ROWS * 16;        // bytes of one 8-channel chunk (K-major, 16 B per row)
 constexpr int ROW0 = 2;              // buffer row of tile row 0
-// per-group activation region: 32 chunks; M1 | M1P, with T2/T3 aliasing M1 and X/XP aliasing M1P
+// per-slot activation region: 32 chunks; M1 | M1P, with T2/T3 aliasing M1 and X/XP aliasing M1P
 constexpr int R_M1 = 0;                     // 16 chunks: 4 branches x (27 real + const-1 + zero pad = 32)
 constexpr int R_M1P = 16 * CS;              // 16 chunks
 constexpr int R_T2 = R_M1, R_T3 = R_M1 + 8 * CS;   // 8 + 8 chunks (live after the M1 readers have completed)
-constexpr int R_X = R_M1P, R_XP = R_M1P + 4 * CS;  // 4 + 4 chunks (live before M1P is produced)
+constexpr int R_X = R_M1P, R_XP = R_M1P + 3 * CS;  // 3 + 3 chunks (live before M1P is produced), one bulk copy
 constexpr int G_BYTES = 32 * CS;
 constexpr int OFF_W = 2 * G_BYTES;          // weight image, shared by the two groups
 // weight image (identical in the global blob)
@@ -52,10 +54,10 @@ constexpr int WI_BIAS = WI_B3B + 5 * WC_TAP;  // fp32: A 4x32, B1 144, B4 32, b2
 constexpr int NBIAS = 128 + 144 + 32 + 16 + 16;
 constexpr int CONV_IMG = WI_BIAS + NBIAS * 4;
 static_assert(CONV_IMG % 16 == 0, "bulk copies need 16-byte multiples");
-constexpr int OFF_RAW = OFF_W + CONV_IMG;     // raw fp16 windows of the next tile, one buffer per group
-constexpr int RAW_BYTES = 4352;               // 4 x 540 halves, padded
-constexpr int OFF_BAR = OFF_RAW + 2 * RAW_BYTES;
+constexpr int OFF_ZERO = OFF_W + CONV_IMG;    // one all-zero chunk: the 4th K chunk of X / XP of both slots
+constexpr int OFF_BAR = OFF_ZERO + CS;
 constexpr int CONV_SMEM = OFF_BAR + 128;
+constexpr int XIMG_TILE_BYTES = 6 * CS;       // fp16 chunk images of a tile's windows: X0 X1 X2 XP0 XP1 XP2, pad rows included
 static_assert(CONV_SMEM <= 232448, "conv kernel shared memory exceeds the 227 KB opt-in limit");
 // blob = conv image + fc image + fp32 tail (fc bias 64, last W 128, last b 2)
 constexpr int FC_IMG = 300 * 64 * 16;
@@ -76,6 +78,10 @@ struct TcState {
   int* status;  // device: 0 ok, else first mbarrier time-out code
   int sm_count;
   long long loff[12][2];  // w_off, b_off per layer
+  bool timing = false;    // bracket tc_conv_kernel launches with events (bench.py roofline)
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evs;
+  size_t ev_used = 0;
+  long long* trace = nullptr;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -111,6 +117,36 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* st
   atomicCAS(status, 0, code);
   if (abort_flag) *abort_flag = 1;
   return false;
+}
+// Converged-warp wait: the (bounded) spin loop lives inside the asm block, so the compiler sees no divergent control
+// flow and keeps warp-uniform values (descriptors, parities) in uniform registers around it.
+__device__ __forceinline__ bool mbar_wait_warp(uint32_t bar, uint32_t parity, int* status, int code, volatile int* abort_flag) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .u32 n;\n\tmov.u32 n, 0;\n\t"
+      "BRL_WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "@p bra BRL_WAIT_DONE;\n\t"
+      "add.u32 n, n, 1;\n\t"
+      "setp.lt.u32 p, n, %3;\n\t"
+      "@p bra BRL_WAIT_LOOP;\n\t"
+      "setp.ne.u32 p, n, n;\n\t"
+      "BRL_WAIT_DONE:\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(*abort_flag ? 1u : SPIN_LIMIT)
+      : "memory");
+  if (!ok) {
+    atomicCAS(status, 0, code);
+    *abort_flag = 1;
+  }
+  __syncwarp();
+  return ok != 0;
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -157,11 +193,25 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+// two fp32 -> packed fp16 pair with the ReLU clamp folded into the conversion
+__device__ __forceinline__ uint32_t pack_relu_h2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
 }
 __device__ __forceinline__ uint4 hmax4(uint4 a, uint4 b) {
   uint4 r;
@@ -428,8 +478,26 @@ TcState* tc_create(int net) {
 void tc_destroy(TcState* s) {
   if (!s) return;
   if (s->status) cudaFree(s->status);
+  for (auto& e : s->evs) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   delete s;
 }
+void tc_timing(TcState* s, bool enable) {
+  s->timing = enable;
+  s->ev_used = 0;
+}
+void tc_timing_read(TcState* s, double* ms, long long* launches) {
+  double t = 0.0;
+  for (size_t i = 0; i < s->ev_used; ++i) {
+    float e = 0.f;
+    cudaEventSynchronize(s->evs[i].second);
+    cudaEventElapsedTime(&e, s->evs[i].first, s->evs[i].second);
+    t += e;
+  }
+  *ms = t;
+  *launches = (long long)s->ev_used;
+  s->ev_used = 0;
+}
+void tc_trace(TcState* s, long long* buf) { s->trace = buf; }
 bool tc_available(const TcState* s) { return s && s->net == BRL_NET_INCEPTION && s->status != nullptr; }
 int tc_status(const TcState* s) {
   int v = -1;
@@ -437,18 +505,26 @@ int tc_status(const TcState* s) {
   return v;
 }
 size_t tc_workspace_bytes(const TcState* s, long long B, long long S) {
-  const long long nt128 = (B + 127) / 128;
-  return (size_t)(S * (long long)BLOB_BYTES + S * nt128 * FEAT_TILE_BYTES + 1024);
+  const long long nt128 = (B + 127) / 128, npair = ((B + 3) / 4 + 1) / 2;
+  return (size_t)(S * (long long)BLOB_BYTES + S * nt128 * FEAT_TILE_BYTES + 2 * npair * XIMG_TILE_BYTES + 1024);
 }
 
 const char* tc_forward(TcState* st, const float* x, long long B, long long S, const float* weights, long long w_sample_stride,
-                       float p_dropout, const brl_noise* noise, float* out, void* ws, size_t ws_bytes, cudaStream_t stream) {
+                       float p_dropout, const brl_noise* noise, float* out, void* ws, size_t ws_bytes, bool pack_x,
+                       cudaStream_t stream) {
   if (!tc_available(st)) return "bayesrul_b200: tensor-core engine is implemented for the Inception net only";
   if (ws_bytes < tc_workspace_bytes(st, B, S)) return "bayesrul_b200: workspace too small for the tensor-core engine";
   const long long nt128 = (B + 127) / 128, nt4 = (B + 3) / 4;
-  unsigned char* blob = reinterpret_cast<unsigned char*>(ws);
+  // workspace: window images (independent of S, so later sample chunks of a batch find them again) | blobs | features
+  const int ntx = (int)((nt4 + 1) / 2 * 2);
+  unsigned char* ximg = reinterpret_cast<unsigned char*>(ws);
+  unsigned char* blob = ximg + (((long long)ntx * XIMG_TILE_BYTES + 255) / 256) * 256;
   const long long nblob = w_sample_stride ? S : 1;
   unsigned char* feat = blob + ((S * (long long)BLOB_BYTES + 255) / 256) * 256;
+  if (pack_x) {  // the windows are shared by all MC samples: their fp16 chunk images are built once per batch
+    tc_packx_kernel<<<(unsigned)(((long long)ntx * 384 + 255) / 256), 256, 0, stream>>>(x, ximg, (int)B, ntx);
+    count_launch(1);
+  }
   PackArgs pa;
   pa.w = weights; pa.w_stride = w_sample_stride; pa.blob = blob;
   for (int l = 0; l < 12; ++l) { pa.off[l][0] = st->loff[l][0]; pa.off[l][1] = st->loff[l][1]; }
@@ -464,15 +540,26 @@ const char* tc_forward(TcState* st, const float* x, long long B, long long S, co
     return r;
   };
   ConvArgs ca;
-  ca.x = x; ca.blob = blob; ca.blob_stride = w_sample_stride ? BLOB_BYTES : 0; ca.feat = feat;
+  ca.ximg = ximg; ca.blob = blob; ca.blob_stride = w_sample_stride ? BLOB_BYTES : 0; ca.feat = feat;
   ca.B = (int)B; ca.S = (int)S; ca.ntile4 = (int)nt4; ca.ntile128 = (int)nt128;
   ca.keep4 = drop ? 1.0f - p_dropout * 0.25f : 1.0f;
   for (int l = 0; l < 12; ++l) ca.drop[l] = nr(l);
   ca.status = st->status;
+  ca.trace = st->trace;
   const long long items = S * ((nt4 + 1) / 2);
   const int grid = (int)std::min<long long>(st->sm_count, items);
-  if (drop) tc_conv_kernel<true><<<grid, 512, CONV_SMEM, stream>>>(ca);
-  else tc_conv_kernel<false><<<grid, 512, CONV_SMEM, stream>>>(ca);
+  if (st->timing) {
+    if (st->ev_used == st->evs.size()) {
+      cudaEvent_t e0, e1;
+      cudaEventCreate(&e0);
+      cudaEventCreate(&e1);
+      st->evs.emplace_back(e0, e1);
+    }
+    cudaEventRecord(st->evs[st->ev_used].first, stream);
+  }
+  if (drop) tc_conv_kernel<true><<<grid, CONV_THREADS, CONV_SMEM, stream>>>(ca);
+  else tc_conv_kernel<false><<<grid, CONV_THREADS, CONV_SMEM, stream>>>(ca);
+  if (st->timing) cudaEventRecord(st->evs[st->ev_used++].second, stream);
   FcArgs fa;
   fa.feat = feat; fa.blob = blob; fa.blob_stride = ca.blob_stride; fa.out = out;
   fa.B = (int)B; fa.S = (int)S; fa.ntile128 = (int)nt128;

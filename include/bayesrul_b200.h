@@ -104,6 +104,15 @@ int64_t brl_workspace_bytes(const brl_ctx* ctx, int64_t B, int64_t S, int train,
  * tcgen05 kernel (waits are bounded so a protocol bug ends the kernel instead of hanging the GPU),
  * < 0 = engine unavailable.  Synchronises the device. */
 int brl_tc_status(const brl_ctx* ctx);
+/* Measurement hooks of the tensor-core engine (bench.py roofline; no reference counterpart).
+ * brl_tc_timing(ctx, 1) starts bracketing every launch of the dominant kernel (tc_conv_kernel) with CUDA
+ * events on the launching stream; brl_tc_timing_read synchronises those events and returns the summed
+ * kernel milliseconds and the number of launches since the last enable / read; brl_tc_timing(ctx, 0) stops. */
+int brl_tc_timing(brl_ctx* ctx, int enable);
+int brl_tc_timing_read(brl_ctx* ctx, double* kernel_ms, int64_t* launches);
+/* Debug: device buffer (int64[>= 16*64], or NULL to switch off) into which CTA 0 of tc_conv_kernel writes
+ * clock64() time stamps of its issuer / epilogue warps for its first 16 work items. */
+int brl_tc_trace(brl_ctx* ctx, int64_t* device_buf);
 
 /* ---- guide: weight sampler (replaces AutoNormal.forward / AutoRadial.forward,
  *      guides/radial.py:31-41,124-144; 24 pyro.sample sites per draw) ------------------- */
