@@ -56,7 +56,7 @@ constexpr int CONV_IMG = WI_BIAS + NBIAS * 4;
 static_assert(CONV_IMG % 16 == 0, "bulk copies need 16-byte multiples");
 constexpr int OFF_ZERO = OFF_W + CONV_IMG;    // one all-zero chunk: the 4th K chunk of X / XP of both slots
 constexpr int OFF_BAR = OFF_ZERO + CS;
-constexpr int CONV_SMEM = OFF_BAR + 128;
+constexpr int CONV_SMEM = OFF_BAR + 256;
 constexpr int XIMG_TILE_BYTES = 6 * CS;       // fp16 chunk images of a tile's windows: X0 X1 X2 XP0 XP1 XP2, pad rows included
 static_assert(CONV_SMEM <= 232448, "conv kernel shared memory exceeds the 227 KB opt-in limit");
 // blob = conv image + fc image + fp32 tail (fc bias 64, last W 128, last b 2)
@@ -71,7 +71,10 @@ constexpr int FC_STAGES = 4;
 constexpr int FC_A_BYTES = FC_KCH * 2048, FC_W_BYTES = FC_KCH * 1024;
 constexpr int FC_STAGE_BYTES = FC_A_BYTES + FC_W_BYTES;
 constexpr int FC_SMEM = FC_STAGES * FC_STAGE_BYTES + 256;
-constexpr uint32_t SPIN_LIMIT = 1u << 22;
+// waits suspend in hardware (time hint) instead of spinning: a spinning issuer / loader warp steals issue slots from the
+// epilogue warps of its scheduler.  SPIN_LIMIT x hint bounds a wait to ~1.3 s before it reports a protocol time-out.
+constexpr uint32_t SPIN_LIMIT = 1u << 16;
+constexpr uint32_t WAIT_HINT_NS = 20000u;
 
 struct TcState {
   int net;
@@ -101,10 +104,10 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(WAIT_HINT_NS)
       : "memory");
   return ok != 0;
 }
@@ -125,7 +128,7 @@ __device__ __forceinline__ bool mbar_wait_warp(uint32_t bar, uint32_t parity, in
   asm volatile(
       "{\n\t.reg .pred p;\n\t.reg .u32 n;\n\tmov.u32 n, 0;\n\t"
       "BRL_WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %4;\n\t"
       "@p bra BRL_WAIT_DONE;\n\t"
       "add.u32 n, n, 1;\n\t"
       "setp.lt.u32 p, n, %3;\n\t"
@@ -134,7 +137,7 @@ __device__ __forceinline__ bool mbar_wait_warp(uint32_t bar, uint32_t parity, in
       "BRL_WAIT_DONE:\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity), "r"(*abort_flag ? 1u : SPIN_LIMIT)
+      : "r"(bar), "r"(parity), "r"(*abort_flag ? 1u : SPIN_LIMIT), "r"(WAIT_HINT_NS)
       : "memory");
   if (!ok) {
     atomicCAS(status, 0, code);
@@ -200,6 +203,14 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
                : "r"(taddr));
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 

@@ -1,7 +1,7 @@
 // tcgen05 conv-stack kernel (included by brl_tc.cu after the PTX wrappers and geometry constants).
 //
-// One persistent CTA per SM, 18 warps (16 epilogue + issuer + loader).  Warp 16 is the ISSUER: it runs converged and one elected lane stages operands with bulk
-// copies and issues every tcgen05.mma.  Warps 0..15 are EPILOGUE warps (TMEM -> registers -> fp16 -> shared memory / feature
+// One persistent CTA per SM, 20 warps (16 epilogue + 3 issuers + loader).  Warps 16..19 are the ISSUERS (phase B + bulk copies of slot 0 / 1, phases C + A of slot
+// 0 / 1; converged, one elected lane issues).  Warps 0..15 are EPILOGUE warps (TMEM -> registers -> fp16 -> shared memory / feature
 // tensor).  Two tile SLOTS are in flight per CTA (a tile = 128 rows = 4 windows x 32 rows, warp quadrant = window,
 // lane = time step); each slot owns a 66 KB activation region, 256 TMEM columns and its own mbarriers.  All sixteen
 // epilogue warps work on ONE slot at a time (thread = row x column quarter) and alternate between the slots, so the
@@ -134,16 +134,28 @@ __device__ __forceinline__ void finish16(float (&v)[16], bool live, const ConvAr
   }
 }
 
-constexpr int CONV_THREADS = 576;  // 16 epilogue warps + issuer warp + loader warp
+#ifdef BRL_NOFEAT
+#define BRL_FEAT_LIVE(x) ((x) && a.B < 0)
+#else
+#define BRL_FEAT_LIVE(x) (x)
+#endif
+#ifndef BRL_TRW0
+#define BRL_TRW0 0
+#define BRL_TRW1 15
+#endif
+constexpr int CONV_THREADS = 640;  // 16 epilogue warps + 4 issuer / loader warps (one per scheduler)
 // mbarriers (byte offsets from OFF_BAR)
-constexpr int BAR_DONE_A = 0, BAR_DONE_B = 16, BAR_DONE_C = 32, BAR_READY = 48, BAR_XFULL = 64, BAR_W = 80, BAR_WFREE = 88,
-              BAR_TMEM_SLOT = 96, BAR_ABORT = 104;
+// every MMA phase commits twice (first / second accumulation chain), so a warp only waits for the columns it reads
+constexpr int BAR_DONE_A = 0, BAR_DONE_A2 = 16, BAR_DONE_B = 32, BAR_DONE_B2 = 48, BAR_DONE_C = 64, BAR_DONE_C2 = 80,
+              BAR_READY_A = 96, BAR_READY_B = 112, BAR_XFULL = 128, BAR_W = 144, BAR_WFREE = 152, BAR_TMEM_SLOT = 160,
+              BAR_ABORT = 168;
 
 template <bool DROP>
 __global__ void __launch_bounds__(CONV_THREADS, 1) tc_conv_kernel(const ConvArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // broadcast: the compiler may treat it as warp-uniform
   const uint32_t bars = sbase + OFF_BAR;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + BAR_TMEM_SLOT);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(smem + OFF_BAR + BAR_ABORT);
@@ -153,8 +165,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) tc_conv_kernel(const ConvArgs
   for (int i = tid; i < CS / 16; i += CONV_THREADS) reinterpret_cast<uint4*>(smem + OFF_ZERO)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
     *abort_flag = 0;
-    for (int i = 0; i < 6; ++i) mbar_init(bars + 8 * i, 1);                 // done A/B/C x 2 slots (tcgen05.commit)
-    for (int i = 0; i < 2; ++i) mbar_init(bars + BAR_READY + 8 * i, 16);    // one arrival per epilogue warp
+    for (int i = 0; i < 12; ++i) mbar_init(bars + 8 * i, 1);                // done A/A2/B/B2/C/C2 x 2 slots (tcgen05.commit)
+    for (int i = 0; i < 4; ++i) mbar_init(bars + BAR_READY_A + 8 * i, 16);  // ready A / B x 2 slots: one arrival per epilogue warp
     for (int i = 0; i < 2; ++i) mbar_init(bars + BAR_XFULL + 8 * i, 1);     // bulk copies of the window images
     mbar_init(bars + BAR_W, 1);                                             // bulk copy of the weight image
     mbar_init(bars + BAR_WFREE, 16);                                        // all warps are done with the old weights
@@ -172,172 +184,141 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) tc_conv_kernel(const ConvArgs
   const long long per = (total + gridDim.x - 1) / gridDim.x;
   const long long beg = per * blockIdx.x, end = min(total, beg + per);
 
-  if (warp == 17) {
-    // =========================================== LOADER ===========================================
-    // Bulk copies (window images of the next tile, weight image of the next MC sample) have ~1.5 us of latency and
-    // their issue must never queue behind tcgen05.mma (whose issue blocks while the tensor pipe is busy), so they
-    // get their own warp.  It runs converged; one elected lane issues.
+  if (warp >= 16) {
+    // ======================================= ISSUERS / LOADERS ====================================
+    // A tcgen05.mma issue blocks while the tensor pipe is busy, and a blocked issuer slows every other warp of its
+    // scheduler, so the MMA stream is spread evenly over the four schedulers:
+    //   warp 16 + k : phase B of slot k, then (its MMAs done = M1P space dead) the bulk copy of the slot's next window
+    //                 images; warp 16 also copies the next MC sample's weight image
+    //   warp 18 + k : phase C of slot k followed by phase A of the slot's next tile
+    // Each warp runs converged (waits included) and one elected lane issues, so descriptors and addresses stay in
+    // uniform registers (a lane-0-only branch costs ~80 cycles per tcgen05.mma).
     if (beg < end) {
       bool ok = true;
-      uint32_t bph = 0u, fph = 0u;
-      auto load_w = [&](int s) {
-        if (elect_one()) {
-          const unsigned char* src = a.blob + (long long)s * a.blob_stride;
-          mbar_expect_tx(bars + BAR_W, CONV_IMG);
-          for (int o = 0; o < CONV_IMG; o += 16384) bulk_g2s(sbase + OFF_W + o, src + o, min(16384, CONV_IMG - o), bars + BAR_W);
-        }
-        __syncwarp();
-      };
-      auto load_x = [&](int pair, int k) {  // one bulk copy: X0 X1 X2 XP0 XP1 XP2 incl. their pad rows
-        if (elect_one()) {
-          const unsigned char* src = a.ximg + (long long)(pair * 2 + k) * XIMG_TILE_BYTES;
-          const uint32_t bar = bars + BAR_XFULL + 8 * k;
-          mbar_expect_tx(bar, XIMG_TILE_BYTES);
-          bulk_g2s(sbase + k * G_BYTES + R_X, src, XIMG_TILE_BYTES, bar);
-        }
-        __syncwarp();
-      };
-      int s = (int)(beg / npair), pair = (int)(beg % npair);
-      load_x(pair, 0);
-      load_x(pair, 1);
-      load_w(s);
-      for (long long it = beg; it + 1 < end && ok; ++it) {
-        int sn = s, pn = pair + 1;
-        if (pn == npair) { pn = 0; ++sn; }
-        // the next tile's window images land in the M1P space as soon as the phase-B MMAs have read it
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          ok = mbar_wait_warp(bars + BAR_DONE_B + 8 * k, bph, a.status, 9, abort_flag) && ok;
-          load_x(pn, k);
-          if (a.trace && blockIdx.x == 0 && lane == 0 && it - beg < 16) a.trace[(it - beg) * 64 + 50 + k] = clock64();
-        }
-        bph ^= 1;
-        if (sn != s) {  // next MC sample: every warp has finished the old weights (MMAs complete, biases read)
-          ok = mbar_wait_warp(bars + BAR_WFREE, fph, a.status, 4, abort_flag) && ok;
-          fph ^= 1;
-          load_w(sn);
-        }
-        s = sn;
-        pair = pn;
-      }
-    }
-  } else if (warp == 16) {
-    // =========================================== ISSUER ===========================================
-    // The whole warp runs this code converged (waits included); one elected lane issues the MMAs, so descriptors
-    // and addresses stay in uniform registers (a lane-0-only branch costs ~80 cycles per tcgen05.mma).
-    if (beg < end) {
-      bool ok = true;
-      uint32_t rph[2] = {0u, 0u}, xph[2] = {0u, 0u}, wph = 0u;
-      const uint64_t dWB1 = umma_desc(sbase + OFF_W + WI_B1, 2304, 128);
-      const uint64_t dWB4 = umma_desc(sbase + OFF_W + WI_B4, 512, 128);
-      const uint64_t dWC2 = umma_desc(sbase + OFF_W + WI_B2B, 48 * 16, 128);
-      const uint64_t dWC3 = umma_desc(sbase + OFF_W + WI_B3B, 80 * 16, 128);
-      long long cur_it = beg;
+      const int k = warp & 1;  // slot
+      const uint32_t rb = sbase + k * G_BYTES, tm = tmem + k * 256;
       auto tr = [&](long long it, int slot) {
-        if (a.trace && blockIdx.x == 0 && lane == 0 && it - beg < 16) a.trace[(it - beg) * 64 + slot] = clock64();
+        if (a.trace && blockIdx.x == 0 && lane == 0 && it - beg < 16) a.trace[(it - beg) * 128 + slot] = clock64();
       };
-      // phase A: module 1.  TMEM cols (slot base + 128 +): conv5 0..31 | conv3 32..63 | conv1 64..95 | convpool 96..127
-      auto issue_A = [&](int k, bool landed) {
-        if (!landed) ok = mbar_wait_warp(bars + BAR_XFULL + 8 * k, xph[k], a.status, 5, abort_flag) && ok;
-        xph[k] ^= 1;
-        tc_fence_after();
-        tr(cur_it, 52 + k);
-        if (elect_one()) {
-          const uint32_t rb = sbase + k * G_BYTES, tm = tmem + k * 256 + 128;
-          // k-step 0 = chunks 0,1; k-step 1 = chunk 2 + the shared zero chunk (leading-dimension offset reaches it)
-          const uint32_t zx = (uint32_t)(OFF_ZERO - (k * G_BYTES + R_X + 2 * CS)), zxp = (uint32_t)(OFF_ZERO - (k * G_BYTES + R_XP + 2 * CS));
-          constexpr int shs[5] = {0, -1, 1, -2, 2}, nsh[5] = {96, 64, 64, 32, 32}, osh[5] = {0, 6144, 10240, 14336, 16384};
-#pragma unroll
-          for (int q = 0; q < 5; ++q)
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks)
-              umma(tm, umma_desc(rb + R_X + 2 * ks * CS + (ROW0 + shs[q]) * 16, ks ? zx : CS, 128),
-                   umma_desc(sbase + OFF_W + WI_A + osh[q] + 2 * ks * nsh[q] * 16, nsh[q] * 16, 128), umma_idesc(nsh[q]), (q | ks) != 0);
-#pragma unroll
-          for (int tp = 0; tp < 3; ++tp)
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks)
-              umma(tm + 96, umma_desc(rb + R_XP + 2 * ks * CS + (ROW0 + tp - 1) * 16, ks ? zxp : CS, 128),
-                   umma_desc(sbase + OFF_W + WI_A + 18432 + tp * 2048 + 2 * ks * 512, 512, 128), umma_idesc(32), (tp | ks) != 0);
-          umma_commit(bars + BAR_DONE_A + 8 * k);
-        }
-        __syncwarp();
-      };
-      auto wait_ready = [&](int k, int code) {
-        ok = mbar_wait_warp(bars + BAR_READY + 8 * k, rph[k], a.status, code, abort_flag) && ok;
-        rph[k] ^= 1;
-        tc_fence_after();
-      };
-      // phase B: module-2 1x1 convs: [b1 | b2a | b3a] (N = 144) on M1, b4 (N = 32) on pooled M1
-      auto issue_B = [&](int k) {
-        if (elect_one()) {
-          const uint32_t rb = sbase + k * G_BYTES, tm = tmem + k * 256;
-          const uint64_t dM1 = umma_desc(rb + R_M1 + ROW0 * 16, CS, 128), dM1P = umma_desc(rb + R_M1P + ROW0 * 16, CS, 128);
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks)
-            umma(tm, dM1 + (uint64_t)((2 * ks * CS) >> 4), dWB1 + (uint64_t)((2 * ks * 2304) >> 4), umma_idesc(144), ks != 0);
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks)
-            umma(tm + 144, dM1P + (uint64_t)((2 * ks * CS) >> 4), dWB4 + (uint64_t)((2 * ks * 512) >> 4), umma_idesc(32), ks != 0);
-          umma_commit(bars + BAR_DONE_B + 8 * k);
-        }
-        __syncwarp();
-      };
-      // phase C: b2b (k3 over T2) / b3b (k5 over T3): taps concatenated along N, shifts applied in the epilogue
-      auto issue_C = [&](int k) {
-        if (elect_one()) {
-          const uint32_t rb = sbase + k * G_BYTES, tm = tmem + k * 256;
-          const uint64_t dT2 = umma_desc(rb + R_T2 + ROW0 * 16, CS, 128), dT3 = umma_desc(rb + R_T3 + ROW0 * 16, CS, 128);
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma(tm, dT2 + (uint64_t)((2 * ks * CS) >> 4), dWC2 + (uint64_t)((2 * ks * 48 * 16) >> 4), umma_idesc(48), ks != 0);
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma(tm + 48, dT3 + (uint64_t)((2 * ks * CS) >> 4), dWC3 + (uint64_t)((2 * ks * 80 * 16) >> 4), umma_idesc(80), ks != 0);
-          umma_commit(bars + BAR_DONE_C + 8 * k);
-        }
-        __syncwarp();
-      };
-
-      int s = (int)(beg / npair), pair = (int)(beg % npair);
-      ok = mbar_wait_warp(bars + BAR_W, wph, a.status, 1, abort_flag) && ok;
-      wph ^= 1;
-      issue_A(0, false);
-      issue_A(1, false);
-      for (long long it = beg; it < end && ok; ++it) {
-        const bool next = it + 1 < end;
-        cur_it = it;
-        int sn = s, pn = pair + 1;
-        if (pn == npair) { pn = 0; ++sn; }
-        const bool reload = next && sn != s;
-#pragma unroll
-        for (int k = 0; k < 2; ++k) { wait_ready(k, 2); tr(it, 40 + 2 * k); issue_B(k); tr(it, 41 + 2 * k); }
-        wait_ready(0, 3);  // T2 / T3 of slot 0 written; its TMEM columns 128..255 drained
-        tr(it, 44);
-        issue_C(0);
-        tr(it, 45);
-        // slot 0's next phase A goes in front of slot 1's phase C only if its windows have already landed
-        bool a0 = false;
-        if (next && !reload && __all_sync(0xffffffffu, mbar_try(bars + BAR_XFULL, xph[0]))) {
-          issue_A(0, true);
-          tr(it, 48);
-          a0 = true;
-        }
-        wait_ready(1, 3);
-        tr(it, 46);
-        issue_C(1);
-        tr(it, 47);
-        if (next) {
-          if (reload) {  // next MC sample: wait for the loader's copy of the new weight image
-            ok = mbar_wait_warp(bars + BAR_W, wph, a.status, 1, abort_flag) && ok;
-            wph ^= 1;
+      if (warp < 18) {
+        // phase B: module-2 1x1 convs: [b1 | b2a | b3a] (N = 144) on M1, b4 (N = 32) on pooled M1
+        const uint64_t dWB1 = umma_desc(sbase + OFF_W + WI_B1, 2304, 128);
+        const uint64_t dWB4 = umma_desc(sbase + OFF_W + WI_B4, 512, 128);
+        const uint64_t dM1 = umma_desc(rb + R_M1 + ROW0 * 16, CS, 128), dM1P = umma_desc(rb + R_M1P + ROW0 * 16, CS, 128);
+        uint32_t rph = 0u, fph = 0u;
+        auto load_w = [&](int s) {
+          if (elect_one()) {
+            const unsigned char* src = a.blob + (long long)s * a.blob_stride;
+            mbar_expect_tx(bars + BAR_W, CONV_IMG);
+            for (int o = 0; o < CONV_IMG; o += 16384) bulk_g2s(sbase + OFF_W + o, src + o, min(16384, CONV_IMG - o), bars + BAR_W);
           }
-          if (!a0) { issue_A(0, false); tr(it, 48); }
-          issue_A(1, false);
-          tr(it, 49);
+          __syncwarp();
+        };
+        auto load_x = [&](int pair) {  // one bulk copy: X0 X1 X2 XP0 XP1 XP2 incl. their pad rows
+          if (elect_one()) {
+            const unsigned char* src = a.ximg + (long long)(pair * 2 + k) * XIMG_TILE_BYTES;
+            mbar_expect_tx(bars + BAR_XFULL + 8 * k, XIMG_TILE_BYTES);
+            bulk_g2s(rb + R_X, src, XIMG_TILE_BYTES, bars + BAR_XFULL + 8 * k);
+          }
+          __syncwarp();
+        };
+        int s = (int)(beg / npair), pair = (int)(beg % npair);
+        load_x(pair);
+        if (k == 0) load_w(s);
+        for (long long it = beg; it < end && ok; ++it) {
+          ok = mbar_wait_warp(bars + BAR_READY_A + 8 * k, rph, a.status, 2, abort_flag) && ok;
+          tc_fence_after();
+          tr(it, 40 + 2 * k);
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              umma(tm, dM1 + (uint64_t)((2 * ks * CS) >> 4), dWB1 + (uint64_t)((2 * ks * 2304) >> 4), umma_idesc(144), ks != 0);
+            umma_commit(bars + BAR_DONE_B + 8 * k);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              umma(tm + 144, dM1P + (uint64_t)((2 * ks * CS) >> 4), dWB4 + (uint64_t)((2 * ks * 512) >> 4), umma_idesc(32), ks != 0);
+            umma_commit(bars + BAR_DONE_B2 + 8 * k);
+          }
+          __syncwarp();
+          tr(it, 41 + 2 * k);
+          if (it + 1 < end) {
+            const bool reload = pair + 1 == npair;
+            if (reload) { pair = 0; ++s; } else ++pair;
+            // the next tile's window images land in the M1P space as soon as the phase-B MMAs have read it
+            ok = mbar_wait_warp(bars + BAR_DONE_B2 + 8 * k, rph, a.status, 9, abort_flag) && ok;
+            load_x(pair);
+            tr(it, 50 + k);
+            if (reload && k == 0) {  // next MC sample: every warp has finished the old weights (MMAs complete, biases read)
+              ok = mbar_wait_warp(bars + BAR_WFREE, fph, a.status, 4, abort_flag) && ok;
+              fph ^= 1;
+              load_w(s);
+            }
+          }
+          rph ^= 1;
         }
-        s = sn;
-        pair = pn;
+      } else {
+        const uint64_t dWC2 = umma_desc(sbase + OFF_W + WI_B2B, 48 * 16, 128);
+        const uint64_t dWC3 = umma_desc(sbase + OFF_W + WI_B3B, 80 * 16, 128);
+        const uint64_t dT2 = umma_desc(rb + R_T2 + ROW0 * 16, CS, 128), dT3 = umma_desc(rb + R_T3 + ROW0 * 16, CS, 128);
+        uint32_t xph = 0u, wph = 0u, rph = 0u;
+        // phase A: module 1.  TMEM cols (slot base + 128 +): conv5 0..31 | conv3 32..63 | conv1 64..95 | convpool 96..127
+        auto issue_A = [&]() {
+          ok = mbar_wait_warp(bars + BAR_XFULL + 8 * k, xph, a.status, 5, abort_flag) && ok;
+          xph ^= 1;
+          tc_fence_after();
+          if (elect_one()) {
+            // k-step 0 = chunks 0,1; k-step 1 = chunk 2 + the shared zero chunk (leading-dimension offset reaches it)
+            const uint32_t zx = (uint32_t)(OFF_ZERO - (k * G_BYTES + R_X + 2 * CS)), zxp = (uint32_t)(OFF_ZERO - (k * G_BYTES + R_XP + 2 * CS));
+            constexpr int shs[5] = {0, -1, 1, -2, 2}, nsh[5] = {96, 64, 64, 32, 32}, osh[5] = {0, 6144, 10240, 14336, 16384};
+#pragma unroll
+            for (int q = 0; q < 5; ++q)
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks)
+                umma(tm + 128, umma_desc(rb + R_X + 2 * ks * CS + (ROW0 + shs[q]) * 16, ks ? zx : CS, 128),
+                     umma_desc(sbase + OFF_W + WI_A + osh[q] + 2 * ks * nsh[q] * 16, nsh[q] * 16, 128), umma_idesc(nsh[q]), (q | ks) != 0);
+            umma_commit(bars + BAR_DONE_A + 8 * k);
+#pragma unroll
+            for (int tp = 0; tp < 3; ++tp)
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks)
+                umma(tm + 224, umma_desc(rb + R_XP + 2 * ks * CS + (ROW0 + tp - 1) * 16, ks ? zxp : CS, 128),
+                     umma_desc(sbase + OFF_W + WI_A + 18432 + tp * 2048 + 2 * ks * 512, 512, 128), umma_idesc(32), (tp | ks) != 0);
+            umma_commit(bars + BAR_DONE_A2 + 8 * k);
+          }
+          __syncwarp();
+        };
+        int pair = (int)(beg % npair);
+        ok = mbar_wait_warp(bars + BAR_W, wph, a.status, 1, abort_flag) && ok;
+        wph ^= 1;
+        issue_A();
+        for (long long it = beg; it < end && ok; ++it) {
+          // phase C: b2b (k3 over T2) / b3b (k5 over T3): taps concatenated along N, shifts applied in the epilogue
+          ok = mbar_wait_warp(bars + BAR_READY_B + 8 * k, rph, a.status, 3, abort_flag) && ok;  // T2 / T3 written, cols 128.. drained
+          rph ^= 1;
+          tc_fence_after();
+          tr(it, 44 + 2 * k);
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma(tm, dT2 + (uint64_t)((2 * ks * CS) >> 4), dWC2 + (uint64_t)((2 * ks * 48 * 16) >> 4), umma_idesc(48), ks != 0);
+            umma_commit(bars + BAR_DONE_C + 8 * k);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma(tm + 48, dT3 + (uint64_t)((2 * ks * CS) >> 4), dWC3 + (uint64_t)((2 * ks * 80 * 16) >> 4), umma_idesc(80), ks != 0);
+            umma_commit(bars + BAR_DONE_C2 + 8 * k);
+          }
+          __syncwarp();
+          tr(it, 45 + 2 * k);
+          if (it + 1 < end) {  // phase A of the slot's next tile
+            if (++pair == npair) {  // next MC sample: wait for the copy of the new weight image
+              pair = 0;
+              ok = mbar_wait_warp(bars + BAR_W, wph, a.status, 1, abort_flag) && ok;
+              wph ^= 1;
+            }
+            issue_A();
+            tr(it, 48 + k);
+          }
+        }
       }
     }
   } else {
@@ -351,26 +332,31 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) tc_conv_kernel(const ConvArgs
     const int brA = q == 0 ? 2 : q == 1 ? 1 : q == 2 ? 0 : 3;  // TMEM column block q of phase A -> M1 channel group
     uint32_t ph = 0;
     bool ok = true;
-    auto arrive_ready = [&](int k) {
+    long long tr_it = beg;
+    int tr_phase = 0;
+    auto arrive_ready = [&](int bar, int k) {
       fence_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bars + BAR_READY + 8 * k);
+      if (lane == 0) mbar_arrive(bars + bar + 8 * k);
+      if (a.trace && blockIdx.x == 0 && lane == 0 && tr_it - beg < 16 && k == 0) a.trace[(tr_it - beg) * 128 + 64 + tr_phase * 16 + warp] = clock64();
     };
-    const int trw = warp == 0 ? 0 : warp == 15 ? 18 : -1;
+    const int trw = warp == BRL_TRW0 ? 0 : warp == BRL_TRW1 ? 18 : -1;
     auto tr = [&](long long it, int slot) {
-      if (a.trace && blockIdx.x == 0 && trw >= 0 && lane == 0 && it - beg < 16) a.trace[(it - beg) * 64 + trw + slot] = clock64();
+      if (a.trace && blockIdx.x == 0 && trw >= 0 && lane == 0 && it - beg < 16) a.trace[(it - beg) * 128 + trw + slot] = clock64();
     };
     int s = (int)(beg / npair), pair = (int)(beg % npair);
     for (long long it = beg; it < end; ++it) {
       // ---- phase A epilogue: ReLU (+dropout) -> M1, MaxPool1d(3,1,1) -> M1P
+      tr_it = it;
+      tr_phase = 0;
 #pragma unroll 1
       for (int k = 0; k < 2; ++k) {
         const int tile = pair * 2 + k, gw = tile * 4 + wq;
         const bool live = t < 30 && gw < a.B && tile < a.ntile4;
         unsigned char* reg = smem + k * G_BYTES;
         tr(it, 0 + 3 * k);
-        ok = mbar_wait(bars + BAR_DONE_A + 8 * k, ph, a.status, 6, abort_flag) && ok;
+        ok = mbar_wait(bars + (q < 3 ? BAR_DONE_A : BAR_DONE_A2) + 8 * k, ph, a.status, 6, abort_flag) && ok;
         tc_fence_after();
         tr(it, 1 + 3 * k);
         float acc[2][16];
@@ -387,11 +373,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) tc_conv_kernel(const ConvArgs
           *reinterpret_cast<uint4*>(dst + R_M1P) = pool3x4(lo, lane);  // R_M1P - R_M1 == 16 chunks
           *reinterpret_cast<uint4*>(dst + R_M1P + CS) = pool3x4(hi, lane);
         }
-        arrive_ready(k);
+        arrive_ready(BAR_READY_A, k);
         tr(it, 2 + 3 * k);
       }
       // ---- phase B epilogue: 11 groups of 16 columns: g0 = b1 -> feat ch 0..15 | g1..4 = b2a -> T2 | g5..8 = b3a -> T3 |
       //      g9,10 = b4 -> feat ch 48..79.  Quarter q takes T groups 1+2q, 2+2q and feat group {0, 9, 10, -}[q].
+      tr_phase = 1;
 #pragma unroll 1
       for (int k = 0; k < 2; ++k) {
         const int tile = pair * 2 + k, gw = tile * 4 + wq;
@@ -405,10 +392,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) tc_conv_kernel(const ConvArgs
         tr(it, 7 + 3 * k);
         const uint32_t la = lane_base + k * 256;
         float acc[3][16];
-        const int gf = q == 0 ? 0 : q == 1 ? 9 : 10;
         tmem_ld16(la + (1 + 2 * q) * 16, acc[0]);
         tmem_ld16(la + (2 + 2 * q) * 16, acc[1]);
-        if (q < 3) tmem_ld16(la + gf * 16, acc[2]);
+        if (q == 0) tmem_ld16(la, acc[2]);
         tmem_ld_wait();
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -416,12 +402,18 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) tc_conv_kernel(const ConvArgs
           *reinterpret_cast<uint4*>(dst) = relu_pack8(acc[h], live);
           *reinterpret_cast<uint4*>(dst + CS) = relu_pack8(acc[h] + 8, live);
         }
-        arrive_ready(k);  // every TMEM column this thread needs is in registers: phase C may start now
+        if (q == 1 || q == 2) {  // b4 columns come from the second accumulation chain of the phase
+          ok = mbar_wait(bars + BAR_DONE_B2 + 8 * k, ph, a.status, 7, abort_flag) && ok;
+          tc_fence_after();
+          tmem_ld16(la + (q == 1 ? 9 : 10) * 16, acc[2]);
+          tmem_ld_wait();
+        }
+        arrive_ready(BAR_READY_B, k);  // every TMEM column this thread needs is in registers: phase C may start now
         if (q < 3) {
           uint4 lo, hi;
           finish16<DROP>(acc[2], live, a, q == 0 ? 4 : 9, s, gw, t, q == 2 ? 16 : 0, q == 0 ? 16 : 32, lo, hi);
           const int fc = q == 0 ? 0 : q == 1 ? 6 : 8;
-          if (live) {
+          if (BRL_FEAT_LIVE(live)) {
             *reinterpret_cast<uint4*>(frow + fc * 2048) = lo;
             *reinterpret_cast<uint4*>(frow + (fc + 1) * 2048) = hi;
           }
@@ -436,7 +428,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) tc_conv_kernel(const ConvArgs
         unsigned char* frow = a.feat + ((long long)s * a.ntile128 + (gw >> 7)) * FEAT_TILE_BYTES + (long long)(gw & 127) * 16 +
                               (long long)t * 10 * 2048;
         tr(it, 12 + 3 * k);
-        ok = mbar_wait(bars + BAR_DONE_C + 8 * k, ph, a.status, 8, abort_flag) && ok;
+        ok = mbar_wait(bars + (q < 2 ? BAR_DONE_C : BAR_DONE_C2) + 8 * k, ph, a.status, 8, abort_flag) && ok;
         tc_fence_after();
         tr(it, 13 + 3 * k);
         const uint32_t la = lane_base + k * 256;
@@ -459,7 +451,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) tc_conv_kernel(const ConvArgs
         }
         tc_fence_before();
         actn<DROP, true, 8>(out, sbias + 304 + q * 8, live, a, q < 2 ? 6 : 8, s, gw, t, (q & 1) * 8, 16);
-        if (live) *reinterpret_cast<uint4*>(frow + (2 + q) * 2048) = pack8(out, true);
+        if (BRL_FEAT_LIVE(live)) *reinterpret_cast<uint4*>(frow + (2 + q) * 2048) = pack8(out, true);
         tr(it, 14 + 3 * k);
       }
       if (++pair == npair) {

@@ -110,7 +110,7 @@ int brl_tc_status(const brl_ctx* ctx);
  * kernel milliseconds and the number of launches since the last enable / read; brl_tc_timing(ctx, 0) stops. */
 int brl_tc_timing(brl_ctx* ctx, int enable);
 int brl_tc_timing_read(brl_ctx* ctx, double* kernel_ms, int64_t* launches);
-/* Debug: device buffer (int64[>= 16*64], or NULL to switch off) into which CTA 0 of tc_conv_kernel writes
+/* Debug: device buffer (int64[>= 16*128], or NULL to switch off) into which CTA 0 of tc_conv_kernel writes
  * clock64() time stamps of its issuer / epilogue warps for its first 16 work items. */
 int brl_tc_trace(brl_ctx* ctx, int64_t* device_buf);
 

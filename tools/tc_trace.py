@@ -16,12 +16,12 @@ mu = init_params("inception", 1).to(dev)
 sg = torch.full_like(mu, 1.351e-3)
 for _ in range(2):
     e.predict_moments(x, mu, sg, S=16, guide="normal", noise=Noise(seed=1), engine="tc")
-buf = torch.zeros(16 * 64, dtype=torch.int64, device=dev)
+buf = torch.zeros(16 * 128, dtype=torch.int64, device=dev)
 e.lib.brl_tc_trace(e.ctx, C.c_void_p(buf.data_ptr()))
 e.predict_moments(x, mu, sg, S=16, guide="normal", noise=Noise(seed=1), engine="tc")
 torch.cuda.synchronize()
 e.lib.brl_tc_trace(e.ctx, None)
-t = buf.cpu().view(16, 64)
+t = buf.cpu().view(16, 128)
 t0 = int(t[2, 0])
 names = {}
 for w, base in (("w0", 0), ("w15", 18)):
@@ -41,6 +41,8 @@ for k in range(2):
 for it in range(2, 6):
     ev = sorted((int(t[it, s]) - t0, names[s]) for s in names if int(t[it, s]) != 0)
     print(f"--- item {it}")
+    for ph, nm in ((0, "A0"), (1, "B0")):
+        print(f"   arrive {nm} per warp:", " ".join(str(int(t[it, 64 + ph * 16 + w]) - t0) for w in range(16)))
     prev = None
     for c, n in ev:
         print(f"{c:8d}  {n}")
