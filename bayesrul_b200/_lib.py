@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libbayesrul_b200.so")
+LIB_PATH = os.environ.get("BRL_LIB_PATH") or os.path.join(HERE, "lib", "libbayesrul_b200.so")
 
 BRL_MAX_LAYERS = 16
 
@@ -54,7 +54,7 @@ SIGNATURES = {
     "brl_engine_available": (_i, [_vp, _i]),
     "brl_tc_status": (_i, [_vp]),
     "brl_tc_timing": (_i, [_vp, _i]),
-    "brl_tc_timing_read": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(_i64)]),
+    "brl_tc_timing_read": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(_i64)]),  # double[2], int64[2]
     "brl_tc_trace": (_i, [_vp, _vp]),
     "brl_workspace_bytes": (_i64, [_vp, _i64, _i64, _i, _i]),
     "brl_sample_weights": (_i, [_vp, _vp, _vp, _i, _i64, _np, _vp, _vp, _vp, _sz, _vp]),

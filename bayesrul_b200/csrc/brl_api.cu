@@ -422,9 +422,10 @@ int brl_tc_timing(brl_ctx* ctx, int enable) {
 }
 int brl_tc_timing_read(brl_ctx* ctx, double* kernel_ms, int64_t* launches) {
   BRL_REQUIRE(ctx && kernel_ms && launches && tc_available(ctx->tc), "brl_tc_timing_read: bad argument");
-  long long n = 0;
-  tc_timing_read(ctx->tc, kernel_ms, &n);
-  *launches = n;
+  long long n[2] = {0, 0};
+  tc_timing_read(ctx->tc, kernel_ms, n);
+  launches[0] = n[0];
+  launches[1] = n[1];
   return BRL_OK;
 }
 int brl_tc_trace(brl_ctx* ctx, int64_t* device_buf) {

@@ -21,9 +21,10 @@ __device__ __forceinline__ float gnoise_normal(const NoiseRef& nz, int s, int b,
   if (nz.ptr) return nz.ptr[((long long)s * B + b) * per_window + e];
   return philox_normal(nz.seed, nz.kind, nz.site, nz.sample0 + s, nz.window0 + b, e);
 }
-__device__ __forceinline__ bool gnoise_keep(const NoiseRef& nz, int s, int b, int B, int per_window, int e, float keep) {
-  if (nz.ptr) return nz.ptr[((long long)s * B + b) * per_window + e] != 0.0f;
-  return philox_uniform(nz.seed, nz.kind, nz.site, nz.sample0 + s, nz.window0 + b, e) < keep;
+// dropout site of an op with C channels x P positions: injected masks are [S,B,C,P] (reference layout)
+__device__ __forceinline__ bool gnoise_keep(const NoiseRef& nz, int s, int b, int B, int C, int P, int ch, int pos, float keep) {
+  if (nz.ptr) return nz.ptr[(((long long)s * B + b) * C + ch) * P + pos] != 0.0f;
+  return philox_keep(nz.seed, nz.kind, nz.site, nz.sample0 + s, nz.window0 + b, C, pos, ch, keep);
 }
 
 // one output element of a forward / input-gradient GEMM
@@ -55,7 +56,7 @@ __device__ __forceinline__ void gemm_epilogue(const ConvGemm& p, int s, int m, i
     v = v + a1 * p.sign_out[img * p.N + n] + p.bias1[(long long)s * p.bs1 + n];
   }
   if (p.relu) v = fmaxf(v, 0.f);
-  if (p.keep < 1.0f) v = gnoise_keep(p.drop, s, b, p.B, p.N * p.P, n * p.P + pp, p.keep) ? v / p.keep : 0.f;
+  if (p.keep < 1.0f) v = gnoise_keep(p.drop, s, b, p.B, p.N, p.P, n, pp, p.keep) ? v / p.keep : 0.f;
   if (p.head) {
     v = v > 20.0f ? v : log1pf(expf(v));
     v = v > 1e-9f ? v : 1e-9f;

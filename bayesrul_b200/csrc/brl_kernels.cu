@@ -19,10 +19,6 @@ __device__ __forceinline__ float noise_normal(const NoiseRef& nz, int s, int b, 
   if (nz.ptr) return nz.ptr[((long long)s * B + b) * per_window + e];
   return philox_normal(nz.seed, nz.kind, nz.site, nz.sample0 + s, nz.window0 + b, e);
 }
-__device__ __forceinline__ bool noise_keep(const NoiseRef& nz, int s, int b, int B, int per_window, int e, float keep) {
-  if (nz.ptr) return nz.ptr[((long long)s * B + b) * per_window + e] != 0.0f;
-  return philox_uniform(nz.seed, nz.kind, nz.site, nz.sample0 + s, nz.window0 + b, e) < keep;
-}
 __device__ __forceinline__ float softplusf(float x) { return x > 20.0f ? x : log1pf(expf(x)); }
 
 __device__ __forceinline__ double block_sum(double v) {

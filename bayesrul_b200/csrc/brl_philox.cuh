@@ -3,6 +3,9 @@
 //   key     = (seed lo32, seed hi32)
 //   counter = (element >> 2, global window index, global MC sample index, kind << 24 | layer/site)
 // and element e takes lane (e & 3) of its block.  Normals are Box-Muller on lanes (0,1) and (2,3).
+// Dropout keep-decisions use 16 bits each (8 per block) and a position-major element order
+//   e = position * roundup8(C) + channel,  block = e >> 3,  half (e & 1) of word (e & 7) >> 1,
+// so the 8 / 16 consecutive channels one epilogue thread owns at its position share 1 / 2 Philox blocks.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -69,6 +72,18 @@ __device__ __forceinline__ float philox_uniform(uint64_t seed, uint32_t kind, ui
                                                 uint32_t window, uint32_t elem) {
   const uint4 r = philox_block(seed, kind, site, sample, window, elem >> 2);
   return u01(lane_of(r, elem & 3u));
+}
+
+// 16-bit keep decision: ((h + 0.5) * 2^-16 < keep) on half `odd` of a Philox word
+__device__ __forceinline__ bool keep16(uint32_t word, uint32_t odd, float keep) {
+  const uint32_t h = odd ? (word >> 16) : (word & 0xFFFFu);
+  return ((float)h + 0.5f) * 1.52587890625e-05f < keep;
+}
+__device__ __forceinline__ bool philox_keep(uint64_t seed, uint32_t kind, uint32_t site, uint32_t sample, uint32_t window,
+                                            uint32_t C, uint32_t pos, uint32_t ch, float keep) {
+  const uint32_t e = pos * ((C + 7u) & ~7u) + ch;
+  const uint4 r = philox_block(seed, kind, site, sample, window, e >> 3);
+  return keep16(lane_of(r, (e & 7u) >> 1), e & 1u, keep);
 }
 
 __device__ __forceinline__ float philox_sign(uint64_t seed, uint32_t kind, uint32_t site, uint32_t sample,

@@ -82,8 +82,8 @@ struct TcState {
   int sm_count;
   long long loff[12][2];  // w_off, b_off per layer
   bool timing = false;    // bracket tc_conv_kernel launches with events (bench.py roofline)
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evs;
-  size_t ev_used = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evs[2];  // 0: tc_conv_kernel, 1: tc_fc_kernel
+  size_t ev_used[2] = {0, 0};
   long long* trace = nullptr;
 };
 
@@ -114,9 +114,14 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
 // bounded wait: a protocol bug must end the kernel, not hang the GPU.  After the first time-out (recorded in
 // *status and in the CTA's shared abort word) every later wait returns immediately, so control flow stays uniform.
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* status, int code, volatile int* abort_flag = nullptr) {
+  if (mbar_try(bar, parity)) return true;  // fast path: the phase has usually completed already
   if (abort_flag && *abort_flag) return false;
-  for (uint32_t i = 0; i < SPIN_LIMIT; ++i)
+  for (uint32_t i = 0; i < SPIN_LIMIT; ++i) {
+#ifdef BRL_WAIT_SLEEP_NS
+    __nanosleep(BRL_WAIT_SLEEP_NS);  // a sleeping warp leaves its issue slots to the warps that have work
+#endif
     if (mbar_try(bar, parity)) return true;
+  }
   atomicCAS(status, 0, code);
   if (abort_flag) *abort_flag = 1;
   return false;
@@ -434,7 +439,15 @@ __global__ void __launch_bounds__(192, 1) tc_fc_kernel(const FcArgs a) {
       const int gw = tile * 128 + row;
       float o0 = __ldg(tail + 192), o1 = __ldg(tail + 193);
 #pragma unroll
-      for (int g = 0; g < 4; ++g)
+      for (int g = 0; g < 4; ++g) {
+        uint32_t kw[2][4];
+        if (DROP && !a.drop.ptr) {  // 16 keep decisions of outputs 16g .. 16g+15: two Philox blocks
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint4 r = philox_block(a.drop.seed, a.drop.kind, a.drop.site, a.drop.sample0 + s, a.drop.window0 + gw, 2 * g + h);
+            kw[h][0] = r.x; kw[h][1] = r.y; kw[h][2] = r.z; kw[h][3] = r.w;
+          }
+        }
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int n = g * 16 + j;
@@ -442,14 +455,14 @@ __global__ void __launch_bounds__(192, 1) tc_fc_kernel(const FcArgs a) {
           if (DROP) {
             if (gw < a.B) {
               const bool keep = a.drop.ptr ? a.drop.ptr[((long long)s * a.B + gw) * 64 + n] != 0.f
-                                           : philox_uniform(a.drop.seed, a.drop.kind, a.drop.site, a.drop.sample0 + s,
-                                                            a.drop.window0 + gw, n) < a.keep;
+                                           : keep16(kw[j >> 3][(j & 7) >> 1], j & 1, a.keep);
               h = keep ? h / a.keep : 0.f;
             }
           }
           o0 = fmaf(h, __ldg(tail + 64 + n), o0);
           o1 = fmaf(h, __ldg(tail + 128 + n), o1);
         }
+      }
       if (gw < a.B) {
         o0 = o0 > 20.f ? o0 : log1pf(expf(o0));
         o1 = o1 > 20.f ? o1 : log1pf(expf(o1));
@@ -489,24 +502,40 @@ TcState* tc_create(int net) {
 void tc_destroy(TcState* s) {
   if (!s) return;
   if (s->status) cudaFree(s->status);
-  for (auto& e : s->evs) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+  for (auto& v : s->evs)
+    for (auto& e : v) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   delete s;
 }
 void tc_timing(TcState* s, bool enable) {
   s->timing = enable;
-  s->ev_used = 0;
+  s->ev_used[0] = s->ev_used[1] = 0;
 }
 void tc_timing_read(TcState* s, double* ms, long long* launches) {
-  double t = 0.0;
-  for (size_t i = 0; i < s->ev_used; ++i) {
-    float e = 0.f;
-    cudaEventSynchronize(s->evs[i].second);
-    cudaEventElapsedTime(&e, s->evs[i].first, s->evs[i].second);
-    t += e;
+  for (int k = 0; k < 2; ++k) {
+    double t = 0.0;
+    for (size_t i = 0; i < s->ev_used[k]; ++i) {
+      float e = 0.f;
+      cudaEventSynchronize(s->evs[k][i].second);
+      cudaEventElapsedTime(&e, s->evs[k][i].first, s->evs[k][i].second);
+      t += e;
+    }
+    ms[k] = t;
+    launches[k] = (long long)s->ev_used[k];
+    s->ev_used[k] = 0;
   }
-  *ms = t;
-  *launches = (long long)s->ev_used;
-  s->ev_used = 0;
+}
+static void tc_time_begin(TcState* st, int k, cudaStream_t stream) {
+  if (!st->timing) return;
+  if (st->ev_used[k] == st->evs[k].size()) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    st->evs[k].emplace_back(e0, e1);
+  }
+  cudaEventRecord(st->evs[k][st->ev_used[k]].first, stream);
+}
+static void tc_time_end(TcState* st, int k, cudaStream_t stream) {
+  if (st->timing) cudaEventRecord(st->evs[k][st->ev_used[k]++].second, stream);
 }
 void tc_trace(TcState* s, long long* buf) { s->trace = buf; }
 bool tc_available(const TcState* s) { return s && s->net == BRL_NET_INCEPTION && s->status != nullptr; }
@@ -559,18 +588,10 @@ const char* tc_forward(TcState* st, const float* x, long long B, long long S, co
   ca.trace = st->trace;
   const long long items = S * ((nt4 + 1) / 2);
   const int grid = (int)std::min<long long>(st->sm_count, items);
-  if (st->timing) {
-    if (st->ev_used == st->evs.size()) {
-      cudaEvent_t e0, e1;
-      cudaEventCreate(&e0);
-      cudaEventCreate(&e1);
-      st->evs.emplace_back(e0, e1);
-    }
-    cudaEventRecord(st->evs[st->ev_used].first, stream);
-  }
+  tc_time_begin(st, 0, stream);
   if (drop) tc_conv_kernel<true><<<grid, CONV_THREADS, CONV_SMEM, stream>>>(ca);
   else tc_conv_kernel<false><<<grid, CONV_THREADS, CONV_SMEM, stream>>>(ca);
-  if (st->timing) cudaEventRecord(st->evs[st->ev_used++].second, stream);
+  tc_time_end(st, 0, stream);
   FcArgs fa;
   fa.feat = feat; fa.blob = blob; fa.blob_stride = ca.blob_stride; fa.out = out;
   fa.B = (int)B; fa.S = (int)S; fa.ntile128 = (int)nt128;
@@ -578,8 +599,10 @@ const char* tc_forward(TcState* st, const float* x, long long B, long long S, co
   fa.drop = nr(10);
   fa.status = st->status;
   const int gridf = (int)std::min<long long>(st->sm_count, S * nt128);
+  tc_time_begin(st, 1, stream);
   if (drop) tc_fc_kernel<true><<<gridf, 192, FC_SMEM, stream>>>(fa);
   else tc_fc_kernel<false><<<gridf, 192, FC_SMEM, stream>>>(fa);
+  tc_time_end(st, 1, stream);
   count_launch(3);
   return nullptr;
 }

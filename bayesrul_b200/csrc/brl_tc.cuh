@@ -12,7 +12,7 @@ void tc_destroy(TcState*);
 bool tc_available(const TcState*);
 int tc_status(const TcState*);  // 0 ok; else the code of the first mbarrier wait that timed out (synchronises)
 void tc_timing(TcState*, bool enable);
-void tc_timing_read(TcState*, double* ms, long long* launches);  // synchronises the recorded events
+void tc_timing_read(TcState*, double ms[2], long long launches[2]);  // [conv, fc]; synchronises the recorded events
 void tc_trace(TcState*, long long* device_buf);
 size_t tc_workspace_bytes(const TcState*, long long B, long long S);
 // returns nullptr on success, else a static error string.  pack_x = false re-uses the fp16 window images a previous

@@ -75,23 +75,34 @@ __global__ void tc_packx_kernel(const float* __restrict__ x, unsigned char* __re
   }
 }
 
-// ReLU (+bias) (+dropout) on N fp32 accumulator columns
+// ReLU (+bias) (+dropout) on N (8 or 16) fp32 accumulator columns = channels ch0.. of a site with `nvalid` channels,
+// at time step t.  Native masks: one Philox block per 8 channels (16-bit decisions, position-major order).
 template <bool DROP, bool BIAS, int N>
 __device__ __forceinline__ void actn(float (&v)[N], const float* bias, bool live, const ConvArgs& a, int layer, int s, int gw,
                                      int t, int ch0, int nvalid) {
 #pragma unroll
-  for (int j = 0; j < N; ++j) {
-    float u = fmaxf(BIAS ? v[j] + bias[j] : v[j], 0.f);
-    if (DROP) {
-      if (ch0 + j < nvalid && live) {
-        const NoiseRef& nz = a.drop[layer];
-        const int e = (ch0 + j) * 30 + t;
-        const bool keep = nz.ptr ? nz.ptr[((long long)s * a.B + gw) * (nvalid * 30) + e] != 0.f
-                                 : philox_uniform(nz.seed, nz.kind, nz.site, nz.sample0 + s, nz.window0 + gw, e) < a.keep4;
-        u = keep ? u / a.keep4 : 0.f;
+  for (int j = 0; j < N; ++j) v[j] = fmaxf(BIAS ? v[j] + bias[j] : v[j], 0.f);
+  if (DROP) {
+    if (live) {
+      const NoiseRef& nz = a.drop[layer];
+      const float inv = 1.0f / a.keep4;
+      if (nz.ptr) {
+        const float* m = nz.ptr + ((long long)s * a.B + gw) * (nvalid * 30) + t;
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+          if (ch0 + j < nvalid) v[j] = m[(ch0 + j) * 30] != 0.f ? v[j] * inv : 0.f;
+      } else {
+        const uint32_t e0 = (uint32_t)t * (uint32_t)((nvalid + 7) & ~7) + (uint32_t)ch0;  // multiple of 8
+#pragma unroll
+        for (int g = 0; g < N / 8; ++g) {
+          const uint4 r = philox_block(nz.seed, nz.kind, nz.site, nz.sample0 + s, nz.window0 + gw, (e0 >> 3) + g);
+          const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (ch0 + 8 * g + j < nvalid) v[8 * g + j] = keep16(w[j >> 1], j & 1, a.keep4) ? v[8 * g + j] * inv : 0.f;
+        }
       }
     }
-    v[j] = u;
   }
 }
 __device__ __forceinline__ uint4 pack8(const float* v, bool live) {

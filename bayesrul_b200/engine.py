@@ -112,6 +112,16 @@ class Engine:
     def has_tc(self) -> bool:
         """True when the tcgen05 (fp16 operand / fp32 accumulate) engine supports this net."""
         return bool(self.lib.brl_engine_available(self.ctx, ENGINE_IDS["tc"]))
+    def tc_timing(self, enable: bool) -> None:
+        """Bracket every tc_conv_kernel launch with CUDA events on the launching stream (bench.py roofline)."""
+        _lib.check(self.lib.brl_tc_timing(self.ctx, int(enable)))
+
+    def tc_timing_read(self):
+        """{kernel: (summed milliseconds, launches)} since the last enable / read; synchronises the recorded events."""
+        ms, n = (C.c_double * 2)(), (C.c_int64 * 2)()
+        _lib.check(self.lib.brl_tc_timing_read(self.ctx, ms, n))
+        return {"tc_conv_kernel": (ms[0], n[0]), "tc_fc_kernel": (ms[1], n[1])}
+
     def tc_status(self) -> int:
         """0 = ok; >0 = an mbarrier wait inside a tcgen05 kernel timed out (synchronises)."""
         return int(self.lib.brl_tc_status(self.ctx))

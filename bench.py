@@ -32,6 +32,8 @@ B_TRAIN = 256
 N_DATASET = 238150
 CFG = dict(q_scale=1.351e-3, prior_scale=0.138793, prior_loc=0.0)
 F_FWD = 2_289_376  # GEMM FLOPs / window / weight sample
+F_FC = 2 * (2400 * 64 + 64 * 2)  # of which the fc + head layers (tc_fc_kernel); the rest is the conv stack (tc_conv_kernel)
+F_CONV = F_FWD - F_FC
 F_TRAIN_LRT = 13_036_416
 METRIC = "mc_predictive_window_samples_per_s"
 UNIT = "window*samples/s"
@@ -147,6 +149,29 @@ def cpu_predict_rate(n_windows, n_samples, threads):
     return n_windows * run_small / dt, dt
 
 
+def cpu_train_rate(mode, particles, q, prior_scale, threads, steps=3):
+    """Oracle port of one ELBO step (forward + autograd backward) on the host cores, B = 256."""
+    from oracle import bnn_oracle as O
+
+    torch.set_num_threads(threads)
+    x, y = synth(B_TRAIN, seed=777)
+    mu = O.init_params(NET, 12345)
+    sg = torch.full_like(mu, q)
+    g = torch.Generator().manual_seed(3)
+    kw = dict(mode=mode, guide="normal", prior_loc=0.0, prior_scale=prior_scale, dataset_size=N_DATASET)
+
+    def step():
+        nz = [O.InjectedNoise(O.make_injected_noise(NET, B_TRAIN, mode, g)) for _ in range(particles)]
+        return O.elbo_loss_and_grads(NET, x, y, mu, sg, noises=nz, **kw)
+
+    step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return B_TRAIN / dt, dt
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path = the plain-PyTorch restatement
     (oracle port; pyro/tyxe are not installable) on all host threads; bounded sample per step."""
@@ -227,16 +252,50 @@ def main():
 
     sampler = ClockSampler(local)
     l0 = lib.brl_launch_count()
-    t_local = timed_steps(pred_step, args.steps, args.warmup, flush_buf, dist)
+    for _ in range(args.warmup):
+        pred_step()
+    if engine == "tc":
+        eng.tc_timing(True)  # CUDA events around every tc_conv_kernel launch, on the launching stream
+    t_local = timed_steps(pred_step, args.steps, 0, flush_buf, dist)
+    conv_ms, conv_launches, fc_ms, fc_launches = 0.0, 0, 0.0, 0
+    if engine == "tc":
+        kt = eng.tc_timing_read()
+        (conv_ms, conv_launches), (fc_ms, fc_launches) = kt["tc_conv_kernel"], kt["tc_fc_kernel"]
+        eng.tc_timing(False)
     launches = lib.brl_launch_count() - l0
     clocks = sampler.stop()
-    launches_timed = launches * args.steps // (args.steps + args.warmup)
+    launches_timed = launches * args.steps // (args.steps + args.warmup)  # warm-up steps launch the same kernels
     t = max_over_ranks(t_local, dist, device)
     units_per_step = B_PRED * S_PRED
     value = world * units_per_step * args.steps / t
     pk = peaks()
     flops_step = units_per_step * F_FWD
-    achieved_tf = flops_step * args.steps / t_local / 1e12
+    step_tf = flops_step * args.steps / t_local / 1e12
+    traffic = None
+    kernels = []
+    tpath = os.path.join(ROOT, "profiles", "conv_traffic.json")
+    if engine == "tc" and conv_launches > 0:
+        # dominant kernel: algorithmic conv-stack FLOPs of the timed steps / summed tc_conv_kernel time (CUDA events)
+        achieved_tf = units_per_step * args.steps * F_CONV / (conv_ms * 1e-3) / 1e12
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            # ncu dram bytes of one 16-sample launch, scaled to the average launch of this run
+            traffic = tj["dram_bytes_per_window_sample"] * units_per_step * args.steps / conv_launches
+        roof_note = (f"tc_conv_kernel: {F_CONV} algorithmic GEMM FLOPs per window-sample x "
+                     f"{units_per_step * args.steps // conv_launches} window-samples per launch (average of {conv_launches} launches) / "
+                     f"{conv_ms / conv_launches:.3f} ms per launch (CUDA events on the launch stream inside the timed region); "
+                     f"kernel share of the step {conv_ms / (t_local * 1e3):.2f}; whole step incl. fc/pack/sampler/moments = {step_tf:.1f} TFLOP/s; "
+                     f"peak = sustained bf16 cuBLAS of {pk['src']} MEASURED_PEAKS.json; traffic = ncu dram read+write per launch "
+                     f"(profiles/conv_traffic.json)")
+        # second kernel: [128 windows x 2400] x [2400 x 64] + head; bound by the read of the fp16 feature tensor
+        fc_bytes = units_per_step * args.steps * 4800.0
+        kernels.append({"kernel": "tc_fc_kernel", "bound": "hbm", "achieved": fc_bytes / (fc_ms * 1e-3) / 1e9, "peak": pk["hbm"],
+                        "unit": "GB/s", "frac": fc_bytes / (fc_ms * 1e-3) / 1e9 / pk["hbm"], "ms_per_launch": fc_ms / max(fc_launches, 1),
+                        "share_of_step": fc_ms / (t_local * 1e3), "algorithmic": "4800 B of fp16 features read per window-sample"})
+    else:
+        achieved_tf = step_tf
+        roof_note = (f"fp32 SIMT engine: algorithmic GEMM FLOPs of the whole step ({F_FWD} per window-sample) / step time; "
+                     f"peak = sustained bf16 cuBLAS of {pk['src']} MEASURED_PEAKS.json")
 
     # ---- e2e: BNN.predict_step through the reference-facing class, pinned host inputs, host results
     net = Inception(30, 18)
@@ -275,6 +334,21 @@ def main():
             tt = max_over_ranks(timed_steps(train_step, 20, 5, flush_buf, dist), dist, device)
             train[mode] = {"windows_per_s": world * B_TRAIN * 20 / tt, "ms_per_step": 1e3 * tt / 20, "batch": B_TRAIN,
                            "particles": particles, "includes": "forward + backward + KL + gradient finalisation (no optimiser)"}
+            if world == 1 and not args.no_cpu:
+                v, dt = cpu_train_rate(mode, particles, q, ps, os.cpu_count() or 1)
+                train[mode]["cpu_windows_per_s"] = v
+                train[mode]["cpu_ms_per_step"] = 1e3 * dt
+
+    # ---- MC-dropout predictive (configs[1]: ncmapss_mcd, p = 0.241437, 100 masks), same engine
+    mcd = {}
+    if not args.no_train:
+        def mcd_step(i=0):
+            eng.predict_moments(xs[i % n_rot], mu, None, S=S_PRED, guide=None, p_dropout=0.241437,
+                                noise=Noise(seed=4048, window0=rank * B_PRED), engine=engine)
+
+        tm = max_over_ranks(timed_steps(mcd_step, 3, 2, flush_buf, dist), dist, device)
+        mcd = {"window_samples_per_s": world * units_per_step * 3 / tm, "ms_per_step": 1e3 * tm / 3, "p_dropout": 0.241437,
+               "masks": S_PRED, "noise": "in-kernel Philox masks (fused)"}
 
     if rank != 0:
         if dist is not None:
@@ -293,10 +367,10 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "bayesrul_b200.compat.BNN.predict_step (pinned host batch -> numpy results)"},
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": pk["tf_sust"], "unit": "TFLOP/s",
-                     "frac": achieved_tf / pk["tf_sust"], "traffic": None,
-                     "note": f"algorithmic GEMM FLOPs of the whole step ({F_FWD} per window-sample) / step time on rank 0; "
-                             f"peak = sustained bf16 cuBLAS of {pk['src']} MEASURED_PEAKS.json"},
-        "train": train,
+                     "frac": achieved_tf / pk["tf_sust"], "traffic": traffic, "kernel": "tc_conv_kernel" if engine == "tc" else "step",
+                     "ms_per_launch": conv_ms / max(conv_launches, 1), "share_of_step": conv_ms / (t_local * 1e3) if conv_launches else None,
+                     "note": roof_note, "other_kernels": kernels},
+        "train": train, "mcd_predict": mcd,
     }
     if world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1

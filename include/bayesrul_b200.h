@@ -105,11 +105,12 @@ int64_t brl_workspace_bytes(const brl_ctx* ctx, int64_t B, int64_t S, int train,
  * < 0 = engine unavailable.  Synchronises the device. */
 int brl_tc_status(const brl_ctx* ctx);
 /* Measurement hooks of the tensor-core engine (bench.py roofline; no reference counterpart).
- * brl_tc_timing(ctx, 1) starts bracketing every launch of the dominant kernel (tc_conv_kernel) with CUDA
- * events on the launching stream; brl_tc_timing_read synchronises those events and returns the summed
- * kernel milliseconds and the number of launches since the last enable / read; brl_tc_timing(ctx, 0) stops. */
+ * brl_tc_timing(ctx, 1) starts bracketing every launch of the two tcgen05 kernels with CUDA events on the
+ * launching stream; brl_tc_timing_read synchronises those events and returns, for [0] tc_conv_kernel and
+ * [1] tc_fc_kernel, the summed kernel milliseconds and the number of launches since the last enable / read;
+ * brl_tc_timing(ctx, 0) stops. */
 int brl_tc_timing(brl_ctx* ctx, int enable);
-int brl_tc_timing_read(brl_ctx* ctx, double* kernel_ms, int64_t* launches);
+int brl_tc_timing_read(brl_ctx* ctx, double kernel_ms[2], int64_t launches[2]);
 /* Debug: device buffer (int64[>= 16*128], or NULL to switch off) into which CTA 0 of tc_conv_kernel writes
  * clock64() time stamps of its issuer / epilogue warps for its first 16 work items. */
 int brl_tc_trace(brl_ctx* ctx, int64_t* device_buf);
