@@ -38,6 +38,7 @@ struct OpTables {
 
 struct brl_ctx {
   int net_id = 0, device = 0;
+  int gemm_backend = BRL_GEMM_SIMT_FP32;  // per-layer GEMM back-end of brl_forward (SIMT engine) / brl_elbo_step / brl_hnn_step
   const NetSpec* net = nullptr;
   std::vector<OpTables> tabs;
   long long* site_off_dev = nullptr;
@@ -214,7 +215,8 @@ static void run_forward(const brl_ctx* ctx, const ActBufs& ab, const FwdArgs& a,
     p.keep = (a.p_dropout > 0.f && L.drop_factor > 0.f) ? 1.0f - a.p_dropout * L.drop_factor : 1.0f;
     p.drop = nref(a.noise, a.noise ? a.noise->drop_mask[op.layer] : nullptr, KIND_DROPOUT, op.layer);
     p.part = ab.part;
-    launch_conv_gemm(p, epi, st);
+    if (ctx->gemm_backend & 1) launch_conv_gemm_tc(p, epi, st);
+    else launch_conv_gemm(p, epi, st);
   }
 }
 
@@ -269,14 +271,14 @@ static void run_backward(const brl_ctx* ctx, const ActBufs& ab, const BwdArgs& a
     dw.a = fwd_gather(ctx, op, oi, ab, a.x);
     dw.G = ab.dpre; dw.gw = a.g0 + L.w_off; dw.gb = a.g0 + L.b_off;
     dw.gb2 = a.mode == BRL_MODE_FLIPOUT ? a.g1 + L.b_off : nullptr;
-    launch_conv_dw(dw, st);
+    ((ctx->gemm_backend & 4) ? launch_conv_dw_tc(dw, st) : launch_conv_dw(dw, st));
     if (a.mode == BRL_MODE_LRT) {
       dw.G = ab.dsec; dw.trA = TRA_SQUARE; dw.gw = a.g1 + L.w_off; dw.gb = a.g1 + L.b_off; dw.gb2 = nullptr;
-      launch_conv_dw(dw, st);
+      ((ctx->gemm_backend & 4) ? launch_conv_dw_tc(dw, st) : launch_conv_dw(dw, st));
     } else if (a.mode == BRL_MODE_FLIPOUT) {
       dw.G = ab.dsec; dw.trA = TRA_SIGN; dw.sign_in = a.sgn_in[op.layer]; dw.sign_C = L.cin;
       dw.gw = a.g1 + L.w_off; dw.gb = nullptr; dw.gb2 = nullptr;
-      launch_conv_dw(dw, st);
+      ((ctx->gemm_backend & 4) ? launch_conv_dw_tc(dw, st) : launch_conv_dw(dw, st));
     }
 
     // input gradient
@@ -298,7 +300,8 @@ static void run_backward(const brl_ctx* ctx, const ActBufs& ab, const BwdArgs& a
       epi = EPI_DX_FLIPOUT; p.W1 = a.wsamp + L.w_off; p.trB = TRB_MINUS_W0; p.sign_in = a.sgn_in[op.layer]; p.sign_C = L.cin;
     }
     p.part = ab.part;
-    launch_conv_gemm(p, epi, st);
+    if (ctx->gemm_backend & 2) launch_conv_gemm_tc(p, epi, st);
+    else launch_conv_gemm(p, epi, st);
   }
 }
 
@@ -414,7 +417,19 @@ int brl_destroy(brl_ctx* ctx) {
   return BRL_OK;
 }
 
-int brl_tc_status(const brl_ctx* ctx) { return ctx ? tc_status(ctx->tc) : -1; }
+int brl_tc_status(const brl_ctx* ctx) {
+  if (!ctx) return -1;
+  const int g = tc_gemm_status();  // TF32 per-layer kernels
+  if (g != 0) return g;
+  return tc_status(ctx->tc);
+}
+int brl_gemm_status(void) { return tc_gemm_status(); }
+int brl_set_gemm_backend(brl_ctx* ctx, int backend) {
+  BRL_REQUIRE(ctx, "brl_set_gemm_backend: NULL context");
+  BRL_REQUIRE(backend >= 0 && backend <= BRL_GEMM_TC_TF32, "brl_set_gemm_backend: unknown back-end");
+  ctx->gemm_backend = backend;
+  return BRL_OK;
+}
 int brl_tc_timing(brl_ctx* ctx, int enable) {
   BRL_REQUIRE(ctx && tc_available(ctx->tc), "brl_tc_timing: tensor-core engine unavailable");
   tc_timing(ctx->tc, enable != 0);

@@ -68,6 +68,9 @@ struct ConvGemm {
 constexpr long long SPLITK_SCRATCH_FLOATS = 2ll * 74 * 128 * 32;
 
 void launch_conv_gemm(const ConvGemm& p, int epi, cudaStream_t st);
+// same operator on the tensor pipe: tcgen05 kind::tf32 dual GEMM, fp32 accumulation in TMEM (brl_tc_gemm.cu)
+void launch_conv_gemm_tc(const ConvGemm& p, int epi, cudaStream_t st);
+int tc_gemm_status();  // 0 ok, else code of the first mbarrier wait that timed out in a TF32 kernel (synchronises)
 
 // weight-gradient GEMM: C[co][k] (+)= sum_m G[m][co] * tr(A[m][k]);  k == K is the bias column (A = 1)
 struct ConvDw {
@@ -82,6 +85,7 @@ struct ConvDw {
   float* gb2;      // second bias destination (flipout), nullable
 };
 void launch_conv_dw(const ConvDw& p, cudaStream_t st);
+void launch_conv_dw_tc(const ConvDw& p, cudaStream_t st);
 
 struct PoolParams {
   const float* in;

@@ -112,6 +112,15 @@ class Engine:
     def has_tc(self) -> bool:
         """True when the tcgen05 (fp16 operand / fp32 accumulate) engine supports this net."""
         return bool(self.lib.brl_engine_available(self.ctx, ENGINE_IDS["tc"]))
+    def set_gemm_backend(self, backend: str) -> None:
+        """'simt' (fp32 FFMA, parity back-end) or 'tc' (tcgen05 TF32 dual GEMMs) for the per-layer kernels of
+        forward(engine='simt') / elbo_step / hnn_step."""
+        _lib.check(self.lib.brl_set_gemm_backend(self.ctx, {"simt": 0, "tc": 7}.get(backend, backend)))
+
+    def gemm_status(self) -> int:
+        """0 = ok; else the code of the first mbarrier time-out inside a TF32 per-layer kernel (synchronises)."""
+        return int(self.lib.brl_gemm_status())
+
     def tc_timing(self, enable: bool) -> None:
         """Bracket every tc_conv_kernel launch with CUDA events on the launching stream (bench.py roofline)."""
         _lib.check(self.lib.brl_tc_timing(self.ctx, int(enable)))

@@ -53,6 +53,11 @@ extern "C" {
 #define BRL_ENGINE_SIMT_FP32 0 /* fp32 FFMA implicit-GEMM kernels: the parity engine (rtol 1e-3 vs oracle) */
 #define BRL_ENGINE_TC_FP16 1   /* tcgen05 / TMEM kernels, fp16 operands (10-bit mantissa) + fp32 accumulate */
 
+/* contraction back-ends of the per-layer kernels (every net, every mode, forward + backward) */
+#define BRL_GEMM_SIMT_FP32 0 /* fp32 FFMA implicit GEMMs: the parity back-end (rtol 1e-3 vs oracle) */
+#define BRL_GEMM_TC_TF32 7   /* tcgen05 kind::tf32 dual GEMMs, fp32 accumulation in TMEM (stated bound 5e-3 vs fp32);
+                              * bit mask: 1 forward, 2 input-gradient, 4 weight-gradient kernels (partial masks: debugging) */
+
 #define BRL_MAX_LAYERS 16
 
 typedef struct brl_ctx brl_ctx;
@@ -104,6 +109,11 @@ int64_t brl_workspace_bytes(const brl_ctx* ctx, int64_t B, int64_t S, int train,
  * tcgen05 kernel (waits are bounded so a protocol bug ends the kernel instead of hanging the GPU),
  * < 0 = engine unavailable.  Synchronises the device. */
 int brl_tc_status(const brl_ctx* ctx);
+/* Selects how the per-layer kernels of brl_forward (BRL_ENGINE_SIMT_FP32), brl_elbo_step and brl_hnn_step contract:
+ * fp32 FFMA (default) or tcgen05 TF32.  Operators, noise, epilogues and results' layout are identical. */
+int brl_set_gemm_backend(brl_ctx* ctx, int backend);
+/* health of the TF32 per-layer kernels: 0 = ok, > 0 = code of the first bounded mbarrier wait that timed out. Synchronises. */
+int brl_gemm_status(void);
 /* Measurement hooks of the tensor-core engine (bench.py roofline; no reference counterpart).
  * brl_tc_timing(ctx, 1) starts bracketing every launch of the two tcgen05 kernels with CUDA events on the
  * launching stream; brl_tc_timing_read synchronises those events and returns, for [0] tc_conv_kernel and
