@@ -1,6 +1,7 @@
 // C ABI (include/bayesrul_b200.h) + host-side tape executor of the fp32 SIMT engine.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -45,6 +46,14 @@ struct brl_ctx {
   int max_site = 0;
   int* table_pool = nullptr;
   TcState* tc = nullptr;
+  // The per-layer kernels of a 256-window training batch fill a fraction of the GPU each, so independent ops run
+  // concurrently: ops of one dependency level of the forward tape go to different streams, and the weight-gradient
+  // kernels of the backward pass leave the critical dX chain for side streams (fork / join with events; capturable).
+  std::vector<int> op_level;
+  int n_levels = 0;
+  bool multi_stream = true;
+  cudaStream_t side[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr}, ev_op[8] = {};
 };
 
 // bump allocator over the caller's workspace (256-byte aligned); base == nullptr only measures
@@ -65,7 +74,8 @@ struct Carve {
 
 struct ActBufs {
   std::vector<float*> act, grad, sd;  // per buffer / per buffer / per op
-  float *dpre = nullptr, *dsec = nullptr, *part = nullptr;
+  std::vector<float*> dpre, dsec;  // per op: gradient w.r.t. the pre-activation / the variance or perturbation path
+  float* part[4] = {nullptr, nullptr, nullptr, nullptr};  // split-K scratch, one per concurrent stream
   float *g0 = nullptr, *g1 = nullptr, *wsamp = nullptr, *delta = nullptr, *norms = nullptr;
   std::vector<float*> sgn_in, sgn_out;  // per layer
   double* acc = nullptr;
@@ -79,15 +89,15 @@ static void carve_train(const NetSpec& n, Carve& c, long long B, ActBufs& ab) {
   ab.grad.resize(n.bufs.size());
   for (size_t i = 0; i < n.bufs.size(); ++i) ab.grad[i] = n.bufs[i].shared ? nullptr : c.take<float>(B * n.bufs[i].elems());
   ab.sd.assign(n.ops.size(), nullptr);
-  long long mx = 0;
+  ab.dpre.assign(n.ops.size(), nullptr);
+  ab.dsec.assign(n.ops.size(), nullptr);
   for (size_t i = 0; i < n.ops.size(); ++i)
     if (n.ops[i].kind == OP_CONV) {
       const long long e = n.layers[n.ops[i].layer].out_elems;
       ab.sd[i] = c.take<float>(B * e);
-      mx = std::max(mx, e);
+      ab.dpre[i] = c.take<float>(B * e);  // per op, so the weight-gradient kernels can run behind the dX chain
+      ab.dsec[i] = c.take<float>(B * e);
     }
-  ab.dpre = c.take<float>(B * mx);
-  ab.dsec = c.take<float>(B * mx);
   ab.g0 = c.take<float>(n.P);
   ab.g1 = c.take<float>(n.P);
   ab.wsamp = c.take<float>(n.P);
@@ -100,7 +110,7 @@ static void carve_train(const NetSpec& n, Carve& c, long long B, ActBufs& ab) {
     ab.sgn_out[l] = c.take<float>(B * n.layers[l].cout);
   }
   ab.acc = c.take<double>(8);
-  ab.part = c.take<float>(SPLITK_SCRATCH_FLOATS);
+  for (int i = 0; i < 4; ++i) ab.part[i] = c.take<float>(SPLITK_SCRATCH_FLOATS);
 }
 
 static NoiseRef nref(const brl_noise* nz, const float* ptr, unsigned kind, unsigned site) {
@@ -176,47 +186,73 @@ static PoolParams pool_params(const NetSpec& n, const OpSpec& op, const ActBufs&
   return p;
 }
 
+static void forward_op(const brl_ctx* ctx, const ActBufs& ab, const FwdArgs& a, size_t oi, cudaStream_t st, int slot) {
+  const NetSpec& n = *ctx->net;
+  const OpSpec& op = n.ops[oi];
+  if (op.kind == OP_MAXPOOL3) { launch_maxpool3(pool_params(n, op, ab, a.x, a.B, a.S), st); return; }
+  if (op.kind == OP_AVGPOOL2) { launch_avgpool2(pool_params(n, op, ab, a.x, a.B, a.S), st); return; }
+  const LayerSpec& L = n.layers[op.layer];
+  ConvGemm p{};
+  p.B = (int)a.B; p.P = op.Hout * op.Wout; p.Wrow = op.Wout; p.N = L.cout; p.K = L.cin * L.kh * L.kw; p.S = (int)a.S;
+  p.a = fwd_gather(ctx, op, oi, ab, a.x);
+  p.kB = nullptr; p.nB = p.K;
+  int epi = EPI_FWD_PLAIN;
+  switch (a.mode) {
+    case BRL_MODE_DET:
+      p.W0 = a.theta + L.w_off; p.bias0 = a.theta + L.b_off; break;
+    case BRL_MODE_WS:
+      p.W0 = a.wsamp + L.w_off; p.ws0 = n.P; p.bias0 = a.wsamp + L.b_off; p.bs0 = n.P; break;
+    case BRL_MODE_LRT:
+      epi = EPI_FWD_LRT;
+      p.W0 = a.theta + L.w_off; p.W1 = a.sigma + L.w_off; p.trA = TRA_SQUARE; p.trB = TRB_SQUARE;
+      p.bias0 = a.theta + L.b_off; p.bias1 = a.sigma + L.b_off;
+      p.eps = nref(a.noise, a.noise ? a.noise->lrt_eps[op.layer] : nullptr, KIND_LRT_EPS, op.layer);
+      p.sd_out = a.save_sd ? ab.sd[oi] : nullptr;
+      break;
+    case BRL_MODE_FLIPOUT:
+      epi = EPI_FWD_FLIPOUT;
+      p.W0 = a.theta + L.w_off; p.W1 = a.wsamp + L.w_off; p.ws1 = n.P; p.trA = TRA_SIGN; p.trB = TRB_MINUS_W0;
+      p.sign_in = a.sgn_in[op.layer]; p.sign_C = L.cin; p.sign_out = a.sgn_out[op.layer];
+      p.bias1 = a.wsamp + L.b_off; p.bs1 = n.P;
+      break;
+  }
+  const bool is_last = op.out_buf == n.out_buf;
+  p.out = (is_last && a.out) ? a.out : ab.act[op.out_buf];
+  p.out_img_stride = n.bufs[op.out_buf].elems();
+  p.out_P = n.bufs[op.out_buf].H * n.bufs[op.out_buf].W;
+  p.co_off = op.co_off; p.relu = op.relu; p.head = op.head;
+  p.keep = (a.p_dropout > 0.f && L.drop_factor > 0.f) ? 1.0f - a.p_dropout * L.drop_factor : 1.0f;
+  p.drop = nref(a.noise, a.noise ? a.noise->drop_mask[op.layer] : nullptr, KIND_DROPOUT, op.layer);
+  p.part = ab.part[slot];
+  if (ctx->gemm_backend & 1) launch_conv_gemm_tc(p, epi, st);
+  else launch_conv_gemm(p, epi, st);
+}
+
 static void run_forward(const brl_ctx* ctx, const ActBufs& ab, const FwdArgs& a, cudaStream_t st) {
   const NetSpec& n = *ctx->net;
-  for (size_t oi = 0; oi < n.ops.size(); ++oi) {
-    const OpSpec& op = n.ops[oi];
-    if (op.kind == OP_MAXPOOL3) { launch_maxpool3(pool_params(n, op, ab, a.x, a.B, a.S), st); continue; }
-    if (op.kind == OP_AVGPOOL2) { launch_avgpool2(pool_params(n, op, ab, a.x, a.B, a.S), st); continue; }
-    const LayerSpec& L = n.layers[op.layer];
-    ConvGemm p{};
-    p.B = (int)a.B; p.P = op.Hout * op.Wout; p.Wrow = op.Wout; p.N = L.cout; p.K = L.cin * L.kh * L.kw; p.S = (int)a.S;
-    p.a = fwd_gather(ctx, op, oi, ab, a.x);
-    p.kB = nullptr; p.nB = p.K;
-    int epi = EPI_FWD_PLAIN;
-    switch (a.mode) {
-      case BRL_MODE_DET:
-        p.W0 = a.theta + L.w_off; p.bias0 = a.theta + L.b_off; break;
-      case BRL_MODE_WS:
-        p.W0 = a.wsamp + L.w_off; p.ws0 = n.P; p.bias0 = a.wsamp + L.b_off; p.bs0 = n.P; break;
-      case BRL_MODE_LRT:
-        epi = EPI_FWD_LRT;
-        p.W0 = a.theta + L.w_off; p.W1 = a.sigma + L.w_off; p.trA = TRA_SQUARE; p.trB = TRB_SQUARE;
-        p.bias0 = a.theta + L.b_off; p.bias1 = a.sigma + L.b_off;
-        p.eps = nref(a.noise, a.noise ? a.noise->lrt_eps[op.layer] : nullptr, KIND_LRT_EPS, op.layer);
-        p.sd_out = a.save_sd ? ab.sd[oi] : nullptr;
-        break;
-      case BRL_MODE_FLIPOUT:
-        epi = EPI_FWD_FLIPOUT;
-        p.W0 = a.theta + L.w_off; p.W1 = a.wsamp + L.w_off; p.ws1 = n.P; p.trA = TRA_SIGN; p.trB = TRB_MINUS_W0;
-        p.sign_in = a.sgn_in[op.layer]; p.sign_C = L.cin; p.sign_out = a.sgn_out[op.layer];
-        p.bias1 = a.wsamp + L.b_off; p.bs1 = n.P;
-        break;
+  // every level of the tape: ops whose inputs are complete; the first op stays on `st`, the others fork to side streams
+  for (int lvl = 0; lvl < ctx->n_levels; ++lvl) {
+    int cnt = 0;
+    for (size_t oi = 0; oi < n.ops.size(); ++oi) cnt += ctx->op_level[oi] == lvl;
+    const bool fork = ctx->multi_stream && cnt > 1;
+    if (fork) cudaEventRecord(ctx->ev_fork, st);  // everything the level reads is complete on `st` at this point
+    int j = 0, used = 0;
+    for (size_t oi = 0; oi < n.ops.size(); ++oi) {
+      if (ctx->op_level[oi] != lvl) continue;
+      if (j == 0 || !fork) {
+        forward_op(ctx, ab, a, oi, st, 0);
+      } else {
+        const int si = (j - 1) % 3;
+        if (!(used & (1 << si))) { cudaStreamWaitEvent(ctx->side[si], ctx->ev_fork, 0); used |= 1 << si; }
+        forward_op(ctx, ab, a, oi, ctx->side[si], 1 + si);
+      }
+      ++j;
     }
-    const bool is_last = op.out_buf == n.out_buf;
-    p.out = (is_last && a.out) ? a.out : ab.act[op.out_buf];
-    p.out_img_stride = n.bufs[op.out_buf].elems();
-    p.out_P = n.bufs[op.out_buf].H * n.bufs[op.out_buf].W;
-    p.co_off = op.co_off; p.relu = op.relu; p.head = op.head;
-    p.keep = (a.p_dropout > 0.f && L.drop_factor > 0.f) ? 1.0f - a.p_dropout * L.drop_factor : 1.0f;
-    p.drop = nref(a.noise, a.noise ? a.noise->drop_mask[op.layer] : nullptr, KIND_DROPOUT, op.layer);
-    p.part = ab.part;
-    if (ctx->gemm_backend & 1) launch_conv_gemm_tc(p, epi, st);
-    else launch_conv_gemm(p, epi, st);
+    for (int si = 0; si < 3; ++si)
+      if (used & (1 << si)) {
+        cudaEventRecord(ctx->ev_join[si], ctx->side[si]);
+        cudaStreamWaitEvent(st, ctx->ev_join[si], 0);
+      }
   }
 }
 
@@ -236,6 +272,7 @@ struct BwdArgs {
 // expects grad[out_buf] to hold dLoss/d(out) and every other grad buffer zeroed
 static void run_backward(const brl_ctx* ctx, const ActBufs& ab, const BwdArgs& a, cudaStream_t st) {
   const NetSpec& n = *ctx->net;
+  int n_dw = 0, used = 0;
   for (int oi = (int)n.ops.size() - 1; oi >= 0; --oi) {
     const OpSpec& op = n.ops[oi];
     if (op.kind != OP_CONV) {
@@ -256,36 +293,47 @@ static void run_backward(const brl_ctx* ctx, const ActBufs& ab, const BwdArgs& a
     ba.out_P = n.bufs[op.out_buf].H * n.bufs[op.out_buf].W;
     ba.co_off = op.co_off; ba.N = L.cout; ba.P = Pout; ba.n_img = a.B; ba.B = (int)a.B;
     ba.relu = op.relu; ba.head = op.head; ba.inv_keep = 1.0f / keep;
-    ba.dpre = ab.dpre;
+    ba.dpre = ab.dpre[oi];
     if (a.mode == BRL_MODE_LRT) {
-      ba.dvar = ab.dsec; ba.sd = ab.sd[oi];
+      ba.dvar = ab.dsec[oi]; ba.sd = ab.sd[oi];
       ba.eps = nref(a.noise, a.noise ? a.noise->lrt_eps[op.layer] : nullptr, KIND_LRT_EPS, op.layer);
     } else if (a.mode == BRL_MODE_FLIPOUT) {
-      ba.dpert = ab.dsec; ba.sign_out = a.sgn_out[op.layer];
+      ba.dpert = ab.dsec[oi]; ba.sign_out = a.sgn_out[op.layer];
     }
     launch_bwd_act(ba, st);
 
-    // weight gradients
+    // weight gradients: off the critical path (the dX chain) -- they only need this op's dpre / dsec and write their own
+    // slice of the flat gradient buffers, so they follow on a side stream
+    cudaStream_t ws = st;
+    if (ctx->multi_stream) {
+      const int si = n_dw % 3;
+      cudaEvent_t ev = ctx->ev_op[n_dw % 8];
+      cudaEventRecord(ev, st);
+      cudaStreamWaitEvent(ctx->side[si], ev, 0);
+      ws = ctx->side[si];
+      used |= 1 << si;
+      ++n_dw;
+    }
     ConvDw dw{};
     dw.B = (int)a.B; dw.P = Pout; dw.Wrow = op.Wout; dw.N = L.cout; dw.K = L.cin * L.kh * L.kw;
     dw.a = fwd_gather(ctx, op, oi, ab, a.x);
-    dw.G = ab.dpre; dw.gw = a.g0 + L.w_off; dw.gb = a.g0 + L.b_off;
+    dw.G = ab.dpre[oi]; dw.gw = a.g0 + L.w_off; dw.gb = a.g0 + L.b_off;
     dw.gb2 = a.mode == BRL_MODE_FLIPOUT ? a.g1 + L.b_off : nullptr;
-    ((ctx->gemm_backend & 4) ? launch_conv_dw_tc(dw, st) : launch_conv_dw(dw, st));
+    ((ctx->gemm_backend & 4) ? launch_conv_dw_tc(dw, ws) : launch_conv_dw(dw, ws));
     if (a.mode == BRL_MODE_LRT) {
-      dw.G = ab.dsec; dw.trA = TRA_SQUARE; dw.gw = a.g1 + L.w_off; dw.gb = a.g1 + L.b_off; dw.gb2 = nullptr;
-      ((ctx->gemm_backend & 4) ? launch_conv_dw_tc(dw, st) : launch_conv_dw(dw, st));
+      dw.G = ab.dsec[oi]; dw.trA = TRA_SQUARE; dw.gw = a.g1 + L.w_off; dw.gb = a.g1 + L.b_off; dw.gb2 = nullptr;
+      ((ctx->gemm_backend & 4) ? launch_conv_dw_tc(dw, ws) : launch_conv_dw(dw, ws));
     } else if (a.mode == BRL_MODE_FLIPOUT) {
-      dw.G = ab.dsec; dw.trA = TRA_SIGN; dw.sign_in = a.sgn_in[op.layer]; dw.sign_C = L.cin;
+      dw.G = ab.dsec[oi]; dw.trA = TRA_SIGN; dw.sign_in = a.sgn_in[op.layer]; dw.sign_C = L.cin;
       dw.gw = a.g1 + L.w_off; dw.gb = nullptr; dw.gb2 = nullptr;
-      ((ctx->gemm_backend & 4) ? launch_conv_dw_tc(dw, st) : launch_conv_dw(dw, st));
+      ((ctx->gemm_backend & 4) ? launch_conv_dw_tc(dw, ws) : launch_conv_dw(dw, ws));
     }
 
     // input gradient
     if (op.in.buf < 0 || n.bufs[op.in.buf].shared) continue;
     ConvGemm p{};
     p.B = (int)a.B; p.P = op.in.H * op.in.W; p.Wrow = op.in.W; p.N = L.cin; p.K = L.cout * L.kh * L.kw; p.S = 1;
-    p.a.base0 = ab.dpre; p.a.base1 = ab.dsec; p.a.img_stride = (long long)L.cout * Pout; p.a.per_sample = 1;
+    p.a.base0 = ab.dpre[oi]; p.a.base1 = ab.dsec[oi]; p.a.img_stride = (long long)L.cout * Pout; p.a.per_sample = 1;
     p.a.Hin = op.Hout; p.a.Win = op.Wout; p.a.sH = op.Wout; p.a.sW = 1;
     p.a.koff = ctx->tabs[oi].koff_dx; p.a.kdhw = ctx->tabs[oi].kdhw_dx; p.a.kci = nullptr;
     p.kB = ctx->tabs[oi].kB_dx; p.nB = L.kh * L.kw;
@@ -299,10 +347,15 @@ static void run_backward(const brl_ctx* ctx, const ActBufs& ab, const BwdArgs& a
     } else if (a.mode == BRL_MODE_FLIPOUT) {
       epi = EPI_DX_FLIPOUT; p.W1 = a.wsamp + L.w_off; p.trB = TRB_MINUS_W0; p.sign_in = a.sgn_in[op.layer]; p.sign_C = L.cin;
     }
-    p.part = ab.part;
+    p.part = ab.part[0];
     if (ctx->gemm_backend & 2) launch_conv_gemm_tc(p, epi, st);
     else launch_conv_gemm(p, epi, st);
   }
+  for (int si = 0; si < 3; ++si)  // join: the caller's stream owns the finished gradient buffers again
+    if (used & (1 << si)) {
+      cudaEventRecord(ctx->ev_join[si], ctx->side[si]);
+      cudaStreamWaitEvent(st, ctx->ev_join[si], 0);
+    }
 }
 
 static int zero_grads(const NetSpec& n, const ActBufs& ab, long long B, cudaStream_t st) {
@@ -404,6 +457,23 @@ int brl_create(brl_ctx** out, int net, int device) {
   BRL_CUDA(cudaMemcpy(c->site_off_dev, ns->site_off.data(), ns->site_off.size() * sizeof(long long), cudaMemcpyHostToDevice));
   for (size_t j = 0; j + 1 < ns->site_off.size(); ++j) c->max_site = std::max(c->max_site, (int)(ns->site_off[j + 1] - ns->site_off[j]));
   c->tc = tc_create(net);
+  // dependency levels of the tape: an op is one level below the last producer of its input buffer
+  c->op_level.assign(ns->ops.size(), 0);
+  for (size_t oi = 0; oi < ns->ops.size(); ++oi) {
+    int lvl = 0;
+    for (size_t pj = 0; pj < oi; ++pj)
+      if (ns->ops[pj].out_buf == ns->ops[oi].in.buf) lvl = std::max(lvl, c->op_level[pj] + 1);
+    c->op_level[oi] = lvl;
+    c->n_levels = std::max(c->n_levels, lvl + 1);
+  }
+  const char* single = getenv("BRL_SINGLE_STREAM");
+  c->multi_stream = !(single && single[0] == '1');
+  for (int i = 0; i < 3; ++i) {
+    BRL_CUDA(cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
+    BRL_CUDA(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+  }
+  BRL_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  for (int i = 0; i < 8; ++i) BRL_CUDA(cudaEventCreateWithFlags(&c->ev_op[i], cudaEventDisableTiming));
   *out = c;
   return BRL_OK;
 }
@@ -413,6 +483,13 @@ int brl_destroy(brl_ctx* ctx) {
   cudaFree(ctx->table_pool);
   cudaFree(ctx->site_off_dev);
   tc_destroy(ctx->tc);
+  for (int i = 0; i < 3; ++i) {
+    if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]);
+    if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
+  }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  for (int i = 0; i < 8; ++i)
+    if (ctx->ev_op[i]) cudaEventDestroy(ctx->ev_op[i]);
   delete ctx;
   return BRL_OK;
 }

@@ -109,9 +109,6 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const ConvGemm p, int* 
   const long long aimg = p.a.per_sample ? (long long)s * p.B + ab : ab;
   const long long rowbase = aimg * p.a.img_stride + (long long)aoh * p.a.sH + (long long)aow * p.a.sW;
   const float* sgn = p.sign_in + ((long long)s * p.B + ab) * p.sign_C;
-  const int bnn = n0 + r;
-  const bool bnv = r < ncol;
-  const long long bcol = (long long)(bnv ? bnn : 0) * p.nB;
   const float* W0 = p.W0 + (long long)s * p.ws0;
   const float* W1 = DUAL ? p.W1 + (long long)s * p.ws1 : nullptr;
 
@@ -123,44 +120,75 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const ConvGemm p, int* 
       tc_fence_after();
     }
     const int k0 = kbeg + ch * TG_K + kq * 16;
+    // three passes so that every load of the stage is in flight at once (the stage is latency-, not bandwidth-bound):
+    // 1. gather tables, 2. operand loads, 3. transforms + TF32 rounding + 16-byte stores
+    int ko[16], kcl[16];
+    bool oka[16];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      float a0[4], a1[4], b0[4], b1[4];
+    for (int j = 0; j < 16; ++j) {
+      const int k = k0 + j;
+      kcl[j] = min(k, p.K - 1);
+      const int dhw = __ldg(p.a.kdhw + kcl[j]);
+      ko[j] = __ldg(p.a.koff + kcl[j]);
+      const int ih = aoh + (int)(short)(dhw & 0xffff), iw = aow + (dhw >> 16);
+      oka[j] = arv && k < kend && (unsigned)ih < (unsigned)p.a.Hin && (unsigned)iw < (unsigned)p.a.Win;
+    }
+    float va[16], va1[16];
+    const bool two_bases = DUAL && p.a.base1 != p.a.base0;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int k = k0 + 4 * g + j;
+    for (int j = 0; j < 16; ++j) {
+      const long long off = oka[j] ? rowbase + ko[j] : 0;
+      va[j] = __ldg(p.a.base0 + off);
+      if (DUAL) {
+        if (two_bases) va1[j] = __ldg(p.a.base1 + off);
+        else if (p.trA == TRA_SIGN) va1[j] = __ldg(sgn + (oka[j] ? __ldg(p.a.kci + kcl[j]) : 0));
+      }
+    }
+    // B operand (weights): NP rows x 8 four-element k chunks = NP * 8 sixteen-byte units, spread over the 256 threads,
+    // so a layer with 16 output channels gathers 1/8 of what a 128-channel tile does
+    const int kb0 = kbeg + ch * TG_K;
+    for (int u = tid; u < NP * 8; u += 256) {
+      const int n = u >> 3, kc4 = u & 7;
+      const bool nv = n < ncol;
+      const long long bcol_u = (long long)(nv ? n0 + n : 0) * p.nB;
+      float w0[4], w1[4];
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int k = kb0 + 4 * kc4 + jj;
         const int kc = min(k, p.K - 1);
-        const int dhw = __ldg(p.a.kdhw + kc);
-        const int ko = __ldg(p.a.koff + kc);
-        const int ih = aoh + (int)(short)(dhw & 0xffff), iw = aow + (dhw >> 16);
-        const bool ok = arv && k < kend && (unsigned)ih < (unsigned)p.a.Hin && (unsigned)iw < (unsigned)p.a.Win;
-        const long long off = ok ? rowbase + ko : 0;
-        const float v = __ldg(p.a.base0 + off);
-        a0[j] = ok ? to_tf32(v) : 0.f;
-        if (DUAL) {
-          float w = (p.a.base1 == p.a.base0) ? v : __ldg(p.a.base1 + off);
-          if (p.trA == TRA_SQUARE) w = w * w;
-          else if (p.trA == TRA_SIGN) w *= __ldg(sgn + (ok ? __ldg(p.a.kci + kc) : 0));
-          a1[j] = ok ? to_tf32(w) : 0.f;
-        }
-        const bool okb = bnv && k < kend;
-        const long long boff = (p.kB ? (long long)__ldg(p.kB + kc) : (long long)kc) + bcol;
+        const long long boff = (p.kB ? (long long)__ldg(p.kB + kc) : (long long)kc) + bcol_u;
+        const bool okb = nv && k < kend;
         const float wv = __ldg(W0 + boff);
-        b0[j] = okb ? to_tf32(wv) : 0.f;
+        w0[jj] = okb ? to_tf32(wv) : 0.f;
         if (DUAL) {
           float w = __ldg(W1 + boff);
           if (p.trB == TRB_SQUARE) w = w * w;
           else if (p.trB == TRB_MINUS_W0) w -= wv;
-          b1[j] = okb ? to_tf32(w) : 0.f;
+          w1[jj] = okb ? to_tf32(w) : 0.f;
+        }
+      }
+      const int off = kc4 * TG_CHUNK + n * 16;
+      *reinterpret_cast<float4*>(stage + 2 * TG_TILE + off) = make_float4(w0[0], w0[1], w0[2], w0[3]);
+      if (DUAL) *reinterpret_cast<float4*>(stage + 3 * TG_TILE + off) = make_float4(w1[0], w1[1], w1[2], w1[3]);
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float a0[4], a1[4];
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = 4 * g + jj;
+        const float v = va[j];
+        a0[jj] = oka[j] ? to_tf32(v) : 0.f;
+        if (DUAL) {
+          float w = two_bases ? va1[j] : v;
+          if (p.trA == TRA_SQUARE) w = w * w;
+          else if (p.trA == TRA_SIGN) w *= va1[j];
+          a1[jj] = oka[j] ? to_tf32(w) : 0.f;
         }
       }
       const int off = (kq * 4 + g) * TG_CHUNK + r * 16;
       *reinterpret_cast<float4*>(stage + off) = make_float4(a0[0], a0[1], a0[2], a0[3]);
-      *reinterpret_cast<float4*>(stage + 2 * TG_TILE + off) = make_float4(b0[0], b0[1], b0[2], b0[3]);
-      if (DUAL) {
-        *reinterpret_cast<float4*>(stage + TG_TILE + off) = make_float4(a1[0], a1[1], a1[2], a1[3]);
-        *reinterpret_cast<float4*>(stage + 3 * TG_TILE + off) = make_float4(b1[0], b1[1], b1[2], b1[3]);
-      }
+      if (DUAL) *reinterpret_cast<float4*>(stage + TG_TILE + off) = make_float4(a1[0], a1[1], a1[2], a1[3]);
     }
     fence_async_smem();
     tc_fence_before();
@@ -209,7 +237,9 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const ConvGemm p, int* 
   }
   tc_fence_before();
   __syncthreads();
-#pragma unroll 1
+  // 4-way unrolled: the read-modify-write / noise loads of four outputs overlap (a fully rolled loop pays one global
+  // round trip per output, a fully unrolled one is instruction-fetch bound: Philox / log / sincos per element)
+#pragma unroll 4
   for (int e = tid; e < 128 * ncol; e += 256) {
     const int mi = e & 127, ni = e >> 7;
     const int m = m0 + mi, n = n0 + ni;
@@ -330,24 +360,34 @@ __global__ void __launch_bounds__(256, 1) tc_dw_kernel(const ConvDw p, int rows_
     }
     const int mb = mbeg + ch * TG_K + mq * 16;
     int b = mb / p.P, pp = mb - b * p.P;
+    // all loads of the stage first (latency-bound), then transforms + TF32 rounding + stores
+    float va[16], vs[16], vg[16];
+    bool oka[16], okg[16], rvv[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int m = mb + j;
+      const bool rv = m < mend;
+      const int oh = pp / p.Wrow, ow = pp - oh * p.Wrow;
+      oka[j] = rv && kmode == 0 && (unsigned)(oh + kdh) < (unsigned)p.a.Hin && (unsigned)(ow + kdw) < (unsigned)p.a.Win;
+      rvv[j] = rv;
+      const long long rowbase = (long long)b * p.a.img_stride + (long long)oh * p.a.sH + (long long)ow * p.a.sW;
+      va[j] = __ldg(p.a.base0 + (oka[j] ? rowbase + ko : 0));
+      if (p.trA == TRA_SIGN) vs[j] = __ldg(p.sign_in + (oka[j] ? (long long)b * p.sign_C + kcc : 0));
+      okg[j] = rv && cov;
+      vg[j] = __ldg(p.G + (okg[j] ? ((long long)b * p.N + co) * p.P + pp : 0));
+      if (++pp == p.P) { pp = 0; ++b; }
+    }
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       float av[4], gv[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int m = mb + 4 * g + j;
-        const bool rv = m < mend;
-        const int oh = pp / p.Wrow, ow = pp - oh * p.Wrow;
-        const bool ok = rv && kmode == 0 && (unsigned)(oh + kdh) < (unsigned)p.a.Hin && (unsigned)(ow + kdw) < (unsigned)p.a.Win;
-        const long long rowbase = (long long)b * p.a.img_stride + (long long)oh * p.a.sH + (long long)ow * p.a.sW;
-        float v = __ldg(p.a.base0 + (ok ? rowbase + ko : 0));
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = 4 * g + jj;
+        float v = va[j];
         if (p.trA == TRA_SQUARE) v = v * v;
-        else if (p.trA == TRA_SIGN) v *= __ldg(p.sign_in + (ok ? (long long)b * p.sign_C + kcc : 0));
-        av[j] = ok ? to_tf32(v) : ((rv && kmode == 1) ? 1.0f : 0.f);
-        const bool okg = rv && cov;
-        const float gval = __ldg(p.G + (okg ? ((long long)b * p.N + co) * p.P + pp : 0));
-        gv[j] = okg ? to_tf32(gval) : 0.f;
-        if (++pp == p.P) { pp = 0; ++b; }
+        else if (p.trA == TRA_SIGN) v *= vs[j];
+        av[jj] = oka[j] ? to_tf32(v) : ((rvv[j] && kmode == 1) ? 1.0f : 0.f);
+        gv[jj] = okg[j] ? to_tf32(vg[j]) : 0.f;
       }
       const int off = (mq * 4 + g) * TG_CHUNK + r * 16;
       *reinterpret_cast<float4*>(stage + off) = make_float4(av[0], av[1], av[2], av[3]);

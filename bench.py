@@ -331,9 +331,19 @@ def main():
                 eng.elbo_step(xt, yt, mu, sg, mode=mode, guide="normal", particles=particles, prior_loc=0.0,
                               prior_scale=ps, dataset_size=N_DATASET, noise=Noise(seed=5000 + st["i"], window0=rank * B_TRAIN))
 
-            tt = max_over_ranks(timed_steps(train_step, 20, 5, flush_buf, dist), dist, device)
+            res = {}
+            for backend in ("simt", "tc"):  # fp32 FFMA kernels vs tcgen05 TF32 dual-GEMM kernels (same operators)
+                eng.set_gemm_backend(backend)
+                res[backend] = max_over_ranks(timed_steps(train_step, 20, 5, flush_buf, dist), dist, device)
+            eng.set_gemm_backend("simt")
+            best = min(res, key=res.get)
+            tt = res[best]
+            flops = F_TRAIN_LRT * particles * B_TRAIN  # 13 036 416 per window per particle
             train[mode] = {"windows_per_s": world * B_TRAIN * 20 / tt, "ms_per_step": 1e3 * tt / 20, "batch": B_TRAIN,
-                           "particles": particles, "includes": "forward + backward + KL + gradient finalisation (no optimiser)"}
+                           "particles": particles, "gemm_backend": {"simt": "fp32 FFMA", "tc": "tcgen05 TF32"}[best],
+                           "ms_per_step_by_backend": {"simt_fp32": 1e3 * res["simt"] / 20, "tc_tf32": 1e3 * res["tc"] / 20},
+                           "achieved_tflops": flops / (tt / 20) / 1e12,
+                           "includes": "forward + backward + KL + gradient finalisation (no optimiser)"}
             if world == 1 and not args.no_cpu:
                 v, dt = cpu_train_rate(mode, particles, q, ps, os.cpu_count() or 1)
                 train[mode]["cpu_windows_per_s"] = v
