@@ -270,67 +270,48 @@ struct BwdArgs {
 };
 
 // expects grad[out_buf] to hold dLoss/d(out) and every other grad buffer zeroed
-static void run_backward(const brl_ctx* ctx, const ActBufs& ab, const BwdArgs& a, cudaStream_t st) {
+// backward of one op on stream `cs` (slot: 0 = the caller's stream, 1.. = side stream): activation backward, input
+// gradient (the critical chain; `ev_dx`, if given, is recorded right behind it) and the weight gradients, which only
+// need this op's dpre / dsec and write their own slice of the flat gradient buffers: they run on `ws`
+static void backward_op(const brl_ctx* ctx, const ActBufs& ab, const BwdArgs& a, int oi, cudaStream_t cs, int slot,
+                        cudaStream_t ws, cudaEvent_t ev_act, cudaEvent_t ev_dx) {
   const NetSpec& n = *ctx->net;
-  int n_dw = 0, used = 0;
-  for (int oi = (int)n.ops.size() - 1; oi >= 0; --oi) {
-    const OpSpec& op = n.ops[oi];
-    if (op.kind != OP_CONV) {
-      if (op.in.buf < 0) continue;  // pooled raw input: no gradient needed
+  const OpSpec& op = n.ops[oi];
+  if (op.kind != OP_CONV) {
+    if (op.in.buf >= 0) {  // (a pooled raw input needs no gradient)
       PoolParams pp = pool_params(n, op, ab, a.x, a.B, 1);
-      if (op.kind == OP_MAXPOOL3) launch_maxpool3_bwd(pp, ab.grad[op.out_buf], ab.grad[op.in.buf], st);
-      else launch_avgpool2_bwd(pp, ab.grad[op.out_buf], ab.grad[op.in.buf], st);
-      continue;
+      if (op.kind == OP_MAXPOOL3) launch_maxpool3_bwd(pp, ab.grad[op.out_buf], ab.grad[op.in.buf], cs);
+      else launch_avgpool2_bwd(pp, ab.grad[op.out_buf], ab.grad[op.in.buf], cs);
     }
-    const LayerSpec& L = n.layers[op.layer];
-    const int Pout = op.Hout * op.Wout;
-    const bool is_last = op.out_buf == n.out_buf;
-    const float keep = (a.p_dropout > 0.f && L.drop_factor > 0.f) ? 1.0f - a.p_dropout * L.drop_factor : 1.0f;
-    BwdAct ba{};
-    ba.gout = ab.grad[op.out_buf];
-    ba.outv = (is_last && a.out) ? a.out : ab.act[op.out_buf];
-    ba.img_stride = n.bufs[op.out_buf].elems();
-    ba.out_P = n.bufs[op.out_buf].H * n.bufs[op.out_buf].W;
-    ba.co_off = op.co_off; ba.N = L.cout; ba.P = Pout; ba.n_img = a.B; ba.B = (int)a.B;
-    ba.relu = op.relu; ba.head = op.head; ba.inv_keep = 1.0f / keep;
-    ba.dpre = ab.dpre[oi];
-    if (a.mode == BRL_MODE_LRT) {
-      ba.dvar = ab.dsec[oi]; ba.sd = ab.sd[oi];
-      ba.eps = nref(a.noise, a.noise ? a.noise->lrt_eps[op.layer] : nullptr, KIND_LRT_EPS, op.layer);
-    } else if (a.mode == BRL_MODE_FLIPOUT) {
-      ba.dpert = ab.dsec[oi]; ba.sign_out = a.sgn_out[op.layer];
-    }
-    launch_bwd_act(ba, st);
+    if (ev_dx) cudaEventRecord(ev_dx, cs);
+    return;
+  }
+  const LayerSpec& L = n.layers[op.layer];
+  const int Pout = op.Hout * op.Wout;
+  const bool is_last = op.out_buf == n.out_buf;
+  const float keep = (a.p_dropout > 0.f && L.drop_factor > 0.f) ? 1.0f - a.p_dropout * L.drop_factor : 1.0f;
+  BwdAct ba{};
+  ba.gout = ab.grad[op.out_buf];
+  ba.outv = (is_last && a.out) ? a.out : ab.act[op.out_buf];
+  ba.img_stride = n.bufs[op.out_buf].elems();
+  ba.out_P = n.bufs[op.out_buf].H * n.bufs[op.out_buf].W;
+  ba.co_off = op.co_off; ba.N = L.cout; ba.P = Pout; ba.n_img = a.B; ba.B = (int)a.B;
+  ba.relu = op.relu; ba.head = op.head; ba.inv_keep = 1.0f / keep;
+  ba.dpre = ab.dpre[oi];
+  if (a.mode == BRL_MODE_LRT) {
+    ba.dvar = ab.dsec[oi]; ba.sd = ab.sd[oi];
+    ba.eps = nref(a.noise, a.noise ? a.noise->lrt_eps[op.layer] : nullptr, KIND_LRT_EPS, op.layer);
+  } else if (a.mode == BRL_MODE_FLIPOUT) {
+    ba.dpert = ab.dsec[oi]; ba.sign_out = a.sgn_out[op.layer];
+  }
+  launch_bwd_act(ba, cs);
+  if (ws != cs) {  // the weight-gradient stream picks up behind the activation backward
+    cudaEventRecord(ev_act, cs);
+    cudaStreamWaitEvent(ws, ev_act, 0);
+  }
 
-    // weight gradients: off the critical path (the dX chain) -- they only need this op's dpre / dsec and write their own
-    // slice of the flat gradient buffers, so they follow on a side stream
-    cudaStream_t ws = st;
-    if (ctx->multi_stream) {
-      const int si = n_dw % 3;
-      cudaEvent_t ev = ctx->ev_op[n_dw % 8];
-      cudaEventRecord(ev, st);
-      cudaStreamWaitEvent(ctx->side[si], ev, 0);
-      ws = ctx->side[si];
-      used |= 1 << si;
-      ++n_dw;
-    }
-    ConvDw dw{};
-    dw.B = (int)a.B; dw.P = Pout; dw.Wrow = op.Wout; dw.N = L.cout; dw.K = L.cin * L.kh * L.kw;
-    dw.a = fwd_gather(ctx, op, oi, ab, a.x);
-    dw.G = ab.dpre[oi]; dw.gw = a.g0 + L.w_off; dw.gb = a.g0 + L.b_off;
-    dw.gb2 = a.mode == BRL_MODE_FLIPOUT ? a.g1 + L.b_off : nullptr;
-    ((ctx->gemm_backend & 4) ? launch_conv_dw_tc(dw, ws) : launch_conv_dw(dw, ws));
-    if (a.mode == BRL_MODE_LRT) {
-      dw.G = ab.dsec[oi]; dw.trA = TRA_SQUARE; dw.gw = a.g1 + L.w_off; dw.gb = a.g1 + L.b_off; dw.gb2 = nullptr;
-      ((ctx->gemm_backend & 4) ? launch_conv_dw_tc(dw, ws) : launch_conv_dw(dw, ws));
-    } else if (a.mode == BRL_MODE_FLIPOUT) {
-      dw.G = ab.dsec[oi]; dw.trA = TRA_SIGN; dw.sign_in = a.sgn_in[op.layer]; dw.sign_C = L.cin;
-      dw.gw = a.g1 + L.w_off; dw.gb = nullptr; dw.gb2 = nullptr;
-      ((ctx->gemm_backend & 4) ? launch_conv_dw_tc(dw, ws) : launch_conv_dw(dw, ws));
-    }
-
-    // input gradient
-    if (op.in.buf < 0 || n.bufs[op.in.buf].shared) continue;
+  // input gradient (accumulated with atomics: the ops of a level may share their input buffer)
+  if (op.in.buf >= 0 && !n.bufs[op.in.buf].shared) {
     ConvGemm p{};
     p.B = (int)a.B; p.P = op.in.H * op.in.W; p.Wrow = op.in.W; p.N = L.cin; p.K = L.cout * L.kh * L.kw; p.S = 1;
     p.a.base0 = ab.dpre[oi]; p.a.base1 = ab.dsec[oi]; p.a.img_stride = (long long)L.cout * Pout; p.a.per_sample = 1;
@@ -347,12 +328,63 @@ static void run_backward(const brl_ctx* ctx, const ActBufs& ab, const BwdArgs& a
     } else if (a.mode == BRL_MODE_FLIPOUT) {
       epi = EPI_DX_FLIPOUT; p.W1 = a.wsamp + L.w_off; p.trB = TRB_MINUS_W0; p.sign_in = a.sgn_in[op.layer]; p.sign_C = L.cin;
     }
-    p.part = ab.part[0];
-    if (ctx->gemm_backend & 2) launch_conv_gemm_tc(p, epi, st);
-    else launch_conv_gemm(p, epi, st);
+    p.part = ab.part[slot];
+    if (ctx->gemm_backend & 2) launch_conv_gemm_tc(p, epi, cs);
+    else launch_conv_gemm(p, epi, cs);
   }
-  for (int si = 0; si < 3; ++si)  // join: the caller's stream owns the finished gradient buffers again
-    if (used & (1 << si)) {
+  if (ev_dx) cudaEventRecord(ev_dx, cs);
+
+  // weight gradients
+  ConvDw dw{};
+  dw.B = (int)a.B; dw.P = Pout; dw.Wrow = op.Wout; dw.N = L.cout; dw.K = L.cin * L.kh * L.kw;
+  dw.a = fwd_gather(ctx, op, oi, ab, a.x);
+  dw.G = ab.dpre[oi]; dw.gw = a.g0 + L.w_off; dw.gb = a.g0 + L.b_off;
+  dw.gb2 = a.mode == BRL_MODE_FLIPOUT ? a.g1 + L.b_off : nullptr;
+  ((ctx->gemm_backend & 4) ? launch_conv_dw_tc(dw, ws) : launch_conv_dw(dw, ws));
+  if (a.mode == BRL_MODE_LRT) {
+    dw.G = ab.dsec[oi]; dw.trA = TRA_SQUARE; dw.gw = a.g1 + L.w_off; dw.gb = a.g1 + L.b_off; dw.gb2 = nullptr;
+    ((ctx->gemm_backend & 4) ? launch_conv_dw_tc(dw, ws) : launch_conv_dw(dw, ws));
+  } else if (a.mode == BRL_MODE_FLIPOUT) {
+    dw.G = ab.dsec[oi]; dw.trA = TRA_SIGN; dw.sign_in = a.sgn_in[op.layer]; dw.sign_C = L.cin;
+    dw.gw = a.g1 + L.w_off; dw.gb = nullptr; dw.gb2 = nullptr;
+    ((ctx->gemm_backend & 4) ? launch_conv_dw_tc(dw, ws) : launch_conv_dw(dw, ws));
+  }
+}
+
+// expects grad[out_buf] to hold dLoss/d(out) and every other grad buffer zeroed.  Tape levels run in reverse; the ops
+// of a level run concurrently (first op on `st`, the others on side streams), the next level waits for their dX only.
+static void run_backward(const brl_ctx* ctx, const ActBufs& ab, const BwdArgs& a, cudaStream_t st) {
+  const NetSpec& n = *ctx->net;
+  if (!ctx->multi_stream) {
+    for (int oi = (int)n.ops.size() - 1; oi >= 0; --oi) backward_op(ctx, ab, a, oi, st, 0, st, nullptr, nullptr);
+    return;
+  }
+  int n_dw = 0, used_any = 0;
+  for (int lvl = ctx->n_levels - 1; lvl >= 0; --lvl) {
+    int cnt = 0;
+    for (size_t oi = 0; oi < n.ops.size(); ++oi) cnt += ctx->op_level[oi] == lvl;
+    const bool fork = cnt > 1;
+    if (fork) cudaEventRecord(ctx->ev_fork, st);
+    int j = 0, used = 0;
+    for (int oi = (int)n.ops.size() - 1; oi >= 0; --oi) {
+      if (ctx->op_level[oi] != lvl) continue;
+      if (j == 0) {  // on the caller's stream; its weight gradients go to a rotating side stream
+        const int wi = n_dw++ % 3;
+        used_any |= 1 << wi;
+        backward_op(ctx, ab, a, oi, st, 0, ctx->side[wi], ctx->ev_op[n_dw % 8], nullptr);
+      } else {
+        const int si = (j - 1) % 3;
+        if (!(used & (1 << si))) { cudaStreamWaitEvent(ctx->side[si], ctx->ev_fork, 0); used |= 1 << si; }
+        backward_op(ctx, ab, a, oi, ctx->side[si], 1 + si, ctx->side[si], nullptr, ctx->ev_join[si]);
+      }
+      ++j;
+    }
+    used_any |= used;
+    for (int si = 0; si < 3; ++si)
+      if (used & (1 << si)) cudaStreamWaitEvent(st, ctx->ev_join[si], 0);  // the side chains' dX (recorded behind each)
+  }
+  for (int si = 0; si < 3; ++si)  // final join: the weight gradients too; the caller's stream owns the buffers again
+    if (used_any & (1 << si)) {
       cudaEventRecord(ctx->ev_join[si], ctx->side[si]);
       cudaStreamWaitEvent(st, ctx->ev_join[si], 0);
     }

@@ -26,7 +26,7 @@ __device__ __forceinline__ void gemm_epilogue(const ConvGemm& p, int s, int m, i
     float g = a0;
     if (EPI == EPI_DX_LRT) g = fmaf(2.0f * p.xin[oidx], a1, g);
     if (EPI == EPI_DX_FLIPOUT) g = fmaf(p.sign_in[img * p.sign_C + n], a1, g);
-    p.out[oidx] += g;
+    atomicAdd(p.out + oidx, g);  // ops of one backward level accumulate into a shared input-gradient buffer concurrently
     return;
   }
   float v = a0;

@@ -80,7 +80,7 @@ __global__ void maxpool3_bwd_kernel(const PoolParams p, const float* gout, float
     float g = 0.f;
     for (int o = max(h - 1, 0); o <= min(h + 1, p.Hin - 1); ++o)
       if (argmax3_first(src, o, p.Hin, p.sH) == h) g += go[(long long)o * p.Win];
-    gin[img * p.in_img_stride + (long long)c * p.sC + (long long)h * p.sH + (long long)w * p.sW] += g;
+    atomicAdd(gin + img * p.in_img_stride + (long long)c * p.sC + (long long)h * p.sH + (long long)w * p.sW, g);
   }
 }
 void launch_maxpool3_bwd(const PoolParams& p, const float* gout, float* gin, cudaStream_t st) {
