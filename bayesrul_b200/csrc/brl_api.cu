@@ -576,7 +576,9 @@ int64_t brl_workspace_bytes(const brl_ctx* ctx, int64_t B, int64_t S, int train,
   c.take<float>(S * B * 2);      // chunk outputs
   if (engine == BRL_ENGINE_TC_FP16) c.used += tc_workspace_bytes(ctx->tc, B, S);
   else carve_forward(n, c, B, S, ab);
-  if (train) carve_train(n, c, B, ab);
+  if (train == 1) carve_train(n, c, B, ab);
+  if (train == 2)  // brl_forward in BRL_MODE_FLIPOUT with native signs: [S,B,Cin] + [S,B,Cout] per layer
+    for (const LayerSpec& L : n.layers) { c.take<float>(S * B * L.cin); c.take<float>(S * B * L.cout); }
   return (int64_t)c.used + 4096;
 }
 

@@ -200,7 +200,7 @@ class Engine:
         if wsamp is not None:
             wsamp = self._theta(wsamp, "wsamp", (S,))
         out = torch.empty(S, B, 2, device=self.device)
-        ws = self._ws_for(B, S, False, engine)
+        ws = self._ws_for(B, S, 2 if mode == "flipout" else 0, engine)
         nz, keep = self._noise(noise)
         p = lambda t: t.data_ptr() if t is not None else None
         _lib.check(self.lib.brl_forward(self.ctx, x.data_ptr(), B, S, MODE_IDS[mode], p(theta), p(sigma), p(wsamp),

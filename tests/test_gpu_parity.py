@@ -297,3 +297,59 @@ def test_full_size_properties(engines):
                                          [O.PhiloxNoise("inception", 11, sample=s) for s in range(S)]))
     for u, v, k in zip(a, ref, ("pred", "std", "ep", "al")):
         assert_close(u[:64], v, rtol=5e-3, atol_scale=1e-3, what=k)
+
+
+# ----------------------------------------------------------------------------- native-RNG mode: statistical parity
+@pytest.mark.parametrize("engine", ["simt", "tc"])
+def test_native_rng_statistical_parity(engines, engine):
+    """north_star, native-RNG mode: predictive mean / variance / NLL / RMSE of the in-kernel Philox stream must agree
+    statistically with the oracle fed by an INDEPENDENT generator (torch.randn), on the same inputs.  A weight draw is
+    shared by every window (bayesian.py:235-239), so window averages do NOT average the Monte-Carlo error away: bounds
+    are k standard errors of an S-sample estimate with fully correlated windows."""
+    from bayesrul_b200 import Noise
+    net, B, S = "inception", 256, 1024
+    e = engines[net]
+    if engine == "tc" and not e.has_tc():
+        pytest.skip("tensor-core engine unavailable")
+    x, y, mu, _ = synth(net, B, seed=41)
+    sg = torch.full_like(mu, 0.02)
+    g = torch.Generator().manual_seed(99)
+    ref = O.predictive_moments(O.predict(net, x, mu, sg, "normal",
+                                         [O.InjectedNoise({"weight_eps": torch.randn(mu.numel(), generator=g)}) for _ in range(S)]))
+    got = e.predict_moments(x.to(DEV), mu.to(DEV), sg.to(DEV), S=S, guide="normal", noise=Noise(seed=2025), engine=engine)
+    pred, std, ep, al = [t.cpu().double() for t in got]
+    rpred, rstd, rep, ral = [t.double() for t in ref]
+    yd = y.double()
+    k = 4.5
+    se_mean = (2.0 * rep.mean().item() / S) ** 0.5          # difference of two S-sample means, windows fully correlated
+    rel_var = k * (2.0 * 2.0 / (S - 1)) ** 0.5               # relative s.e. of a variance estimate sqrt(2/(S-1)), two of them
+
+    def nll(p, s):
+        return (0.5 * (torch.log(s * s) + (p - yd) ** 2 / (s * s))).mean().item()
+
+    assert abs(pred.mean().item() - rpred.mean().item()) <= k * se_mean, (engine, "mean pred", pred.mean().item(), rpred.mean().item())
+    rm, rrm = ((pred - yd) ** 2).mean().sqrt().item(), ((rpred - yd) ** 2).mean().sqrt().item()
+    assert abs(rm - rrm) <= k * se_mean, (engine, "rmse", rm, rrm)
+    assert abs(ep.mean().item() / rep.mean().item() - 1) <= rel_var, (engine, "epistemic var", ep.mean().item(), rep.mean().item())
+    # the aleatoric variance is a mean over samples of scale^2: its Monte-Carlo error is far below the epistemic one
+    assert abs(al.mean().item() / ral.mean().item() - 1) <= 0.05, (engine, "aleatoric var", al.mean().item(), ral.mean().item())
+    assert abs(std.mean().item() / rstd.mean().item() - 1) <= 0.05, (engine, "std", std.mean().item(), rstd.mean().item())
+    assert abs(nll(pred, std) - nll(rpred, rstd)) <= 0.05 * abs(nll(rpred, rstd)) + k * se_mean, (engine, "nll")
+    # per window: the two predictive means differ by less than k standard errors of their own estimate
+    z = (pred - rpred).abs() / ((2.0 * rep / S).sqrt() + 1e-9)
+    assert (z > k).double().mean().item() < 0.02, (engine, z.max().item())
+
+
+def test_flipout_forward_multi_sample_workspace(engines):
+    """brl_forward in Flipout mode with native signs needs [S,B,Cin] + [S,B,Cout] per layer on top of the activations
+    (brl_workspace_bytes(train=2)); S = 3 samples x 256 windows used to overflow the default query."""
+    from bayesrul_b200 import Noise
+    e = engines["inception"]
+    B, S = 256, 3
+    x, _, mu, sg = synth("inception", B, seed=5, sigma=0.05)
+    x, mu, sg = x.to(DEV), mu.to(DEV), sg.to(DEV)
+    w = e.sample_weights(mu, sg, "normal", S, Noise(seed=5))
+    out = e.forward(x, "flipout", theta=mu, wsamp=w, S=S, noise=Noise(seed=11))
+    one = e.forward(x, "flipout", theta=mu, wsamp=w[1:2].contiguous(), S=1, noise=Noise(seed=11, sample0=1))
+    assert out.shape == (S, B, 2) and torch.isfinite(out).all()
+    assert_close(out[1], one[0], rtol=1e-6, what="sample 1 of a 3-sample call == single-sample call at sample0=1")
