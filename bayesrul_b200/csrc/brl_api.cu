@@ -675,10 +675,12 @@ int brl_predict_moments(brl_ctx* ctx, const float* x, int64_t B, int64_t S, int 
   cudaStream_t st = (cudaStream_t)stream;
   const NetSpec& n = *ctx->net;
   const int nsites = 2 * (int)n.layers.size();
-  // largest chunk of samples that fits
-  long long Sc = std::min<long long>(S, 16);
+  // largest chunk of samples that fits (at most 32 on the fused engine, whose per-sample footprint is 4.8 KB per window,
+  // 16 on the per-layer engines), then equal chunks: S = 100 runs as 4 x 25, not 6 x 16 + 4
+  long long Sc = std::min<long long>(S, engine == BRL_ENGINE_TC_FP16 ? 32 : 16);
   for (; Sc >= 1; --Sc)
     if ((size_t)brl_workspace_bytes(ctx, B, Sc, 0, engine) <= workspace_bytes) break;
+  if (Sc >= 1) Sc = (S + (S + Sc - 1) / Sc - 1) / ((S + Sc - 1) / Sc);
   if (Sc < 1) return fail(BRL_ERR_WORKSPACE, "brl_predict_moments: workspace too small for one MC sample; need " +
                                                  std::to_string(brl_workspace_bytes(ctx, B, 1, 0, engine)) + " bytes");
   Carve c(workspace, workspace_bytes);

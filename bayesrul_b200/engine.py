@@ -220,7 +220,7 @@ class Engine:
                 raise RuntimeError("Guide unknown. Choose from 'normal', 'radial'.")
             sigma = self._theta(sigma, "sigma")
         eid = ENGINE_IDS[engine]
-        sc = min(S, chunk or 16)
+        sc = min(S, chunk or (32 if engine == "tc" else 16))
         while sc > 1 and self.lib.brl_workspace_bytes(self.ctx, B, sc, 0, eid) > self.max_workspace_bytes:
             sc -= 1
         ws = self.workspace(self.lib.brl_workspace_bytes(self.ctx, B, sc, 0, eid))
