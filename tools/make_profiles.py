@@ -25,7 +25,7 @@ for r in rows[1:]:
 tot = sum(v[1] for v in d.values())
 with open(os.path.join(P, f"{rnd}_launches_predict_tc.txt"), "w") as f:
     f.write(f"# {rnd} -- ncu launch list (gpu__time_duration.sum, --clock-control none) of\n"
-            "#   python bench.py --steps 2 --warmup 3 --no-cpu --no-train   (tcgen05 engine, B=10000 x S=100, chunks of 16 samples)\n"
+            "#   python bench.py --steps 2 --warmup 3 --no-cpu --no-train   (tcgen05 engine, B=10000 x S=100, chunks of 25 samples)\n"
             f"# per-launch times are cold-cache / serialised: read SHARES.  raw csv: gpurun_out/launches_{tag}.csv (scratch)\n")
     for k, (n, t) in sorted(d.items(), key=lambda x: -x[1][1]):
         f.write(f"{k:72s} n={n:4d} total={t / 1e6:9.3f} ms  avg={t / n / 1e3:9.1f} us share={100 * t / tot:5.1f}%\n")
@@ -68,12 +68,12 @@ def bytes_of(v, u):
 with open(os.path.join(P, f"{rnd}_ncu_tc_kernels.txt"), "w") as f:
     for name, rep, head in (
         ("tc_conv_kernel", f"prof_conv_{tag}.ncu-rep",
-         "one launch = 16 MC samples x 10000 windows = 160000 window-samples; algorithmic GEMM FLOPs/launch = 160000 x 1 981 920 = 317 GFLOP\n"
-         "# algorithmic bytes/launch: out 160000 x 4800 B = 768 MB (feature tensor), in 31.7 MB (fp16 window images, re-read from L2 per sample) + 16 x 87 KB weights"),
+         "one launch = 25 MC samples x 10000 windows = 250000 window-samples; algorithmic GEMM FLOPs/launch = 250000 x 1 981 920 = 495 GFLOP\n"
+         "# algorithmic bytes/launch: out 250000 x 4800 B = 1200 MB (feature tensor), in 31.7 MB (fp16 window images, re-read from L2 per sample) + 25 x 87 KB weights"),
         ("tc_fc_kernel", f"prof_fc_{tag}.ncu-rep",
-         "algorithmic FLOPs/launch = 160000 x 307 456 = 49 GFLOP; bytes: feature tensor read 768 MB + fc weights 307 KB x 79 tiles x 16 samples = 388 MB (L2)")):
+         "algorithmic FLOPs/launch = 250000 x 307 456 = 77 GFLOP; bytes: feature tensor read 1200 MB + fc weights 307 KB x 79 tiles x 25 samples = 606 MB (L2)")):
         m, tot, stalls, mnem = capture(os.path.join(G, rep))
-        f.write(f"# {rnd} -- ncu --set full --clock-control none --import-source on, {name}<false> (launch 5 of bench.py --steps 1 --warmup 3 --no-cpu --no-train)\n# {head}\n")
+        f.write(f"# {rnd} -- ncu --set full --clock-control none --import-source on, {name}<false> (launch 3 of bench.py --steps 1 --warmup 3 --no-cpu --no-train)\n# {head}\n")
         for k in keys:
             if k in m:
                 f.write(f"{k} [{m[k][1]}]: {m[k][0]}\n")
@@ -81,8 +81,8 @@ with open(os.path.join(P, f"{rnd}_ncu_tc_kernels.txt"), "w") as f:
         f.write("async-unit SASS executed (warp-instructions): " + ", ".join(f"{k} {v}" for k, v in sorted(mnem.items())) + "\n\n")
         if name == "tc_conv_kernel":
             db = bytes_of(*m['dram__bytes_read.sum']) + bytes_of(*m['dram__bytes_write.sum'])
-            json.dump({"kernel": name, "launch": "16 MC samples x 10000 windows (160000 window-samples)", "dram_bytes_per_launch": db,
-                       "dram_bytes_per_window_sample": db / 160000, "algorithmic_bytes_per_window_sample": 4800 + 2160 / 100,
+            json.dump({"kernel": name, "launch": "25 MC samples x 10000 windows (250000 window-samples)", "dram_bytes_per_launch": db,
+                       "dram_bytes_per_window_sample": db / 250000, "algorithmic_bytes_per_window_sample": 4800 + 2160 / 100,
                        "source": f"profiles/{rnd}_ncu_tc_kernels.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"},
                       open(os.path.join(P, "conv_traffic.json"), "w"), indent=1)
 print(open(os.path.join(P, f"{rnd}_ncu_tc_kernels.txt")).read())

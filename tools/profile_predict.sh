@@ -6,7 +6,7 @@ set -x
 python bench.py --steps 2 --warmup 3 --no-cpu --no-train > gpurun_out/bench_${tag}.json 2> gpurun_out/bench_${tag}.err || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${tag}.csv \
   python bench.py --steps 2 --warmup 3 --no-cpu --no-train > gpurun_out/ncu_list_${tag}.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:tc_conv_kernel -s 4 -c 1 -o gpurun_out/prof_conv_${tag} -f \
+ncu --set full --clock-control none --import-source on -k regex:tc_conv_kernel -s 2 -c 1 -o gpurun_out/prof_conv_${tag} -f \
   python bench.py --steps 1 --warmup 3 --no-cpu --no-train > gpurun_out/ncu_conv_${tag}.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:tc_fc_kernel -s 4 -c 1 -o gpurun_out/prof_fc_${tag} -f \
+ncu --set full --clock-control none --import-source on -k regex:tc_fc_kernel -s 2 -c 1 -o gpurun_out/prof_fc_${tag} -f \
   python bench.py --steps 1 --warmup 3 --no-cpu --no-train > gpurun_out/ncu_fc_${tag}.log 2>&1
