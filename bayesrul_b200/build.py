@@ -41,7 +41,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if verbose and out:
             print(out)
     if force or procs or _stale(LIB, objs):
-        cmd = [NVCC, "-shared", "-o", LIB, *objs, "-lcudart", "-lcuda"]
+        cmd = [NVCC, "-shared", "-o", LIB, *objs, "-lcudart"]
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}")

@@ -21,6 +21,8 @@
 #include <utility>
 #include <vector>
 
+#include <cuda.h>
+
 #include "../../include/bayesrul_b200.h"
 #include "brl_kernels.cuh"
 #include "brl_nets.h"
@@ -61,17 +63,20 @@ constexpr int CONV_SMEM = OFF_BAR + 256;
 constexpr int XIMG_TILE_BYTES = 6 * CS;       // fp16 chunk images of a tile's windows: X0 X1 X2 XP0 XP1 XP2, pad rows included
 static_assert(CONV_SMEM <= 232448, "conv kernel shared memory exceeds the 227 KB opt-in limit");
 // blob = conv image + fc image + fp32 tail (fc bias 64, last W 128, last b 2)
-constexpr int FC_IMG = 300 * 64 * 16;
+constexpr int FC_KPAD = 2432;                // K of the fc GEMM padded to 38 x 64 (zero weights behind 2400)
+constexpr int FC_IMG = (FC_KPAD / 8) * 64 * 16;  // [304 k-chunks][64 n][16 B]
 constexpr int BLOB_FC = CONV_IMG;
 constexpr int BLOB_TAIL = BLOB_FC + FC_IMG;
 constexpr int BLOB_BYTES = ((BLOB_TAIL + 194 * 4) + 255) / 256 * 256;
-constexpr int FEAT_TILE_BYTES = 300 * 2048;  // [300 k-chunks][128 windows][16 B]
-// fc kernel
-constexpr int FC_KCH = 10;                   // k-chunks per pipeline stage (K = 80)
-constexpr int FC_STAGES = 4;
-constexpr int FC_A_BYTES = FC_KCH * 2048, FC_W_BYTES = FC_KCH * 1024;
+constexpr int FEAT_ROW_BYTES = 4800;         // feature tensor: row-major [S][Bpad][2400] fp16, k' = (c / 8) * 240 + t * 8 + c % 8
+// fc kernel: A = 128 windows x 64 k per stage through a TMA tensor map (SWIZZLE_128B), B = 8 k-chunks of the weight image
+constexpr int FC_BK = 64;
+constexpr int FC_NKB = FC_KPAD / FC_BK;      // 38 (the last box is half out of bounds: TMA fills zeros)
+constexpr int FC_STAGES = 6;
+constexpr int FC_A_BYTES = 128 * 128, FC_W_BYTES = (FC_BK / 8) * 1024;
 constexpr int FC_STAGE_BYTES = FC_A_BYTES + FC_W_BYTES;
-constexpr int FC_SMEM = FC_STAGES * FC_STAGE_BYTES + 256;
+constexpr int FC_SMEM = FC_STAGES * FC_STAGE_BYTES + 256 + 1024;  // + barriers + slack to align the ring to 1024 B
+
 struct TcState {
   int net;
   int* status;  // device: 0 ok, else first mbarrier time-out code
@@ -103,7 +108,7 @@ __global__ void tc_pack_kernel(const PackArgs a) {
   unsigned char* blob = a.blob + (long long)s * BLOB_BYTES;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   constexpr int N_A = 12 * 32 * 32, N_B1 = 144 * 128, N_B4 = 32 * 128, N_C2 = 3 * 16 * 64, N_C3 = 5 * 16 * 64;
-  constexpr int N_FC = 64 * 2400;
+  constexpr int N_FC = 64 * FC_KPAD;
   int j = i;
   if (j < N_A) {  // module 1: tap-major [tap][k/8][n][k%8]
     const int tap = j / 1024, r = j % 1024, n = r / 32, k = r % 32;
@@ -174,9 +179,14 @@ __global__ void tc_pack_kernel(const PackArgs a) {
     return;
   }
   j -= NBIAS;
-  if (j < N_FC) {  // fc: k' = t*80 + c  <-  original column c*30 + t
-    const int n = j / 2400, kp = j % 2400, t = kp / 80, c = kp % 80;
-    put_h(blob, BLOB_FC + (kp >> 3) * 1024 + n * 16 + (kp & 7) * 2, w[a.off[10][0] + (long long)n * 2400 + c * 30 + t]);
+  if (j < N_FC) {  // fc: k' = (c / 8) * 240 + t * 8 + c % 8  <-  original column c*30 + t; zero behind 2400
+    const int n = j / FC_KPAD, kp = j % FC_KPAD;
+    float v = 0.f;
+    if (kp < 2400) {
+      const int cb = kp / 240, r = kp % 240, t = r >> 3, c = cb * 8 + (r & 7);
+      v = w[a.off[10][0] + (long long)n * 2400 + c * 30 + t];
+    }
+    put_h(blob, BLOB_FC + (kp >> 3) * 1024 + n * 16 + (kp & 7) * 2, v);
     return;
   }
   j -= N_FC;
@@ -185,7 +195,7 @@ __global__ void tc_pack_kernel(const PackArgs a) {
     *reinterpret_cast<float*>(blob + BLOB_TAIL + j * 4) = v;
   }
 }
-constexpr int PACK_THREADS_TOTAL = 12 * 1024 + 144 * 128 + 32 * 128 + 3 * 1024 + 5 * 1024 + NBIAS + 64 * 2400 + 194;
+constexpr int PACK_THREADS_TOTAL = 12 * 1024 + 144 * 128 + 32 * 128 + 3 * 1024 + 5 * 1024 + NBIAS + 64 * FC_KPAD + 194;
 
 #include "brl_tc_conv.cuh"
 
@@ -193,27 +203,39 @@ constexpr int PACK_THREADS_TOTAL = 12 * 1024 + 144 * 128 + 32 * 128 + 3 * 1024 +
 // fc + head kernel
 // ------------------------------------------------------------------------------------------------
 struct FcArgs {
-  const unsigned char* feat;
   const unsigned char* blob;
   long long blob_stride;
   float* out;  // [S,B,2]
-  int B, S, ntile128;
+  int B, S, ntile128;  // feature rows per sample = ntile128 * 128
   float keep;  // dropout keep of the fc site
   NoiseRef drop;
   int* status;
 };
 
+// K-major SWIZZLE_128B shared-memory matrix descriptor (what a TMA SWIZZLE_128B box of 64 fp16 columns produces):
+// 8-row x 128-byte atoms of 1024 B, SBO = 1024 between 8-row groups, layout type 2; k advances by +32 B inside the atom
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+
 template <bool DROP>
-__global__ void __launch_bounds__(192, 1) tc_fc_kernel(const FcArgs a) {
-  extern __shared__ __align__(128) unsigned char smem[];
+__global__ void __launch_bounds__(192, 1) tc_fc_kernel(const FcArgs a, const __grid_constant__ CUtensorMap fmap) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // SWIZZLE_128B atoms: 1024-byte aligned
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bars = sbase + FC_STAGES * FC_STAGE_BYTES;
-  // full[4] @0, empty[4] @32, tmem_full[2] @64, tmem_empty[2] @80, tmem slot @96
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + FC_STAGES * FC_STAGE_BYTES + 96);
+  // full[6] @0, empty[6] @48, tmem_full[2] @96, tmem_empty[2] @112, tmem slot @128
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + FC_STAGES * FC_STAGE_BYTES + 128);
   if (tid == 0) {
-    for (int i = 0; i < FC_STAGES; ++i) { mbar_init(bars + 8 * i, 1); mbar_init(bars + 32 + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(bars + 64 + 8 * i, 1); mbar_init(bars + 80 + 8 * i, 128); }
+    for (int i = 0; i < FC_STAGES; ++i) { mbar_init(bars + 8 * i, 1); mbar_init(bars + 48 + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bars + 96 + 8 * i, 1); mbar_init(bars + 112 + 8 * i, 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 128);
@@ -222,7 +244,7 @@ __global__ void __launch_bounds__(192, 1) tc_fc_kernel(const FcArgs a) {
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const long long total = (long long)a.S * a.ntile128;
-  constexpr int NKB = 300 / FC_KCH;
+  constexpr int NKB = FC_NKB;
 
   if (warp == 0) {
     if (lane == 0) {  // ===== producer: bulk copies of the A (features) and B (fc weights) k-blocks
@@ -230,13 +252,13 @@ __global__ void __launch_bounds__(192, 1) tc_fc_kernel(const FcArgs a) {
       bool ok = true;
       for (long long it = blockIdx.x; it < total && ok; it += gridDim.x) {
         const int s = (int)(it / a.ntile128);
-        const unsigned char* ga = a.feat + it * (long long)FEAT_TILE_BYTES;
+        const int row0 = (int)(it * 128);  // == (s * ntile128 + tile) * 128: rows of the [S * Bpad, 2400] feature matrix
         const unsigned char* gb = a.blob + (long long)s * a.blob_stride + BLOB_FC;
         for (int kb = 0; kb < NKB && ok; ++kb) {
-          ok = mbar_wait(bars + 32 + 8 * stage, ph, a.status, 10);
+          ok = mbar_wait(bars + 48 + 8 * stage, ph, a.status, 10);
           const uint32_t dst = sbase + stage * FC_STAGE_BYTES;
           mbar_expect_tx(bars + 8 * stage, FC_STAGE_BYTES);
-          bulk_g2s(dst, ga + (long long)kb * FC_A_BYTES, FC_A_BYTES, bars + 8 * stage);
+          tma_load_2d(dst, &fmap, kb * FC_BK, row0, bars + 8 * stage);
           bulk_g2s(dst + FC_A_BYTES, gb + (long long)kb * FC_W_BYTES, FC_W_BYTES, bars + 8 * stage);
           if (++stage == FC_STAGES) { stage = 0; ph ^= 1; }
         }
@@ -248,20 +270,19 @@ __global__ void __launch_bounds__(192, 1) tc_fc_kernel(const FcArgs a) {
       uint32_t stage = 0, ph = 0, acc_i = 0, aph = 1;
       bool ok = true;
       for (long long it = blockIdx.x; it < total && ok; it += gridDim.x) {
-        ok = mbar_wait(bars + 80 + 8 * acc_i, aph, a.status, 11);
+        ok = mbar_wait(bars + 112 + 8 * acc_i, aph, a.status, 11);
         tc_fence_after();
         for (int kb = 0; kb < NKB && ok; ++kb) {
           ok = mbar_wait(bars + 8 * stage, ph, a.status, 12);
           tc_fence_after();
           const uint32_t sa = sbase + stage * FC_STAGE_BYTES, sb = sa + FC_A_BYTES;
 #pragma unroll
-          for (int ks = 0; ks < FC_KCH / 2; ++ks)
-            umma(tmem + acc_i * 64, umma_desc(sa + 2 * ks * 2048, 2048, 128), umma_desc(sb + 2 * ks * 1024, 1024, 128), idesc,
-                 (kb | ks) != 0);
-          umma_commit(bars + 32 + 8 * stage);
+          for (int ks = 0; ks < FC_BK / 16; ++ks)
+            umma(tmem + acc_i * 64, umma_desc_sw128(sa + ks * 32), umma_desc(sb + 2 * ks * 1024, 1024, 128), idesc, (kb | ks) != 0);
+          umma_commit(bars + 48 + 8 * stage);
           if (++stage == FC_STAGES) { stage = 0; ph ^= 1; }
         }
-        umma_commit(bars + 64 + 8 * acc_i);
+        umma_commit(bars + 96 + 8 * acc_i);
         if (++acc_i == 2) { acc_i = 0; aph ^= 1; }
       }
     }
@@ -272,14 +293,14 @@ __global__ void __launch_bounds__(192, 1) tc_fc_kernel(const FcArgs a) {
     for (long long it = blockIdx.x; it < total && ok; it += gridDim.x) {
       const int s = (int)(it / a.ntile128), tile = (int)(it % a.ntile128);
       const float* tail = reinterpret_cast<const float*>(a.blob + (long long)s * a.blob_stride + BLOB_TAIL);
-      ok = mbar_wait(bars + 64 + 8 * acc_i, aph, a.status, 13);
+      ok = mbar_wait(bars + 96 + 8 * acc_i, aph, a.status, 13);
       tc_fence_after();
       float acc[4][16];
 #pragma unroll
       for (int g = 0; g < 4; ++g) tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + acc_i * 64 + g * 16, acc[g]);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(bars + 80 + 8 * acc_i);  // accumulator drained: the issuer may reuse it
+      mbar_arrive(bars + 112 + 8 * acc_i);  // accumulator drained: the issuer may reuse it
       const int gw = tile * 128 + row;
       float o0 = __ldg(tail + 192), o1 = __ldg(tail + 193);
 #pragma unroll
@@ -390,7 +411,7 @@ int tc_status(const TcState* s) {
 }
 size_t tc_workspace_bytes(const TcState* s, long long B, long long S) {
   const long long nt128 = (B + 127) / 128, npair = ((B + 3) / 4 + 1) / 2;
-  return (size_t)(S * (long long)BLOB_BYTES + S * nt128 * FEAT_TILE_BYTES + 2 * npair * XIMG_TILE_BYTES + 1024);
+  return (size_t)(S * (long long)BLOB_BYTES + S * nt128 * 128 * FEAT_ROW_BYTES + 2 * npair * XIMG_TILE_BYTES + 2048);
 }
 
 const char* tc_forward(TcState* st, const float* x, long long B, long long S, const float* weights, long long w_sample_stride,
@@ -437,15 +458,38 @@ const char* tc_forward(TcState* st, const float* x, long long B, long long S, co
   else tc_conv_kernel<false><<<grid, CONV_THREADS, CONV_SMEM, stream>>>(ca);
   tc_time_end(st, 0, stream);
   FcArgs fa;
-  fa.feat = feat; fa.blob = blob; fa.blob_stride = ca.blob_stride; fa.out = out;
+  fa.blob = blob; fa.blob_stride = ca.blob_stride; fa.out = out;
   fa.B = (int)B; fa.S = (int)S; fa.ntile128 = (int)nt128;
   fa.keep = drop ? 1.0f - p_dropout : 1.0f;
   fa.drop = nr(10);
   fa.status = st->status;
   const int gridf = (int)std::min<long long>(st->sm_count, S * nt128);
+  // TMA view of the feature tensor: [S * Bpad rows][2400 fp16], boxes of 128 rows x 64 columns, 128-byte swizzle
+  CUtensorMap fmap;
+  {
+    const cuuint64_t gdim[2] = {2400, (cuuint64_t)(S * nt128 * 128)};
+    const cuuint64_t gstr[1] = {FEAT_ROW_BYTES};
+    const cuuint32_t box[2] = {FC_BK, 128};
+    const cuuint32_t estr[2] = {1, 1};
+    // resolved through the runtime so that the library carries no link-time dependency on libcuda.so (it must load, and
+    // export every symbol, on a machine without a driver)
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
+        return "bayesrul_b200: cuTensorMapEncodeTiled is not available from this driver";
+      encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    const CUresult r = encode(&fmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, feat, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return "bayesrul_b200: cuTensorMapEncodeTiled failed for the feature tensor";
+  }
   tc_time_begin(st, 1, stream);
-  if (drop) tc_fc_kernel<true><<<gridf, 192, FC_SMEM, stream>>>(fa);
-  else tc_fc_kernel<false><<<gridf, 192, FC_SMEM, stream>>>(fa);
+  if (drop) tc_fc_kernel<true><<<gridf, 192, FC_SMEM, stream>>>(fa, fmap);
+  else tc_fc_kernel<false><<<gridf, 192, FC_SMEM, stream>>>(fa, fmap);
   tc_time_end(st, 1, stream);
   count_launch(3);
   return nullptr;

@@ -30,7 +30,7 @@ struct ConvArgs {
   const unsigned char* ximg;  // [2 * npair][X0 X1 X2 XP0 XP1 XP2][132 rows][16 B]  (tc_packx_kernel)
   const unsigned char* blob;  // [S or 1][BLOB_BYTES]
   long long blob_stride;      // BLOB_BYTES or 0
-  unsigned char* feat;        // [S][NT128][300][128][16 B]
+  unsigned char* feat;        // row-major [S][ntile128 * 128 windows][10 chunks][30 steps][8 fp16] (= [.., 2400] for the fc GEMM)
   int B, S, ntile4, ntile128;
   float keep4;                // dropout keep of the branch sites (1 = off)
   NoiseRef drop[12];
@@ -395,8 +395,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) tc_conv_kernel(const ConvArgs
         const int tile = pair * 2 + k, gw = tile * 4 + wq;
         const bool live = t < 30 && gw < a.B && tile < a.ntile4;
         unsigned char* reg = smem + k * G_BYTES;
-        unsigned char* frow = a.feat + ((long long)s * a.ntile128 + (gw >> 7)) * FEAT_TILE_BYTES + (long long)(gw & 127) * 16 +
-                              (long long)t * 10 * 2048;
+        // feature row of window gw: chunk c of time step t at c * 480 + t * 16 -> a warp (one window, 30 steps) stores 480
+        // contiguous bytes per chunk
+        unsigned char* frow = a.feat + ((long long)s * a.ntile128 * 128 + gw) * FEAT_ROW_BYTES + t * 16;
         tr(it, 6 + 3 * k);
         ok = mbar_wait(bars + BAR_DONE_B + 8 * k, ph, a.status, 7, abort_flag) && ok;
         tc_fence_after();
@@ -425,8 +426,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) tc_conv_kernel(const ConvArgs
           finish16<DROP>(acc[2], live, a, q == 0 ? 4 : 9, s, gw, t, q == 2 ? 16 : 0, q == 0 ? 16 : 32, lo, hi);
           const int fc = q == 0 ? 0 : q == 1 ? 6 : 8;
           if (BRL_FEAT_LIVE(live)) {
-            *reinterpret_cast<uint4*>(frow + fc * 2048) = lo;
-            *reinterpret_cast<uint4*>(frow + (fc + 1) * 2048) = hi;
+            *reinterpret_cast<uint4*>(frow + fc * 480) = lo;
+            *reinterpret_cast<uint4*>(frow + (fc + 1) * 480) = hi;
           }
         }
         tr(it, 8 + 3 * k);
@@ -436,8 +437,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) tc_conv_kernel(const ConvArgs
       for (int k = 0; k < 2; ++k) {
         const int tile = pair * 2 + k, gw = tile * 4 + wq;
         const bool live = t < 30 && gw < a.B && tile < a.ntile4;
-        unsigned char* frow = a.feat + ((long long)s * a.ntile128 + (gw >> 7)) * FEAT_TILE_BYTES + (long long)(gw & 127) * 16 +
-                              (long long)t * 10 * 2048;
+        // feature row of window gw: chunk c of time step t at c * 480 + t * 16 -> a warp (one window, 30 steps) stores 480
+        // contiguous bytes per chunk
+        unsigned char* frow = a.feat + ((long long)s * a.ntile128 * 128 + gw) * FEAT_ROW_BYTES + t * 16;
         tr(it, 12 + 3 * k);
         ok = mbar_wait(bars + (q < 2 ? BAR_DONE_C : BAR_DONE_C2) + 8 * k, ph, a.status, 8, abort_flag) && ok;
         tc_fence_after();
@@ -462,7 +464,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) tc_conv_kernel(const ConvArgs
         }
         tc_fence_before();
         actn<DROP, true, 8>(out, sbias + 304 + q * 8, live, a, q < 2 ? 6 : 8, s, gw, t, (q & 1) * 8, 16);
-        if (BRL_FEAT_LIVE(live)) *reinterpret_cast<uint4*>(frow + (2 + q) * 2048) = pack8(out, true);
+        if (BRL_FEAT_LIVE(live)) *reinterpret_cast<uint4*>(frow + (2 + q) * 480) = pack8(out, true);
         tr(it, 14 + 3 * k);
       }
       if (++pair == npair) {
