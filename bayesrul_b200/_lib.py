@@ -54,6 +54,7 @@ SIGNATURES = {
     "brl_engine_available": (_i, [_vp, _i]),
     "brl_tc_status": (_i, [_vp]),
     "brl_set_gemm_backend": (_i, [_vp, _i]),
+    "brl_set_step_graph": (_i, [_vp, _i]),
     "brl_gemm_status": (_i, []),
     "brl_tc_timing": (_i, [_vp, _i]),
     "brl_tc_timing_read": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(_i64)]),  # double[2], int64[2]

@@ -163,3 +163,14 @@ def enable_dropout(model):
     for m in model.modules():
         if isinstance(m, TableNet):
             m.mc_dropout = True
+
+
+def init_flat_params(kind: str = "inception", seed: int = 12345) -> torch.Tensor:
+    """Flat [P] parameter vector of a freshly built net after `weights_init` under `torch.manual_seed(seed)`
+    (the pre-training initialisation of tasks/train.py + utils/miscellaneous.py:53-63); synthetic-weight helper."""
+    cls = {"inception": Inception, "conv": Conv, "linear": Linear}[kind]
+    with torch.random.fork_rng(devices=[]):
+        torch.manual_seed(seed)
+        net = cls(30, 18)
+        weights_init(net)
+        return net.flat().detach().clone()

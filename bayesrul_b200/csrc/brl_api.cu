@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
+#include <list>
 #include <string>
 #include <vector>
 
@@ -54,6 +55,22 @@ struct brl_ctx {
   bool multi_stream = true;
   cudaStream_t side[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr}, ev_op[8] = {};
+  // CUDA-graph replay of brl_elbo_step (native Philox noise only): a step is ~60-110 small launches + event fork / joins,
+  // i.e. 0.5 ms (LRT) to 1.7 ms (Flipout, 2 particles) of host enqueue time -- more than the GPU needs to run it.
+  // The second call with the same key captures the step (on `cap`, since the caller's stream may be the legacy default
+  // stream) over staging buffers in the caller's workspace; later calls replay it.
+  struct StepKey {
+    long long B, dataset_size;
+    int mode, guide, particles, compute_grads, backend, has_log_sigma;
+    float prior_loc, prior_scale;
+    const void *mu, *sigma, *ws;
+    size_t ws_bytes;
+    bool operator==(const StepKey& o) const { return memcmp(this, &o, sizeof(StepKey)) == 0; }
+  };
+  struct StepGraph { StepKey key; cudaGraphExec_t exec = nullptr; int seen = 0, launches = 0; bool bad = false; };
+  std::list<StepGraph> graphs;
+  bool graph_enabled = true;
+  cudaStream_t cap = nullptr;
 };
 
 // bump allocator over the caller's workspace (256-byte aligned); base == nullptr only measures
@@ -79,7 +96,12 @@ struct ActBufs {
   float *g0 = nullptr, *g1 = nullptr, *wsamp = nullptr, *delta = nullptr, *norms = nullptr;
   std::vector<float*> sgn_in, sgn_out;  // per layer
   double* acc = nullptr;
+  // staging of a captured ELBO step: the graph reads / writes these, plain copies connect them to the caller's tensors
+  float *st_x = nullptr, *st_y = nullptr, *st_out = nullptr, *st_gmu = nullptr, *st_gsig = nullptr, *st_glog = nullptr;
+  double* st_scal = nullptr;
+  unsigned long long* dyn = nullptr;
 };
+constexpr int GRAPH_MAX_PARTICLES = 8;
 
 static void carve_forward(const NetSpec& n, Carve& c, long long B, long long S, ActBufs& ab) {
   ab.act.resize(n.bufs.size());
@@ -111,11 +133,28 @@ static void carve_train(const NetSpec& n, Carve& c, long long B, ActBufs& ab) {
   }
   ab.acc = c.take<double>(8);
   for (int i = 0; i < 4; ++i) ab.part[i] = c.take<float>(SPLITK_SCRATCH_FLOATS);
+  ab.st_x = c.take<float>(B * 540);
+  ab.st_y = c.take<float>(B);
+  ab.st_out = c.take<float>(GRAPH_MAX_PARTICLES * B * 2);
+  ab.st_gmu = c.take<float>(n.P);
+  ab.st_gsig = c.take<float>(n.P);
+  ab.st_glog = c.take<float>(n.P);
+  ab.st_scal = c.take<double>(4);
+  ab.dyn = c.take<unsigned long long>(4);
+}
+
+// device {seed, sample0, window0} of the step being captured (nullptr outside a capture): every Philox stream built by
+// nref() then reads the per-step part of its key from there
+static thread_local const unsigned long long* g_dyn = nullptr;
+__global__ void set_noise_key_kernel(unsigned long long* dyn, unsigned long long seed, unsigned long long sample0,
+                                     unsigned long long window0) {
+  dyn[0] = seed; dyn[1] = sample0; dyn[2] = window0;
 }
 
 static NoiseRef nref(const brl_noise* nz, const float* ptr, unsigned kind, unsigned site) {
   NoiseRef r;
   r.ptr = ptr;
+  r.dyn = ptr ? nullptr : g_dyn;
   r.seed = nz ? nz->seed : 0ull;
   r.kind = kind;
   r.site = site;
@@ -505,6 +544,9 @@ int brl_create(brl_ctx** out, int net, int device) {
     BRL_CUDA(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
   }
   BRL_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  BRL_CUDA(cudaStreamCreateWithFlags(&c->cap, cudaStreamNonBlocking));
+  const char* nograph = getenv("BRL_NO_GRAPH");
+  c->graph_enabled = !(nograph && nograph[0] == '1');
   for (int i = 0; i < 8; ++i) BRL_CUDA(cudaEventCreateWithFlags(&c->ev_op[i], cudaEventDisableTiming));
   *out = c;
   return BRL_OK;
@@ -520,6 +562,9 @@ int brl_destroy(brl_ctx* ctx) {
     if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
   }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  for (auto& g : ctx->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (ctx->cap) cudaStreamDestroy(ctx->cap);
   for (int i = 0; i < 8; ++i)
     if (ctx->ev_op[i]) cudaEventDestroy(ctx->ev_op[i]);
   delete ctx;
@@ -741,24 +786,12 @@ int brl_aggregate_predictions(const float* out, int64_t S, int64_t B, float* agg
   return BRL_OK;
 }
 
-int brl_elbo_step(brl_ctx* ctx, const float* x, const float* y, int64_t B, const float* mu, const float* sigma, int mode,
-                  int guide, int particles, float prior_loc, float prior_scale, int64_t dataset_size,
-                  const brl_noise* noise, int compute_grads, double* scalars, float* grad_mu, float* grad_sigma,
-                  float* grad_log_sigma, float* out, void* workspace, size_t workspace_bytes, void* stream) {
-  BRL_REQUIRE(ctx && x && y && mu && sigma && scalars && out && workspace, "brl_elbo_step: NULL argument");
-  BRL_REQUIRE(B > 0 && particles > 0 && dataset_size > 0 && prior_scale > 0.f, "brl_elbo_step: bad sizes");
-  BRL_REQUIRE(guide == BRL_GUIDE_NORMAL || guide == BRL_GUIDE_RADIAL, "Guide unknown. Choose from 'normal', 'radial'.");
-  BRL_REQUIRE(mode == BRL_MODE_WS || mode == BRL_MODE_LRT || mode == BRL_MODE_FLIPOUT, "brl_elbo_step: mode must be WS, LRT or FLIPOUT");
-  BRL_REQUIRE(!compute_grads || (grad_mu && grad_sigma), "brl_elbo_step: gradient buffers are NULL");
-  if (guide == BRL_GUIDE_RADIAL) mode = BRL_MODE_WS;  // bayesian.py:81-83: radial forces nullcontext
-  cudaStream_t st = (cudaStream_t)stream;
+// the launches of one ELBO step (every pointer final); captured as is by the graph path of brl_elbo_step
+static int elbo_body(brl_ctx* ctx, const ActBufs& ab, const float* x, const float* y, int64_t B, const float* mu, const float* sigma,
+                     int mode, int guide, int particles, float prior_loc, float prior_scale, int64_t dataset_size,
+                     const brl_noise* noise, int compute_grads, double* scalars, float* grad_mu, float* grad_sigma,
+                     float* grad_log_sigma, float* out, cudaStream_t st) {
   const NetSpec& n = *ctx->net;
-  Carve c(workspace, workspace_bytes);
-  ActBufs ab;
-  carve_forward(n, c, B, 1, ab);
-  carve_train(n, c, B, ab);
-  if (!c.ok) return fail(BRL_ERR_WORKSPACE, "brl_elbo_step: workspace too small; need " +
-                                                std::to_string(brl_workspace_bytes(ctx, B, 1, 1, 0)) + " bytes");
   const double cc = 1.0 / ((double)dataset_size * 30.0 * 18.0);
   const double c_nll = cc * (double)dataset_size / (double)B;
   BRL_CUDA(cudaMemsetAsync(ab.acc, 0, 8 * sizeof(double), st));
@@ -808,6 +841,105 @@ int brl_elbo_step(brl_ctx* ctx, const float* x, const float* y, int64_t B, const
   if (compute_grads && grad_log_sigma) launch_log_sigma_grad(grad_sigma, sigma, grad_log_sigma, n.P, st);
   BRL_CUDA(cudaGetLastError());
   return BRL_OK;
+}
+
+static bool noise_is_native(const brl_noise* nz) {
+  if (!nz) return true;
+  if (nz->weight_eps || nz->radial_r) return false;
+  for (int l = 0; l < BRL_MAX_LAYERS; ++l)
+    if (nz->lrt_eps[l] || nz->flip_in[l] || nz->flip_out[l] || nz->drop_mask[l]) return false;
+  return true;
+}
+
+int brl_set_step_graph(brl_ctx* ctx, int enable) {
+  BRL_REQUIRE(ctx, "brl_set_step_graph: NULL context");
+  ctx->graph_enabled = enable != 0;
+  return BRL_OK;
+}
+
+int brl_elbo_step(brl_ctx* ctx, const float* x, const float* y, int64_t B, const float* mu, const float* sigma, int mode,
+                  int guide, int particles, float prior_loc, float prior_scale, int64_t dataset_size,
+                  const brl_noise* noise, int compute_grads, double* scalars, float* grad_mu, float* grad_sigma,
+                  float* grad_log_sigma, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  BRL_REQUIRE(ctx && x && y && mu && sigma && scalars && out && workspace, "brl_elbo_step: NULL argument");
+  BRL_REQUIRE(B > 0 && particles > 0 && dataset_size > 0 && prior_scale > 0.f, "brl_elbo_step: bad sizes");
+  BRL_REQUIRE(guide == BRL_GUIDE_NORMAL || guide == BRL_GUIDE_RADIAL, "Guide unknown. Choose from 'normal', 'radial'.");
+  BRL_REQUIRE(mode == BRL_MODE_WS || mode == BRL_MODE_LRT || mode == BRL_MODE_FLIPOUT, "brl_elbo_step: mode must be WS, LRT or FLIPOUT");
+  BRL_REQUIRE(!compute_grads || (grad_mu && grad_sigma), "brl_elbo_step: gradient buffers are NULL");
+  if (guide == BRL_GUIDE_RADIAL) mode = BRL_MODE_WS;  // bayesian.py:81-83: radial forces nullcontext
+  cudaStream_t st = (cudaStream_t)stream;
+  const NetSpec& n = *ctx->net;
+  Carve c(workspace, workspace_bytes);
+  ActBufs ab;
+  carve_forward(n, c, B, 1, ab);
+  carve_train(n, c, B, ab);
+  if (!c.ok) return fail(BRL_ERR_WORKSPACE, "brl_elbo_step: workspace too small; need " +
+                                                std::to_string(brl_workspace_bytes(ctx, B, 1, 1, 0)) + " bytes");
+  // ---- graph replay (native Philox noise): eager on first sight of a configuration, captured on the second, replayed after
+  brl_ctx::StepGraph* sg = nullptr;
+  if (ctx->graph_enabled && noise_is_native(noise) && particles <= GRAPH_MAX_PARTICLES) {
+    brl_ctx::StepKey key;
+    memset(&key, 0, sizeof(key));
+    key.B = B; key.dataset_size = dataset_size; key.mode = mode; key.guide = guide; key.particles = particles;
+    key.compute_grads = compute_grads; key.backend = ctx->gemm_backend; key.has_log_sigma = grad_log_sigma != nullptr;
+    key.prior_loc = prior_loc; key.prior_scale = prior_scale; key.mu = mu; key.sigma = sigma; key.ws = workspace;
+    key.ws_bytes = workspace_bytes;
+    for (auto it = ctx->graphs.begin(); it != ctx->graphs.end(); ++it)
+      if (it->key == key) { ctx->graphs.splice(ctx->graphs.begin(), ctx->graphs, it); sg = &ctx->graphs.front(); break; }
+    if (!sg) {
+      if (ctx->graphs.size() >= 16) {
+        if (ctx->graphs.back().exec) cudaGraphExecDestroy(ctx->graphs.back().exec);
+        ctx->graphs.pop_back();
+      }
+      ctx->graphs.emplace_front();
+      ctx->graphs.front().key = key;
+      sg = &ctx->graphs.front();
+    }
+    ++sg->seen;
+    if (sg->seen >= 2 && !sg->exec && !sg->bad) {
+      cudaGraph_t graph = nullptr;
+      int rc = BRL_OK;
+      if (cudaStreamBeginCapture(ctx->cap, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        g_dyn = ab.dyn;
+        const long long l0 = launch_count();
+        brl_noise zero;
+        memset(&zero, 0, sizeof(zero));
+        rc = elbo_body(ctx, ab, ab.st_x, ab.st_y, B, mu, sigma, mode, guide, particles, prior_loc, prior_scale, dataset_size, &zero,
+                       compute_grads, ab.st_scal, compute_grads ? ab.st_gmu : nullptr, compute_grads ? ab.st_gsig : nullptr,
+                       (compute_grads && grad_log_sigma) ? ab.st_glog : nullptr, ab.st_out, ctx->cap);
+        g_dyn = nullptr;
+        sg->launches = (int)(launch_count() - l0);
+        count_launch(-sg->launches);  // captured, not executed
+        const cudaError_t e = cudaStreamEndCapture(ctx->cap, &graph);
+        if (rc != BRL_OK || e != cudaSuccess || !graph || cudaGraphInstantiate(&sg->exec, graph, 0) != cudaSuccess) {
+          sg->exec = nullptr;
+          sg->bad = true;
+        }
+        if (graph) cudaGraphDestroy(graph);
+      } else {
+        sg->bad = true;
+      }
+      cudaGetLastError();  // a failed capture must not poison the eager path below
+    }
+  }
+  if (sg && sg->exec) {
+    count_launch(1 + sg->launches);
+    set_noise_key_kernel<<<1, 1, 0, st>>>(ab.dyn, noise ? noise->seed : 0ull, noise ? (unsigned long long)noise->sample0 : 0ull,
+                                          noise ? (unsigned long long)noise->window0 : 0ull);
+    BRL_CUDA(cudaMemcpyAsync(ab.st_x, x, sizeof(float) * B * 540, cudaMemcpyDeviceToDevice, st));
+    BRL_CUDA(cudaMemcpyAsync(ab.st_y, y, sizeof(float) * B, cudaMemcpyDeviceToDevice, st));
+    BRL_CUDA(cudaGraphLaunch(sg->exec, st));
+    BRL_CUDA(cudaMemcpyAsync(scalars, ab.st_scal, 4 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    BRL_CUDA(cudaMemcpyAsync(out, ab.st_out, sizeof(float) * particles * B * 2, cudaMemcpyDeviceToDevice, st));
+    if (compute_grads) {
+      BRL_CUDA(cudaMemcpyAsync(grad_mu, ab.st_gmu, sizeof(float) * n.P, cudaMemcpyDeviceToDevice, st));
+      BRL_CUDA(cudaMemcpyAsync(grad_sigma, ab.st_gsig, sizeof(float) * n.P, cudaMemcpyDeviceToDevice, st));
+      if (grad_log_sigma) BRL_CUDA(cudaMemcpyAsync(grad_log_sigma, ab.st_glog, sizeof(float) * n.P, cudaMemcpyDeviceToDevice, st));
+    }
+    return BRL_OK;
+  }
+  return elbo_body(ctx, ab, x, y, B, mu, sigma, mode, guide, particles, prior_loc, prior_scale, dataset_size, noise, compute_grads,
+                   scalars, grad_mu, grad_sigma, grad_log_sigma, out, st);
 }
 
 int brl_hnn_step(brl_ctx* ctx, const float* x, const float* y, int64_t B, const float* theta, float p_dropout,

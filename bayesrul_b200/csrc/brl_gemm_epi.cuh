@@ -8,12 +8,14 @@ namespace brl {
 
 __device__ __forceinline__ float gnoise_normal(const NoiseRef& nz, int s, int b, int B, int per_window, int e) {
   if (nz.ptr) return nz.ptr[((long long)s * B + b) * per_window + e];
-  return philox_normal(nz.seed, nz.kind, nz.site, nz.sample0 + s, nz.window0 + b, e);
+  const NoiseKey k = noise_key(nz);
+  return philox_normal(k.seed, nz.kind, nz.site, k.sample0 + s, k.window0 + b, e);
 }
 // dropout site of an op with C channels x P positions: injected masks are [S,B,C,P] (reference layout)
 __device__ __forceinline__ bool gnoise_keep(const NoiseRef& nz, int s, int b, int B, int C, int P, int ch, int pos, float keep) {
   if (nz.ptr) return nz.ptr[(((long long)s * B + b) * C + ch) * P + pos] != 0.0f;
-  return philox_keep(nz.seed, nz.kind, nz.site, nz.sample0 + s, nz.window0 + b, C, pos, ch, keep);
+  const NoiseKey k = noise_key(nz);
+  return philox_keep(k.seed, nz.kind, nz.site, k.sample0 + s, k.window0 + b, C, pos, ch, keep);
 }
 
 // one output element of a forward / input-gradient GEMM

@@ -17,7 +17,8 @@ void count_launch(int n) { g_launch_count.fetch_add(n); }
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float noise_normal(const NoiseRef& nz, int s, int b, int B, int per_window, int e) {
   if (nz.ptr) return nz.ptr[((long long)s * B + b) * per_window + e];
-  return philox_normal(nz.seed, nz.kind, nz.site, nz.sample0 + s, nz.window0 + b, e);
+  const NoiseKey k = noise_key(nz);
+  return philox_normal(k.seed, nz.kind, nz.site, k.sample0 + s, k.window0 + b, e);
 }
 __device__ __forceinline__ float softplusf(float x) { return x > 20.0f ? x : log1pf(expf(x)); }
 
@@ -169,7 +170,8 @@ __global__ void sample_normal_kernel(const float* __restrict__ mu, const float* 
 #pragma unroll
       for (int l = 0; l < 4; ++l) z[l] = e0 + l < P ? eps.ptr[(long long)s * P + e0 + l] : 0.f;
     } else {
-      const float4 n4 = normal4(philox_block(eps.seed, KIND_WEIGHT_EPS, 0, eps.sample0 + s, 0, (uint32_t)blk));
+      const NoiseKey k = noise_key(eps);
+      const float4 n4 = normal4(philox_block(k.seed, KIND_WEIGHT_EPS, 0, k.sample0 + s, 0, (uint32_t)blk));
       z[0] = n4.x; z[1] = n4.y; z[2] = n4.z; z[3] = n4.w;
     }
 #pragma unroll
@@ -192,7 +194,8 @@ void launch_sample_normal(const float* mu, const float* sigma, long long P, long
 
 __device__ __forceinline__ float weight_eps_at(const NoiseRef& eps, int s, long long P, long long e) {
   if (eps.ptr) return eps.ptr[(long long)s * P + e];
-  return philox_normal(eps.seed, KIND_WEIGHT_EPS, 0, eps.sample0 + s, 0, (uint32_t)e);
+  const NoiseKey k = noise_key(eps);
+  return philox_normal(k.seed, KIND_WEIGHT_EPS, 0, k.sample0 + s, 0, (uint32_t)e);
 }
 __global__ void radial_norm_kernel(long long P, const long long* __restrict__ site_off, int n_sites, NoiseRef eps,
                                    float* __restrict__ norms) {
@@ -213,8 +216,9 @@ __global__ void radial_apply_kernel(const float* __restrict__ mu, const float* _
   const long long beg = site_off[j], end = site_off[j + 1];
   const long long e = beg + blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (e >= end) return;
+  const NoiseKey rk = noise_key(r);
   const float rr = r.ptr ? r.ptr[(long long)s * n_sites + j]
-                         : philox_normal(r.seed, KIND_RADIAL_R, 0, r.sample0 + s, 0, (uint32_t)j);
+                         : philox_normal(rk.seed, KIND_RADIAL_R, 0, rk.sample0 + s, 0, (uint32_t)j);
   const float d = weight_eps_at(eps, s, P, e) / norms[(long long)s * n_sites + j] * rr;
   w[(long long)s * P + e] = fmaf(d, sigma[e], mu[e]);
   if (delta) delta[(long long)s * P + e] = d;
@@ -231,11 +235,12 @@ void launch_sample_radial(const float* mu, const float* sigma, long long P, long
 
 __global__ void gen_signs_kernel(float* dst, long long S, long long B, int C, NoiseRef nz) {
   const long long total = S * B * C;
+  const NoiseKey k = noise_key(nz);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = i % C;
     const long long sb = i / C;
     const int b = sb % B, s = sb / B;
-    dst[i] = philox_sign(nz.seed, nz.kind, nz.site, nz.sample0 + s, nz.window0 + b, c);
+    dst[i] = philox_sign(k.seed, nz.kind, nz.site, k.sample0 + s, k.window0 + b, c);
   }
 }
 void launch_gen_signs(float* dst, long long S, long long B, int C, NoiseRef nz, cudaStream_t st) {

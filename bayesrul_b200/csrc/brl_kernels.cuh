@@ -31,7 +31,22 @@ struct NoiseRef {       // one noise stream: injected tensor or Philox
   const float* ptr;     // injected [S, B, per_window]; nullptr -> Philox
   unsigned long long seed;
   unsigned int kind, site, sample0, window0;
+  // CUDA-graph replay (brl_elbo_step): the per-step part of the key lives in device memory, {seed, sample0, window0} as
+  // three 64-bit words that a one-thread kernel rewrites before every launch of the captured step; nullptr = by value
+  const unsigned long long* dyn;
 };
+#ifdef __CUDACC__
+struct NoiseKey { unsigned long long seed; unsigned int sample0, window0; };
+__device__ __forceinline__ NoiseKey noise_key(const NoiseRef& nz) {
+  NoiseKey k{nz.seed, nz.sample0, nz.window0};
+  if (nz.dyn) {
+    k.seed = __ldg(nz.dyn);
+    k.sample0 += (unsigned int)__ldg(nz.dyn + 1);
+    k.window0 += (unsigned int)__ldg(nz.dyn + 2);
+  }
+  return k;
+}
+#endif
 
 struct ConvGemm {
   int B, P, Wrow;  // rows per sample = B*P; Wrow = row-space width (Wout for fwd, Win for dX)

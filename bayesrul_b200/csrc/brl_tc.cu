@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <utility>
 #include <vector>
 
@@ -442,6 +443,7 @@ const char* tc_forward(TcState* st, const float* x, long long B, long long S, co
     r.kind = KIND_DROPOUT; r.site = layer;
     r.sample0 = noise ? (unsigned)noise->sample0 : 0u;
     r.window0 = noise ? (unsigned)noise->window0 : 0u;
+    r.dyn = nullptr;
     return r;
   };
   ConvArgs ca;
@@ -452,7 +454,9 @@ const char* tc_forward(TcState* st, const float* x, long long B, long long S, co
   ca.status = st->status;
   ca.trace = st->trace;
   const long long items = S * ((nt4 + 1) / 2);
-  const int grid = (int)std::min<long long>(st->sm_count, items);
+  static const int env_conv = getenv("BRL_CONV_GRID") ? atoi(getenv("BRL_CONV_GRID")) : 0;  // experiment knobs
+  static const int env_fc = getenv("BRL_FC_GRID") ? atoi(getenv("BRL_FC_GRID")) : 0;
+  const int grid = (int)std::min<long long>(env_conv > 0 ? env_conv : st->sm_count, items);
   tc_time_begin(st, 0, stream);
   if (drop) tc_conv_kernel<true><<<grid, CONV_THREADS, CONV_SMEM, stream>>>(ca);
   else tc_conv_kernel<false><<<grid, CONV_THREADS, CONV_SMEM, stream>>>(ca);
@@ -463,7 +467,7 @@ const char* tc_forward(TcState* st, const float* x, long long B, long long S, co
   fa.keep = drop ? 1.0f - p_dropout : 1.0f;
   fa.drop = nr(10);
   fa.status = st->status;
-  const int gridf = (int)std::min<long long>(st->sm_count, S * nt128);
+  const int gridf = (int)std::min<long long>(env_fc > 0 ? env_fc : st->sm_count, S * nt128);
   // TMA view of the feature tensor: [S * Bpad rows][2400 fp16], boxes of 128 rows x 64 columns, 128-byte swizzle
   CUtensorMap fmap;
   {

@@ -117,6 +117,10 @@ class Engine:
         forward(engine='simt') / elbo_step / hnn_step."""
         _lib.check(self.lib.brl_set_gemm_backend(self.ctx, {"simt": 0, "tc": 7}.get(backend, backend)))
 
+    def set_step_graph(self, enable: bool) -> None:
+        """CUDA-graph replay of elbo_step with native noise (on by default; identical results, far less host time)."""
+        _lib.check(self.lib.brl_set_step_graph(self.ctx, int(enable)))
+
     def gemm_status(self) -> int:
         """0 = ok; else the code of the first mbarrier time-out inside a TF32 per-layer kernel (synchronises)."""
         return int(self.lib.brl_gemm_status())

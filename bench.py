@@ -240,8 +240,8 @@ def main():
     # ---- synthetic workload: each rank owns its own shard of windows (global window index offset)
     n_rot = 8  # rotate 8 distinct batches (8 x 21.6 MB of windows > L2 together with the flush)
     xs = [synth(B_PRED, seed=12345 + 17 * rank + i)[0].to(device) for i in range(n_rot)]
-    from oracle.bnn_oracle import init_params  # parameter initialisation only (weights_init statistics)
-    mu = init_params(NET, 12345).to(device)
+    from bayesrul_b200.compat.nets import init_flat_params
+    mu = init_flat_params(NET, 12345).to(device)  # weights_init under manual_seed(12345), SURVEY 8(d)
     sigma = torch.full_like(mu, CFG["q_scale"])
     flush_buf = torch.zeros(64 * 1024 * 1024, device=device)
     outs = {}
@@ -322,28 +322,44 @@ def main():
     if not args.no_train:
         xt, yt = synth(B_TRAIN, seed=777 + rank)
         xt, yt = xt.to(device), yt.to(device)
-        for mode, particles, q, ps in (("lrt", 1, 1.351e-3, 0.138793), ("flipout", 2, 2.14e-4, 0.198768)):
-            sg = torch.full_like(mu, q)
+        from bayesrul_b200.dist import allreduce_elbo_grads
+        NT = 40
+        for mode, particles, q, ps, lr in (("lrt", 1, 1.351e-3, 0.138793, 1.0e-3), ("flipout", 2, 2.14e-4, 0.198768, 1.0e-3)):
+            # one svi.step of the reference (bayesian.py:147): ELBO forward + backward, then pyro's ClippedAdam on (loc, log scale)
+            # (conf/model/bnn.yaml:6-10); data-parallel ranks average the flat gradient with ONE NCCL all-reduce first
+            P = mu.numel()
+            par = {"mu": mu.clone(), "ls": torch.full_like(mu, float(torch.log(torch.tensor(q)))), "sg": torch.full_like(mu, q)}
+            opt = {k: torch.zeros(P, device=device) for k in ("m_mu", "v_mu", "m_ls", "v_ls")}
             st = {"i": 0}
 
             def train_step(i=0):
                 st["i"] += 1
-                eng.elbo_step(xt, yt, mu, sg, mode=mode, guide="normal", particles=particles, prior_loc=0.0,
-                              prior_scale=ps, dataset_size=N_DATASET, noise=Noise(seed=5000 + st["i"], window0=rank * B_TRAIN))
+                r = eng.elbo_step(xt, yt, par["mu"], par["sg"], mode=mode, guide="normal", particles=particles, prior_loc=0.0,
+                                  prior_scale=ps, dataset_size=N_DATASET, noise=Noise(seed=5000 + st["i"], window0=rank * B_TRAIN))
+                if dist is not None:
+                    r = allreduce_elbo_grads(r)
+                eng.clipped_adam(par["mu"], r["grad_mu"].contiguous(), opt["m_mu"], opt["v_mu"], st["i"], lr, (0.95, 0.999), 1e-8, 15.0)
+                eng.clipped_adam(par["ls"], r["grad_log_sigma"].contiguous(), opt["m_ls"], opt["v_ls"], st["i"], lr, (0.95, 0.999), 1e-8, 15.0)
+                torch.exp(par["ls"], out=par["sg"])
 
             res = {}
             for backend in ("simt", "tc"):  # fp32 FFMA kernels vs tcgen05 TF32 dual-GEMM kernels (same operators)
                 eng.set_gemm_backend(backend)
-                res[backend] = max_over_ranks(timed_steps(train_step, 20, 5, flush_buf, dist), dist, device)
+                res[backend] = max_over_ranks(timed_steps(train_step, NT, 6, flush_buf, dist), dist, device)
             eng.set_gemm_backend("simt")
+            eng.set_step_graph(False)  # the same step without the CUDA-graph replay (eager launches), for the record
+            t_eager = max_over_ranks(timed_steps(train_step, NT, 3, flush_buf, dist), dist, device)
+            eng.set_step_graph(True)
             best = min(res, key=res.get)
             tt = res[best]
             flops = F_TRAIN_LRT * particles * B_TRAIN  # 13 036 416 per window per particle
-            train[mode] = {"windows_per_s": world * B_TRAIN * 20 / tt, "ms_per_step": 1e3 * tt / 20, "batch": B_TRAIN,
+            train[mode] = {"windows_per_s": world * B_TRAIN * NT / tt, "ms_per_step": 1e3 * tt / NT, "batch_per_gpu": B_TRAIN,
                            "particles": particles, "gemm_backend": {"simt": "fp32 FFMA", "tc": "tcgen05 TF32"}[best],
-                           "ms_per_step_by_backend": {"simt_fp32": 1e3 * res["simt"] / 20, "tc_tf32": 1e3 * res["tc"] / 20},
-                           "achieved_tflops": flops / (tt / 20) / 1e12,
-                           "includes": "forward + backward + KL + gradient finalisation (no optimiser)"}
+                           "ms_per_step_by_backend": {"simt_fp32": 1e3 * res["simt"] / NT, "tc_tf32": 1e3 * res["tc"] / NT},
+                           "ms_per_step_eager_simt": 1e3 * t_eager / NT,
+                           "achieved_tflops": flops / (tt / NT) / 1e12,
+                           "includes": "ELBO forward + backward + KL + gradient finalisation (CUDA-graph replay) + ClippedAdam on (loc, log scale)"
+                                       + (f" + NCCL all-reduce of the flat gradient over {world} ranks" if dist is not None else "")}
             if world == 1 and not args.no_cpu:
                 v, dt = cpu_train_rate(mode, particles, q, ps, os.cpu_count() or 1)
                 train[mode]["cpu_windows_per_s"] = v

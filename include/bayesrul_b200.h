@@ -167,6 +167,13 @@ int brl_elbo_step(brl_ctx* ctx, const float* x, const float* y, int64_t B, const
                   double* scalars, float* grad_mu, float* grad_sigma, float* grad_log_sigma, float* out,
                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* brl_elbo_step replays a CUDA graph of the step when the noise is native Philox (no injected tensor): the first call with
+ * a given configuration (sizes, mode, parameter / workspace pointers) runs eagerly, the second captures it, later calls
+ * replay it with the per-step Philox key {seed, sample0, window0} rewritten in device memory; x, y and the results go
+ * through staging buffers inside the workspace, so the caller's tensors may change from step to step.  Results are
+ * identical to the eager path.  enable = 0 switches the replay off (also: environment BRL_NO_GRAPH=1). */
+int brl_set_step_graph(brl_ctx* ctx, int enable);
+
 /* ---- heteroscedastic NN step (replaces HNN.step + backward: frequentist.py:39-48) ------
  * loss = F.gaussian_nll_loss(loc, y, scale^2); scalars (device double[2]) = {loss, mse}. */
 int brl_hnn_step(brl_ctx* ctx, const float* x, const float* y, int64_t B, const float* theta,
