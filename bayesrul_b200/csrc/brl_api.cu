@@ -379,6 +379,14 @@ static void backward_op(const brl_ctx* ctx, const ActBufs& ab, const BwdArgs& a,
   dw.a = fwd_gather(ctx, op, oi, ab, a.x);
   dw.G = ab.dpre[oi]; dw.gw = a.g0 + L.w_off; dw.gb = a.g0 + L.b_off;
   dw.gb2 = a.mode == BRL_MODE_FLIPOUT ? a.g1 + L.b_off : nullptr;
+  if (!(ctx->gemm_backend & 4) && (a.mode == BRL_MODE_LRT || a.mode == BRL_MODE_FLIPOUT)) {
+    // fp32 SIMT back-end: the mean-path and the variance- / perturbation-path weight gradients share one gather
+    dw.G1 = ab.dsec[oi]; dw.gw1 = a.g1 + L.w_off;
+    if (a.mode == BRL_MODE_LRT) { dw.trA1 = TRA_SQUARE; dw.gb1 = a.g1 + L.b_off; }
+    else { dw.trA1 = TRA_SIGN; dw.sign_in = a.sgn_in[op.layer]; dw.sign_C = L.cin; dw.gb1 = nullptr; }
+    launch_conv_dw(dw, ws);
+    return;
+  }
   ((ctx->gemm_backend & 4) ? launch_conv_dw_tc(dw, ws) : launch_conv_dw(dw, ws));
   if (a.mode == BRL_MODE_LRT) {
     dw.G = ab.dsec[oi]; dw.trA = TRA_SQUARE; dw.gw = a.g1 + L.w_off; dw.gb = a.g1 + L.b_off; dw.gb2 = nullptr;
@@ -806,13 +814,22 @@ static int elbo_body(brl_ctx* ctx, const ActBufs& ab, const float* x, const floa
                                 nref(&nz, nz.radial_r, KIND_RADIAL_R, 0), ab.norms, ab.wsamp, ab.delta, st);
     }
     std::vector<const float*> sin_(n.layers.size(), nullptr), sout_(n.layers.size(), nullptr);
-    if (mode == BRL_MODE_FLIPOUT) {
+    if (mode == BRL_MODE_FLIPOUT) {  // native sign tensors of all layers: one launch per particle
+      SignJobs jobs;
+      jobs.n = 0;
+      jobs.start[0] = 0;
+      auto add = [&](float* dst, int C, unsigned kind, unsigned site) {
+        jobs.dst[jobs.n] = dst; jobs.C[jobs.n] = C; jobs.kind[jobs.n] = kind; jobs.site[jobs.n] = site;
+        jobs.start[jobs.n + 1] = jobs.start[jobs.n] + B * C;
+        ++jobs.n;
+      };
       for (size_t l = 0; l < n.layers.size(); ++l) {
         if (nz.flip_in[l]) sin_[l] = nz.flip_in[l];
-        else { launch_gen_signs(ab.sgn_in[l], 1, B, n.layers[l].cin, nref(&nz, nullptr, KIND_FLIP_IN, (unsigned)l), st); sin_[l] = ab.sgn_in[l]; }
+        else { add(ab.sgn_in[l], n.layers[l].cin, KIND_FLIP_IN, (unsigned)l); sin_[l] = ab.sgn_in[l]; }
         if (nz.flip_out[l]) sout_[l] = nz.flip_out[l];
-        else { launch_gen_signs(ab.sgn_out[l], 1, B, n.layers[l].cout, nref(&nz, nullptr, KIND_FLIP_OUT, (unsigned)l), st); sout_[l] = ab.sgn_out[l]; }
+        else { add(ab.sgn_out[l], n.layers[l].cout, KIND_FLIP_OUT, (unsigned)l); sout_[l] = ab.sgn_out[l]; }
       }
+      if (jobs.n) launch_gen_signs_multi(jobs, B, nref(&nz, nullptr, 0, 0), st);
     }
     float* outp = out + (long long)pt * B * 2;
     FwdArgs fa{x, B, 1, mode, mu, sigma, ab.wsamp, 0.f, &nz, sin_.data(), sout_.data(), outp, compute_grads != 0};

@@ -20,13 +20,21 @@ extern std::atomic<long long> g_launch_count;
 
 constexpr int BN = 32, BK = 16;
 
-// BM = 128 (256 threads) for large row counts; BM = 32 (64 threads) when the grid would otherwise leave SMs with a
-// single 8-warp CTA (training batches): many small CTAs per SM hide the gather latency.
-template <bool DUAL, int EPI, int BM>
-__global__ void __launch_bounds__(BM * 2) conv_gemm_kernel(const ConvGemm p) {
-  constexpr int NT = BM * 2;          // threads
+// Tile shapes (BM rows x 32 columns, TM x TN outputs per thread):
+//   128 x 32, 4 x 4, 256 threads  large row counts (predictive batches): FFMA-bound, wide micro-tiles
+//    32 x 32, 2 x 2, 256 threads  training batches: a 256-window layer is a few hundred tiles, i.e. one or two warps per
+//                                 scheduler with 4 x 4 micro-tiles, and the kernel then runs at the latency of its own
+//                                 dependent chain (ncu: 22 % issue slots, 3.7 long-scoreboard stalls per issue); quartering
+//                                 the per-thread tile gives 4x the warps and a third of the serial instructions per warp
+template <bool DUAL, int EPI, int BM, int TM, int TN>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN)) conv_gemm_kernel(const ConvGemm p) {
+  constexpr int NT = (BM / TM) * (BN / TN);  // threads
+  constexpr int AKS = NT / BM;        // k-rows of the A tile staged per pass
+  constexpr int ALD = BK / AKS;       // A loads per thread
   constexpr int BROWS = NT / BN;      // k-rows of the B tile staged per pass
   constexpr int BLD = BK / BROWS;     // B loads per thread
+  constexpr int TXN = BN / TN;        // threads along n
+  static_assert(ALD >= 1 && BLD >= 1 && (TM == 4 || TM == 2) && (TN == 4 || TN == 2), "tile shape");
   // K-loop tiles and (afterwards) the accumulator tile of the rolled epilogue share one buffer
   constexpr int LOOP_FLOATS = (DUAL ? 2 : 1) * (BK * BM + BK * BN);
   constexpr int EPI_FLOATS = (DUAL ? 2 : 1) * BM * BN;
@@ -63,15 +71,15 @@ __global__ void __launch_bounds__(BM * 2) conv_gemm_kernel(const ConvGemm p) {
   const long long bcol = (long long)(bnv ? bnn : 0) * p.nB;
   const float* W0 = p.W0 + (long long)s * p.ws0;
   const float* W1 = DUAL ? p.W1 + (long long)s * p.ws1 : nullptr;
-  const int tx = tid & 7, ty = tid >> 3;
+  const int tx = tid % TXN, ty = tid / TXN;
 
-  float ra0[8], ra1[8], rb0[BLD], rb1[BLD];
+  float ra0[ALD], ra1[ALD], rb0[BLD], rb1[BLD];
   auto fetch = [&](int k0) {
-    int ko[8], kc[8];
-    bool ok[8];
+    int ko[ALD], kc[ALD];
+    bool ok[ALD];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {  // gather tables: unconditional, clamped
-      const int k = k0 + ak0 + 2 * j;
+    for (int j = 0; j < ALD; ++j) {  // gather tables: unconditional, clamped
+      const int k = k0 + ak0 + AKS * j;
       kc[j] = min(k, p.K - 1);
       const int dhw = __ldg(p.a.kdhw + kc[j]);
       ko[j] = __ldg(p.a.koff + kc[j]);
@@ -79,7 +87,7 @@ __global__ void __launch_bounds__(BM * 2) conv_gemm_kernel(const ConvGemm p) {
       ok[j] = arv && k < kend && (unsigned)ih < (unsigned)p.a.Hin && (unsigned)iw < (unsigned)p.a.Win;
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {  // data: always-valid address + select (no branches between loads)
+    for (int j = 0; j < ALD; ++j) {  // data: always-valid address + select (no branches between loads)
       const long long off = ok[j] ? rowbase + ko[j] : 0;
       const float v = __ldg(p.a.base0 + off);
       ra0[j] = ok[j] ? v : 0.f;
@@ -107,18 +115,27 @@ __global__ void __launch_bounds__(BM * 2) conv_gemm_kernel(const ConvGemm p) {
     }
   };
 
-  float acc0[4][4], acc1[4][4];
+  float acc0[TM][TN], acc1[TM][TN];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < TM; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc0[i][j] = acc1[i][j] = 0.f;
+    for (int j = 0; j < TN; ++j) acc0[i][j] = acc1[i][j] = 0.f;
+  auto frag = [&](const float* src, float (&dst)[4], int n) {  // n = 2 or 4 consecutive floats
+    if (n == 4) {
+      const float4 v = *reinterpret_cast<const float4*>(src);
+      dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+    } else {
+      const float2 v = *reinterpret_cast<const float2*>(src);
+      dst[0] = v.x; dst[1] = v.y;
+    }
+  };
 
   if (kbeg < kend) fetch(kbeg);
   for (int k0 = kbeg; k0 < kend; k0 += BK) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      As0[ak0 + 2 * j][ar] = ra0[j];
-      if (DUAL) As1[ak0 + 2 * j][ar] = ra1[j];
+    for (int j = 0; j < ALD; ++j) {
+      As0[ak0 + AKS * j][ar] = ra0[j];
+      if (DUAL) As1[ak0 + AKS * j][ar] = ra1[j];
     }
 #pragma unroll
     for (int j = 0; j < BLD; ++j) {
@@ -129,21 +146,21 @@ __global__ void __launch_bounds__(BM * 2) conv_gemm_kernel(const ConvGemm p) {
     if (k0 + BK < kend) fetch(k0 + BK);  // next tile's loads fly while this one is multiplied
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
-      const float4 a = *reinterpret_cast<const float4*>(&As0[kk][ty * 4]);
-      const float4 b = *reinterpret_cast<const float4*>(&Bs0[kk][tx * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+      float av[4], bv[4];
+      frag(&As0[kk][ty * TM], av, TM);
+      frag(&Bs0[kk][tx * TN], bv, TN);
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc0[i][j] = fmaf(av[i], bv[j], acc0[i][j]);
+        for (int j = 0; j < TN; ++j) acc0[i][j] = fmaf(av[i], bv[j], acc0[i][j]);
       if (DUAL) {
-        const float4 a1 = *reinterpret_cast<const float4*>(&As1[kk][ty * 4]);
-        const float4 b1 = *reinterpret_cast<const float4*>(&Bs1[kk][tx * 4]);
-        const float av1[4] = {a1.x, a1.y, a1.z, a1.w}, bv1[4] = {b1.x, b1.y, b1.z, b1.w};
+        float av1[4], bv1[4];
+        frag(&As1[kk][ty * TM], av1, TM);
+        frag(&Bs1[kk][tx * TN], bv1, TN);
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < TM; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc1[i][j] = fmaf(av1[i], bv1[j], acc1[i][j]);
+          for (int j = 0; j < TN; ++j) acc1[i][j] = fmaf(av1[i], bv1[j], acc1[i][j]);
       }
     }
     __syncthreads();
@@ -155,11 +172,12 @@ __global__ void __launch_bounds__(BM * 2) conv_gemm_kernel(const ConvGemm p) {
   float* Cs0 = sm;
   float* Cs1 = sm + BM * BN;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    *reinterpret_cast<float4*>(&Cs0[(tx * 4 + j) * BM + ty * 4]) = make_float4(acc0[0][j], acc0[1][j], acc0[2][j], acc0[3][j]);
-    if (DUAL)
-      *reinterpret_cast<float4*>(&Cs1[(tx * 4 + j) * BM + ty * 4]) = make_float4(acc1[0][j], acc1[1][j], acc1[2][j], acc1[3][j]);
-  }
+  for (int j = 0; j < TN; ++j)
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+      Cs0[(tx * TN + j) * BM + ty * TM + i] = acc0[i][j];
+      if (DUAL) Cs1[(tx * TN + j) * BM + ty * TM + i] = acc1[i][j];
+    }
   __syncthreads();
 #pragma unroll 1
   for (int e = tid; e < BM * BN; e += NT) {
@@ -196,9 +214,9 @@ static void launch_one(const ConvGemm& p, cudaStream_t st) {
   const int z = p.ksplit > 1 ? p.ksplit : p.S;
   ++g_launch_count;
   if (small_tiles(p))
-    conv_gemm_kernel<DUAL, EPI, 32><<<dim3((Mtot + 31) / 32, (p.N + BN - 1) / BN, z), 64, 0, st>>>(p);
+    conv_gemm_kernel<DUAL, EPI, 32, 2, 2><<<dim3((Mtot + 31) / 32, (p.N + BN - 1) / BN, z), 256, 0, st>>>(p);
   else
-    conv_gemm_kernel<DUAL, EPI, 128><<<dim3((Mtot + 127) / 128, (p.N + BN - 1) / BN, z), 256, 0, st>>>(p);
+    conv_gemm_kernel<DUAL, EPI, 128, 4, 4><<<dim3((Mtot + 127) / 128, (p.N + BN - 1) / BN, z), 256, 0, st>>>(p);
   if (p.ksplit > 1) {
     const long long total = (long long)Mtot * p.N;
     ++g_launch_count;
@@ -236,9 +254,10 @@ void launch_conv_gemm(const ConvGemm& p0, int epi, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------
 constexpr int DW_CO = 32, DW_K = 128, DW_M = 16, DW_PAD = 4;
 
-__global__ void __launch_bounds__(256) conv_dw_kernel(const ConvDw p, int rows_per_split) {
-  __shared__ __align__(16) float Gs[DW_M][DW_CO];
-  __shared__ __align__(16) float As[DW_M][DW_K + DW_PAD];
+template <bool DUAL>
+__global__ void __launch_bounds__(256, 2) conv_dw_kernel(const ConvDw p, int rows_per_split) {
+  __shared__ __align__(16) float Gs[DUAL ? 2 : 1][DW_M][DW_CO];
+  __shared__ __align__(16) float As[DUAL ? 2 : 1][DW_M][DW_K + DW_PAD];
   const int tid = threadIdx.x;
   const int kt0 = blockIdx.x * DW_K, co0 = blockIdx.y * DW_CO;
   const int Mtot = p.B * p.P;
@@ -246,6 +265,7 @@ __global__ void __launch_bounds__(256) conv_dw_kernel(const ConvDw p, int rows_p
   const int mend = min(Mtot, mbeg + rows_per_split);
   const int r = tid & 15, c0 = tid >> 4;
   const int tx = tid & 31, ty = tid >> 5;
+  const int tr1 = DUAL ? p.trA1 : p.trA;  // the transform that needs the sign tensor, if any
 
   // per-thread column constants (the 8 k-columns and 2 co-columns this thread stages never change)
   int ko[8], kdh[8], kdw[8], kcc[8], kmode[8];  // kmode: 0 gather, 1 bias column (A = 1), 2 out of range
@@ -258,9 +278,9 @@ __global__ void __launch_bounds__(256) conv_dw_kernel(const ConvDw p, int rows_p
     ko[j] = __ldg(p.a.koff + kc);
     kdh[j] = (int)(short)(dhw & 0xffff);
     kdw[j] = dhw >> 16;
-    kcc[j] = p.trA == TRA_SIGN ? __ldg(p.a.kci + kc) : 0;
+    kcc[j] = tr1 == TRA_SIGN ? __ldg(p.a.kci + kc) : 0;
   }
-  float rg[2], ra[8];
+  float rg[2], rg1[2], ra[8], ra1[8];
   auto fetch = [&](int mb) {
     const int m = mb + r;
     const bool rv = m < mend;
@@ -272,43 +292,70 @@ __global__ void __launch_bounds__(256) conv_dw_kernel(const ConvDw p, int rows_p
     for (int j = 0; j < 2; ++j) {
       const int co = co0 + c0 + 16 * j;
       const bool ok = rv && co < p.N;
-      const float v = __ldg(p.G + (ok ? ((long long)b * p.N + co) * p.P + pp : 0));
+      const long long gi = ok ? ((long long)b * p.N + co) * p.P + pp : 0;
+      const float v = __ldg(p.G + gi);
       rg[j] = ok ? v : 0.f;
+      if (DUAL) {
+        const float v1 = __ldg(p.G1 + gi);
+        rg1[j] = ok ? v1 : 0.f;
+      }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const bool ok = rv && kmode[j] == 0 && (unsigned)(oh + kdh[j]) < (unsigned)p.a.Hin &&
                       (unsigned)(ow + kdw[j]) < (unsigned)p.a.Win;
-      float v = __ldg(p.a.base0 + (ok ? rowbase + ko[j] : 0));
-      if (p.trA == TRA_SQUARE) v = v * v;
-      else if (p.trA == TRA_SIGN) v *= __ldg(p.sign_in + (ok ? (long long)b * p.sign_C + kcc[j] : 0));
-      ra[j] = ok ? v : ((rv && kmode[j] == 1) ? 1.0f : 0.f);
+      const float v = __ldg(p.a.base0 + (ok ? rowbase + ko[j] : 0));
+      float t = v;
+      if (tr1 == TRA_SQUARE) t = v * v;
+      else if (tr1 == TRA_SIGN) t = v * __ldg(p.sign_in + (ok ? (long long)b * p.sign_C + kcc[j] : 0));
+      const float one = (rv && kmode[j] == 1) ? 1.0f : 0.f;
+      if (DUAL) {
+        ra[j] = ok ? v : one;
+        ra1[j] = ok ? t : one;
+      } else {
+        ra[j] = ok ? t : one;
+      }
     }
   };
 
-  float acc[4][4];
+  float acc[4][4], acc1[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc[i][j] = acc1[i][j] = 0.f;
 
   if (mbeg < mend) fetch(mbeg);
   for (int mb = mbeg; mb < mend; mb += DW_M) {
 #pragma unroll
-    for (int j = 0; j < 2; ++j) Gs[r][c0 + 16 * j] = rg[j];
+    for (int j = 0; j < 2; ++j) {
+      Gs[0][r][c0 + 16 * j] = rg[j];
+      if (DUAL) Gs[DUAL ? 1 : 0][r][c0 + 16 * j] = rg1[j];
+    }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) As[r][c0 + 16 * j] = ra[j];
+    for (int j = 0; j < 8; ++j) {
+      As[0][r][c0 + 16 * j] = ra[j];
+      if (DUAL) As[DUAL ? 1 : 0][r][c0 + 16 * j] = ra1[j];
+    }
     __syncthreads();
     if (mb + DW_M < mend) fetch(mb + DW_M);
 #pragma unroll
     for (int mm = 0; mm < DW_M; ++mm) {
-      const float4 g = *reinterpret_cast<const float4*>(&Gs[mm][ty * 4]);
-      const float4 a = *reinterpret_cast<const float4*>(&As[mm][tx * 4]);
+      const float4 g = *reinterpret_cast<const float4*>(&Gs[0][mm][ty * 4]);
+      const float4 a = *reinterpret_cast<const float4*>(&As[0][mm][tx * 4]);
       const float gv[4] = {g.x, g.y, g.z, g.w}, av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(gv[i], av[j], acc[i][j]);
+      if (DUAL) {
+        const float4 g1 = *reinterpret_cast<const float4*>(&Gs[DUAL ? 1 : 0][mm][ty * 4]);
+        const float4 a1 = *reinterpret_cast<const float4*>(&As[DUAL ? 1 : 0][mm][tx * 4]);
+        const float gv1[4] = {g1.x, g1.y, g1.z, g1.w}, av1[4] = {a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc1[i][j] = fmaf(gv1[i], av1[j], acc1[i][j]);
+      }
     }
     __syncthreads();
   }
@@ -321,9 +368,11 @@ __global__ void __launch_bounds__(256) conv_dw_kernel(const ConvDw p, int rows_p
       const int k = kt0 + tx * 4 + j;
       if (k < p.K) {
         atomicAdd(p.gw + (long long)co * p.K + k, acc[i][j]);
+        if (DUAL) atomicAdd(p.gw1 + (long long)co * p.K + k, acc1[i][j]);
       } else if (k == p.K) {
         if (p.gb) atomicAdd(p.gb + co, acc[i][j]);
         if (p.gb2) atomicAdd(p.gb2 + co, acc[i][j]);
+        if (DUAL && p.gb1) atomicAdd(p.gb1 + co, acc1[i][j]);
       }
     }
   }
@@ -337,7 +386,8 @@ void launch_conv_dw(const ConvDw& p, cudaStream_t st) {
   rows = (rows + DW_M - 1) / DW_M * DW_M;
   split = (Mtot + rows - 1) / rows;
   ++g_launch_count;
-  conv_dw_kernel<<<dim3(gx, gy, split), 256, 0, st>>>(p, rows);
+  if (p.G1) conv_dw_kernel<true><<<dim3(gx, gy, split), 256, 0, st>>>(p, rows);
+  else conv_dw_kernel<false><<<dim3(gx, gy, split), 256, 0, st>>>(p, rows);
 }
 
 }  // namespace brl

@@ -243,6 +243,23 @@ __global__ void gen_signs_kernel(float* dst, long long S, long long B, int C, No
     dst[i] = philox_sign(k.seed, nz.kind, nz.site, k.sample0 + s, k.window0 + b, c);
   }
 }
+__global__ void gen_signs_multi_kernel(const SignJobs jobs, long long B, NoiseRef base) {
+  const long long total = jobs.start[jobs.n];
+  const NoiseKey k = noise_key(base);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int j = 0;
+    while (j + 1 < jobs.n && i >= jobs.start[j + 1]) ++j;
+    const long long e = i - jobs.start[j];
+    const int C = jobs.C[j], c = (int)(e % C), b = (int)(e / C);
+    jobs.dst[j][e] = philox_sign(k.seed, jobs.kind[j], jobs.site[j], k.sample0, k.window0 + b, c);
+  }
+}
+void launch_gen_signs_multi(const SignJobs& jobs, long long B, NoiseRef base, cudaStream_t st) {
+  const long long total = jobs.start[jobs.n];
+  if (total <= 0) return;
+  ++g_launch_count;
+  gen_signs_multi_kernel<<<(unsigned)min((total + 255) / 256, (long long)148 * 8), 256, 0, st>>>(jobs, B, base);
+}
 void launch_gen_signs(float* dst, long long S, long long B, int C, NoiseRef nz, cudaStream_t st) {
   const long long total = S * B * C;
   ++g_launch_count;

@@ -98,6 +98,12 @@ struct ConvDw {
   float* gw;       // flat gradient buffer: gw[w_off + co*K + k]
   float* gb;       // bias gradient: gb[co] (nullable)
   float* gb2;      // second bias destination (flipout), nullable
+  // optional second contraction sharing the gather (fp32 SIMT kernel only): C1[co][k] += sum_m G1[m][co] * tr1(A[m][k]),
+  // i.e. the sigma^2-path (tr1 = square) or perturbation-path (tr1 = sign flip) gradient of the same layer; trA must be NONE
+  const float* G1;  // nullptr -> single contraction
+  int trA1;
+  float* gw1;
+  float* gb1;  // nullable
 };
 void launch_conv_dw(const ConvDw& p, cudaStream_t st);
 void launch_conv_dw_tc(const ConvDw& p, cudaStream_t st);
@@ -142,6 +148,16 @@ void launch_sample_radial(const float* mu, const float* sigma, long long P, long
                           int n_sites, int max_site, NoiseRef eps, NoiseRef r, float* norms /*[S,n_sites]*/, float* w,
                           float* delta, cudaStream_t st);
 void launch_gen_signs(float* dst, long long S, long long B, int C, NoiseRef nz, cudaStream_t st);
+// all sign tensors of one particle in ONE launch (a Flipout step needs 2 per layer): job j fills dst[j][B][C[j]] with stream
+// (kind[j], site[j]) of the key in `base`
+struct SignJobs {
+  float* dst[32];
+  int C[32];
+  unsigned int kind[32], site[32];
+  long long start[33];  // element offsets of the jobs in the launch's index space
+  int n;
+};
+void launch_gen_signs_multi(const SignJobs& jobs, long long B, NoiseRef base, cudaStream_t st);
 
 void launch_nll_elbo(const float* out, const float* y, long long B, float gscale, double* acc /*[nll, mse]*/,
                      float* gout, cudaStream_t st);
