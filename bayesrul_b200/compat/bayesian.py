@@ -9,6 +9,7 @@ Differences are confined to performance: `svi.step` is one fused CUDA ELBO step;
 """
 from __future__ import annotations
 
+import os
 import contextlib
 import copy
 from functools import partial
@@ -166,9 +167,16 @@ class BNN(_Base):
         param_store_to(self.device)
 
     def predict_step(self, batch, batch_idx, dataloader_idx=0):  # bayesian.py:231-250
-        x = batch[0].to(self.device, non_blocking=True)
         pred = dict()
-        loc, scale, ep_var, al_var = self.bnn.predict_moments(x, self.hparams.mc_samples_eval)
+        if batch[0].device.type == "cpu" and int(os.environ.get("BRL_HOST_CHUNKS", "1")) > 1:
+            # optional: chunked copy overlapped with the compute.  Measured on B200 (tools/probe_e2e.py, B = 10 000, S = 100):
+            # one shot 5.29 ms, 2 chunks 5.30-5.38 ms, 3 chunks 5.56 ms -- every extra call repeats the weight sampling /
+            # packing and the kernels' ramp-up, which costs what the hidden copy saves, so the default stays one shot
+            loc, scale, ep_var, al_var = self.bnn.predict_moments_host(
+                batch[0], self.hparams.mc_samples_eval, float(os.environ.get("BRL_HOST_FIRST", "0.25")),
+                int(os.environ.get("BRL_HOST_CHUNKS", "1")))
+        else:
+            loc, scale, ep_var, al_var = self.bnn.predict_moments(batch[0].to(self.device), self.hparams.mc_samples_eval)
         packed = torch.stack([ep_var, al_var, loc, scale]).cpu()  # one D2H instead of four
         pred["labels"] = batch[1].cpu().numpy()
         pred["ep_vars"], pred["al_vars"], pred["preds"], pred["stds"] = (packed[i].numpy() for i in range(4))

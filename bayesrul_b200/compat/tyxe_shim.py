@@ -186,6 +186,43 @@ class VariationalBNN:
         return self.engine.predict_moments(x.contiguous(), g.loc, g.scale, S=num_predictions, guide=g.family,
                                            noise=self._noise(), engine=self.engine_kind)
 
+    def predict_moments_host(self, x_host, num_predictions: int, first_fraction: float = 0.25, n_chunks: int = 2):
+        """predict_moments for a HOST batch (pinned memory for a truly asynchronous copy): the windows travel in
+        chunks on a copy stream while the previous chunk is being computed, so only the first (small) chunk's
+        transfer is exposed.  The weight draws do not depend on the window index and per-window noise is keyed by
+        the global window index (Noise.window0), so the result equals the un-chunked call."""
+        g = self.net_guide
+        dev = g.loc.device
+        B = x_host.shape[0]
+        if B < 2048 or n_chunks < 2:
+            return self.predict_moments(x_host.to(dev, non_blocking=True), num_predictions)
+        first = max(512, int(B * first_fraction))
+        rest = (B - first + n_chunks - 2) // (n_chunks - 1)
+        bounds = [0, first]
+        while bounds[-1] < B:
+            bounds.append(min(B, bounds[-1] + rest))
+        if getattr(self, "_xstage", None) is None or self._xstage.shape[0] < B:
+            self._xstage = torch.empty((B,) + tuple(x_host.shape[1:]), device=dev)
+            self._copy_stream = torch.cuda.Stream(dev)
+        stage, cs, main = self._xstage, self._copy_stream, torch.cuda.current_stream(dev)
+        cs.wait_stream(main)  # the staging buffer may still be read by the previous call's kernels
+        events = []
+        with torch.cuda.stream(cs):
+            for a, b in zip(bounds[:-1], bounds[1:]):
+                stage[a:b].copy_(x_host[a:b], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+                events.append(ev)
+        nz = self._noise()
+        outs = [torch.empty(B, device=dev) for _ in range(4)]
+        for (a, b), ev in zip(zip(bounds[:-1], bounds[1:]), events):
+            main.wait_event(ev)
+            part = self.engine.predict_moments(stage[a:b], g.loc, g.scale, S=num_predictions, guide=g.family,
+                                               noise=Noise(seed=nz.seed, window0=nz.window0 + a), engine=self.engine_kind)
+            for o, p in zip(outs, part):
+                o[a:b] = p
+        return tuple(outs)
+
 
 class bnn:  # namespace mirror of tyxe.bnn
     VariationalBNN = VariationalBNN

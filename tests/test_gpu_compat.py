@@ -129,3 +129,21 @@ def test_shims_installable():
     assert callable(tyxe.poutine.local_reparameterization) and callable(tyxe.poutine.flipout)
     pyro.clear_param_store()
     assert pyro.get_param_store().get_state()["params"] == {}
+
+
+@pytest.mark.parametrize("engine", ["simt", "tc"])
+def test_chunked_host_predict_equals_device_predict(engine):
+    """predict_moments_host overlaps chunked copies of a pinned HOST batch with the compute; the chunks see the same
+    weight draws (the Philox key of a draw has no window index), so the result equals the one-shot device call."""
+    from bayesrul_b200.compat import BNN, Inception
+    m = BNN(Inception(30, 18), None, 0, 1, 6, 238150, "lrt", 0.0, 0.138793, "normal", 0.05, device=DEV, engine=engine)
+    m.on_predict_start()
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(3000, 30, 18, generator=g).pin_memory()
+    y = torch.rand(3000, generator=g)
+    step0 = m.bnn._step
+    got = m.bnn.predict_moments_host(x, 6, first_fraction=0.2, n_chunks=3)  # 600 + 1200 + 1200 windows
+    m.bnn._step = step0  # same Philox key again
+    ref = m.bnn.predict_moments(x.to(DEV), 6)
+    for a, b in zip(got, ref):
+        np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-5, atol=1e-6)
