@@ -50,11 +50,19 @@ struct brl_ctx {
   // The per-layer kernels of a 256-window training batch fill a fraction of the GPU each, so independent ops run
   // concurrently: ops of one dependency level of the forward tape go to different streams, and the weight-gradient
   // kernels of the backward pass leave the critical dX chain for side streams (fork / join with events; capturable).
+  // The particles of a multi-particle ELBO step are independent until their gradients are summed, so two of them run side
+  // by side in two LANES (each a main stream + three side streams + its own activation / gradient buffers).
+  struct Lane {
+    cudaStream_t main = nullptr;  // lane 0: the caller's stream of the current call; lane 1: owned
+    cudaStream_t side[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr}, ev_op[8] = {};
+  };
   std::vector<int> op_level;
   int n_levels = 0;
   bool multi_stream = true;
-  cudaStream_t side[3] = {nullptr, nullptr, nullptr};
-  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr}, ev_op[8] = {};
+  Lane lanes[2];
+  cudaStream_t lane1_main = nullptr;
+  cudaEvent_t ev_lane_fork = nullptr, ev_lane_join = nullptr;
   // CUDA-graph replay of brl_elbo_step (native Philox noise only): a step is ~60-110 small launches + event fork / joins,
   // i.e. 0.5 ms (LRT) to 1.7 ms (Flipout, 2 particles) of host enqueue time -- more than the GPU needs to run it.
   // The second call with the same key captures the step (on `cap`, since the caller's stream may be the legacy default
@@ -267,14 +275,15 @@ static void forward_op(const brl_ctx* ctx, const ActBufs& ab, const FwdArgs& a, 
   else launch_conv_gemm(p, epi, st);
 }
 
-static void run_forward(const brl_ctx* ctx, const ActBufs& ab, const FwdArgs& a, cudaStream_t st) {
+static void run_forward(const brl_ctx* ctx, const ActBufs& ab, const FwdArgs& a, cudaStream_t st, int lane_id = 0) {
   const NetSpec& n = *ctx->net;
+  const brl_ctx::Lane& ln = ctx->lanes[lane_id];
   // every level of the tape: ops whose inputs are complete; the first op stays on `st`, the others fork to side streams
   for (int lvl = 0; lvl < ctx->n_levels; ++lvl) {
     int cnt = 0;
     for (size_t oi = 0; oi < n.ops.size(); ++oi) cnt += ctx->op_level[oi] == lvl;
     const bool fork = ctx->multi_stream && cnt > 1;
-    if (fork) cudaEventRecord(ctx->ev_fork, st);  // everything the level reads is complete on `st` at this point
+    if (fork) cudaEventRecord(ln.ev_fork, st);  // everything the level reads is complete on `st` at this point
     int j = 0, used = 0;
     for (size_t oi = 0; oi < n.ops.size(); ++oi) {
       if (ctx->op_level[oi] != lvl) continue;
@@ -282,15 +291,15 @@ static void run_forward(const brl_ctx* ctx, const ActBufs& ab, const FwdArgs& a,
         forward_op(ctx, ab, a, oi, st, 0);
       } else {
         const int si = (j - 1) % 3;
-        if (!(used & (1 << si))) { cudaStreamWaitEvent(ctx->side[si], ctx->ev_fork, 0); used |= 1 << si; }
-        forward_op(ctx, ab, a, oi, ctx->side[si], 1 + si);
+        if (!(used & (1 << si))) { cudaStreamWaitEvent(ln.side[si], ln.ev_fork, 0); used |= 1 << si; }
+        forward_op(ctx, ab, a, oi, ln.side[si], 1 + si);
       }
       ++j;
     }
     for (int si = 0; si < 3; ++si)
       if (used & (1 << si)) {
-        cudaEventRecord(ctx->ev_join[si], ctx->side[si]);
-        cudaStreamWaitEvent(st, ctx->ev_join[si], 0);
+        cudaEventRecord(ln.ev_join[si], ln.side[si]);
+        cudaStreamWaitEvent(st, ln.ev_join[si], 0);
       }
   }
 }
@@ -400,8 +409,9 @@ static void backward_op(const brl_ctx* ctx, const ActBufs& ab, const BwdArgs& a,
 
 // expects grad[out_buf] to hold dLoss/d(out) and every other grad buffer zeroed.  Tape levels run in reverse; the ops
 // of a level run concurrently (first op on `st`, the others on side streams), the next level waits for their dX only.
-static void run_backward(const brl_ctx* ctx, const ActBufs& ab, const BwdArgs& a, cudaStream_t st) {
+static void run_backward(const brl_ctx* ctx, const ActBufs& ab, const BwdArgs& a, cudaStream_t st, int lane_id = 0) {
   const NetSpec& n = *ctx->net;
+  const brl_ctx::Lane& ln = ctx->lanes[lane_id];
   if (!ctx->multi_stream) {
     for (int oi = (int)n.ops.size() - 1; oi >= 0; --oi) backward_op(ctx, ab, a, oi, st, 0, st, nullptr, nullptr);
     return;
@@ -411,29 +421,29 @@ static void run_backward(const brl_ctx* ctx, const ActBufs& ab, const BwdArgs& a
     int cnt = 0;
     for (size_t oi = 0; oi < n.ops.size(); ++oi) cnt += ctx->op_level[oi] == lvl;
     const bool fork = cnt > 1;
-    if (fork) cudaEventRecord(ctx->ev_fork, st);
+    if (fork) cudaEventRecord(ln.ev_fork, st);
     int j = 0, used = 0;
     for (int oi = (int)n.ops.size() - 1; oi >= 0; --oi) {
       if (ctx->op_level[oi] != lvl) continue;
       if (j == 0) {  // on the caller's stream; its weight gradients go to a rotating side stream
         const int wi = n_dw++ % 3;
         used_any |= 1 << wi;
-        backward_op(ctx, ab, a, oi, st, 0, ctx->side[wi], ctx->ev_op[n_dw % 8], nullptr);
+        backward_op(ctx, ab, a, oi, st, 0, ln.side[wi], ln.ev_op[n_dw % 8], nullptr);
       } else {
         const int si = (j - 1) % 3;
-        if (!(used & (1 << si))) { cudaStreamWaitEvent(ctx->side[si], ctx->ev_fork, 0); used |= 1 << si; }
-        backward_op(ctx, ab, a, oi, ctx->side[si], 1 + si, ctx->side[si], nullptr, ctx->ev_join[si]);
+        if (!(used & (1 << si))) { cudaStreamWaitEvent(ln.side[si], ln.ev_fork, 0); used |= 1 << si; }
+        backward_op(ctx, ab, a, oi, ln.side[si], 1 + si, ln.side[si], nullptr, ln.ev_join[si]);
       }
       ++j;
     }
     used_any |= used;
     for (int si = 0; si < 3; ++si)
-      if (used & (1 << si)) cudaStreamWaitEvent(st, ctx->ev_join[si], 0);  // the side chains' dX (recorded behind each)
+      if (used & (1 << si)) cudaStreamWaitEvent(st, ln.ev_join[si], 0);  // the side chains' dX (recorded behind each)
   }
   for (int si = 0; si < 3; ++si)  // final join: the weight gradients too; the caller's stream owns the buffers again
     if (used_any & (1 << si)) {
-      cudaEventRecord(ctx->ev_join[si], ctx->side[si]);
-      cudaStreamWaitEvent(st, ctx->ev_join[si], 0);
+      cudaEventRecord(ln.ev_join[si], ln.side[si]);
+      cudaStreamWaitEvent(st, ln.ev_join[si], 0);
     }
 }
 
@@ -547,15 +557,21 @@ int brl_create(brl_ctx** out, int net, int device) {
   }
   const char* single = getenv("BRL_SINGLE_STREAM");
   c->multi_stream = !(single && single[0] == '1');
-  for (int i = 0; i < 3; ++i) {
-    BRL_CUDA(cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
-    BRL_CUDA(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+  for (brl_ctx::Lane& ln : c->lanes) {
+    for (int i = 0; i < 3; ++i) {
+      BRL_CUDA(cudaStreamCreateWithFlags(&ln.side[i], cudaStreamNonBlocking));
+      BRL_CUDA(cudaEventCreateWithFlags(&ln.ev_join[i], cudaEventDisableTiming));
+    }
+    BRL_CUDA(cudaEventCreateWithFlags(&ln.ev_fork, cudaEventDisableTiming));
+    for (int i = 0; i < 8; ++i) BRL_CUDA(cudaEventCreateWithFlags(&ln.ev_op[i], cudaEventDisableTiming));
   }
-  BRL_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  BRL_CUDA(cudaStreamCreateWithFlags(&c->lane1_main, cudaStreamNonBlocking));
+  c->lanes[1].main = c->lane1_main;
+  BRL_CUDA(cudaEventCreateWithFlags(&c->ev_lane_fork, cudaEventDisableTiming));
+  BRL_CUDA(cudaEventCreateWithFlags(&c->ev_lane_join, cudaEventDisableTiming));
   BRL_CUDA(cudaStreamCreateWithFlags(&c->cap, cudaStreamNonBlocking));
   const char* nograph = getenv("BRL_NO_GRAPH");
   c->graph_enabled = !(nograph && nograph[0] == '1');
-  for (int i = 0; i < 8; ++i) BRL_CUDA(cudaEventCreateWithFlags(&c->ev_op[i], cudaEventDisableTiming));
   *out = c;
   return BRL_OK;
 }
@@ -565,16 +581,21 @@ int brl_destroy(brl_ctx* ctx) {
   cudaFree(ctx->table_pool);
   cudaFree(ctx->site_off_dev);
   tc_destroy(ctx->tc);
-  for (int i = 0; i < 3; ++i) {
-    if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]);
-    if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
+  for (brl_ctx::Lane& ln : ctx->lanes) {
+    for (int i = 0; i < 3; ++i) {
+      if (ln.side[i]) cudaStreamDestroy(ln.side[i]);
+      if (ln.ev_join[i]) cudaEventDestroy(ln.ev_join[i]);
+    }
+    if (ln.ev_fork) cudaEventDestroy(ln.ev_fork);
+    for (int i = 0; i < 8; ++i)
+      if (ln.ev_op[i]) cudaEventDestroy(ln.ev_op[i]);
   }
-  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->lane1_main) cudaStreamDestroy(ctx->lane1_main);
+  if (ctx->ev_lane_fork) cudaEventDestroy(ctx->ev_lane_fork);
+  if (ctx->ev_lane_join) cudaEventDestroy(ctx->ev_lane_join);
   for (auto& g : ctx->graphs)
     if (g.exec) cudaGraphExecDestroy(g.exec);
   if (ctx->cap) cudaStreamDestroy(ctx->cap);
-  for (int i = 0; i < 8; ++i)
-    if (ctx->ev_op[i]) cudaEventDestroy(ctx->ev_op[i]);
   delete ctx;
   return BRL_OK;
 }
@@ -630,6 +651,11 @@ int64_t brl_workspace_bytes(const brl_ctx* ctx, int64_t B, int64_t S, int train,
   if (engine == BRL_ENGINE_TC_FP16) c.used += tc_workspace_bytes(ctx->tc, B, S);
   else carve_forward(n, c, B, S, ab);
   if (train == 1) carve_train(n, c, B, ab);
+  if (train == 1 && S >= 2) {  // second lane of brl_elbo_step: two particles side by side
+    ActBufs ab1;
+    carve_forward(n, c, B, 1, ab1);
+    carve_train(n, c, B, ab1);
+  }
   if (train == 2)  // brl_forward in BRL_MODE_FLIPOUT with native signs: [S,B,Cin] + [S,B,Cout] per layer
     for (const LayerSpec& L : n.layers) { c.take<float>(S * B * L.cin); c.take<float>(S * B * L.cout); }
   return (int64_t)c.used + 4096;
@@ -794,67 +820,90 @@ int brl_aggregate_predictions(const float* out, int64_t S, int64_t B, float* agg
   return BRL_OK;
 }
 
-// the launches of one ELBO step (every pointer final); captured as is by the graph path of brl_elbo_step
-static int elbo_body(brl_ctx* ctx, const ActBufs& ab, const float* x, const float* y, int64_t B, const float* mu, const float* sigma,
-                     int mode, int guide, int particles, float prior_loc, float prior_scale, int64_t dataset_size,
-                     const brl_noise* noise, int compute_grads, double* scalars, float* grad_mu, float* grad_sigma,
-                     float* grad_log_sigma, float* out, cudaStream_t st) {
+// the launches of one ELBO step (every pointer final); captured as is by the graph path of brl_elbo_step.
+// lanes[0] always exists and owns the shared accumulators; with a second buffer set (lanes[1]) two particles run side by
+// side: lane 0 on `st`, lane 1 on the context's own stream, forked / joined with events.  The gradient finalisation of the
+// particles (first one writes, the others accumulate) stays in particle order on `st`.
+static int elbo_body(brl_ctx* ctx, const ActBufs* const* lanes, int n_lanes, const float* x, const float* y, int64_t B,
+                     const float* mu, const float* sigma, int mode, int guide, int particles, float prior_loc, float prior_scale,
+                     int64_t dataset_size, const brl_noise* noise, int compute_grads, double* scalars, float* grad_mu,
+                     float* grad_sigma, float* grad_log_sigma, float* out, cudaStream_t st) {
   const NetSpec& n = *ctx->net;
+  const ActBufs& ab0 = *lanes[0];
   const double cc = 1.0 / ((double)dataset_size * 30.0 * 18.0);
   const double c_nll = cc * (double)dataset_size / (double)B;
-  BRL_CUDA(cudaMemsetAsync(ab.acc, 0, 8 * sizeof(double), st));
+  BRL_CUDA(cudaMemsetAsync(ab0.acc, 0, 8 * sizeof(double), st));
   const int nsites = 2 * (int)n.layers.size();
-  for (int pt = 0; pt < particles; ++pt) {
-    brl_noise nz = noise_at_sample(n, noise, pt, B);
-    const bool need_w = mode != BRL_MODE_LRT;
-    if (need_w) {
-      NoiseRef eps = nref(&nz, nz.weight_eps, KIND_WEIGHT_EPS, 0);
-      if (guide == BRL_GUIDE_NORMAL) launch_sample_normal(mu, sigma, n.P, 1, eps, ab.wsamp, ab.delta, st);
-      else launch_sample_radial(mu, sigma, n.P, 1, ctx->site_off_dev, nsites, ctx->max_site, eps,
-                                nref(&nz, nz.radial_r, KIND_RADIAL_R, 0), ab.norms, ab.wsamp, ab.delta, st);
+  if (!ctx->multi_stream) n_lanes = 1;
+  for (int p0 = 0; p0 < particles; p0 += n_lanes) {
+    const int nl = std::min(n_lanes, particles - p0);
+    if (nl > 1) {
+      BRL_CUDA(cudaEventRecord(ctx->ev_lane_fork, st));
+      BRL_CUDA(cudaStreamWaitEvent(ctx->lane1_main, ctx->ev_lane_fork, 0));
     }
-    std::vector<const float*> sin_(n.layers.size(), nullptr), sout_(n.layers.size(), nullptr);
-    if (mode == BRL_MODE_FLIPOUT) {  // native sign tensors of all layers: one launch per particle
-      SignJobs jobs;
-      jobs.n = 0;
-      jobs.start[0] = 0;
-      auto add = [&](float* dst, int C, unsigned kind, unsigned site) {
-        jobs.dst[jobs.n] = dst; jobs.C[jobs.n] = C; jobs.kind[jobs.n] = kind; jobs.site[jobs.n] = site;
-        jobs.start[jobs.n + 1] = jobs.start[jobs.n] + B * C;
-        ++jobs.n;
-      };
-      for (size_t l = 0; l < n.layers.size(); ++l) {
-        if (nz.flip_in[l]) sin_[l] = nz.flip_in[l];
-        else { add(ab.sgn_in[l], n.layers[l].cin, KIND_FLIP_IN, (unsigned)l); sin_[l] = ab.sgn_in[l]; }
-        if (nz.flip_out[l]) sout_[l] = nz.flip_out[l];
-        else { add(ab.sgn_out[l], n.layers[l].cout, KIND_FLIP_OUT, (unsigned)l); sout_[l] = ab.sgn_out[l]; }
+    for (int l = 0; l < nl; ++l) {
+      const int pt = p0 + l;
+      const ActBufs& ab = *lanes[l];
+      cudaStream_t ls = l == 0 ? st : ctx->lane1_main;
+      brl_noise nz = noise_at_sample(n, noise, pt, B);
+      const bool need_w = mode != BRL_MODE_LRT;
+      if (need_w) {
+        NoiseRef eps = nref(&nz, nz.weight_eps, KIND_WEIGHT_EPS, 0);
+        if (guide == BRL_GUIDE_NORMAL) launch_sample_normal(mu, sigma, n.P, 1, eps, ab.wsamp, ab.delta, ls);
+        else launch_sample_radial(mu, sigma, n.P, 1, ctx->site_off_dev, nsites, ctx->max_site, eps,
+                                  nref(&nz, nz.radial_r, KIND_RADIAL_R, 0), ab.norms, ab.wsamp, ab.delta, ls);
       }
-      if (jobs.n) launch_gen_signs_multi(jobs, B, nref(&nz, nullptr, 0, 0), st);
+      std::vector<const float*> sin_(n.layers.size(), nullptr), sout_(n.layers.size(), nullptr);
+      if (mode == BRL_MODE_FLIPOUT) {  // native sign tensors of all layers: one launch per particle
+        SignJobs jobs;
+        jobs.n = 0;
+        jobs.start[0] = 0;
+        auto add = [&](float* dst, int C, unsigned kind, unsigned site) {
+          jobs.dst[jobs.n] = dst; jobs.C[jobs.n] = C; jobs.kind[jobs.n] = kind; jobs.site[jobs.n] = site;
+          jobs.start[jobs.n + 1] = jobs.start[jobs.n] + B * C;
+          ++jobs.n;
+        };
+        for (size_t ly = 0; ly < n.layers.size(); ++ly) {
+          if (nz.flip_in[ly]) sin_[ly] = nz.flip_in[ly];
+          else { add(ab.sgn_in[ly], n.layers[ly].cin, KIND_FLIP_IN, (unsigned)ly); sin_[ly] = ab.sgn_in[ly]; }
+          if (nz.flip_out[ly]) sout_[ly] = nz.flip_out[ly];
+          else { add(ab.sgn_out[ly], n.layers[ly].cout, KIND_FLIP_OUT, (unsigned)ly); sout_[ly] = ab.sgn_out[ly]; }
+        }
+        if (jobs.n) launch_gen_signs_multi(jobs, B, nref(&nz, nullptr, 0, 0), ls);
+      }
+      float* outp = out + (long long)pt * B * 2;
+      FwdArgs fa{x, B, 1, mode, mu, sigma, ab.wsamp, 0.f, &nz, sin_.data(), sout_.data(), outp, compute_grads != 0};
+      run_forward(ctx, ab, fa, ls, l);
+      if (compute_grads) {
+        int rc = zero_grads(n, ab, B, ls);
+        if (rc) return rc;
+        BRL_CUDA(cudaMemsetAsync(ab.g0, 0, sizeof(float) * n.P, ls));
+        BRL_CUDA(cudaMemsetAsync(ab.g1, 0, sizeof(float) * n.P, ls));
+      }
+      launch_nll_elbo(outp, y, B, (float)(c_nll / particles), ab0.acc, compute_grads ? ab.grad[n.out_buf] : nullptr, ls);
+      if (compute_grads) {
+        BwdArgs ba{x, B, mode, mode == BRL_MODE_WS ? ab.wsamp : mu, sigma, ab.wsamp, 0.f, &nz, sin_.data(), sout_.data(), outp, ab.g0, ab.g1};
+        run_backward(ctx, ab, ba, ls, l);
+      }
     }
-    float* outp = out + (long long)pt * B * 2;
-    FwdArgs fa{x, B, 1, mode, mu, sigma, ab.wsamp, 0.f, &nz, sin_.data(), sout_.data(), outp, compute_grads != 0};
-    run_forward(ctx, ab, fa, st);
-    if (compute_grads) {
-      int rc = zero_grads(n, ab, B, st);
-      if (rc) return rc;
-      BRL_CUDA(cudaMemsetAsync(ab.g0, 0, sizeof(float) * n.P, st));
-      BRL_CUDA(cudaMemsetAsync(ab.g1, 0, sizeof(float) * n.P, st));
+    if (nl > 1) {
+      BRL_CUDA(cudaEventRecord(ctx->ev_lane_join, ctx->lane1_main));
+      BRL_CUDA(cudaStreamWaitEvent(st, ctx->ev_lane_join, 0));
     }
-    launch_nll_elbo(outp, y, B, (float)(c_nll / particles), ab.acc, compute_grads ? ab.grad[n.out_buf] : nullptr, st);
-    if (compute_grads) {
-      BwdArgs ba{x, B, mode, mode == BRL_MODE_WS ? ab.wsamp : mu, sigma, ab.wsamp, 0.f, &nz, sin_.data(), sout_.data(), outp, ab.g0, ab.g1};
-      run_backward(ctx, ab, ba, st);
+    for (int l = 0; l < nl; ++l) {
+      const int pt = p0 + l;
+      const ActBufs& ab = *lanes[l];
+      Finalize f{};
+      f.P = n.P; f.mode = mode; f.guide = guide; f.first = pt == 0;
+      f.mu = mu; f.sigma = sigma; f.w = ab.wsamp; f.delta = ab.delta;
+      f.g0 = compute_grads ? ab.g0 : nullptr; f.g1 = compute_grads ? ab.g1 : nullptr;
+      f.prior_loc = prior_loc; f.prior_scale = prior_scale; f.c_kl = (float)(cc / particles);
+      f.grad_mu = compute_grads ? grad_mu : nullptr; f.grad_sigma = compute_grads ? grad_sigma : nullptr;
+      f.kl_acc = ab0.acc + 2;
+      launch_finalize(f, st);
     }
-    Finalize f{};
-    f.P = n.P; f.mode = mode; f.guide = guide; f.first = pt == 0;
-    f.mu = mu; f.sigma = sigma; f.w = ab.wsamp; f.delta = ab.delta;
-    f.g0 = compute_grads ? ab.g0 : nullptr; f.g1 = compute_grads ? ab.g1 : nullptr;
-    f.prior_loc = prior_loc; f.prior_scale = prior_scale; f.c_kl = (float)(cc / particles);
-    f.grad_mu = compute_grads ? grad_mu : nullptr; f.grad_sigma = compute_grads ? grad_sigma : nullptr;
-    f.kl_acc = ab.acc + 2;
-    launch_finalize(f, st);
   }
-  launch_post_scalars(scalars, ab.acc, c_nll, cc, particles, B, st);
+  launch_post_scalars(scalars, ab0.acc, c_nll, cc, particles, B, st);
   if (compute_grads && grad_log_sigma) launch_log_sigma_grad(grad_sigma, sigma, grad_log_sigma, n.P, st);
   BRL_CUDA(cudaGetLastError());
   return BRL_OK;
@@ -892,6 +941,15 @@ int brl_elbo_step(brl_ctx* ctx, const float* x, const float* y, int64_t B, const
   carve_train(n, c, B, ab);
   if (!c.ok) return fail(BRL_ERR_WORKSPACE, "brl_elbo_step: workspace too small; need " +
                                                 std::to_string(brl_workspace_bytes(ctx, B, 1, 1, 0)) + " bytes");
+  // a second buffer set, if the workspace has room for it (brl_workspace_bytes(B, S >= 2, train = 1)): two particles at a time
+  ActBufs ab1;
+  int n_lanes = 1;
+  if (particles > 1) {
+    carve_forward(n, c, B, 1, ab1);
+    carve_train(n, c, B, ab1);
+    if (c.ok) n_lanes = 2;
+  }
+  const ActBufs* lanes[2] = {&ab, &ab1};
   // ---- graph replay (native Philox noise): eager on first sight of a configuration, captured on the second, replayed after
   brl_ctx::StepGraph* sg = nullptr;
   if (ctx->graph_enabled && noise_is_native(noise) && particles <= GRAPH_MAX_PARTICLES) {
@@ -921,7 +979,7 @@ int brl_elbo_step(brl_ctx* ctx, const float* x, const float* y, int64_t B, const
         const long long l0 = launch_count();
         brl_noise zero;
         memset(&zero, 0, sizeof(zero));
-        rc = elbo_body(ctx, ab, ab.st_x, ab.st_y, B, mu, sigma, mode, guide, particles, prior_loc, prior_scale, dataset_size, &zero,
+        rc = elbo_body(ctx, lanes, n_lanes, ab.st_x, ab.st_y, B, mu, sigma, mode, guide, particles, prior_loc, prior_scale, dataset_size, &zero,
                        compute_grads, ab.st_scal, compute_grads ? ab.st_gmu : nullptr, compute_grads ? ab.st_gsig : nullptr,
                        (compute_grads && grad_log_sigma) ? ab.st_glog : nullptr, ab.st_out, ctx->cap);
         g_dyn = nullptr;
@@ -955,7 +1013,7 @@ int brl_elbo_step(brl_ctx* ctx, const float* x, const float* y, int64_t B, const
     }
     return BRL_OK;
   }
-  return elbo_body(ctx, ab, x, y, B, mu, sigma, mode, guide, particles, prior_loc, prior_scale, dataset_size, noise, compute_grads,
+  return elbo_body(ctx, lanes, n_lanes, x, y, B, mu, sigma, mode, guide, particles, prior_loc, prior_scale, dataset_size, noise, compute_grads,
                    scalars, grad_mu, grad_sigma, grad_log_sigma, out, st);
 }
 

@@ -272,7 +272,7 @@ class Engine:
         scalars = torch.empty(4, dtype=torch.float64, device=self.device)
         out = torch.empty(particles, B, 2, device=self.device)
         g = [torch.empty(self.P, device=self.device) for _ in range(3)] if compute_grads else [None] * 3
-        ws = self._ws_for(B, 1, True, "simt")
+        ws = self._ws_for(B, 2 if particles > 1 else 1, True, "simt")  # S >= 2: room for two particles side by side
         nz, keep = self._noise(noise)
         p = lambda t: t.data_ptr() if t is not None else None
         _lib.check(self.lib.brl_elbo_step(self.ctx, x.data_ptr(), y.data_ptr(), B, mu.data_ptr(), sigma.data_ptr(),

@@ -101,7 +101,8 @@ int64_t brl_net_flops_fwd(int net);
 int brl_create(brl_ctx** ctx, int net, int device);
 int brl_destroy(brl_ctx* ctx);
 /* bytes of scratch needed by the calls below for B windows x S concurrently-resident samples;
- * train == 1 adds the saved activations / gradient buffers of brl_elbo_step / brl_hnn_step,
+ * train == 1 adds the saved activations / gradient buffers of brl_elbo_step / brl_hnn_step (with S >= 2: a second set, so
+ * that brl_elbo_step runs two particles side by side on two stream lanes),
  * train == 2 the sign tensors brl_forward generates in BRL_MODE_FLIPOUT when none are injected */
 /* 1 when `engine` can run this net's forward on this build, else 0 */
 int brl_engine_available(const brl_ctx* ctx, int engine);
