@@ -192,19 +192,32 @@ void launch_sample_normal(const float* mu, const float* sigma, long long P, long
   sample_normal_kernel<<<grid, 256, 0, st>>>(mu, sigma, P, eps, w, delta);
 }
 
-__device__ __forceinline__ float weight_eps_at(const NoiseRef& eps, int s, long long P, long long e) {
-  if (eps.ptr) return eps.ptr[(long long)s * P + e];
-  const NoiseKey k = noise_key(eps);
-  return philox_normal(k.seed, KIND_WEIGHT_EPS, 0, k.sample0 + s, 0, (uint32_t)e);
+// The radial guide needs ||eps|| over each whole site before any weight of the site exists, so the draw is two passes over
+// the same Philox stream (the stream of sample_normal_kernel: block = element >> 2, four normals per block).
+__device__ __forceinline__ void weight_eps4(const NoiseRef& eps, const NoiseKey& k, int s, long long P, long long blk, float (&z)[4]) {
+  const long long e0 = blk << 2;
+  if (eps.ptr) {
+#pragma unroll
+    for (int l = 0; l < 4; ++l) z[l] = e0 + l < P ? eps.ptr[(long long)s * P + e0 + l] : 0.f;
+  } else {
+    const float4 n4 = normal4(philox_block(k.seed, KIND_WEIGHT_EPS, 0, k.sample0 + s, 0, (uint32_t)blk));
+    z[0] = n4.x; z[1] = n4.y; z[2] = n4.z; z[3] = n4.w;
+  }
 }
 __global__ void radial_norm_kernel(long long P, const long long* __restrict__ site_off, int n_sites, NoiseRef eps,
                                    float* __restrict__ norms) {
   const int j = blockIdx.x, s = blockIdx.y;
   const long long beg = site_off[j], end = site_off[j + 1];
+  const NoiseKey k = noise_key(eps);
   double acc = 0.0;
-  for (long long e = beg + threadIdx.x; e < end; e += blockDim.x) {
-    const float z = weight_eps_at(eps, s, P, e);
-    acc += (double)z * z;
+  for (long long blk = (beg >> 2) + threadIdx.x; blk <= ((end - 1) >> 2); blk += blockDim.x) {
+    float z[4];
+    weight_eps4(eps, k, s, P, blk, z);
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      const long long e = (blk << 2) + l;
+      if (e >= beg && e < end) acc += (double)z[l] * z[l];
+    }
   }
   acc = block_sum(acc);
   if (threadIdx.x == 0) norms[(long long)s * n_sites + j] = (float)sqrt(acc);
@@ -212,16 +225,37 @@ __global__ void radial_norm_kernel(long long P, const long long* __restrict__ si
 __global__ void radial_apply_kernel(const float* __restrict__ mu, const float* __restrict__ sigma, long long P,
                                     const long long* __restrict__ site_off, int n_sites, NoiseRef eps, NoiseRef r,
                                     const float* __restrict__ norms, float* __restrict__ w, float* __restrict__ delta) {
-  const int j = blockIdx.y, s = blockIdx.z;
-  const long long beg = site_off[j], end = site_off[j + 1];
-  const long long e = beg + blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (e >= end) return;
-  const NoiseKey rk = noise_key(r);
-  const float rr = r.ptr ? r.ptr[(long long)s * n_sites + j]
-                         : philox_normal(rk.seed, KIND_RADIAL_R, 0, rk.sample0 + s, 0, (uint32_t)j);
-  const float d = weight_eps_at(eps, s, P, e) / norms[(long long)s * n_sites + j] * rr;
-  w[(long long)s * P + e] = fmaf(d, sigma[e], mu[e]);
-  if (delta) delta[(long long)s * P + e] = d;
+  const int s = blockIdx.y;
+  const long long nblk = (P + 3) >> 2;
+  const NoiseKey k = noise_key(eps), rk = noise_key(r);
+  for (long long blk = blockIdx.x * (long long)blockDim.x + threadIdx.x; blk < nblk; blk += (long long)gridDim.x * blockDim.x) {
+    float z[4];
+    weight_eps4(eps, k, s, P, blk, z);
+    const long long e0 = blk << 2;
+    int lo = 0, hi = n_sites - 1;  // site of e0: last j with site_off[j] <= e0
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (site_off[mid] <= e0) lo = mid; else hi = mid - 1;
+    }
+    int j = lo;
+    float scale = 0.f;
+    bool have = false;
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      const long long e = e0 + l;
+      if (e >= P) break;
+      while (e >= site_off[j + 1]) { ++j; have = false; }
+      if (!have) {
+        const float rr = r.ptr ? r.ptr[(long long)s * n_sites + j]
+                               : philox_normal(rk.seed, KIND_RADIAL_R, 0, rk.sample0 + s, 0, (uint32_t)j);
+        scale = rr / norms[(long long)s * n_sites + j];
+        have = true;
+      }
+      const float d = z[l] * scale;
+      w[(long long)s * P + e] = fmaf(d, sigma[e], mu[e]);
+      if (delta) delta[(long long)s * P + e] = d;
+    }
+  }
 }
 void launch_sample_radial(const float* mu, const float* sigma, long long P, long long S, const long long* site_off,
                           int n_sites, int max_site, NoiseRef eps, NoiseRef r, float* norms, float* w, float* delta,
@@ -229,8 +263,9 @@ void launch_sample_radial(const float* mu, const float* sigma, long long P, long
   ++g_launch_count;
   radial_norm_kernel<<<dim3(n_sites, (unsigned)S), 256, 0, st>>>(P, site_off, n_sites, eps, norms);
   ++g_launch_count;
-  radial_apply_kernel<<<dim3((max_site + 255) / 256, n_sites, (unsigned)S), 256, 0, st>>>(mu, sigma, P, site_off, n_sites,
-                                                                                        eps, r, norms, w, delta);
+  const long long nblk = (P + 3) >> 2;
+  radial_apply_kernel<<<dim3((unsigned)min((nblk + 255) / 256, (long long)148 * 8), (unsigned)S), 256, 0, st>>>(
+      mu, sigma, P, site_off, n_sites, eps, r, norms, w, delta);
 }
 
 __global__ void gen_signs_kernel(float* dst, long long S, long long B, int C, NoiseRef nz) {

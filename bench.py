@@ -224,6 +224,8 @@ def main():
     device = torch.device("cuda", local)
     dist = None
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         import torch.distributed as dist_mod
         dist_mod.init_process_group("nccl", device_id=device)
         dist = dist_mod
@@ -376,6 +378,43 @@ def main():
         mcd = {"window_samples_per_s": world * units_per_step * 3 / tm, "ms_per_step": 1e3 * tm / 3, "p_dropout": 0.241437,
                "masks": S_PRED, "noise": "in-kernel Philox masks (fused)"}
 
+    # ---- configs[3]: Radial BNN (ncmapss_rad: q_scale 1.241e-3), MC-sample sweep, the S samples SHARDED across the ranks
+    #      (every rank sees the same windows; per-window (n, mean, M2, sum sigma^2) merged with one all-gather + Chan's formula)
+    radial = {}
+    if not args.no_train:
+        from bayesrul_b200.dist import all_gather_moments, shard_range
+        sg_rad = torch.full_like(mu, 1.241e-3)
+        x_rad = synth(B_PRED, seed=4242)[0].to(device)  # the same windows on every rank
+        for S_tot in (10, 100, 1000):
+            s_lo, s_hi = shard_range(S_tot, rank, world)
+
+            def rad_step(i=0):
+                m = eng.predict_moments(x_rad, mu, sg_rad, S=s_hi - s_lo, guide="radial", noise=Noise(seed=777, sample0=s_lo), engine=engine)
+                if dist is not None:
+                    m = all_gather_moments(s_hi - s_lo, m[0], m[2], m[3])
+                outs["rad"] = m
+
+            nrep = 3
+            tr = max_over_ranks(timed_steps(rad_step, nrep, 2, flush_buf, dist), dist, device)
+            radial[f"S={S_tot}"] = {"window_samples_per_s": B_PRED * S_tot * nrep / tr, "ms_per_step": 1e3 * tr / nrep,
+                                    "samples_per_rank": s_hi - s_lo}
+        radial["note"] = (f"{B_PRED} windows, AutoRadial guide (eps/||eps||*r sampler, two-phase norm), samples sharded over {world} rank(s)"
+                          + (", NCCL all-gather of the per-window moments + Chan merge inside the timed region" if dist is not None else ""))
+
+    # ---- configs[4]: deep ensemble of 5 HNN members (deterministic heteroscedastic nets) + mixture moments (deepens.py:21-24);
+    #      windows sharded across the ranks like the headline workload
+    deepens = {}
+    if not args.no_train:
+        members = [init_flat_params(NET, 100 + k).to(device) for k in range(5)]
+
+        def de_step(i=0):
+            o = torch.stack([eng.forward(xs[i % n_rot], "det", theta=th, engine=engine)[0] for th in members])  # [5,B,2]
+            outs["de"] = eng.mixture_moments(o[:, :, 0].contiguous(), o[:, :, 1].contiguous())
+
+        td = max_over_ranks(timed_steps(de_step, 5, 2, flush_buf, dist), dist, device)
+        deepens = {"window_members_per_s": world * B_PRED * 5 * 5 / td, "ms_per_step": 1e3 * td / 5, "members": 5,
+                   "windows_per_step_per_gpu": B_PRED}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -396,7 +435,7 @@ def main():
                      "frac": achieved_tf / pk["tf_sust"], "traffic": traffic, "kernel": "tc_conv_kernel" if engine == "tc" else "step",
                      "ms_per_launch": conv_ms / max(conv_launches, 1), "share_of_step": conv_ms / (t_local * 1e3) if conv_launches else None,
                      "note": roof_note, "other_kernels": kernels},
-        "train": train, "mcd_predict": mcd,
+        "train": train, "mcd_predict": mcd, "radial_sweep": radial, "deep_ensemble": deepens,
     }
     if world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
