@@ -224,8 +224,7 @@ def main():
     device = torch.device("cuda", local)
     dist = None
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version banner / warnings go to stderr: stdout is ONE JSON line
         import torch.distributed as dist_mod
         dist_mod.init_process_group("nccl", device_id=device)
         dist = dist_mod
