@@ -3,9 +3,17 @@
 //   key     = (seed lo32, seed hi32)
 //   counter = (element >> 2, global window index, global MC sample index, kind << 24 | layer/site)
 // and element e takes lane (e & 3) of its block.  Normals are Box-Muller on lanes (0,1) and (2,3).
-// Dropout keep-decisions use 16 bits each (8 per block) and a position-major element order
-//   e = position * roundup8(C) + channel,  block = e >> 3,  half (e & 1) of word (e & 7) >> 1,
-// so the 8 / 16 consecutive channels one epilogue thread owns at its position share 1 / 2 Philox blocks.
+// Dropout keep-decisions: SIXTEEN per block, 16-bit resolution.  Element order is position-major,
+//   e = position * roundup16(C) + channel,  block = e >> 4,  decision bi = (e & 12) | {0, 2, 1, 3}[e & 3] of the block
+// (the middle two of every four are swapped so that the two 16-bit lanes of one SIMD compare are two ADJACENT channels,
+// i.e. one packed half2 of the fused kernel is masked with a single AND), so the 8 / 16 consecutive channels one
+// epilogue thread owns at its position share one Philox block.  With B[0..15] the
+// bytes of the block (little-endian words x, y, z, w), decision bi compares the 16-bit number
+//   u = B[(bi + 1) & 15] << 8 | B[bi]      with      T = min(ceil(keep * 2^16 - 0.5), 65535)   (keep iff u < T),
+// i.e. the sixteen overlapping 16-bit windows of the 128 bits: every decision has exactly the 16-bit marginal T / 2^16, and
+// two neighbouring decisions share only the byte that is the LOW byte of one of them (their covariance is < 2^-8 of a
+// Bernoulli variance; tests/test_host_logic.py bounds the empirical correlations).  All sixteen come out of eight
+// two-lane SIMD compares, branch-free.  (Eight independent 16-bit decisions per block made MC-dropout Philox-bound.)
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -74,16 +82,37 @@ __device__ __forceinline__ float philox_uniform(uint64_t seed, uint32_t kind, ui
   return u01(lane_of(r, elem & 3u));
 }
 
-// 16-bit keep decision: ((h + 0.5) * 2^-16 < keep) on half `odd` of a Philox word
-__device__ __forceinline__ bool keep16(uint32_t word, uint32_t odd, float keep) {
-  const uint32_t h = odd ? (word >> 16) : (word & 0xFFFFu);
-  return ((float)h + 0.5f) * 1.52587890625e-05f < keep;
+// integer threshold of a keep probability: u < T  <=>  (u + 0.5) * 2^-16 < keep   (u a 16-bit number)
+__host__ __device__ __forceinline__ uint32_t keep_threshold(float keep) {
+  const uint32_t t = (uint32_t)ceilf(keep * 65536.0f - 0.5f);
+  return t > 65535u ? 65535u : t;
 }
+// all sixteen decisions of block r: ev[i] / od[i] hold decisions 4i, 4i+2 / 4i+1, 4i+3 as all-ones 16-bit lanes
+struct KeepBits { uint32_t ev[4], od[4]; };
+__device__ __forceinline__ KeepBits keep_bits(const uint4& r, uint32_t T) {
+  const uint32_t T2 = T | (T << 16);
+  KeepBits k;
+  k.ev[0] = __vcmpltu2(r.x, T2); k.ev[1] = __vcmpltu2(r.y, T2); k.ev[2] = __vcmpltu2(r.z, T2); k.ev[3] = __vcmpltu2(r.w, T2);
+  k.od[0] = __vcmpltu2(__funnelshift_r(r.x, r.y, 8), T2);
+  k.od[1] = __vcmpltu2(__funnelshift_r(r.y, r.z, 8), T2);
+  k.od[2] = __vcmpltu2(__funnelshift_r(r.z, r.w, 8), T2);
+  k.od[3] = __vcmpltu2(__funnelshift_r(r.w, r.x, 8), T2);
+  return k;
+}
+// all-ones / all-zeros 16-bit lanes for the channel pair (2p, 2p + 1) of the block's sixteen channels, p = 0..7: channels
+// 4i, 4i+1 take decisions 4i, 4i+2 (the lanes of ev[i]); channels 4i+2, 4i+3 take decisions 4i+1, 4i+3 (the lanes of od[i])
+__device__ __forceinline__ uint32_t keep_pair(const KeepBits& k, uint32_t p) {
+  const uint32_t i = p >> 1;
+  return (p & 1u) ? (i == 0 ? k.od[0] : i == 1 ? k.od[1] : i == 2 ? k.od[2] : k.od[3])
+                  : (i == 0 ? k.ev[0] : i == 1 ? k.ev[1] : i == 2 ? k.ev[2] : k.ev[3]);
+}
+// channel c (0..15) of the block
+__device__ __forceinline__ bool keep_at(const KeepBits& k, uint32_t c) { return (keep_pair(k, c >> 1) >> (16u * (c & 1u))) & 1u; }
 __device__ __forceinline__ bool philox_keep(uint64_t seed, uint32_t kind, uint32_t site, uint32_t sample, uint32_t window,
                                             uint32_t C, uint32_t pos, uint32_t ch, float keep) {
-  const uint32_t e = pos * ((C + 7u) & ~7u) + ch;
-  const uint4 r = philox_block(seed, kind, site, sample, window, e >> 3);
-  return keep16(lane_of(r, (e & 7u) >> 1), e & 1u, keep);
+  const uint32_t e = pos * ((C + 15u) & ~15u) + ch;
+  const uint4 r = philox_block(seed, kind, site, sample, window, e >> 4);
+  return keep_at(keep_bits(r, keep_threshold(keep)), e & 15u);
 }
 
 __device__ __forceinline__ float philox_sign(uint64_t seed, uint32_t kind, uint32_t site, uint32_t sample,

@@ -306,14 +306,10 @@ __global__ void __launch_bounds__(192, 1) tc_fc_kernel(const FcArgs a, const __g
       float o0 = __ldg(tail + 192), o1 = __ldg(tail + 193);
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        uint32_t kw[2][4];
-        if (DROP && !a.drop.ptr) {  // 16 keep decisions of outputs 16g .. 16g+15: two Philox blocks
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const uint4 r = philox_block(a.drop.seed, a.drop.kind, a.drop.site, a.drop.sample0 + s, a.drop.window0 + gw, 2 * g + h);
-            kw[h][0] = r.x; kw[h][1] = r.y; kw[h][2] = r.z; kw[h][3] = r.w;
-          }
-        }
+        KeepBits kb = {};
+        if (DROP && !a.drop.ptr)  // 16 keep decisions of outputs 16g .. 16g+15: one Philox block
+          kb = keep_bits(philox_block(a.drop.seed, a.drop.kind, a.drop.site, a.drop.sample0 + s, a.drop.window0 + gw, g),
+                         keep_threshold(a.keep));
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int n = g * 16 + j;
@@ -321,7 +317,7 @@ __global__ void __launch_bounds__(192, 1) tc_fc_kernel(const FcArgs a, const __g
           if (DROP) {
             if (gw < a.B) {
               const bool keep = a.drop.ptr ? a.drop.ptr[((long long)s * a.B + gw) * 64 + n] != 0.f
-                                           : keep16(kw[j >> 3][(j & 7) >> 1], j & 1, a.keep);
+                                           : keep_at(kb, j);
               h = keep ? h / a.keep : 0.f;
             }
           }

@@ -75,34 +75,47 @@ __global__ void tc_packx_kernel(const float* __restrict__ x, unsigned char* __re
   }
 }
 
-// ReLU (+bias) (+dropout) on N (8 or 16) fp32 accumulator columns = channels ch0.. of a site with `nvalid` channels,
-// at time step t.  Native masks: one Philox block per 8 channels (16-bit decisions, position-major order).
-template <bool DROP, bool BIAS, int N>
-__device__ __forceinline__ void actn(float (&v)[N], const float* bias, bool live, const ConvArgs& a, int layer, int s, int gw,
-                                     int t, int ch0, int nvalid) {
+// Injected dropout masks (parity tests): ReLU (+bias) and the mask of site `layer` on N fp32 accumulator columns = channels
+// ch0.. of a site with `nvalid` channels, at time step t
+template <bool BIAS, int N>
+__device__ __forceinline__ void act_injected(float (&v)[N], const float* bias, bool live, const ConvArgs& a, int layer, int s, int gw,
+                                             int t, int ch0, int nvalid) {
 #pragma unroll
   for (int j = 0; j < N; ++j) v[j] = fmaxf(BIAS ? v[j] + bias[j] : v[j], 0.f);
-  if (DROP) {
-    if (live) {
-      const NoiseRef& nz = a.drop[layer];
-      const float inv = 1.0f / a.keep4;
-      if (nz.ptr) {
-        const float* m = nz.ptr + ((long long)s * a.B + gw) * (nvalid * 30) + t;
+  if (live) {
+    const float inv = 1.0f / a.keep4;
+    const float* m = a.drop[layer].ptr + ((long long)s * a.B + gw) * (nvalid * 30) + t;
 #pragma unroll
-        for (int j = 0; j < N; ++j)
-          if (ch0 + j < nvalid) v[j] = m[(ch0 + j) * 30] != 0.f ? v[j] * inv : 0.f;
-      } else {
-        const uint32_t e0 = (uint32_t)t * (uint32_t)((nvalid + 7) & ~7) + (uint32_t)ch0;  // multiple of 8
+    for (int j = 0; j < N; ++j)
+      if (ch0 + j < nvalid) v[j] = m[(ch0 + j) * 30] != 0.f ? v[j] * inv : 0.f;
+  }
+}
+// Native dropout masks work on the PACKED halves: the 1 / keep scale is applied in fp32 before the ReLU-and-pack convert
+// (relu(v * c) == relu(v) * c for c > 0), the keep decisions of a channel pair are the two 16-bit lanes of one SIMD
+// compare (brl_philox.cuh: keep_pair), so a pair is masked by ONE `and`.  One Philox block per 16 channels; N = 8 uses the
+// half of the block selected by ch0 (the neighbouring thread uses the other half).  Channels >= nvalid (zero columns and
+// conv1's constant-1 column that carries the next module's biases) are neither scaled nor masked.
+template <bool BIAS, int N>
+__device__ __forceinline__ void act_drop_packed(float (&v)[N], const float* bias, bool live, const ConvArgs& a, int layer, int s, int gw,
+                                                int t, int ch0, int nvalid, uint32_t (&h)[N / 2]) {
+  const NoiseRef& nz = a.drop[layer];
+  const float inv = 1.0f / a.keep4;
 #pragma unroll
-        for (int g = 0; g < N / 8; ++g) {
-          const uint4 r = philox_block(nz.seed, nz.kind, nz.site, nz.sample0 + s, nz.window0 + gw, (e0 >> 3) + g);
-          const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  for (int j = 0; j < N; ++j) {
+    if (BIAS) v[j] += bias[j];
+    if (ch0 + j < nvalid) v[j] *= inv;
+  }
+  const uint32_t e0 = (uint32_t)t * (uint32_t)((nvalid + 15) & ~15) + (uint32_t)ch0;
+  KeepBits kb = keep_bits(philox_block(nz.seed, nz.kind, nz.site, nz.sample0 + s, nz.window0 + gw, e0 >> 4), keep_threshold(a.keep4));
+  if (N < 16 && (e0 & 8u)) {  // upper half of the block (warp-uniform): channel pairs 4..7 move to 0..3
+    kb.ev[0] = kb.ev[2]; kb.ev[1] = kb.ev[3]; kb.od[0] = kb.od[2]; kb.od[1] = kb.od[3];
+  }
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (ch0 + 8 * g + j < nvalid) v[8 * g + j] = keep16(w[j >> 1], j & 1, a.keep4) ? v[8 * g + j] * inv : 0.f;
-        }
-      }
-    }
+  for (int p = 0; p < N / 2; ++p) {
+    uint32_t m = keep_pair(kb, p);
+    if (ch0 + 2 * p + 1 >= nvalid) m |= 0xFFFF0000u;
+    if (ch0 + 2 * p >= nvalid) m = 0xFFFFFFFFu;
+    h[p] = live ? (pack_relu_h2(v[2 * p], v[2 * p + 1]) & m) : 0u;
   }
 }
 __device__ __forceinline__ uint4 pack8(const float* v, bool live) {
@@ -136,9 +149,16 @@ template <bool DROP>
 __device__ __forceinline__ void finish16(float (&v)[16], bool live, const ConvArgs& a, int layer, int s, int gw, int t,
                                          int ch0, int nvalid, uint4& lo, uint4& hi) {
   if (DROP) {
-    actn<true, false, 16>(v, nullptr, live, a, layer, s, gw, t, ch0, nvalid);
-    lo = pack8(v, live);
-    hi = pack8(v + 8, live);
+    if (a.drop[layer].ptr) {
+      act_injected<false, 16>(v, nullptr, live, a, layer, s, gw, t, ch0, nvalid);
+      lo = pack8(v, live);
+      hi = pack8(v + 8, live);
+    } else {
+      uint32_t h[8];
+      act_drop_packed<false, 16>(v, nullptr, live, a, layer, s, gw, t, ch0, nvalid, h);
+      lo = make_uint4(h[0], h[1], h[2], h[3]);
+      hi = make_uint4(h[4], h[5], h[6], h[7]);
+    }
   } else {
     lo = relu_pack8(v, live);
     hi = relu_pack8(v + 8, live);
@@ -463,8 +483,20 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) tc_conv_kernel(const ConvArgs
             out[j] = shf(p[0][j], lm2) + shf(p[1][j], lm1) + p[2][j] + shf(p[3][j], lp1) + shf(p[4][j], lp2);
         }
         tc_fence_before();
-        actn<DROP, true, 8>(out, sbias + 304 + q * 8, live, a, q < 2 ? 6 : 8, s, gw, t, (q & 1) * 8, 16);
-        if (BRL_FEAT_LIVE(live)) *reinterpret_cast<uint4*>(frow + (2 + q) * 480) = pack8(out, true);
+        uint4 o4;
+        if (DROP && !a.drop[q < 2 ? 6 : 8].ptr) {
+          uint32_t h[4];
+          act_drop_packed<true, 8>(out, sbias + 304 + q * 8, live, a, q < 2 ? 6 : 8, s, gw, t, (q & 1) * 8, 16, h);
+          o4 = make_uint4(h[0], h[1], h[2], h[3]);
+        } else if (DROP) {
+          act_injected<true, 8>(out, sbias + 304 + q * 8, live, a, q < 2 ? 6 : 8, s, gw, t, (q & 1) * 8, 16);
+          o4 = pack8(out, true);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) out[j] = fmaxf(out[j] + sbias[304 + q * 8 + j], 0.f);
+          o4 = pack8(out, true);
+        }
+        if (BRL_FEAT_LIVE(live)) *reinterpret_cast<uint4*>(frow + (2 + q) * 480) = o4;
         tr(it, 14 + 3 * k);
       }
       if (++pair == npair) {

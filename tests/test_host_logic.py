@@ -61,3 +61,22 @@ def test_param_store_roundtrip_cpu():
     assert torch.allclose(g.loc, net.flat() + 1.0)
     pyro_shim.clear_param_store()
     assert pyro_shim.get_param_store().get_state()["params"] == {}
+
+
+def test_dropout_decisions_rate_and_tie_path():
+    """Sixteen keep decisions per Philox block: the byte decides unless it ties with the threshold's high byte; the
+    realised keep rate must match `keep` to sampling accuracy, also for thresholds whose low byte matters."""
+    import numpy as np
+    from oracle import bnn_oracle as O
+    n = 1 << 16
+    blk = np.arange(n, dtype=np.int64)
+    r = O._philox_block(1234, O.KIND_DROPOUT, 3, 0, np.zeros(n, dtype=np.int64), blk)
+    for keep in (0.93964075, 0.758563, 0.5, 240.5 / 256.0):
+        T = O.keep_threshold(keep)
+        assert abs(T / 65536.0 - keep) <= 1.0 / 65536.0
+        rate = np.mean([O.keep_decisions(r, np.full(n, bi, dtype=np.uint32), keep).mean() for bi in range(16)])
+        assert abs(rate - keep) < 4.0 * np.sqrt(keep * (1 - keep) / (16 * n)), (keep, rate)
+    # decisions of the 16 byte positions are (empirically) uncorrelated
+    m = np.stack([O.keep_decisions(r, np.full(n, bi, dtype=np.uint32), 0.5) for bi in range(16)]).astype(np.float64)
+    c = np.corrcoef(m)
+    assert np.abs(c - np.eye(16)).max() < 0.02
