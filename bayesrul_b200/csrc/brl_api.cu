@@ -271,6 +271,8 @@ static void forward_op(const brl_ctx* ctx, const ActBufs& ab, const FwdArgs& a, 
   p.keep = (a.p_dropout > 0.f && L.drop_factor > 0.f) ? 1.0f - a.p_dropout * L.drop_factor : 1.0f;
   p.drop = nref(a.noise, a.noise ? a.noise->drop_mask[op.layer] : nullptr, KIND_DROPOUT, op.layer);
   p.part = ab.part[slot];
+  static const int ablate = getenv("BRL_ABLATE") ? atoi(getenv("BRL_ABLATE")) : 0;
+  if (ablate & 8) return;
   if (ctx->gemm_backend & 1) launch_conv_gemm_tc(p, epi, st);
   else launch_conv_gemm(p, epi, st);
 }
@@ -352,7 +354,8 @@ static void backward_op(const brl_ctx* ctx, const ActBufs& ab, const BwdArgs& a,
   } else if (a.mode == BRL_MODE_FLIPOUT) {
     ba.dpert = ab.dsec[oi]; ba.sign_out = a.sgn_out[op.layer];
   }
-  launch_bwd_act(ba, cs);
+  static const int ablate = getenv("BRL_ABLATE") ? atoi(getenv("BRL_ABLATE")) : 0;  // timing experiments only (wrong results)
+  if (!(ablate & 4)) launch_bwd_act(ba, cs);
   if (ws != cs) {  // the weight-gradient stream picks up behind the activation backward
     cudaEventRecord(ev_act, cs);
     cudaStreamWaitEvent(ws, ev_act, 0);
@@ -377,10 +380,12 @@ static void backward_op(const brl_ctx* ctx, const ActBufs& ab, const BwdArgs& a,
       epi = EPI_DX_FLIPOUT; p.W1 = a.wsamp + L.w_off; p.trB = TRB_MINUS_W0; p.sign_in = a.sgn_in[op.layer]; p.sign_C = L.cin;
     }
     p.part = ab.part[slot];
-    if (ctx->gemm_backend & 2) launch_conv_gemm_tc(p, epi, cs);
+    if (ablate & 2) {}
+    else if (ctx->gemm_backend & 2) launch_conv_gemm_tc(p, epi, cs);
     else launch_conv_gemm(p, epi, cs);
   }
   if (ev_dx) cudaEventRecord(ev_dx, cs);
+  if (ablate & 1) return;
 
   // weight gradients
   ConvDw dw{};

@@ -9,6 +9,7 @@
 // one-thread-per-output epilogue kernel.
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 
 #include "brl_kernels.cuh"
 #include "brl_philox.cuh"
@@ -213,9 +214,14 @@ static void launch_one(const ConvGemm& p, cudaStream_t st) {
   const int Mtot = p.B * p.P;
   const int z = p.ksplit > 1 ? p.ksplit : p.S;
   ++g_launch_count;
-  if (small_tiles(p))
-    conv_gemm_kernel<DUAL, EPI, 32, 2, 2><<<dim3((Mtot + 31) / 32, (p.N + BN - 1) / BN, z), 256, 0, st>>>(p);
-  else
+  static const int small_shape = getenv("BRL_SMALL_TILE") ? atoi(getenv("BRL_SMALL_TILE")) : 42;  // experiment knob
+  if (small_tiles(p)) {
+    const dim3 grid((Mtot + 31) / 32, (p.N + BN - 1) / BN, z);
+    if (small_shape == 42) conv_gemm_kernel<DUAL, EPI, 32, 4, 2><<<grid, 128, 0, st>>>(p);
+    else if (small_shape == 24) conv_gemm_kernel<DUAL, EPI, 32, 2, 4><<<grid, 128, 0, st>>>(p);
+    else if (small_shape == 44) conv_gemm_kernel<DUAL, EPI, 32, 4, 4><<<grid, 64, 0, st>>>(p);
+    else conv_gemm_kernel<DUAL, EPI, 32, 2, 2><<<grid, 256, 0, st>>>(p);
+  } else
     conv_gemm_kernel<DUAL, EPI, 128, 4, 4><<<dim3((Mtot + 127) / 128, (p.N + BN - 1) / BN, z), 256, 0, st>>>(p);
   if (p.ksplit > 1) {
     const long long total = (long long)Mtot * p.N;
@@ -229,6 +235,8 @@ int conv_gemm_ksplit(const ConvGemm& p) {
   if (p.S != 1 || p.part == nullptr) return 1;
   const int ctas = ((p.B * p.P + 127) / 128) * ((p.N + BN - 1) / BN);  // scratch is sized for < 74 tiles of 128x32
   if (ctas >= 74 || p.K < 8 * BK) return 1;
+  static const int ks_min32 = getenv("BRL_KSPLIT_MIN32") ? atoi(getenv("BRL_KSPLIT_MIN32")) : 0;  // experiment knob
+  if (ks_min32 > 0 && ((p.B * p.P + 31) / 32) * ((p.N + BN - 1) / BN) >= ks_min32) return 1;
   return std::max(1, std::min(p.K / (4 * BK), 296 / ctas));
 }
 
@@ -381,7 +389,8 @@ __global__ void __launch_bounds__(256, 2) conv_dw_kernel(const ConvDw p, int row
 void launch_conv_dw(const ConvDw& p, cudaStream_t st) {
   const int Mtot = p.B * p.P;
   const int gx = (p.K + 1 + DW_K - 1) / DW_K, gy = (p.N + DW_CO - 1) / DW_CO;
-  int split = std::max(1, std::min((Mtot + 31) / 32, (592 + gx * gy - 1) / (gx * gy)));
+  static const int dw_ctas = getenv("BRL_DW_CTAS") ? atoi(getenv("BRL_DW_CTAS")) : 148;  // experiment knob
+  int split = std::max(1, std::min((Mtot + 31) / 32, (dw_ctas + gx * gy - 1) / (gx * gy)));
   int rows = (Mtot + split - 1) / split;
   rows = (rows + DW_M - 1) / DW_M * DW_M;
   split = (Mtot + rows - 1) / rows;
