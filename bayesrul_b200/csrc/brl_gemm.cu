@@ -27,23 +27,23 @@ constexpr int BN = 32, BK = 16;
 //                                 scheduler with 4 x 4 micro-tiles, and the kernel then runs at the latency of its own
 //                                 dependent chain (ncu: 22 % issue slots, 3.7 long-scoreboard stalls per issue); quartering
 //                                 the per-thread tile gives 4x the warps and a third of the serial instructions per warp
-template <bool DUAL, int EPI, int BM, int TM, int TN>
+template <bool DUAL, int EPI, int BM, int TM, int TN, int BKT>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN)) conv_gemm_kernel(const ConvGemm p) {
   constexpr int NT = (BM / TM) * (BN / TN);  // threads
   constexpr int AKS = NT / BM;        // k-rows of the A tile staged per pass
-  constexpr int ALD = BK / AKS;       // A loads per thread
+  constexpr int ALD = BKT / AKS;       // A loads per thread
   constexpr int BROWS = NT / BN;      // k-rows of the B tile staged per pass
-  constexpr int BLD = BK / BROWS;     // B loads per thread
+  constexpr int BLD = BKT / BROWS;     // B loads per thread
   constexpr int TXN = BN / TN;        // threads along n
   static_assert(ALD >= 1 && BLD >= 1 && (TM == 4 || TM == 2) && (TN == 4 || TN == 2), "tile shape");
   // K-loop tiles and (afterwards) the accumulator tile of the rolled epilogue share one buffer
-  constexpr int LOOP_FLOATS = (DUAL ? 2 : 1) * (BK * BM + BK * BN);
+  constexpr int LOOP_FLOATS = (DUAL ? 2 : 1) * (BKT * BM + BKT * BN);
   constexpr int EPI_FLOATS = (DUAL ? 2 : 1) * BM * BN;
   __shared__ __align__(16) float sm[LOOP_FLOATS > EPI_FLOATS ? LOOP_FLOATS : EPI_FLOATS];
   float(*As0)[BM] = reinterpret_cast<float(*)[BM]>(sm);
-  float(*Bs0)[BN] = reinterpret_cast<float(*)[BN]>(sm + BK * BM);
-  float(*As1)[BM] = reinterpret_cast<float(*)[BM]>(sm + BK * BM + BK * BN);
-  float(*Bs1)[BN] = reinterpret_cast<float(*)[BN]>(sm + 2 * BK * BM + BK * BN);
+  float(*Bs0)[BN] = reinterpret_cast<float(*)[BN]>(sm + BKT * BM);
+  float(*As1)[BM] = reinterpret_cast<float(*)[BM]>(sm + BKT * BM + BKT * BN);
+  float(*Bs1)[BN] = reinterpret_cast<float(*)[BN]>(sm + 2 * BKT * BM + BKT * BN);
 
   const bool split = p.ksplit > 1;
   const int s = split ? 0 : blockIdx.z;
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) conv_gemm_kernel(const 
   const int Mtot = p.B * p.P;
   int kbeg = 0, kend = p.K;
   if (split) {
-    const int per = ((p.K + p.ksplit - 1) / p.ksplit + BK - 1) / BK * BK;
+    const int per = ((p.K + p.ksplit - 1) / p.ksplit + BKT - 1) / BKT * BKT;
     kbeg = blockIdx.z * per;
     kend = min(p.K, kbeg + per);
   }
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) conv_gemm_kernel(const 
   };
 
   if (kbeg < kend) fetch(kbeg);
-  for (int k0 = kbeg; k0 < kend; k0 += BK) {
+  for (int k0 = kbeg; k0 < kend; k0 += BKT) {
 #pragma unroll
     for (int j = 0; j < ALD; ++j) {
       As0[ak0 + AKS * j][ar] = ra0[j];
@@ -144,9 +144,9 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) conv_gemm_kernel(const 
       if (DUAL) Bs1[bk0 + BROWS * j][bn] = rb1[j];
     }
     __syncthreads();
-    if (k0 + BK < kend) fetch(k0 + BK);  // next tile's loads fly while this one is multiplied
+    if (k0 + BKT < kend) fetch(k0 + BKT);  // next tile's loads fly while this one is multiplied
 #pragma unroll
-    for (int kk = 0; kk < BK; ++kk) {
+    for (int kk = 0; kk < BKT; ++kk) {
       float av[4], bv[4];
       frag(&As0[kk][ty * TM], av, TM);
       frag(&Bs0[kk][tx * TN], bv, TN);
@@ -217,12 +217,12 @@ static void launch_one(const ConvGemm& p, cudaStream_t st) {
   static const int small_shape = getenv("BRL_SMALL_TILE") ? atoi(getenv("BRL_SMALL_TILE")) : 42;  // experiment knob
   if (small_tiles(p)) {
     const dim3 grid((Mtot + 31) / 32, (p.N + BN - 1) / BN, z);
-    if (small_shape == 42) conv_gemm_kernel<DUAL, EPI, 32, 4, 2><<<grid, 128, 0, st>>>(p);
-    else if (small_shape == 24) conv_gemm_kernel<DUAL, EPI, 32, 2, 4><<<grid, 128, 0, st>>>(p);
-    else if (small_shape == 44) conv_gemm_kernel<DUAL, EPI, 32, 4, 4><<<grid, 64, 0, st>>>(p);
-    else conv_gemm_kernel<DUAL, EPI, 32, 2, 2><<<grid, 256, 0, st>>>(p);
+    if (small_shape == 42) conv_gemm_kernel<DUAL, EPI, 32, 4, 2, 16><<<grid, 128, 0, st>>>(p);
+    else if (small_shape == 423) conv_gemm_kernel<DUAL, EPI, 32, 4, 2, 32><<<grid, 128, 0, st>>>(p);
+    else if (small_shape == 223) conv_gemm_kernel<DUAL, EPI, 32, 2, 2, 32><<<grid, 256, 0, st>>>(p);
+    else conv_gemm_kernel<DUAL, EPI, 32, 2, 2, 16><<<grid, 256, 0, st>>>(p);
   } else
-    conv_gemm_kernel<DUAL, EPI, 128, 4, 4><<<dim3((Mtot + 127) / 128, (p.N + BN - 1) / BN, z), 256, 0, st>>>(p);
+    conv_gemm_kernel<DUAL, EPI, 128, 4, 4, 16><<<dim3((Mtot + 127) / 128, (p.N + BN - 1) / BN, z), 256, 0, st>>>(p);
   if (p.ksplit > 1) {
     const long long total = (long long)Mtot * p.N;
     ++g_launch_count;
