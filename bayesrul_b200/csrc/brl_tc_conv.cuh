@@ -75,6 +75,11 @@ __global__ void tc_packx_kernel(const float* __restrict__ x, unsigned char* __re
   }
 }
 
+template <bool BIAS, int N>
+__device__ __forceinline__ void act_plain(float (&v)[N], const float* bias) {
+#pragma unroll
+  for (int j = 0; j < N; ++j) v[j] = fmaxf(BIAS ? v[j] + bias[j] : v[j], 0.f);
+}
 // Injected dropout masks (parity tests): ReLU (+bias) and the mask of site `layer` on N fp32 accumulator columns = channels
 // ch0.. of a site with `nvalid` channels, at time step t
 template <bool BIAS, int N>
@@ -483,20 +488,21 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) tc_conv_kernel(const ConvArgs
             out[j] = shf(p[0][j], lm2) + shf(p[1][j], lm1) + p[2][j] + shf(p[3][j], lp1) + shf(p[4][j], lp2);
         }
         tc_fence_before();
-        uint4 o4;
-        if (DROP && !a.drop[q < 2 ? 6 : 8].ptr) {
-          uint32_t h[4];
-          act_drop_packed<true, 8>(out, sbias + 304 + q * 8, live, a, q < 2 ? 6 : 8, s, gw, t, (q & 1) * 8, 16, h);
-          o4 = make_uint4(h[0], h[1], h[2], h[3]);
-        } else if (DROP) {
-          act_injected<true, 8>(out, sbias + 304 + q * 8, live, a, q < 2 ? 6 : 8, s, gw, t, (q & 1) * 8, 16);
-          o4 = pack8(out, true);
+        if (DROP) {
+          uint4 o4;
+          if (!a.drop[q < 2 ? 6 : 8].ptr) {
+            uint32_t h[4];
+            act_drop_packed<true, 8>(out, sbias + 304 + q * 8, live, a, q < 2 ? 6 : 8, s, gw, t, (q & 1) * 8, 16, h);
+            o4 = make_uint4(h[0], h[1], h[2], h[3]);
+          } else {
+            act_injected<true, 8>(out, sbias + 304 + q * 8, live, a, q < 2 ? 6 : 8, s, gw, t, (q & 1) * 8, 16);
+            o4 = pack8(out, true);
+          }
+          if (BRL_FEAT_LIVE(live)) *reinterpret_cast<uint4*>(frow + (2 + q) * 480) = o4;
         } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) out[j] = fmaxf(out[j] + sbias[304 + q * 8 + j], 0.f);
-          o4 = pack8(out, true);
+          act_plain<true, 8>(out, sbias + 304 + q * 8);
+          if (BRL_FEAT_LIVE(live)) *reinterpret_cast<uint4*>(frow + (2 + q) * 480) = pack8(out, true);
         }
-        if (BRL_FEAT_LIVE(live)) *reinterpret_cast<uint4*>(frow + (2 + q) * 480) = o4;
         tr(it, 14 + 3 * k);
       }
       if (++pair == npair) {
