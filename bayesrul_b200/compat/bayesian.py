@@ -168,13 +168,13 @@ class BNN(_Base):
 
     def predict_step(self, batch, batch_idx, dataloader_idx=0):  # bayesian.py:231-250
         pred = dict()
-        if batch[0].device.type == "cpu" and int(os.environ.get("BRL_HOST_CHUNKS", "1")) > 1:
-            # optional: chunked copy overlapped with the compute.  Measured on B200 (tools/probe_e2e.py, B = 10 000, S = 100):
-            # one shot 5.29 ms, 2 chunks 5.30-5.38 ms, 3 chunks 5.56 ms -- every extra call repeats the weight sampling /
-            # packing and the kernels' ramp-up, which costs what the hidden copy saves, so the default stays one shot
+        if batch[0].device.type == "cpu" and batch[0].dtype == torch.float32 and int(os.environ.get("BRL_HOST_CHUNKS", "0")) != 1:
+            # host batch (the DataLoader's): brl_predict_moments_host copies it in window chunks underneath the compute and
+            # writes the four result vectors into one pinned host tensor.  (BRL_HOST_CHUNKS >= 2: the Python-level chunking,
+            # measured slower: every extra call repeats the weight sampling / packing; = 1: plain .to(device) + device call.)
             loc, scale, ep_var, al_var = self.bnn.predict_moments_host(
                 batch[0], self.hparams.mc_samples_eval, float(os.environ.get("BRL_HOST_FIRST", "0.25")),
-                int(os.environ.get("BRL_HOST_CHUNKS", "1")))
+                int(os.environ.get("BRL_HOST_CHUNKS", "0")))
         else:
             loc, scale, ep_var, al_var = self.bnn.predict_moments(batch[0].to(self.device), self.hparams.mc_samples_eval)
         packed = torch.stack([ep_var, al_var, loc, scale]).cpu()  # one D2H instead of four

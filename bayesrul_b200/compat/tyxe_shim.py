@@ -194,6 +194,10 @@ class VariationalBNN:
         g = self.net_guide
         dev = g.loc.device
         B = x_host.shape[0]
+        if n_chunks == 0:  # the library's own host entry point (window chunks share the packed weight images)
+            out = self.engine.predict_moments_host(x_host, g.loc, g.scale, S=num_predictions, guide=g.family,
+                                                   noise=self._noise(), engine=self.engine_kind)
+            return tuple(out[i] for i in range(4))
         if B < 2048 or n_chunks < 2:
             return self.predict_moments(x_host.to(dev, non_blocking=True), num_predictions)
         first = max(512, int(B * first_fraction))

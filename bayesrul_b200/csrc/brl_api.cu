@@ -63,6 +63,9 @@ struct brl_ctx {
   Lane lanes[2];
   cudaStream_t lane1_main = nullptr;
   cudaEvent_t ev_lane_fork = nullptr, ev_lane_join = nullptr;
+  // brl_predict_moments_host: the batch travels in window chunks on `copy` while the previous chunk is computed
+  cudaStream_t copy = nullptr;
+  cudaEvent_t ev_copy_start = nullptr, ev_chunk[8] = {};
   // CUDA-graph replay of brl_elbo_step (native Philox noise only): a step is ~60-110 small launches + event fork / joins,
   // i.e. 0.5 ms (LRT) to 1.7 ms (Flipout, 2 particles) of host enqueue time -- more than the GPU needs to run it.
   // The second call with the same key captures the step (on `cap`, since the caller's stream may be the legacy default
@@ -575,6 +578,9 @@ int brl_create(brl_ctx** out, int net, int device) {
   BRL_CUDA(cudaEventCreateWithFlags(&c->ev_lane_fork, cudaEventDisableTiming));
   BRL_CUDA(cudaEventCreateWithFlags(&c->ev_lane_join, cudaEventDisableTiming));
   BRL_CUDA(cudaStreamCreateWithFlags(&c->cap, cudaStreamNonBlocking));
+  BRL_CUDA(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
+  BRL_CUDA(cudaEventCreateWithFlags(&c->ev_copy_start, cudaEventDisableTiming));
+  for (int i = 0; i < 8; ++i) BRL_CUDA(cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
   const char* nograph = getenv("BRL_NO_GRAPH");
   c->graph_enabled = !(nograph && nograph[0] == '1');
   *out = c;
@@ -601,6 +607,10 @@ int brl_destroy(brl_ctx* ctx) {
   for (auto& g : ctx->graphs)
     if (g.exec) cudaGraphExecDestroy(g.exec);
   if (ctx->cap) cudaStreamDestroy(ctx->cap);
+  if (ctx->copy) cudaStreamDestroy(ctx->copy);
+  if (ctx->ev_copy_start) cudaEventDestroy(ctx->ev_copy_start);
+  for (int i = 0; i < 8; ++i)
+    if (ctx->ev_chunk[i]) cudaEventDestroy(ctx->ev_chunk[i]);
   delete ctx;
   return BRL_OK;
 }
@@ -805,6 +815,133 @@ int brl_predict_moments(brl_ctx* ctx, const float* x, int64_t B, int64_t S, int 
     launch_moments_update(outc, sc, B, state, s0 == 0, st);
   }
   launch_moments_final(state, B, pred, std, ep_var, al_var, st);
+  BRL_CUDA(cudaGetLastError());
+  return BRL_OK;
+}
+
+// ---- host-buffer variant of brl_predict_moments --------------------------------------------------------------------
+// Window chunks: NW = 2 for large batches on the fused engine (measured, B = 10 000 x S = 100, ms per step end to end:
+// NW = 1 4.99, 2 4.87, 3 5.05, 4 4.97, 6 5.17, 8 5.36 -- every further chunk costs ~0.1 ms of kernel ramp-up / drain, more than
+// the copy it hides), rounded to 128 windows.  Per chunk, MC samples run in sub-chunks that fit the feature buffer.  The fp16 weight images of ALL S samples are packed once, up front (while the
+// first chunk is still in flight), and shared by the chunks.
+struct HostPlan {
+  long long Bc, n_chunks, Sc, Sw;  // windows per chunk, chunks, samples per feature-buffer pass, samples per sampler pass
+};
+static bool noise_is_native(const brl_noise* nz);
+static HostPlan host_plan(const brl_ctx* ctx, long long B, long long S, int engine, bool native) {
+  HostPlan p;
+  static const int env_nw = getenv("BRL_HOST_NW") ? atoi(getenv("BRL_HOST_NW")) : 0;  // experiment knob
+  p.n_chunks = (engine == BRL_ENGINE_TC_FP16 && native && B >= 4096) ? (env_nw > 0 ? std::min(env_nw, 8) : 2) : 1;
+  p.Bc = p.n_chunks == 1 ? B : (((B + p.n_chunks - 1) / p.n_chunks + 127) / 128) * 128;
+  p.n_chunks = (B + p.Bc - 1) / p.Bc;
+  p.Sw = std::min<long long>(S, 16);
+  p.Sc = S;
+  if (engine == BRL_ENGINE_TC_FP16)
+    while (p.Sc > 1 && tc_workspace_bytes(ctx->tc, p.Bc, p.Sc) > ((size_t)3 << 29)) p.Sc = (p.Sc + 1) / 2;  // feature buffer <= 1.5 GB
+  return p;
+}
+struct HostCarve {
+  float *x_dev, *res, *state, *wsamp, *norms, *outc;
+  unsigned char* images;
+  void* tc_ws;
+  size_t tc_bytes;
+};
+static bool host_carve(const brl_ctx* ctx, Carve& c, long long B, long long S, int guide, const HostPlan& pl, HostCarve& h) {
+  const NetSpec& n = *ctx->net;
+  h.x_dev = c.take<float>(B * 540);
+  h.res = c.take<float>(4 * B);
+  h.state = c.take<float>(4 * pl.Bc);
+  h.wsamp = c.take<float>(pl.Sw * n.P);
+  h.norms = c.take<float>(pl.Sw * 2 * (long long)n.layers.size());
+  h.outc = c.take<float>(pl.Sc * pl.Bc * 2);
+  h.images = c.take<unsigned char>((guide >= 0 ? S : 1) * (long long)tc_weight_image_bytes());
+  h.tc_bytes = tc_workspace_bytes(ctx->tc, pl.Bc, pl.Sc);
+  h.tc_ws = c.take<char>((long long)h.tc_bytes);
+  return c.ok;
+}
+
+int64_t brl_workspace_bytes_host(const brl_ctx* ctx, int64_t B, int64_t S, int engine) {
+  if (!ctx || B <= 0 || S <= 0) return BRL_ERR_INVALID;
+  if (engine != BRL_ENGINE_TC_FP16 || !tc_available(ctx->tc))
+    return brl_workspace_bytes(ctx, B, std::min<int64_t>(S, 16), 0, BRL_ENGINE_SIMT_FP32) + (B * 540 + 4 * B) * (int64_t)sizeof(float) + 1024;
+  Carve c(nullptr, 0);
+  HostCarve h;
+  host_carve(ctx, c, B, S, 0, host_plan(ctx, B, S, engine, true), h);
+  return (int64_t)c.used + 4096;
+}
+
+int brl_predict_moments_host(brl_ctx* ctx, const float* x_host, int64_t B, int64_t S, int guide, const float* mu,
+                             const float* sigma, float p_dropout, const brl_noise* noise, float* out_host, int engine,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  BRL_REQUIRE(ctx && x_host && mu && out_host && workspace, "brl_predict_moments_host: NULL argument");
+  BRL_REQUIRE(B > 0 && S > 0 && B * 30 < (1ll << 31) / 512, "brl_predict_moments_host: bad B or S");
+  BRL_REQUIRE(guide < 0 || sigma, "brl_predict_moments_host: sigma is NULL");
+  BRL_REQUIRE(guide <= BRL_GUIDE_RADIAL, "Guide unknown. Choose from 'normal', 'radial'.");
+  cudaStream_t st = (cudaStream_t)stream;
+  const NetSpec& n = *ctx->net;
+  const size_t xbytes = sizeof(float) * (size_t)B * 540;
+  if (engine != BRL_ENGINE_TC_FP16 || !tc_available(ctx->tc)) {
+    // per-layer engine: one copy, then the device entry point on the rest of the workspace
+    Carve c(workspace, workspace_bytes);
+    float* x_dev = c.take<float>(B * 540);
+    float* res = c.take<float>(4 * B);
+    if (!c.ok) return fail(BRL_ERR_WORKSPACE, "brl_predict_moments_host: workspace too small");
+    BRL_CUDA(cudaMemcpyAsync(x_dev, x_host, xbytes, cudaMemcpyHostToDevice, st));
+    int rc = brl_predict_moments(ctx, x_dev, B, S, guide, mu, sigma, p_dropout, noise, res, res + B, res + 2 * B, res + 3 * B,
+                                 BRL_ENGINE_SIMT_FP32, (char*)workspace + c.used, workspace_bytes - c.used, stream);
+    if (rc) return rc;
+    BRL_CUDA(cudaMemcpyAsync(out_host, res, sizeof(float) * 4 * B, cudaMemcpyDeviceToHost, st));
+    return BRL_OK;
+  }
+  const HostPlan pl = host_plan(ctx, B, S, engine, noise_is_native(noise));
+  BRL_REQUIRE(pl.n_chunks <= 8, "brl_predict_moments_host: too many window chunks");
+  Carve c(workspace, workspace_bytes);
+  HostCarve h;
+  if (!host_carve(ctx, c, B, S, guide, pl, h))
+    return fail(BRL_ERR_WORKSPACE, "brl_predict_moments_host: workspace too small; need " +
+                                       std::to_string(brl_workspace_bytes_host(ctx, B, S, engine)) + " bytes");
+  // ---- copies: one per window chunk, on the copy stream, behind whatever still uses the workspace on `st`
+  BRL_CUDA(cudaEventRecord(ctx->ev_copy_start, st));
+  BRL_CUDA(cudaStreamWaitEvent(ctx->copy, ctx->ev_copy_start, 0));
+  for (long long ci = 0; ci < pl.n_chunks; ++ci) {
+    const long long w0 = ci * pl.Bc, bc = std::min(pl.Bc, B - w0);
+    BRL_CUDA(cudaMemcpyAsync(h.x_dev + w0 * 540, x_host + w0 * 540, sizeof(float) * bc * 540, cudaMemcpyHostToDevice, ctx->copy));
+    BRL_CUDA(cudaEventRecord(ctx->ev_chunk[ci], ctx->copy));
+  }
+  // ---- weight images of all MC samples (no dependence on x: runs underneath the first copy)
+  const int nsites = 2 * (int)n.layers.size();
+  if (guide >= 0) {
+    for (long long s0 = 0; s0 < S; s0 += pl.Sw) {
+      const long long sw = std::min(pl.Sw, S - s0);
+      brl_noise nz = noise_at_sample(n, noise, s0, B);
+      NoiseRef eps = nref(&nz, nz.weight_eps, KIND_WEIGHT_EPS, 0);
+      if (guide == BRL_GUIDE_NORMAL) launch_sample_normal(mu, sigma, n.P, sw, eps, h.wsamp, nullptr, st);
+      else launch_sample_radial(mu, sigma, n.P, sw, ctx->site_off_dev, nsites, ctx->max_site, eps,
+                                nref(&nz, nz.radial_r, KIND_RADIAL_R, 0), h.norms, h.wsamp, nullptr, st);
+      const char* err = tc_pack_weights(ctx->tc, h.wsamp, n.P, sw, h.images + s0 * (long long)tc_weight_image_bytes(), st);
+      if (err) return fail(BRL_ERR_UNSUPPORTED, err);
+    }
+  } else {
+    const char* err = tc_pack_weights(ctx->tc, mu, 0, 1, h.images, st);
+    if (err) return fail(BRL_ERR_UNSUPPORTED, err);
+  }
+  // ---- chunks of windows x sub-chunks of samples
+  for (long long ci = 0; ci < pl.n_chunks; ++ci) {
+    const long long w0 = ci * pl.Bc, bc = std::min(pl.Bc, B - w0);
+    BRL_CUDA(cudaStreamWaitEvent(st, ctx->ev_chunk[ci], 0));
+    for (long long s0 = 0; s0 < S; s0 += pl.Sc) {
+      const long long sc = std::min(pl.Sc, S - s0);
+      brl_noise nz = noise_at_sample(n, noise, s0, B);
+      nz.window0 += w0;
+      const unsigned char* img = h.images + (guide >= 0 ? s0 * (long long)tc_weight_image_bytes() : 0);
+      const char* err = tc_forward(ctx->tc, h.x_dev + w0 * 540, bc, sc, nullptr, guide >= 0 ? n.P : 0, p_dropout, &nz, h.outc,
+                                   h.tc_ws, h.tc_bytes, s0 == 0, st, img);
+      if (err) return fail(BRL_ERR_UNSUPPORTED, err);
+      launch_moments_update(h.outc, sc, bc, h.state, s0 == 0, st);
+    }
+    launch_moments_final(h.state, bc, h.res + w0, h.res + B + w0, h.res + 2 * B + w0, h.res + 3 * B + w0, st);
+  }
+  BRL_CUDA(cudaMemcpyAsync(out_host, h.res, sizeof(float) * 4 * B, cudaMemcpyDeviceToHost, st));
   BRL_CUDA(cudaGetLastError());
   return BRL_OK;
 }

@@ -411,9 +411,22 @@ size_t tc_workspace_bytes(const TcState* s, long long B, long long S) {
   return (size_t)(S * (long long)BLOB_BYTES + S * nt128 * 128 * FEAT_ROW_BYTES + 2 * npair * XIMG_TILE_BYTES + 2048);
 }
 
+size_t tc_weight_image_bytes() { return BLOB_BYTES; }
+
+const char* tc_pack_weights(TcState* st, const float* weights, long long w_sample_stride, long long n, unsigned char* images,
+                            cudaStream_t stream) {
+  if (!tc_available(st)) return "bayesrul_b200: tensor-core engine is implemented for the Inception net only";
+  PackArgs pa;
+  pa.w = weights; pa.w_stride = w_sample_stride; pa.blob = images;
+  for (int l = 0; l < 12; ++l) { pa.off[l][0] = st->loff[l][0]; pa.off[l][1] = st->loff[l][1]; }
+  tc_pack_kernel<<<dim3((PACK_THREADS_TOTAL + 255) / 256, (unsigned)n), 256, 0, stream>>>(pa);
+  count_launch(1);
+  return nullptr;
+}
+
 const char* tc_forward(TcState* st, const float* x, long long B, long long S, const float* weights, long long w_sample_stride,
                        float p_dropout, const brl_noise* noise, float* out, void* ws, size_t ws_bytes, bool pack_x,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, const unsigned char* prepacked) {
   if (!tc_available(st)) return "bayesrul_b200: tensor-core engine is implemented for the Inception net only";
   if (ws_bytes < tc_workspace_bytes(st, B, S)) return "bayesrul_b200: workspace too small for the tensor-core engine";
   const long long nt128 = (B + 127) / 128, nt4 = (B + 3) / 4;
@@ -427,10 +440,15 @@ const char* tc_forward(TcState* st, const float* x, long long B, long long S, co
     tc_packx_kernel<<<(unsigned)(((long long)ntx * 384 + 255) / 256), 256, 0, stream>>>(x, ximg, (int)B, ntx);
     count_launch(1);
   }
-  PackArgs pa;
-  pa.w = weights; pa.w_stride = w_sample_stride; pa.blob = blob;
-  for (int l = 0; l < 12; ++l) { pa.off[l][0] = st->loff[l][0]; pa.off[l][1] = st->loff[l][1]; }
-  tc_pack_kernel<<<dim3((PACK_THREADS_TOTAL + 255) / 256, (unsigned)nblob), 256, 0, stream>>>(pa);
+  if (prepacked) {
+    blob = const_cast<unsigned char*>(prepacked);
+  } else {
+    PackArgs pa;
+    pa.w = weights; pa.w_stride = w_sample_stride; pa.blob = blob;
+    for (int l = 0; l < 12; ++l) { pa.off[l][0] = st->loff[l][0]; pa.off[l][1] = st->loff[l][1]; }
+    tc_pack_kernel<<<dim3((PACK_THREADS_TOTAL + 255) / 256, (unsigned)nblob), 256, 0, stream>>>(pa);
+    count_launch(1);
+  }
   const bool drop = p_dropout > 0.f;
   auto nr = [&](int layer) {
     NoiseRef r;
@@ -491,7 +509,7 @@ const char* tc_forward(TcState* st, const float* x, long long B, long long S, co
   if (drop) tc_fc_kernel<true><<<gridf, 192, FC_SMEM, stream>>>(fa, fmap);
   else tc_fc_kernel<false><<<gridf, 192, FC_SMEM, stream>>>(fa, fmap);
   tc_time_end(st, 1, stream);
-  count_launch(3);
+  count_launch(2);
   return nullptr;
 }
 

@@ -17,7 +17,13 @@ void tc_trace(TcState*, long long* device_buf);
 size_t tc_workspace_bytes(const TcState*, long long B, long long S);
 // returns nullptr on success, else a static error string.  pack_x = false re-uses the fp16 window images a previous
 // call built in the same workspace for the same x (later chunks of MC samples of one batch).
+// prepacked != nullptr: the fp16 weight images of the S samples (tc_pack_weights) are taken from there instead of being
+// packed from `weights` into the workspace (window chunks of one batch share the images of all MC samples).
 const char* tc_forward(TcState*, const float* x, long long B, long long S, const float* weights, long long w_sample_stride,
                        float p_dropout, const brl_noise* noise, float* out, void* ws, size_t ws_bytes, bool pack_x,
-                       cudaStream_t st);
+                       cudaStream_t st, const unsigned char* prepacked = nullptr);
+size_t tc_weight_image_bytes();  // bytes of one sample's fp16 weight image
+// fp32 weights [n, P] (or one shared [P] vector: n = 1) -> n fp16 weight images at `images` (tc_weight_image_bytes() apart)
+const char* tc_pack_weights(TcState*, const float* weights, long long w_sample_stride, long long n, unsigned char* images,
+                            cudaStream_t st);
 }  // namespace brl

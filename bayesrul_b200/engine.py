@@ -237,6 +237,36 @@ class Engine:
                                                 ws.data_ptr(), nbytes, self._stream()))
         return tuple(outs)
 
+    def predict_moments_host(self, x_host: torch.Tensor, mu, sigma=None, S: int = 20, guide: Optional[str] = "normal",
+                             p_dropout: float = 0.0, noise: Optional[Noise] = None, engine: str = "simt") -> torch.Tensor:
+        """predict_moments for a HOST batch [B,30,18] (pinned memory makes the copies asynchronous).  Returns a pinned
+        host tensor [4,B] = (pred, std, ep_var, al_var); the call synchronises the current stream before returning.
+        On the fused engine the batch travels in window chunks while the previous chunk is computed."""
+        if not isinstance(x_host, torch.Tensor) or x_host.device.type != "cpu" or x_host.dtype != torch.float32:
+            raise RuntimeError("bayesrul_b200: x_host must be a float32 CPU tensor")
+        if x_host.dim() != 3 or x_host.shape[1] != WIN_LENGTH or x_host.shape[2] != N_FEATURES or x_host.shape[0] == 0:
+            raise RuntimeError(f"bayesrul_b200: x_host must be [B,{WIN_LENGTH},{N_FEATURES}], got {tuple(x_host.shape)}")
+        x_host = x_host.contiguous()
+        B = x_host.shape[0]
+        mu = self._theta(mu, "mu")
+        if guide is not None:
+            if guide not in GUIDE_IDS:
+                raise RuntimeError("Guide unknown. Choose from 'normal', 'radial'.")
+            sigma = self._theta(sigma, "sigma")
+        eid = ENGINE_IDS[engine]
+        nbytes = self.lib.brl_workspace_bytes_host(self.ctx, B, S, eid)
+        if nbytes < 0:
+            raise RuntimeError("bayesrul_b200: bad workspace query")
+        ws = self.workspace(nbytes)
+        out = torch.empty(4, B, dtype=torch.float32, pin_memory=True)
+        nz, keep = self._noise(noise)
+        _lib.check(self.lib.brl_predict_moments_host(self.ctx, x_host.data_ptr(), B, S, GUIDE_IDS[guide] if guide else -1,
+                                                     mu.data_ptr(), sigma.data_ptr() if sigma is not None else None,
+                                                     float(p_dropout), nz, out.data_ptr(), eid, ws.data_ptr(), ws.numel(),
+                                                     self._stream()))
+        torch.cuda.current_stream(self.device).synchronize()
+        return out
+
     def moments(self, out: torch.Tensor):
         out = _chk(out, self.device, "out")
         if out.dim() != 3 or out.shape[2] != 2:

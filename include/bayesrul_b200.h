@@ -150,6 +150,18 @@ int brl_predict_moments(brl_ctx* ctx, const float* x, int64_t B, int64_t S, int 
                         float* std, float* ep_var, float* al_var, int engine, void* workspace,
                         size_t workspace_bytes, void* stream);
 
+/* ---- the same with HOST buffers (replaces predict_step as a whole, bayesian.py:231-250: `x.to(device)`, bnn.predict,
+ *      the moments and the five `.cpu()` reads).  x_host [B,30,18] and out_host [4,B] = (pred, std, ep_var, al_var) are HOST
+ *      pointers (pinned memory makes the copies asynchronous).  On the fused engine the batch travels in window chunks on a
+ *      private copy stream while the previous chunk is computed; the fp16 weight images of all S samples are packed once
+ *      and shared by the chunks, so only the first chunk's copy is exposed.  Results equal brl_predict_moments (a weight
+ *      draw has no window index; per-window noise is keyed by the global window index).  Nothing synchronises the host:
+ *      out_host is valid once `stream` has been synchronised.  Workspace: brl_workspace_bytes_host. */
+int64_t brl_workspace_bytes_host(const brl_ctx* ctx, int64_t B, int64_t S, int engine);
+int brl_predict_moments_host(brl_ctx* ctx, const float* x_host, int64_t B, int64_t S, int guide, const float* mu,
+                             const float* sigma, float p_dropout, const brl_noise* noise, float* out_host /*[4,B]*/,
+                             int engine, void* workspace, size_t workspace_bytes, void* stream);
+
 /* moment reduction of an explicit [S,B,2] tensor (bayesian.py:212-215) */
 int brl_moments(const float* out, int64_t S, int64_t B, float* pred, float* std, float* ep_var,
                 float* al_var, void* stream);

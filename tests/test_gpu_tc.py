@@ -61,3 +61,58 @@ def test_tc_mc_dropout(eng):
     b = eng.forward(x, "det", theta=mu, S=S, p_dropout=p, noise=Noise(seed=77), engine="tc")
     assert eng.tc_status() == 0
     assert_close(b, a, rtol=1e-2, atol_scale=2e-3, what="tc mcd")
+
+
+def test_tc_full_size_shard_properties(eng):
+    """BASELINE size on the fused engine (B = 10 000 windows x S = 100): the result must not depend on how the windows are
+    sharded over ranks (bit-exact: a weight draw has no window index, per-window noise is keyed by the global index) nor on
+    how the MC samples are sharded (Chan merge of per-shard moments, dist.merge_moments), for weight sampling and MC-dropout."""
+    from bayesrul_b200 import Noise
+    from bayesrul_b200.dist import merge_moments, shard_range
+    B, S = 10000, 100
+    x, _, mu, sg = synth("inception", B, seed=78, sigma=0.02)
+    x, mu, sg = x.to(DEV), mu.to(DEV), sg.to(DEV)
+    for kw in (dict(sigma=sg, guide="normal"), dict(sigma=None, guide=None, p_dropout=0.241437)):
+        full = eng.predict_moments(x, mu, S=S, noise=Noise(seed=21), engine="tc", **kw)
+        # windows sharded over 3 "ranks" (ragged: 3334 / 3333 / 3333)
+        parts = []
+        for r in range(3):
+            a, b = shard_range(B, r, 3)
+            parts.append(eng.predict_moments(x[a:b].contiguous(), mu, S=S, noise=Noise(seed=21, window0=a), engine="tc", **kw))
+        for i in range(4):
+            assert torch.equal(torch.cat([p[i] for p in parts]), full[i]), (kw["guide"], i)
+        # samples sharded over 4 "ranks" (25 each) + Chan merge
+        sh = []
+        for r in range(4):
+            a, b = shard_range(S, r, 4)
+            m = eng.predict_moments(x, mu, S=b - a, noise=Noise(seed=21, sample0=a), engine="tc", **kw)
+            sh.append((b - a, m[0], m[2], m[3]))
+        merged = merge_moments(sh)
+        for u, v, k in zip(merged, full, ("pred", "std", "ep", "al")):
+            assert_close(u, v, rtol=2e-4, atol_scale=1e-5, what=f"{kw['guide']} sample-sharded {k}")
+        assert eng.tc_status() == 0
+
+
+@pytest.mark.parametrize("B", [300, 5000])
+@pytest.mark.parametrize("engine", ["tc", "simt"])
+def test_host_entry_point_equals_device_entry_point(B, engine):
+    """brl_predict_moments_host (host x, host results, window chunks overlapped with the copies on the fused engine) must
+    give what brl_predict_moments gives on the device-resident batch: weight sampling (normal, radial) and MC-dropout."""
+    from bayesrul_b200 import Engine, Noise
+    e = Engine("inception", DEV)
+    x, _, mu, sg = synth("inception", B, seed=79, sigma=0.02)
+    xh = x.pin_memory()
+    x, mu, sg = x.to(DEV), mu.to(DEV), sg.to(DEV)
+    S = 7 if engine == "tc" else 3
+    for kw in (dict(sigma=sg, guide="normal"), dict(sigma=sg, guide="radial"), dict(sigma=None, guide=None, p_dropout=0.241437)):
+        ref = e.predict_moments(x, mu, S=S, noise=Noise(seed=5, window0=17), engine=engine, **kw)
+        got = e.predict_moments_host(xh, mu, S=S, noise=Noise(seed=5, window0=17), engine=engine, **kw)
+        assert got.shape == (4, B) and got.is_pinned()
+        for i in range(4):
+            assert_close(got[i], ref[i], rtol=1e-6, atol_scale=1e-7, what=f"{engine} {kw['guide']} output {i}")
+    # pageable host memory works too (the copies are then synchronous)
+    got2 = e.predict_moments_host(xh.clone(), mu, sg, S=S, guide="normal", noise=Noise(seed=5, window0=17), engine=engine)
+    ref = e.predict_moments(x, mu, sg, S=S, guide="normal", noise=Noise(seed=5, window0=17), engine=engine)
+    assert_close(got2[0], ref[0], rtol=1e-6, atol_scale=1e-7, what="pageable")
+    with pytest.raises(RuntimeError):
+        e.predict_moments_host(x, mu, sg, S=S, engine=engine)  # a device tensor is not a host batch
