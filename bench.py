@@ -429,7 +429,7 @@ def main():
                    "l2": "256 MiB flush between timed steps + 8 rotating input batches", "parallelism": f"windows sharded x{world}"},
         "clocks": clocks, "gpu_launches": int(launches_timed),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "bayesrul_b200.compat.BNN.predict_step (pinned host batch -> numpy results)"},
+                "api": "bayesrul_b200.compat.BNN.predict_step -> brl_predict_moments_host (pinned host batch -> host results)"},
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": pk["tf_sust"], "unit": "TFLOP/s",
                      "frac": achieved_tf / pk["tf_sust"], "traffic": traffic, "kernel": "tc_conv_kernel" if engine == "tc" else "step",
                      "ms_per_launch": conv_ms / max(conv_launches, 1), "share_of_step": conv_ms / (t_local * 1e3) if conv_launches else None,
