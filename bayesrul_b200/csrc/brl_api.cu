@@ -1094,7 +1094,13 @@ int brl_elbo_step(brl_ctx* ctx, const float* x, const float* y, int64_t B, const
   const ActBufs* lanes[2] = {&ab, &ab1};
   // ---- graph replay (native Philox noise): eager on first sight of a configuration, captured on the second, replayed after
   brl_ctx::StepGraph* sg = nullptr;
-  if (ctx->graph_enabled && noise_is_native(noise) && particles <= GRAPH_MAX_PARTICLES) {
+  bool caller_captures = false;  // the caller is capturing `st` itself (e.g. torch.cuda.graph): stay on the eager, capturable path
+  {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); caller_captures = true; }
+    else caller_captures = cs != cudaStreamCaptureStatusNone;
+  }
+  if (ctx->graph_enabled && !caller_captures && noise_is_native(noise) && particles <= GRAPH_MAX_PARTICLES) {
     brl_ctx::StepKey key;
     memset(&key, 0, sizeof(key));
     key.B = B; key.dataset_size = dataset_size; key.mode = mode; key.guide = guide; key.particles = particles;

@@ -344,8 +344,10 @@ def main():
                 torch.exp(par["ls"], out=par["sg"])
 
             res = {}
-            for backend in ("simt", "tc"):  # fp32 FFMA kernels vs tcgen05 TF32 dual-GEMM kernels (same operators)
-                eng.set_gemm_backend(backend)
+            # fp32 FFMA kernels / tcgen05 TF32 dual-GEMM kernels (same operators) / TF32 forward + input-gradient kernels with the
+            # fp32 dual weight-gradient kernel (bit mask of brl_set_gemm_backend: 1 forward, 2 input gradient, 4 weight gradient)
+            for backend, mask in (("simt", 0), ("tc", 7), ("mixed", 3)):
+                eng.set_gemm_backend(mask)
                 res[backend] = max_over_ranks(timed_steps(train_step, NT, 6, flush_buf, dist), dist, device)
             eng.set_gemm_backend("simt")
             eng.set_step_graph(False)  # the same step without the CUDA-graph replay (eager launches), for the record
@@ -355,8 +357,10 @@ def main():
             tt = res[best]
             flops = F_TRAIN_LRT * particles * B_TRAIN  # 13 036 416 per window per particle
             train[mode] = {"windows_per_s": world * B_TRAIN * NT / tt, "ms_per_step": 1e3 * tt / NT, "batch_per_gpu": B_TRAIN,
-                           "particles": particles, "gemm_backend": {"simt": "fp32 FFMA", "tc": "tcgen05 TF32"}[best],
-                           "ms_per_step_by_backend": {"simt_fp32": 1e3 * res["simt"] / NT, "tc_tf32": 1e3 * res["tc"] / NT},
+                           "particles": particles,
+                           "gemm_backend": {"simt": "fp32 FFMA", "tc": "tcgen05 TF32", "mixed": "tcgen05 TF32 forward + dX, fp32 FFMA dW"}[best],
+                           "ms_per_step_by_backend": {"simt_fp32": 1e3 * res["simt"] / NT, "tc_tf32": 1e3 * res["tc"] / NT,
+                                                      "tc_tf32_fwd_dx+simt_dw": 1e3 * res["mixed"] / NT},
                            "ms_per_step_eager_simt": 1e3 * t_eager / NT,
                            "achieved_tflops": flops / (tt / NT) / 1e12,
                            "includes": "ELBO forward + backward + KL + gradient finalisation (CUDA-graph replay) + ClippedAdam on (loc, log scale)"
