@@ -219,12 +219,15 @@ def main():
         run_reference(args, rank, world)
         return
     args.warmup = max(args.warmup, 3)
+    # stdout carries ONE JSON line: whatever libraries print to fd 1 (NCCL's version banner, NCCL_DEBUG=INFO logs) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
 
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     dist = None
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version banner / warnings go to stderr: stdout is ONE JSON line
         import torch.distributed as dist_mod
         dist_mod.init_process_group("nccl", device_id=device)
         dist = dist_mod
@@ -447,7 +450,7 @@ def main():
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": f"{B_PRED} windows x 10 of the {S_PRED} MC samples ({dt:.1f} s), plain-PyTorch "
                                           f"restatement on torch {torch.__version__} CPU"}
-    print(json.dumps(line))
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.destroy_process_group()
 
