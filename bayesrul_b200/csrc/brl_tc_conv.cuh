@@ -242,11 +242,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) tc_conv_kernel(const ConvArgs
         const uint64_t dWB4 = umma_desc(sbase + OFF_W + WI_B4, 512, 128);
         const uint64_t dM1 = umma_desc(rb + R_M1 + ROW0 * 16, CS, 128), dM1P = umma_desc(rb + R_M1P + ROW0 * 16, CS, 128);
         uint32_t rph = 0u, fph = 0u;
+        const uint64_t pol = l2_policy_evict_last();
         auto load_w = [&](int s) {
           if (elect_one()) {
             const unsigned char* src = a.blob + (long long)s * a.blob_stride;
             mbar_expect_tx(bars + BAR_W, CONV_IMG);
-            for (int o = 0; o < CONV_IMG; o += 16384) bulk_g2s(sbase + OFF_W + o, src + o, min(16384, CONV_IMG - o), bars + BAR_W);
+            for (int o = 0; o < CONV_IMG; o += 16384) bulk_g2s_hint(sbase + OFF_W + o, src + o, min(16384, CONV_IMG - o), bars + BAR_W, pol);
           }
           __syncwarp();
         };
@@ -254,7 +255,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) tc_conv_kernel(const ConvArgs
           if (elect_one()) {
             const unsigned char* src = a.ximg + (long long)(pair * 2 + k) * XIMG_TILE_BYTES;
             mbar_expect_tx(bars + BAR_XFULL + 8 * k, XIMG_TILE_BYTES);
-            bulk_g2s(rb + R_X, src, XIMG_TILE_BYTES, bars + BAR_XFULL + 8 * k);
+            bulk_g2s_hint(rb + R_X, src, XIMG_TILE_BYTES, bars + BAR_XFULL + 8 * k, pol);
           }
           __syncwarp();
         };
@@ -451,8 +452,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) tc_conv_kernel(const ConvArgs
           finish16<DROP>(acc[2], live, a, q == 0 ? 4 : 9, s, gw, t, q == 2 ? 16 : 0, q == 0 ? 16 : 32, lo, hi);
           const int fc = q == 0 ? 0 : q == 1 ? 6 : 8;
           if (BRL_FEAT_LIVE(live)) {
-            *reinterpret_cast<uint4*>(frow + fc * 480) = lo;
-            *reinterpret_cast<uint4*>(frow + (fc + 1) * 480) = hi;
+            st_global_cs(frow + fc * 480, lo);
+            st_global_cs(frow + (fc + 1) * 480, hi);
           }
         }
         tr(it, 8 + 3 * k);
@@ -498,10 +499,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) tc_conv_kernel(const ConvArgs
             act_injected<true, 8>(out, sbias + 304 + q * 8, live, a, q < 2 ? 6 : 8, s, gw, t, (q & 1) * 8, 16);
             o4 = pack8(out, true);
           }
-          if (BRL_FEAT_LIVE(live)) *reinterpret_cast<uint4*>(frow + (2 + q) * 480) = o4;
+          if (BRL_FEAT_LIVE(live)) st_global_cs(frow + (2 + q) * 480, o4);
         } else {
           act_plain<true, 8>(out, sbias + 304 + q * 8);
-          if (BRL_FEAT_LIVE(live)) *reinterpret_cast<uint4*>(frow + (2 + q) * 480) = pack8(out, true);
+          if (BRL_FEAT_LIVE(live)) st_global_cs(frow + (2 + q) * 480, pack8(out, true));
         }
         tr(it, 14 + 3 * k);
       }
