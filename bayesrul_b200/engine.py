@@ -99,7 +99,7 @@ class Engine:
         _lib.check(self.lib.brl_create(C.byref(ctx), NET_IDS[net], self.device.index))
         self.ctx = ctx
         self._ws: Optional[torch.Tensor] = None
-        self.max_workspace_bytes = 6 << 30
+        self.max_workspace_bytes = 8 << 30  # 180 GB of HBM per GPU: S = 100 x B = 10 000 on the fused engine is one 4.9 GB pass
 
     def __del__(self):
         try:
@@ -224,7 +224,7 @@ class Engine:
                 raise RuntimeError("Guide unknown. Choose from 'normal', 'radial'.")
             sigma = self._theta(sigma, "sigma")
         eid = ENGINE_IDS[engine]
-        sc = min(S, chunk or (32 if engine == "tc" else 16))
+        sc = min(S, chunk or (128 if engine == "tc" else 16))
         while sc > 1 and self.lib.brl_workspace_bytes(self.ctx, B, sc, 0, eid) > self.max_workspace_bytes:
             sc -= 1
         ws = self.workspace(self.lib.brl_workspace_bytes(self.ctx, B, sc, 0, eid))

@@ -5,6 +5,8 @@ import collections, csv, io, json, os, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag, rnd = sys.argv[1], sys.argv[2]
+SPL = int(sys.argv[3]) if len(sys.argv) > 3 else 100  # MC samples per fused launch
+WS = SPL * 10000
 G = os.path.join(ROOT, "gpurun_out")
 P = os.path.join(ROOT, "profiles")
 
@@ -25,7 +27,7 @@ for r in rows[1:]:
 tot = sum(v[1] for v in d.values())
 with open(os.path.join(P, f"{rnd}_launches_predict_tc.txt"), "w") as f:
     f.write(f"# {rnd} -- ncu launch list (gpu__time_duration.sum, --clock-control none) of\n"
-            "#   python bench.py --steps 2 --warmup 3 --no-cpu --no-train   (tcgen05 engine, B=10000 x S=100, chunks of 25 samples)\n"
+            f"#   python bench.py --steps 2 --warmup 3 --no-cpu --no-train   (tcgen05 engine, B=10000 x S=100, {SPL} samples per launch)\n"
             f"# per-launch times are cold-cache / serialised: read SHARES.  raw csv: gpurun_out/launches_{tag}.csv (scratch)\n")
     for k, (n, t) in sorted(d.items(), key=lambda x: -x[1][1]):
         f.write(f"{k:72s} n={n:4d} total={t / 1e6:9.3f} ms  avg={t / n / 1e3:9.1f} us share={100 * t / tot:5.1f}%\n")
@@ -68,10 +70,10 @@ def bytes_of(v, u):
 with open(os.path.join(P, f"{rnd}_ncu_tc_kernels.txt"), "w") as f:
     for name, rep, head in (
         ("tc_conv_kernel", f"prof_conv_{tag}.ncu-rep",
-         "one launch = 25 MC samples x 10000 windows = 250000 window-samples; algorithmic GEMM FLOPs/launch = 250000 x 1 981 920 = 495 GFLOP\n"
-         "# algorithmic bytes/launch: out 250000 x 4800 B = 1200 MB (feature tensor), in 31.7 MB (fp16 window images, re-read from L2 per sample) + 25 x 87 KB weights"),
+         f"one launch = {SPL} MC samples x 10000 windows = {WS} window-samples; algorithmic GEMM FLOPs/launch = {WS} x 1 981 920 = {WS * 1981920 / 1e9:.0f} GFLOP\n"
+         f"# algorithmic bytes/launch: out {WS} x 4800 B = {WS * 4800 / 1e6:.0f} MB (feature tensor), in 31.7 MB (fp16 window images, re-read from L2 per sample) + {SPL} x 87 KB weights"),
         ("tc_fc_kernel", f"prof_fc_{tag}.ncu-rep",
-         "algorithmic FLOPs/launch = 250000 x 307 456 = 77 GFLOP; bytes: feature tensor read 1200 MB + fc weights 307 KB x 79 tiles x 25 samples = 606 MB (L2)")):
+         f"algorithmic FLOPs/launch = {WS} x 307 456 = {WS * 307456 / 1e9:.0f} GFLOP; bytes: feature tensor read {WS * 4800 / 1e6:.0f} MB + fc weights 307 KB x 79 tiles x {SPL} samples = {0.307 * 79 * SPL:.0f} MB (L2)")):
         m, tot, stalls, mnem = capture(os.path.join(G, rep))
         f.write(f"# {rnd} -- ncu --set full --clock-control none --import-source on, {name}<false> (launch 3 of bench.py --steps 1 --warmup 3 --no-cpu --no-train)\n# {head}\n")
         for k in keys:
@@ -81,8 +83,8 @@ with open(os.path.join(P, f"{rnd}_ncu_tc_kernels.txt"), "w") as f:
         f.write("async-unit SASS executed (warp-instructions): " + ", ".join(f"{k} {v}" for k, v in sorted(mnem.items())) + "\n\n")
         if name == "tc_conv_kernel":
             db = bytes_of(*m['dram__bytes_read.sum']) + bytes_of(*m['dram__bytes_write.sum'])
-            json.dump({"kernel": name, "launch": "25 MC samples x 10000 windows (250000 window-samples)", "dram_bytes_per_launch": db,
-                       "dram_bytes_per_window_sample": db / 250000, "algorithmic_bytes_per_window_sample": 4800 + 2160 / 100,
+            json.dump({"kernel": name, "launch": f"{SPL} MC samples x 10000 windows ({WS} window-samples)", "dram_bytes_per_launch": db,
+                       "dram_bytes_per_window_sample": db / WS, "algorithmic_bytes_per_window_sample": 4800 + 2160 / 100,
                        "source": f"profiles/{rnd}_ncu_tc_kernels.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"},
                       open(os.path.join(P, "conv_traffic.json"), "w"), indent=1)
 print(open(os.path.join(P, f"{rnd}_ncu_tc_kernels.txt")).read())
