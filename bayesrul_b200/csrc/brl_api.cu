@@ -827,15 +827,26 @@ int brl_predict_moments(brl_ctx* ctx, const float* x, int64_t B, int64_t S, int 
 // the copy it hides), rounded to 128 windows.  Per chunk, MC samples run in sub-chunks that fit the feature buffer.  The fp16 weight images of ALL S samples are packed once, up front (while the
 // first chunk is still in flight), and shared by the chunks.
 struct HostPlan {
-  long long Bc, n_chunks, Sc, Sw;  // windows per chunk, chunks, samples per feature-buffer pass, samples per sampler pass
+  long long B0, Bc, n_chunks, Sc, Sw;  // windows of the first / of every later chunk, chunks, samples per feature-buffer pass,
+                                       // samples per sampler pass.  Buffers are sized for Bc >= B0.
+  void range(long long B, long long ci, long long& w0, long long& bc) const {
+    w0 = ci == 0 ? 0 : B0 + (ci - 1) * Bc;
+    bc = ci == 0 ? B0 : std::min(Bc, B - w0);
+  }
 };
 static bool noise_is_native(const brl_noise* nz);
 static HostPlan host_plan(const brl_ctx* ctx, long long B, long long S, int engine, bool native) {
   HostPlan p;
   static const int env_nw = getenv("BRL_HOST_NW") ? atoi(getenv("BRL_HOST_NW")) : 0;  // experiment knob
   p.n_chunks = (engine == BRL_ENGINE_TC_FP16 && native && B >= 4096) ? (env_nw > 0 ? std::min(env_nw, 8) : 2) : 1;
-  p.Bc = p.n_chunks == 1 ? B : (((B + p.n_chunks - 1) / p.n_chunks + 127) / 128) * 128;
-  p.n_chunks = (B + p.Bc - 1) / p.Bc;
+  static const int env_first = getenv("BRL_HOST_FIRST_PCT") ? atoi(getenv("BRL_HOST_FIRST_PCT")) : 30;  // experiment knob
+  if (p.n_chunks == 1) {
+    p.B0 = p.Bc = B;
+  } else {  // a smaller first chunk exposes less of its copy; the later chunks share the rest evenly
+    p.B0 = std::min(B, std::max<long long>(128, (B * env_first / 100 + 127) / 128 * 128));
+    p.Bc = std::max(p.B0, (((B - p.B0) + p.n_chunks - 2) / (p.n_chunks - 1) + 127) / 128 * 128);
+    p.n_chunks = 1 + (B - p.B0 + p.Bc - 1) / p.Bc;
+  }
   p.Sw = std::min<long long>(S, 16);
   p.Sc = S;
   if (engine == BRL_ENGINE_TC_FP16)
@@ -906,7 +917,8 @@ int brl_predict_moments_host(brl_ctx* ctx, const float* x_host, int64_t B, int64
   BRL_CUDA(cudaEventRecord(ctx->ev_copy_start, st));
   BRL_CUDA(cudaStreamWaitEvent(ctx->copy, ctx->ev_copy_start, 0));
   for (long long ci = 0; ci < pl.n_chunks; ++ci) {
-    const long long w0 = ci * pl.Bc, bc = std::min(pl.Bc, B - w0);
+    long long w0, bc;
+    pl.range(B, ci, w0, bc);
     BRL_CUDA(cudaMemcpyAsync(h.x_dev + w0 * 540, x_host + w0 * 540, sizeof(float) * bc * 540, cudaMemcpyHostToDevice, ctx->copy));
     BRL_CUDA(cudaEventRecord(ctx->ev_chunk[ci], ctx->copy));
   }
@@ -929,7 +941,8 @@ int brl_predict_moments_host(brl_ctx* ctx, const float* x_host, int64_t B, int64
   }
   // ---- chunks of windows x sub-chunks of samples
   for (long long ci = 0; ci < pl.n_chunks; ++ci) {
-    const long long w0 = ci * pl.Bc, bc = std::min(pl.Bc, B - w0);
+    long long w0, bc;
+    pl.range(B, ci, w0, bc);
     BRL_CUDA(cudaStreamWaitEvent(st, ctx->ev_chunk[ci], 0));
     for (long long s0 = 0; s0 < S; s0 += pl.Sc) {
       const long long sc = std::min(pl.Sc, S - s0);
