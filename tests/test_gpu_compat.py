@@ -147,3 +147,33 @@ def test_chunked_host_predict_equals_device_predict(engine):
     ref = m.bnn.predict_moments(x.to(DEV), 6)
     for a, b in zip(got, ref):
         np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_predict_task_writer_and_deep_ensemble_gen(tmp_path):
+    """The predict task end to end (tasks/predict.py:52-64 -> results/predictions.py:31-56): HNN members write
+    `<method>_<run>_<subset>.parquet` through predict_step, the frames are read back and mixed by deep_ensemble_gen."""
+    import random
+    from itertools import combinations
+    import pandas as pd
+    from bayesrul_b200.compat import HNN, Inception, ResultSaver, deep_ensemble_gen, write_predictions
+    g = torch.Generator().manual_seed(3)
+    batches = [(torch.randn(n, 30, 18, generator=g), torch.rand(n, generator=g) * 100) for n in (40, 40, 17)]
+    frames = []
+    for run in range(3):
+        torch.manual_seed(100 + run)
+        m = HNN(Inception(30, 18), None, mc_samples=1, p_dropout=0, device=DEV)  # HNN applies weights_init itself
+        name = f"HNN_{run:03d}_test.parquet"
+        f = write_predictions(m, batches, tmp_path, name)
+        assert list(f.columns) == ["labels", "preds", "stds"] and len(f) == 97  # no MC-dropout: no variance split (frequentist.py:132-151)
+        np.testing.assert_allclose(f.labels.values, torch.cat([b[1] for b in batches]).numpy(), rtol=1e-6)
+        frames.append(ResultSaver(tmp_path, name).load().assign(model=f"HNN_{run:03d}", method="HNN"))
+    df = pd.concat(frames).reset_index(drop=True)
+    out = list(deep_ensemble_gen(df, ["HNN"], 2, 2))
+    random.seed(1)
+    picks = random.sample(list(combinations(range(3), 2)), 2)
+    assert [o.model.iloc[0] for o in out] == ["DE_000", "DE_001"] and all((o.method == "DE").all() for o in out)
+    for o, ens in zip(out, picks):
+        mu = np.stack([frames[k].preds.values for k in ens]).astype(np.float64)
+        sd = np.stack([frames[k].stds.values for k in ens]).astype(np.float64)
+        np.testing.assert_allclose(o.preds.values, mu.mean(0), rtol=1e-5)
+        np.testing.assert_allclose(o.stds.values, np.sqrt((mu**2 + sd**2).mean(0) - mu.mean(0) ** 2), rtol=1e-3, atol=1e-4)

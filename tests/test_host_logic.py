@@ -80,3 +80,25 @@ def test_dropout_decisions_rate_and_tie_path():
     m = np.stack([O.keep_decisions(r, np.full(n, bi, dtype=np.uint32), 0.5) for bi in range(16)]).astype(np.float64)
     c = np.corrcoef(m)
     assert np.abs(c - np.eye(16)).max() < 0.02
+
+
+def test_prediction_frame_and_result_saver(tmp_path):
+    """per-batch predict_step dicts -> one row per window, parquet round trip (tasks/predict.py:52-64)."""
+    import numpy as np
+    import pandas as pd
+    from bayesrul_b200.compat.predictions import PREDICTION_COLUMNS, ResultSaver, predictions_to_frame
+    rng = np.random.default_rng(0)
+    batches = [{c: rng.normal(size=n).astype(np.float32) for c in PREDICTION_COLUMNS} for n in (5, 3, 1)]
+    frame = predictions_to_frame(batches)
+    # the reference's own two lines give the same values
+    ref = pd.DataFrame.from_records(batches)
+    ref = ref.explode(ref.columns.tolist()).reset_index(drop=True)
+    assert list(frame.columns) == PREDICTION_COLUMNS and len(frame) == 9
+    np.testing.assert_array_equal(frame.to_numpy(dtype=np.float32), ref.to_numpy(dtype=np.float32))
+    sav = ResultSaver(tmp_path / "preds", "LRT_000_test.parquet")
+    sav.save(frame)
+    back = sav.load()
+    pd.testing.assert_frame_equal(back, frame)
+    sav.append({"errs": (frame.preds - frame.labels).to_numpy()})
+    assert list(sav.load().columns) == PREDICTION_COLUMNS + ["errs"]
+    assert len(predictions_to_frame([])) == 0
