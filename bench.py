@@ -8,9 +8,12 @@ q_scale 1.351e-3, prior 0.138793) predicting B=10 000 synthetic N-CMAPSS windows
 Monte-Carlo weight samples per step (reference semantics: bnn.predict draws one full weight sample
 per MC sample, bayesian.py:235-249) + the predictive-moment reduction.
 A "step" = one such batch; `value` = window x samples / s with inputs resident in HBM; `e2e` = the
-same through BNN.predict_step with pinned HOST inputs and host results.  The ELBO-train throughput
-(LRT and Flipout, B=256) rides along under "train".  One process per GPU; windows are sharded
-across ranks, no data-path collective (weak scaling).
+same through BNN.predict_step -> brl_predict_moments_host with pinned HOST inputs and host results.
+Riding along: "train" (one whole svi.step of the LRT / Flipout experiments at B=256 per GPU: ELBO
+forward + backward + ClippedAdam, + the NCCL all-reduce at N > 1), "mcd_predict" (configs[1]),
+"radial_sweep" (configs[3], MC samples sharded over the ranks + moment merge), "deep_ensemble"
+(configs[4]).  One process per GPU; windows are sharded across ranks, no data-path collective in the
+headline (weak scaling).  Only the JSON line is written to stdout.
 """
 import argparse
 import json
