@@ -110,9 +110,18 @@ class HNN(_Base):
         self.log("sharp/test", sharpness(scale))
 
     def predict_step(self, batch, batch_idx, dataloader_idx=0):  # frequentist.py:132-151
-        batch = (batch[0].to(self.get_device(), non_blocking=True), batch[1])
         pred = dict()
         pred["labels"] = batch[1].cpu().numpy()
+        if self.net.dropout > 0 and batch[0].device.type == "cpu" and batch[0].dtype == torch.float32:
+            # MC-dropout on a host batch (the DataLoader's): brl_predict_moments_host -- chunked copy underneath the compute
+            enable_dropout(self.net)
+            out = self.net.engine().predict_moments_host(batch[0], self.net.flat(), None, S=self.hparams.mc_samples, guide=None,
+                                                         p_dropout=float(self.net.dropout), noise=self._noise(),
+                                                         engine=self._engine_kind)
+            pred["ep_vars"], pred["al_vars"] = out[2].numpy(), out[3].numpy()
+            pred["preds"], pred["stds"] = out[0].numpy(), out[1].numpy()
+            return pred
+        batch = (batch[0].to(self.get_device(), non_blocking=True), batch[1])
         if self.net.dropout > 0:
             enable_dropout(self.net)
             loc, scale, ep_var, al_var = self._mc_moments(batch)

@@ -97,6 +97,13 @@ def test_hnn_train_and_mc_dropout_predict():
     p = m.predict_step((x.cpu(), y.cpu()), 0)
     assert set(p) == {"labels", "ep_vars", "al_vars", "preds", "stds"} and p["preds"].shape == (100,)
     assert (p["ep_vars"] > 0).all()
+    # a host batch goes through brl_predict_moments_host, a device batch through brl_predict_moments: same masks, same numbers
+    it0 = m._it
+    p_host = m.predict_step((x.cpu(), y.cpu()), 0)
+    m._it = it0
+    p_dev = m.predict_step((x, y), 0)
+    for k in ("preds", "stds", "ep_vars", "al_vars"):
+        np.testing.assert_allclose(p_host[k], p_dev[k], rtol=1e-5, atol=1e-6)
     out = m.validation_step((x, y), 0)
     assert set(out) == {"loss", "label", "pred", "std"}
     m.test_step((x, y), 0)
