@@ -29,9 +29,10 @@ enum NoiseKind : uint32_t {
   KIND_DROPOUT = 6,
 };
 
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+template <int ROUNDS>
+__device__ __forceinline__ uint4 philox4x32(uint4 c, uint2 k) {
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < ROUNDS; ++r) {
     const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
     const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
     c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
@@ -41,9 +42,19 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   return c;
 }
 
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) { return philox4x32<10>(c, k); }
+
 __device__ __forceinline__ uint4 philox_block(uint64_t seed, uint32_t kind, uint32_t site, uint32_t sample,
                                               uint32_t window, uint32_t block) {
-  return philox4x32_10(make_uint4(block, window, sample, (kind << 24) | (site & 0xFFFFFFu)),
+  return philox4x32<10>(make_uint4(block, window, sample, (kind << 24) | (site & 0xFFFFFFu)),
+                        make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+}
+// Dropout masks use Philox4x32-7: seven rounds are the smallest Crush-resistant member of the family (Salmon et al., SC'11;
+// ten is its safety margin), one mask bit decision consumes 8 of the 128 output bits, and the generator sits on the critical
+// path of the fused kernel's epilogue warps.  Normals and signs keep ten rounds.
+__device__ __forceinline__ uint4 philox_block_mask(uint64_t seed, uint32_t kind, uint32_t site, uint32_t sample,
+                                                   uint32_t window, uint32_t block) {
+  return philox4x32<7>(make_uint4(block, window, sample, (kind << 24) | (site & 0xFFFFFFu)),
                        make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
 }
 
@@ -111,7 +122,7 @@ __device__ __forceinline__ bool keep_at(const KeepBits& k, uint32_t c) { return 
 __device__ __forceinline__ bool philox_keep(uint64_t seed, uint32_t kind, uint32_t site, uint32_t sample, uint32_t window,
                                             uint32_t C, uint32_t pos, uint32_t ch, float keep) {
   const uint32_t e = pos * ((C + 15u) & ~15u) + ch;
-  const uint4 r = philox_block(seed, kind, site, sample, window, e >> 4);
+  const uint4 r = philox_block_mask(seed, kind, site, sample, window, e >> 4);
   return keep_at(keep_bits(r, keep_threshold(keep)), e & 15u);
 }
 

@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(192, 1) tc_fc_kernel(const FcArgs a, const __g
       for (int g = 0; g < 4; ++g) {
         KeepBits kb = {};
         if (DROP && !a.drop.ptr)  // 16 keep decisions of outputs 16g .. 16g+15: one Philox block
-          kb = keep_bits(philox_block(a.drop.seed, a.drop.kind, a.drop.site, a.drop.sample0 + s, a.drop.window0 + gw, g),
+          kb = keep_bits(philox_block_mask(a.drop.seed, a.drop.kind, a.drop.site, a.drop.sample0 + s, a.drop.window0 + gw, g),
                          keep_threshold(a.keep));
 #pragma unroll
         for (int j = 0; j < 16; ++j) {

@@ -111,7 +111,7 @@ __device__ __forceinline__ void act_drop_packed(float (&v)[N], const float* bias
     if (ch0 + j < nvalid) v[j] *= inv;
   }
   const uint32_t e0 = (uint32_t)t * (uint32_t)((nvalid + 15) & ~15) + (uint32_t)ch0;
-  KeepBits kb = keep_bits(philox_block(nz.seed, nz.kind, nz.site, nz.sample0 + s, nz.window0 + gw, e0 >> 4), keep_threshold(a.keep4));
+  KeepBits kb = keep_bits(philox_block_mask(nz.seed, nz.kind, nz.site, nz.sample0 + s, nz.window0 + gw, e0 >> 4), keep_threshold(a.keep4));
   if (N < 16 && (e0 & 8u)) {  // upper half of the block (warp-uniform): channel pairs 4..7 move to 0..3
     kb.ev[0] = kb.ev[2]; kb.ev[1] = kb.ev[3]; kb.od[0] = kb.od[2]; kb.od[1] = kb.od[3];
   }

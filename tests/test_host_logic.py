@@ -70,7 +70,7 @@ def test_dropout_decisions_rate_and_tie_path():
     from oracle import bnn_oracle as O
     n = 1 << 16
     blk = np.arange(n, dtype=np.int64)
-    r = O._philox_block(1234, O.KIND_DROPOUT, 3, 0, np.zeros(n, dtype=np.int64), blk)
+    r = O._philox_block(1234, O.KIND_DROPOUT, 3, 0, np.zeros(n, dtype=np.int64), blk, rounds=7)
     for keep in (0.93964075, 0.758563, 0.5, 240.5 / 256.0):
         T = O.keep_threshold(keep)
         assert abs(T / 65536.0 - keep) <= 1.0 / 65536.0

@@ -111,6 +111,16 @@ def test_philox_known_answers():
     for c, k, want in kats:
         got = O.philox4x32_10(*[np.array([v]) for v in c], k[0], k[1])
         assert tuple(int(g[0]) for g in got) == want
+    # Random123 kat_vectors: philox4x32-7 (the dropout-mask generator)
+    kats7 = [
+        ((0, 0, 0, 0), (0, 0), (0x5F6FB709, 0x0D893F64, 0x4F121F81, 0x4F730A48)),
+        ((0xFFFFFFFF,) * 4, (0xFFFFFFFF,) * 2, (0x5207DDC2, 0x45165E59, 0x4D8EE751, 0x8C52F662)),
+        ((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0),
+         (0x4DFCCABA, 0x190A87F0, 0xC47362BA, 0xB6B5242A)),
+    ]
+    for c, k, want in kats7:
+        got = O.philox4x32_10(*[np.array([v]) for v in c], k[0], k[1], rounds=7)
+        assert tuple(int(g[0]) for g in got) == want
 
 
 def test_philox_normal_moments():
