@@ -414,10 +414,11 @@ def main():
     #      windows sharded across the ranks like the headline workload
     deepens = {}
     if not args.no_train:
-        members = [init_flat_params(NET, 100 + k).to(device) for k in range(5)]
+        members = torch.stack([init_flat_params(NET, 100 + k) for k in range(5)]).to(device)  # [5,P]: five trained-net stand-ins
 
         def de_step(i=0):
-            o = torch.stack([eng.forward(xs[i % n_rot], "det", theta=th, engine=engine)[0] for th in members])  # [5,B,2]
+            # the members are five weight sets: ONE forward in weight-sample mode (wsamp = [M,P]) instead of five launches
+            o = eng.forward(xs[i % n_rot], "ws", wsamp=members, S=5, engine=engine)  # [5,B,2]
             outs["de"] = eng.mixture_moments(o[:, :, 0].contiguous(), o[:, :, 1].contiguous())
 
         td = max_over_ranks(timed_steps(de_step, 5, 2, flush_buf, dist), dist, device)
