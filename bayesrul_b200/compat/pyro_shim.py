@@ -138,6 +138,18 @@ class ClippedAdam:
             engine.clipped_adam(p, g, st["m"], st["v"], st["step"], a["lr"], tuple(a["betas"]), a["eps"], a["clip_norm"],
                                 a["lrd"], a["weight_decay"])
 
+    def step_vi(self, engine, guide, g_loc, g_log_scale):
+        """The step over a mean-field guide's two flat buffers in ONE launch (brl_clipped_adam_vi), scale refresh included;
+        same per-parameter state as step_flat."""
+        sts = [self.state.setdefault(id(p), dict(step=0, m=torch.zeros_like(p), v=torch.zeros_like(p)))
+               for p in (guide.loc, guide.log_scale)]
+        for st in sts:
+            st["step"] += 1
+        a = self.args
+        engine.clipped_adam_vi(guide.loc, guide.log_scale, guide.scale, g_loc.contiguous(), g_log_scale.contiguous(), sts[0]["m"],
+                               sts[0]["v"], sts[1]["m"], sts[1]["v"], sts[0]["step"], a["lr"], tuple(a["betas"]), a["eps"],
+                               a["clip_norm"], a["lrd"], a["weight_decay"])
+
     def get_state(self):
         return {k: dict(step=v["step"], m=v["m"].clone(), v=v["v"].clone()) for k, v in self.state.items()}
 
@@ -184,8 +196,11 @@ class SVI:
             g_mu, g_ls = g_mu * k, g_ls * k
         guide = self.bnn.net_guide
         if self.optim is not None:
-            self.optim.step_flat(self.bnn.engine, [guide.loc, guide.log_scale], [g_mu, g_ls])
-            guide.refresh()
+            if hasattr(self.optim, "step_vi") and guide.loc.is_contiguous() and guide.log_scale.is_contiguous():
+                self.optim.step_vi(self.bnn.engine, guide, g_mu, g_ls)  # one launch: both buffers + scale = exp(log scale)
+            else:
+                self.optim.step_flat(self.bnn.engine, [guide.loc, guide.log_scale], [g_mu, g_ls])
+                guide.refresh()
         return float(loss.item())  # device boundary #2 of the reference (.item() sync every step)
 
     def evaluate_loss(self, x, y=None) -> float:

@@ -602,6 +602,42 @@ __global__ void clipped_adam_kernel(float* __restrict__ p, const float* __restri
     p[i] = pi - step_size * mi / (sqrtf(vi) + eps);
   }
 }
+// the optimiser step of a mean-field guide in one launch: ClippedAdam on loc and on log scale (the unconstrained parameter of
+// Pyro's positive constraint), then scale = exp(log scale) for the next forward pass
+__global__ void clipped_adam_vi_kernel(float* __restrict__ loc, float* __restrict__ ls, float* __restrict__ scale,
+                                       const float* __restrict__ g_loc, const float* __restrict__ g_ls, float* __restrict__ m_loc,
+                                       float* __restrict__ v_loc, float* __restrict__ m_ls, float* __restrict__ v_ls, long long n,
+                                       float step_size, float b1, float b2, float eps, float clip, float wd) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    {
+      float gr = fminf(fmaxf(g_loc[i], -clip), clip);
+      const float pi = loc[i];
+      if (wd != 0.f) gr = fmaf(wd, pi, gr);
+      const float mi = b1 * m_loc[i] + (1.f - b1) * gr, vi = b2 * v_loc[i] + (1.f - b2) * gr * gr;
+      m_loc[i] = mi;
+      v_loc[i] = vi;
+      loc[i] = pi - step_size * mi / (sqrtf(vi) + eps);
+    }
+    {
+      float gr = fminf(fmaxf(g_ls[i], -clip), clip);
+      const float pi = ls[i];
+      if (wd != 0.f) gr = fmaf(wd, pi, gr);
+      const float mi = b1 * m_ls[i] + (1.f - b1) * gr, vi = b2 * v_ls[i] + (1.f - b2) * gr * gr;
+      m_ls[i] = mi;
+      v_ls[i] = vi;
+      const float pn = pi - step_size * mi / (sqrtf(vi) + eps);
+      ls[i] = pn;
+      scale[i] = expf(pn);
+    }
+  }
+}
+void launch_clipped_adam_vi(float* loc, float* ls, float* scale, const float* g_loc, const float* g_ls, float* m_loc, float* v_loc,
+                            float* m_ls, float* v_ls, long long n, float step_size, float b1, float b2, float eps, float clip, float wd,
+                            cudaStream_t st) {
+  ++g_launch_count;
+  clipped_adam_vi_kernel<<<(unsigned)min((n + 255) / 256, (long long)148 * 8), 256, 0, st>>>(loc, ls, scale, g_loc, g_ls, m_loc, v_loc,
+                                                                                            m_ls, v_ls, n, step_size, b1, b2, eps, clip, wd);
+}
 void launch_clipped_adam(float* p, const float* g, float* m, float* v, long long n, float step_size, float b1,
                          float b2, float eps, float clip, float wd, cudaStream_t st) {
   ++g_launch_count;

@@ -190,5 +190,8 @@ void launch_test_metrics(const float* pred, const float* std, const float* y, lo
                          unsigned int* hist, cudaStream_t st);
 void launch_clipped_adam(float* p, const float* g, float* m, float* v, long long n, float step_size, float b1,
                          float b2, float eps, float clip, float wd, cudaStream_t st);
+void launch_clipped_adam_vi(float* loc, float* ls, float* scale, const float* g_loc, const float* g_ls, float* m_loc, float* v_loc,
+                            float* m_ls, float* v_ls, long long n, float step_size, float b1, float b2, float eps, float clip, float wd,
+                            cudaStream_t st);
 
 }  // namespace brl

@@ -358,3 +358,14 @@ class Engine:
         _lib.check(self.lib.brl_clipped_adam(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(),
                                              exp_avg_sq.data_ptr(), param.numel(), int(step), lr, betas[0], betas[1],
                                              eps, clip_norm, lrd, weight_decay, self._stream()))
+
+    def clipped_adam_vi(self, loc, log_scale, scale, grad_loc, grad_log_scale, m_loc, v_loc, m_ls, v_ls, step: int, lr: float,
+                        betas=(0.95, 0.999), eps=1e-8, clip_norm=15.0, lrd=1.0, weight_decay=0.0) -> None:
+        """One launch: ClippedAdam on `loc` and on `log_scale`, then scale = exp(log_scale) (all in place)."""
+        ts = (loc, log_scale, scale, grad_loc, grad_log_scale, m_loc, v_loc, m_ls, v_ls)
+        for t in ts:
+            _chk(t, self.device, "clipped_adam_vi tensor")
+            if t.numel() != loc.numel():
+                raise RuntimeError("bayesrul_b200: clipped_adam_vi tensors must have the same number of elements")
+        _lib.check(self.lib.brl_clipped_adam_vi(*[t.data_ptr() for t in ts], loc.numel(), int(step), lr, betas[0], betas[1], eps,
+                                                clip_norm, lrd, weight_decay, self._stream()))

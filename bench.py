@@ -345,9 +345,8 @@ def main():
                                   prior_scale=ps, dataset_size=N_DATASET, noise=Noise(seed=5000 + st["i"], window0=rank * B_TRAIN))
                 if dist is not None:
                     r = allreduce_elbo_grads(r)
-                eng.clipped_adam(par["mu"], r["grad_mu"].contiguous(), opt["m_mu"], opt["v_mu"], st["i"], lr, (0.95, 0.999), 1e-8, 15.0)
-                eng.clipped_adam(par["ls"], r["grad_log_sigma"].contiguous(), opt["m_ls"], opt["v_ls"], st["i"], lr, (0.95, 0.999), 1e-8, 15.0)
-                torch.exp(par["ls"], out=par["sg"])
+                eng.clipped_adam_vi(par["mu"], par["ls"], par["sg"], r["grad_mu"].contiguous(), r["grad_log_sigma"].contiguous(),
+                                    opt["m_mu"], opt["v_mu"], opt["m_ls"], opt["v_ls"], st["i"], lr, (0.95, 0.999), 1e-8, 15.0)
 
             res = {}
             # fp32 FFMA kernels / tcgen05 TF32 dual-GEMM kernels (same operators) / TF32 forward + input-gradient kernels with the

@@ -208,6 +208,12 @@ int brl_clipped_adam(float* param, const float* grad, float* exp_avg, float* exp
                      int64_t step, float lr, float beta1, float beta2, float eps, float clip_norm,
                      float lrd, float weight_decay, void* stream);
 
+/* the same for the two flat buffers of a mean-field guide in ONE launch: ClippedAdam on `loc` and on `log_scale` (the
+ * unconstrained parameter behind Pyro's positive constraint, guides/radial.py:85-94), then scale = exp(log_scale) */
+int brl_clipped_adam_vi(float* loc, float* log_scale, float* scale, const float* grad_loc, const float* grad_log_scale,
+                        float* m_loc, float* v_loc, float* m_log_scale, float* v_log_scale, int64_t n, int64_t step, float lr,
+                        float beta1, float beta2, float eps, float clip_norm, float lrd, float weight_decay, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -253,6 +253,20 @@ def test_test_metrics_and_adam(engines):
         e.clipped_adam(q, gr.to(DEV), m, v, step, 1e-3)
         pr, mr, vr = O.clipped_adam_step(pr, gr.double(), mr, vr, step, 1e-3)
     assert_close(q, pr, rtol=1e-5, what="adam")
+    # the fused step of a mean-field guide: both buffers in one launch + scale = exp(log scale)
+    loc0, ls0 = torch.randn(1000, generator=g), torch.randn(1000, generator=g) * 0.1 - 6.0
+    loc, ls, sc = loc0.clone().to(DEV), ls0.clone().to(DEV), torch.empty(1000, device=DEV)
+    st = [torch.zeros(1000, device=DEV) for _ in range(4)]
+    ref = [[loc0.double(), torch.zeros(1000, dtype=torch.float64), torch.zeros(1000, dtype=torch.float64)],
+           [ls0.double(), torch.zeros(1000, dtype=torch.float64), torch.zeros(1000, dtype=torch.float64)]]
+    for step in range(1, 5):
+        g1, g2 = torch.randn(1000, generator=g) * 20, torch.randn(1000, generator=g) * 20
+        e.clipped_adam_vi(loc, ls, sc, g1.to(DEV), g2.to(DEV), st[0], st[1], st[2], st[3], step, 1e-3)
+        ref[0] = list(O.clipped_adam_step(ref[0][0], g1.double(), ref[0][1], ref[0][2], step, 1e-3))
+        ref[1] = list(O.clipped_adam_step(ref[1][0], g2.double(), ref[1][1], ref[1][2], step, 1e-3))
+    assert_close(loc, ref[0][0], rtol=1e-5, what="adam_vi loc")
+    assert_close(ls, ref[1][0], rtol=1e-5, what="adam_vi log scale")
+    assert_close(sc, ref[1][0].exp(), rtol=1e-5, what="adam_vi scale")
 
 
 # ----------------------------------------------------------------------------- edge cases / errors
