@@ -56,6 +56,8 @@ struct brl_ctx {
     cudaStream_t main = nullptr;  // lane 0: the caller's stream of the current call; lane 1: owned
     cudaStream_t side[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr}, ev_op[8] = {};
+    cudaStream_t zero = nullptr;    // the gradient buffers are cleared here, underneath the forward pass
+    cudaEvent_t ev_zero = nullptr;
   };
   std::vector<int> op_level;
   int n_levels = 0;
@@ -571,6 +573,8 @@ int brl_create(brl_ctx** out, int net, int device) {
       BRL_CUDA(cudaEventCreateWithFlags(&ln.ev_join[i], cudaEventDisableTiming));
     }
     BRL_CUDA(cudaEventCreateWithFlags(&ln.ev_fork, cudaEventDisableTiming));
+    BRL_CUDA(cudaEventCreateWithFlags(&ln.ev_zero, cudaEventDisableTiming));
+    BRL_CUDA(cudaStreamCreateWithFlags(&ln.zero, cudaStreamNonBlocking));
     for (int i = 0; i < 8; ++i) BRL_CUDA(cudaEventCreateWithFlags(&ln.ev_op[i], cudaEventDisableTiming));
   }
   BRL_CUDA(cudaStreamCreateWithFlags(&c->lane1_main, cudaStreamNonBlocking));
@@ -598,6 +602,8 @@ int brl_destroy(brl_ctx* ctx) {
       if (ln.ev_join[i]) cudaEventDestroy(ln.ev_join[i]);
     }
     if (ln.ev_fork) cudaEventDestroy(ln.ev_fork);
+    if (ln.ev_zero) cudaEventDestroy(ln.ev_zero);
+    if (ln.zero) cudaStreamDestroy(ln.zero);
     for (int i = 0; i < 8; ++i)
       if (ln.ev_op[i]) cudaEventDestroy(ln.ev_op[i]);
   }
@@ -1029,14 +1035,22 @@ static int elbo_body(brl_ctx* ctx, const ActBufs* const* lanes, int n_lanes, con
         if (jobs.n) launch_gen_signs_multi(jobs, B, nref(&nz, nullptr, 0, 0), ls);
       }
       float* outp = out + (long long)pt * B * 2;
+      const brl_ctx::Lane& ln = ctx->lanes[l];
+      if (compute_grads) {  // a dozen memsets: on a side stream underneath the forward pass, joined before the NLL
+        cudaStream_t zs = ctx->multi_stream ? ln.zero : ls;
+        if (zs != ls) {
+          BRL_CUDA(cudaEventRecord(ln.ev_zero, ls));
+          BRL_CUDA(cudaStreamWaitEvent(zs, ln.ev_zero, 0));
+        }
+        int rc = zero_grads(n, ab, B, zs);
+        if (rc) return rc;
+        BRL_CUDA(cudaMemsetAsync(ab.g0, 0, sizeof(float) * n.P, zs));
+        BRL_CUDA(cudaMemsetAsync(ab.g1, 0, sizeof(float) * n.P, zs));
+        if (zs != ls) BRL_CUDA(cudaEventRecord(ln.ev_zero, zs));
+      }
       FwdArgs fa{x, B, 1, mode, mu, sigma, ab.wsamp, 0.f, &nz, sin_.data(), sout_.data(), outp, compute_grads != 0};
       run_forward(ctx, ab, fa, ls, l);
-      if (compute_grads) {
-        int rc = zero_grads(n, ab, B, ls);
-        if (rc) return rc;
-        BRL_CUDA(cudaMemsetAsync(ab.g0, 0, sizeof(float) * n.P, ls));
-        BRL_CUDA(cudaMemsetAsync(ab.g1, 0, sizeof(float) * n.P, ls));
-      }
+      if (compute_grads && ctx->multi_stream) BRL_CUDA(cudaStreamWaitEvent(ls, ln.ev_zero, 0));
       launch_nll_elbo(outp, y, B, (float)(c_nll / particles), ab0.acc, compute_grads ? ab.grad[n.out_buf] : nullptr, ls);
       if (compute_grads) {
         BwdArgs ba{x, B, mode, mode == BRL_MODE_WS ? ab.wsamp : mu, sigma, ab.wsamp, 0.f, &nz, sin_.data(), sout_.data(), outp, ab.g0, ab.g1};
