@@ -883,10 +883,14 @@ int64_t brl_workspace_bytes_host(const brl_ctx* ctx, int64_t B, int64_t S, int e
   if (!ctx || B <= 0 || S <= 0) return BRL_ERR_INVALID;
   if (engine != BRL_ENGINE_TC_FP16 || !tc_available(ctx->tc))
     return brl_workspace_bytes(ctx, B, std::min<int64_t>(S, 16), 0, BRL_ENGINE_SIMT_FP32) + (B * 540 + 4 * B) * (int64_t)sizeof(float) + 1024;
-  Carve c(nullptr, 0);
-  HostCarve h;
-  host_carve(ctx, c, B, S, 0, host_plan(ctx, B, S, engine, true), h);
-  return (int64_t)c.used + 4096;
+  size_t need = 0;
+  for (int native = 0; native < 2; ++native) {  // injected noise runs as ONE window chunk (larger per-chunk buffers): size for both
+    Carve c(nullptr, 0);
+    HostCarve h;
+    host_carve(ctx, c, B, S, 0, host_plan(ctx, B, S, engine, native != 0), h);
+    need = std::max(need, c.used);
+  }
+  return (int64_t)need + 4096;
 }
 
 int brl_predict_moments_host(brl_ctx* ctx, const float* x_host, int64_t B, int64_t S, int guide, const float* mu,
