@@ -78,7 +78,12 @@ struct brl_ctx {
     float prior_loc, prior_scale;
     const void *mu, *sigma, *ws;
     size_t ws_bytes;
-    bool operator==(const StepKey& o) const { return memcmp(this, &o, sizeof(StepKey)) == 0; }
+    bool operator==(const StepKey& o) const {
+      return B == o.B && dataset_size == o.dataset_size && mode == o.mode && guide == o.guide && particles == o.particles &&
+             compute_grads == o.compute_grads && backend == o.backend && has_log_sigma == o.has_log_sigma &&
+             prior_loc == o.prior_loc && prior_scale == o.prior_scale && mu == o.mu && sigma == o.sigma && ws == o.ws &&
+             ws_bytes == o.ws_bytes;
+    }
   };
   struct StepGraph { StepKey key; cudaGraphExec_t exec = nullptr; int seen = 0, launches = 0; bool bad = false; };
   std::list<StepGraph> graphs;
