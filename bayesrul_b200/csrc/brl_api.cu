@@ -1079,12 +1079,12 @@ static int elbo_body(brl_ctx* ctx, const ActBufs* const* lanes, int n_lanes, con
       f.g0 = compute_grads ? ab.g0 : nullptr; f.g1 = compute_grads ? ab.g1 : nullptr;
       f.prior_loc = prior_loc; f.prior_scale = prior_scale; f.c_kl = (float)(cc / particles);
       f.grad_mu = compute_grads ? grad_mu : nullptr; f.grad_sigma = compute_grads ? grad_sigma : nullptr;
+      f.grad_log_sigma = (compute_grads && pt == particles - 1) ? grad_log_sigma : nullptr;  // the last particle completes the sum
       f.kl_acc = ab0.acc + 2;
       launch_finalize(f, st);
     }
   }
   launch_post_scalars(scalars, ab0.acc, c_nll, cc, particles, B, st);
-  if (compute_grads && grad_log_sigma) launch_log_sigma_grad(grad_sigma, sigma, grad_log_sigma, n.P, st);
   BRL_CUDA(cudaGetLastError());
   return BRL_OK;
 }

@@ -391,8 +391,10 @@ __global__ void finalize_kernel(const Finalize p) {
     if (p.grad_mu) {
       gmu = fmaf(p.c_kl, dmu_kl, gmu);
       gsg = fmaf(p.c_kl, dsg_kl, gsg);
-      if (p.first) { p.grad_mu[i] = gmu; p.grad_sigma[i] = gsg; }
-      else { p.grad_mu[i] += gmu; p.grad_sigma[i] += gsg; }
+      if (!p.first) { gmu += p.grad_mu[i]; gsg += p.grad_sigma[i]; }
+      p.grad_mu[i] = gmu;
+      p.grad_sigma[i] = gsg;
+      if (p.grad_log_sigma) p.grad_log_sigma[i] = gsg * sg;
     }
   }
   kl = block_sum(kl);

@@ -170,6 +170,7 @@ struct Finalize {
   const float *mu, *sigma, *w, *delta, *g0, *g1;
   float prior_loc, prior_scale, c_kl;  // c_kl = c / particles
   float *grad_mu, *grad_sigma;
+  float* grad_log_sigma;  // last particle only (nullable): d/d(log sigma) = d/d(sigma) * sigma of the summed gradient
   double* kl_acc;  // += KL (unscaled) of this particle
 };
 void launch_finalize(const Finalize& p, cudaStream_t st);
