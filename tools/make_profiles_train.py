@@ -17,7 +17,7 @@ for r in rows[1:]:
         launches.append((r[ki][:60], r[gi], r[bi], float(r[vi].replace(",", "")) / 1e3))
     except ValueError:
         continue
-ends = [i for i, l in enumerate(launches) if "log_sigma_grad" in l[0]]
+ends = [i for i, l in enumerate(launches) if "post_scalars" in l[0]]  # the last kernel of a step
 step = launches[ends[-2] + 1: ends[-1] + 1]  # the last complete step
 agg = collections.OrderedDict()
 for k, g, b, t in step:
@@ -28,7 +28,7 @@ tot = sum(v[1] for v in agg.values())
 with open(os.path.join(P, f"{rnd}_launches_train_lrt.txt"), "w") as f:
     f.write(f"# {rnd} -- ncu launch list (gpu__time_duration.sum, --clock-control none) of ONE LRT ELBO step, Inception, B = 256,\n"
             "#   BRL_NO_GRAPH=1 python tools/profile_train.py lrt 2 simt   (eager launches; brl_elbo_step replays the same kernels as a CUDA graph)\n"
-            f"# per-launch times are cold-cache and serialised (sum {tot:.0f} us; the CUDA-graph replay of the step takes ~0.56 ms with its four streams): read SHARES.\n"
+            f"# per-launch times are cold-cache and serialised (sum {tot:.0f} us; the CUDA-graph replay of the step takes ~0.54 ms with its four streams): read SHARES.\n"
             f"# raw csv: gpurun_out/launches_train_{tag}.csv (scratch)\n")
     for k, (n, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
         f.write(f"{k:62s} n={n:3d} total={t:8.1f} us  avg={t / n:6.1f} us share={100 * t / tot:5.1f}%\n")
