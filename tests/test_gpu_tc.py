@@ -116,3 +116,24 @@ def test_host_entry_point_equals_device_entry_point(B, engine):
     assert_close(got2[0], ref[0], rtol=1e-6, atol_scale=1e-7, what="pageable")
     with pytest.raises(RuntimeError):
         e.predict_moments_host(x, mu, sg, S=S, engine=engine)  # a device tensor is not a host batch
+
+
+def test_tc_maximum_batch_and_limits(eng):
+    """The largest batch one call accepts (B * 30 rows < 2^22: B <= 139 810) on the fused engine: first / last windows agree
+    with the fp32 engine, one MC sample gives NaN epistemic variance like Tensor.var(0) of a single row (bayesian.py:148),
+    and a larger batch is refused with an error, not truncated."""
+    from bayesrul_b200 import Noise
+    B = 139_810
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, 30, 18, generator=g).to(DEV)
+    _, _, mu, sg = synth("inception", 4, seed=80, sigma=0.02)
+    mu, sg = mu.to(DEV), sg.to(DEV)
+    out = eng.forward(x, "det", theta=mu, engine="tc")[0]
+    idx = torch.cat([torch.arange(0, 64), torch.arange(B - 64, B)]).to(DEV)
+    ref = eng.forward(x[idx].contiguous(), "det", theta=mu, engine="simt")[0]
+    assert_close(out[idx], ref, rtol=1e-2, atol_scale=2e-3, what="max batch det")
+    pred, std, ep, al = eng.predict_moments(x, mu, sg, S=1, guide="normal", noise=Noise(seed=3), engine="tc")
+    assert torch.isnan(ep).all() and torch.isfinite(pred).all() and (al > 0).all()
+    assert eng.tc_status() == 0
+    with pytest.raises(RuntimeError):
+        eng.forward(torch.zeros(B + 1, 30, 18, device=DEV), "det", theta=mu, engine="tc")
