@@ -164,9 +164,31 @@ static void carve_train(const NetSpec& n, Carve& c, long long B, ActBufs& ab) {
 // device {seed, sample0, window0} of the step being captured (nullptr outside a capture): every Philox stream built by
 // nref() then reads the per-step part of its key from there
 static thread_local const unsigned long long* g_dyn = nullptr;
-__global__ void set_noise_key_kernel(unsigned long long* dyn, unsigned long long seed, unsigned long long sample0,
-                                     unsigned long long window0) {
-  dyn[0] = seed; dyn[1] = sample0; dyn[2] = window0;
+// Staging of a replayed step in ONE launch per side: a few (dst, src, floats) copies (+ the Philox key on the way in) instead of a
+// chain of tiny memcpy nodes on the critical path.  All pointers are 4-byte aligned device pointers.
+struct CopyJobs {
+  float* dst[6];
+  const float* src[6];
+  long long n[6], start[7];  // floats per job; offsets in the launch's index space
+  int njobs;
+  unsigned long long* dyn;  // nullable: {seed, sample0, window0} written by thread 0
+  unsigned long long seed, sample0, window0;
+};
+__global__ void copy_jobs_kernel(const CopyJobs j) {
+  if (j.dyn && blockIdx.x == 0 && threadIdx.x == 0) { j.dyn[0] = j.seed; j.dyn[1] = j.sample0; j.dyn[2] = j.window0; }
+  const long long total = j.start[j.njobs];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int k = 0;
+    while (k + 1 < j.njobs && i >= j.start[k + 1]) ++k;
+    j.dst[k][i - j.start[k]] = j.src[k][i - j.start[k]];
+  }
+}
+static void launch_copy_jobs(CopyJobs& j, cudaStream_t st) {
+  j.start[0] = 0;
+  for (int k = 0; k < j.njobs; ++k) j.start[k + 1] = j.start[k] + j.n[k];
+  const long long total = std::max<long long>(j.start[j.njobs], 1);
+  count_launch(1);
+  copy_jobs_kernel<<<(unsigned)std::min<long long>((total + 255) / 256, 148 * 8), 256, 0, st>>>(j);
 }
 
 static NoiseRef nref(const brl_noise* nz, const float* ptr, unsigned kind, unsigned site) {
@@ -1184,19 +1206,29 @@ int brl_elbo_step(brl_ctx* ctx, const float* x, const float* y, int64_t B, const
     }
   }
   if (sg && sg->exec) {
-    count_launch(1 + sg->launches);
-    set_noise_key_kernel<<<1, 1, 0, st>>>(ab.dyn, noise ? noise->seed : 0ull, noise ? (unsigned long long)noise->sample0 : 0ull,
-                                          noise ? (unsigned long long)noise->window0 : 0ull);
-    BRL_CUDA(cudaMemcpyAsync(ab.st_x, x, sizeof(float) * B * 540, cudaMemcpyDeviceToDevice, st));
-    BRL_CUDA(cudaMemcpyAsync(ab.st_y, y, sizeof(float) * B, cudaMemcpyDeviceToDevice, st));
+    count_launch(sg->launches);
+    CopyJobs in{};  // x, y and the Philox key of this step -> staging
+    in.dst[0] = ab.st_x; in.src[0] = x; in.n[0] = B * 540;
+    in.dst[1] = ab.st_y; in.src[1] = y; in.n[1] = B;
+    in.njobs = 2;
+    in.dyn = ab.dyn;
+    in.seed = noise ? noise->seed : 0ull;
+    in.sample0 = noise ? (unsigned long long)noise->sample0 : 0ull;
+    in.window0 = noise ? (unsigned long long)noise->window0 : 0ull;
+    launch_copy_jobs(in, st);
     BRL_CUDA(cudaGraphLaunch(sg->exec, st));
-    BRL_CUDA(cudaMemcpyAsync(scalars, ab.st_scal, 4 * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    BRL_CUDA(cudaMemcpyAsync(out, ab.st_out, sizeof(float) * particles * B * 2, cudaMemcpyDeviceToDevice, st));
+    CopyJobs o{};  // staging -> the caller's result tensors (the four doubles travel as eight floats)
+    o.dst[0] = reinterpret_cast<float*>(scalars); o.src[0] = reinterpret_cast<const float*>(ab.st_scal); o.n[0] = 8;
+    o.dst[1] = out; o.src[1] = ab.st_out; o.n[1] = (long long)particles * B * 2;
+    o.njobs = 2;
     if (compute_grads) {
-      BRL_CUDA(cudaMemcpyAsync(grad_mu, ab.st_gmu, sizeof(float) * n.P, cudaMemcpyDeviceToDevice, st));
-      BRL_CUDA(cudaMemcpyAsync(grad_sigma, ab.st_gsig, sizeof(float) * n.P, cudaMemcpyDeviceToDevice, st));
-      if (grad_log_sigma) BRL_CUDA(cudaMemcpyAsync(grad_log_sigma, ab.st_glog, sizeof(float) * n.P, cudaMemcpyDeviceToDevice, st));
+      o.dst[2] = grad_mu; o.src[2] = ab.st_gmu; o.n[2] = n.P;
+      o.dst[3] = grad_sigma; o.src[3] = ab.st_gsig; o.n[3] = n.P;
+      o.njobs = 4;
+      if (grad_log_sigma) { o.dst[4] = grad_log_sigma; o.src[4] = ab.st_glog; o.n[4] = n.P; o.njobs = 5; }
     }
+    launch_copy_jobs(o, st);
+    BRL_CUDA(cudaGetLastError());
     return BRL_OK;
   }
   return elbo_body(ctx, lanes, n_lanes, x, y, B, mu, sigma, mode, guide, particles, prior_loc, prior_scale, dataset_size, noise, compute_grads,
