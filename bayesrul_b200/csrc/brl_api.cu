@@ -1235,19 +1235,10 @@ int brl_elbo_step(brl_ctx* ctx, const float* x, const float* y, int64_t B, const
                    scalars, grad_mu, grad_sigma, grad_log_sigma, out, st);
 }
 
-int brl_hnn_step(brl_ctx* ctx, const float* x, const float* y, int64_t B, const float* theta, float p_dropout,
-                 const brl_noise* noise, int compute_grads, double* scalars, float* grad_theta, float* out,
-                 void* workspace, size_t workspace_bytes, void* stream) {
-  BRL_REQUIRE(ctx && x && y && theta && scalars && out && workspace, "brl_hnn_step: NULL argument");
-  BRL_REQUIRE(B > 0 && p_dropout >= 0.f && p_dropout < 1.f, "brl_hnn_step: bad B or p_dropout");
-  BRL_REQUIRE(!compute_grads || grad_theta, "brl_hnn_step: grad_theta is NULL");
-  cudaStream_t st = (cudaStream_t)stream;
+// the launches of one heteroscedastic-NN step (every pointer final); captured as is by the graph path of brl_hnn_step
+static int hnn_body(brl_ctx* ctx, const ActBufs& ab, const float* x, const float* y, int64_t B, const float* theta, float p_dropout,
+                    const brl_noise* noise, int compute_grads, double* scalars, float* grad_theta, float* out, cudaStream_t st) {
   const NetSpec& n = *ctx->net;
-  Carve c(workspace, workspace_bytes);
-  ActBufs ab;
-  carve_forward(n, c, B, 1, ab);
-  carve_train(n, c, B, ab);
-  if (!c.ok) return fail(BRL_ERR_WORKSPACE, "brl_hnn_step: workspace too small");
   brl_noise nz = noise_at_sample(n, noise, 0, B);
   FwdArgs fa{x, B, 1, BRL_MODE_DET, theta, nullptr, nullptr, p_dropout, &nz, nullptr, nullptr, out, false};
   run_forward(ctx, ab, fa, st);
@@ -1264,6 +1255,92 @@ int brl_hnn_step(brl_ctx* ctx, const float* x, const float* y, int64_t B, const 
   }
   BRL_CUDA(cudaGetLastError());
   return BRL_OK;
+}
+
+int brl_hnn_step(brl_ctx* ctx, const float* x, const float* y, int64_t B, const float* theta, float p_dropout,
+                 const brl_noise* noise, int compute_grads, double* scalars, float* grad_theta, float* out,
+                 void* workspace, size_t workspace_bytes, void* stream) {
+  BRL_REQUIRE(ctx && x && y && theta && scalars && out && workspace, "brl_hnn_step: NULL argument");
+  BRL_REQUIRE(B > 0 && p_dropout >= 0.f && p_dropout < 1.f, "brl_hnn_step: bad B or p_dropout");
+  BRL_REQUIRE(!compute_grads || grad_theta, "brl_hnn_step: grad_theta is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  const NetSpec& n = *ctx->net;
+  Carve c(workspace, workspace_bytes);
+  ActBufs ab;
+  carve_forward(n, c, B, 1, ab);
+  carve_train(n, c, B, ab);
+  if (!c.ok) return fail(BRL_ERR_WORKSPACE, "brl_hnn_step: workspace too small");
+  // ---- graph replay, same scheme as brl_elbo_step (native dropout masks or no dropout): eager, capture, replay
+  brl_ctx::StepGraph* sg = nullptr;
+  bool caller_captures = false;
+  {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); caller_captures = true; }
+    else caller_captures = cs != cudaStreamCaptureStatusNone;
+  }
+  if (ctx->graph_enabled && !caller_captures && noise_is_native(noise)) {
+    brl_ctx::StepKey key;
+    memset(&key, 0, sizeof(key));
+    key.B = B; key.mode = -1 /* HNN */; key.particles = 1; key.compute_grads = compute_grads; key.backend = ctx->gemm_backend;
+    key.prior_loc = p_dropout; key.mu = theta; key.ws = workspace; key.ws_bytes = workspace_bytes;
+    for (auto it = ctx->graphs.begin(); it != ctx->graphs.end(); ++it)
+      if (it->key == key) { ctx->graphs.splice(ctx->graphs.begin(), ctx->graphs, it); sg = &ctx->graphs.front(); break; }
+    if (!sg) {
+      if (ctx->graphs.size() >= 16) {
+        if (ctx->graphs.back().exec) cudaGraphExecDestroy(ctx->graphs.back().exec);
+        ctx->graphs.pop_back();
+      }
+      ctx->graphs.emplace_front();
+      ctx->graphs.front().key = key;
+      sg = &ctx->graphs.front();
+    }
+    ++sg->seen;
+    if (sg->seen >= 2 && !sg->exec && !sg->bad) {
+      cudaGraph_t graph = nullptr;
+      if (cudaStreamBeginCapture(ctx->cap, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        g_dyn = ab.dyn;
+        const long long l0 = launch_count();
+        brl_noise zero;
+        memset(&zero, 0, sizeof(zero));
+        const int rc = hnn_body(ctx, ab, ab.st_x, ab.st_y, B, theta, p_dropout, &zero, compute_grads, ab.st_scal,
+                                compute_grads ? ab.st_gmu : nullptr, ab.st_out, ctx->cap);
+        g_dyn = nullptr;
+        sg->launches = (int)(launch_count() - l0);
+        count_launch(-sg->launches);  // captured, not executed
+        const cudaError_t e = cudaStreamEndCapture(ctx->cap, &graph);
+        if (rc != BRL_OK || e != cudaSuccess || !graph || cudaGraphInstantiate(&sg->exec, graph, 0) != cudaSuccess) {
+          sg->exec = nullptr;
+          sg->bad = true;
+        }
+        if (graph) cudaGraphDestroy(graph);
+      } else {
+        sg->bad = true;
+      }
+      cudaGetLastError();
+    }
+  }
+  if (sg && sg->exec) {
+    count_launch(sg->launches);
+    CopyJobs in{};
+    in.dst[0] = ab.st_x; in.src[0] = x; in.n[0] = B * 540;
+    in.dst[1] = ab.st_y; in.src[1] = y; in.n[1] = B;
+    in.njobs = 2;
+    in.dyn = ab.dyn;
+    in.seed = noise ? noise->seed : 0ull;
+    in.sample0 = noise ? (unsigned long long)noise->sample0 : 0ull;
+    in.window0 = noise ? (unsigned long long)noise->window0 : 0ull;
+    launch_copy_jobs(in, st);
+    BRL_CUDA(cudaGraphLaunch(sg->exec, st));
+    CopyJobs o{};
+    o.dst[0] = reinterpret_cast<float*>(scalars); o.src[0] = reinterpret_cast<const float*>(ab.st_scal); o.n[0] = 4;
+    o.dst[1] = out; o.src[1] = ab.st_out; o.n[1] = B * 2;
+    o.njobs = 2;
+    if (compute_grads) { o.dst[2] = grad_theta; o.src[2] = ab.st_gmu; o.n[2] = n.P; o.njobs = 3; }
+    launch_copy_jobs(o, st);
+    BRL_CUDA(cudaGetLastError());
+    return BRL_OK;
+  }
+  return hnn_body(ctx, ab, x, y, B, theta, p_dropout, noise, compute_grads, scalars, grad_theta, out, st);
 }
 
 int brl_mixture_moments(const float* mu_m, const float* sigma_m, int64_t M, int64_t nn, float* mu, float* sigma, void* stream) {

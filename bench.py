@@ -375,6 +375,31 @@ def main():
                 train[mode]["cpu_windows_per_s"] = v
                 train[mode]["cpu_ms_per_step"] = 1e3 * dt
 
+        # the frequentist twin (configs[1] / [4] train their HNNs with it): HNN.step (frequentist.py:39-48: forward with dropout,
+        # gaussian_nll_loss, backward) + Adam on the flat parameter buffer (brl_clipped_adam with the clip disabled)
+        th = mu.clone()
+        hm, hv = torch.zeros_like(th), torch.zeros_like(th)
+        hs = {"i": 0}
+
+        def hnn_train_step(i=0):
+            hs["i"] += 1
+            r = eng.hnn_step(xt, yt, th, p_dropout=0.241437, noise=Noise(seed=7000 + hs["i"], window0=rank * B_TRAIN))
+            g = r["grad"]
+            if dist is not None:
+                dist.all_reduce(g)
+                g /= world
+            eng.clipped_adam(th, g, hm, hv, hs["i"], 1e-3, (0.9, 0.999), 1e-8, 1e30)
+
+        th_t = max_over_ranks(timed_steps(hnn_train_step, NT, 6, flush_buf, dist), dist, device)
+        eng.set_step_graph(False)
+        th_e = max_over_ranks(timed_steps(hnn_train_step, NT, 3, flush_buf, dist), dist, device)
+        eng.set_step_graph(True)
+        train["hnn_mcd"] = {"windows_per_s": world * B_TRAIN * NT / th_t, "ms_per_step": 1e3 * th_t / NT, "batch_per_gpu": B_TRAIN,
+                            "p_dropout": 0.241437, "ms_per_step_eager": 1e3 * th_e / NT, "gemm_backend": "fp32 FFMA",
+                            "ms_per_step_by_backend": {"simt_fp32": 1e3 * th_t / NT},
+                            "includes": "HNN.step forward (fused dropout masks) + gaussian_nll_loss + backward (CUDA-graph replay) + Adam"
+                                        + (f" + NCCL all-reduce over {world} ranks" if dist is not None else "")}
+
     # ---- MC-dropout predictive (configs[1]: ncmapss_mcd, p = 0.241437, 100 masks), same engine
     mcd = {}
     if not args.no_train:

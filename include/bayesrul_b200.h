@@ -188,7 +188,9 @@ int brl_elbo_step(brl_ctx* ctx, const float* x, const float* y, int64_t B, const
 int brl_set_step_graph(brl_ctx* ctx, int enable);
 
 /* ---- heteroscedastic NN step (replaces HNN.step + backward: frequentist.py:39-48) ------
- * loss = F.gaussian_nll_loss(loc, y, scale^2); scalars (device double[2]) = {loss, mse}. */
+ * loss = F.gaussian_nll_loss(loc, y, scale^2); scalars (device double[2]) = {loss, mse}.
+ * Replayed as a CUDA graph under the same conditions as brl_elbo_step (native dropout masks or none; key = sizes,
+ * p_dropout, theta / workspace pointers). */
 int brl_hnn_step(brl_ctx* ctx, const float* x, const float* y, int64_t B, const float* theta,
                  float p_dropout, const brl_noise* noise, int compute_grads, double* scalars,
                  float* grad_theta, float* out /*[B,2]*/, void* workspace, size_t workspace_bytes,

@@ -68,3 +68,32 @@ def test_graph_replay_loss_only_and_injected_noise_stays_eager():
     w = mu + sg * eps[0]
     out = e.forward(x, "det", theta=w.contiguous())
     assert_close(r["out"][0], out[0], rtol=1e-5, what="injected weight draw")
+
+
+@pytest.mark.parametrize("net,p", [("inception", 0.241437), ("conv", 0.0), ("linear", 0.3)])
+def test_hnn_graph_replay_matches_eager(net, p):
+    """brl_hnn_step (frequentist.py:39-48) replays a captured graph too: same losses, outputs and gradients as the eager launches
+    for changing batches and (MC-dropout) mask keys."""
+    from bayesrul_b200 import Engine, Noise
+    e = Engine(net, DEV)
+    B = 80
+    x0, y0, th, _ = (t.to(DEV) for t in synth(net, B, seed=6))
+    x1, y1, _, _ = (t.to(DEV) for t in synth(net, B, seed=7))
+    plan = [(x0, y0, 1), (x0, y0, 2), (x1, y1, 3), (x0, y0, 1)]
+
+    def run():
+        return [{k: (v.clone() if v is not None else None) for k, v in
+                 e.hnn_step(x, y, th, p_dropout=p, noise=Noise(seed=s, window0=5 * s)).items()} for x, y, s in plan]
+
+    e.set_step_graph(False)
+    eager = run()
+    e.set_step_graph(True)
+    replay = run()
+    torch.cuda.synchronize()
+    for i, (a, b) in enumerate(zip(eager, replay)):
+        assert_close(b["out"], a["out"], rtol=1e-5, what=f"step {i} out")
+        assert_close(b["scalars"], a["scalars"], rtol=1e-5, what=f"step {i} scalars")
+        assert_close(b["grad"], a["grad"], rtol=1e-3, atol_scale=1e-3, what=f"step {i} grad")
+    if p > 0:
+        assert not torch.allclose(replay[1]["out"], replay[0]["out"])  # another mask key, another mask
+    assert_close(replay[3]["out"], replay[0]["out"], rtol=1e-6, what="same key replayed")

@@ -12,7 +12,7 @@ for k in r.get("other_kernels", []):
     print(f"  {k['kernel']}: {k['achieved']:.0f} / {k['peak']:.0f} {k['unit']} = {k['frac']:.3f}, {k['ms_per_launch']:.3f} ms/launch")
 for m, v in d.get("train", {}).items():
     print(f"  train {m}: {v['ms_per_step']:.3f} ms/step = {v['windows_per_s'] / 1e3:.0f} k windows/s [{v['gemm_backend']}] {v['ms_per_step_by_backend']} "
-          f"eager {v.get('ms_per_step_eager_simt')} cpu {v.get('cpu_windows_per_s')}")
+          f"eager {v.get('ms_per_step_eager_simt', v.get('ms_per_step_eager'))} cpu {v.get('cpu_windows_per_s')}")
 if d.get("mcd_predict"):
     print(f"  mcd {d['mcd_predict']['window_samples_per_s'] / 1e6:.1f} M")
 if d.get("radial_sweep"):
