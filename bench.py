@@ -175,6 +175,14 @@ def cpu_train_rate(mode, particles, q, prior_scale, threads, steps=3):
     return B_TRAIN / dt, dt
 
 
+def workload_config(engine, world):
+    """`config` of both arms: the headline workload (BASELINE.json configs[0], predictive half)."""
+    return {"workload": f"ncmapss_lrt Inception BNN predict (configs[0]), B={B_PRED} windows x S={S_PRED} weight samples "
+                        "+ predictive moments per step per GPU", "net": NET, "engine": engine,
+            "windows_per_step_per_gpu": B_PRED, "mc_samples": S_PRED, "q_scale": CFG["q_scale"],
+            "l2": "256 MiB flush between timed steps + 8 rotating input batches", "parallelism": f"windows sharded x{world}"}
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path = the plain-PyTorch restatement
     (oracle port; pyro/tyxe are not installable) on all host threads; bounded sample per step."""
@@ -195,8 +203,8 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"ncmapss_lrt Inception BNN predict, B={B_PRED} windows x S={S_PRED} weight samples + moments",
-                   "net": NET, "windows_per_step": nb, "samples_per_step": ns},
+        "config": dict(workload_config("cpu-port (plain PyTorch restatement)", 1), l2="n/a (CPU)", parallelism="rank 0 only, all host threads",
+                       sample=f"each step = {nb} windows x {ns} of the {S_PRED} MC samples"),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"each step = {nb} windows x {ns} of the {S_PRED} MC samples (plain-PyTorch restatement, "
                                    f"torch {torch.__version__} CPU, {threads} threads)"},
@@ -458,10 +466,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16 operands / f32 accumulate" if engine == "tc" else "f32", "data": "synthetic",
-        "config": {"workload": f"ncmapss_lrt Inception BNN predict (configs[0]), B={B_PRED} windows x S={S_PRED} weight samples "
-                               "+ predictive moments per step per GPU", "net": NET, "engine": engine,
-                   "windows_per_step_per_gpu": B_PRED, "mc_samples": S_PRED, "q_scale": CFG["q_scale"],
-                   "l2": "256 MiB flush between timed steps + 8 rotating input batches", "parallelism": f"windows sharded x{world}"},
+        "config": workload_config(engine, world),
         "clocks": clocks, "gpu_launches": int(launches_timed),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "bayesrul_b200.compat.BNN.predict_step -> brl_predict_moments_host (pinned host batch -> host results)"},
