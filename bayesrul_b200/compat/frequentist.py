@@ -12,6 +12,28 @@ from .metrics import rms_calibration_error, sharpness
 from .nets import enable_dropout, weights_init
 
 
+class _FusedStepLoss(torch.autograd.Function):
+    """Autograd node of the fused step.  brl_hnn_step has already computed d loss / d theta (one flat vector); this node
+    hands its per-site slices to autograd, so `loss.backward()` -- Lightning's automatic optimisation runs training_step,
+    `optimizer.zero_grad()`, `loss.backward()`, `optimizer.step()` in that order -- fills `param.grad` like the reference's
+    autograd graph does (frequentist.py:39-48)."""
+
+    @staticmethod
+    def forward(ctx, loss, grad_flat, sites, *params):
+        ctx.grad_flat, ctx.sites = grad_flat, sites
+        return loss.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        grads = []
+        for off, shape in ctx.sites:
+            n = 1
+            for d in shape:
+                n *= d
+            grads.append(g * ctx.grad_flat[off: off + n].view(shape))
+        return (None, None, None, *grads)
+
+
 class HNN(_Base):
     def __init__(self, net, optimizer, mc_samples: int, p_dropout, device=None, engine: str = "simt"):
         super().__init__()
@@ -45,10 +67,9 @@ class HNN(_Base):
         train = phase == "train"
         p = float(self.net.dropout) if (train or getattr(self.net, "mc_dropout", False)) else 0.0
         res = self.net.engine().hnn_step(x.contiguous(), y.contiguous(), self.net.flat(), p, self._noise(), compute_grads=train)
-        if train:  # hand the flat gradient to the per-site parameters (views of the same buffer)
-            for prm, (off, shape) in zip(self.net._params, self.net._sites):
-                prm.grad = res["grad"][off: off + prm.numel()].view(shape)
         loss = res["scalars"][0].float()
+        if train:  # the returned loss carries a grad_fn whose backward writes the fused step's gradient into param.grad
+            loss = _FusedStepLoss.apply(loss, res["grad"], tuple(self.net._sites), *self.net._params)
         self.log(f"nll/{phase}", loss, on_step=False, on_epoch=True)
         return loss, res["out"][:, 0], res["out"][:, 1]
 

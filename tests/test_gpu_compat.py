@@ -86,10 +86,13 @@ def test_hnn_train_and_mc_dropout_predict():
     opt = m.configure_optimizers()
     x, y = _batch(100, 5)
     losses = []
-    for i in range(8):
-        opt.zero_grad()
+    for i in range(8):  # Lightning's automatic-optimisation closure order: training_step, zero_grad, backward, step
         m.net.train()
         loss = m.training_step((x, y), i)
+        assert loss.requires_grad and loss.grad_fn is not None
+        opt.zero_grad()
+        loss.backward()
+        assert all(p.grad is not None and p.grad.shape == p.shape for p in m.net.parameters())
         opt.step()
         losses.append(float(loss))
     assert losses[-1] < losses[0]
