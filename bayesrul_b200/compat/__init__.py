@@ -4,8 +4,8 @@
     bayesrul.models.frequentist.HNN         -> compat.HNN
     bayesrul.models.nets.{Inception,Conv,Linear}
     bayesrul.models.guides.radial.AutoRadial
-    bayesrul.models.deepens.deep_ensemble / deep_ensemble_gen
-    bayesrul.utils.miscellaneous.ResultSaver + the parquet writing loop of tasks/predict.py -> compat.predictions
+    bayesrul.models.deepens.deep_ensemble (the mixture-moment formula; the generator stays in the reference)
+    the parquet writing loop of tasks/predict.py -> compat.predictions
     tyxe.* / pyro.* names used by bayesian.py  -> compat.tyxe_shim / compat.pyro_shim
 """
 import sys
@@ -13,8 +13,8 @@ import types
 
 from . import pyro_shim, tyxe_shim
 from .bayesian import BNN, param_store_to, remove_dict_entry_startswith
-from .deepens import deep_ensemble, deep_ensemble_gen, mixture_moments
-from .predictions import ResultSaver, predictions_to_frame, write_predictions
+from .deepens import deep_ensemble, mixture_moments
+from .predictions import predictions_to_frame, write_predictions
 from .frequentist import HNN
 from .metrics import rms_calibration_error, sharpness
 from .nets import Conv, Inception, Linear, enable_dropout, weights_init
@@ -48,6 +48,6 @@ def install_shims(force: bool = False) -> None:
         sys.modules.update({"pyro.infer": infer, "pyro.optim": optim, "pyro.distributions": dist})
 
 
-__all__ = ["BNN", "HNN", "Inception", "Conv", "Linear", "AutoRadial", "Radial", "deep_ensemble", "deep_ensemble_gen", "mixture_moments", "ResultSaver", "predictions_to_frame", "write_predictions",
+__all__ = ["BNN", "HNN", "Inception", "Conv", "Linear", "AutoRadial", "Radial", "deep_ensemble", "mixture_moments", "predictions_to_frame", "write_predictions",
            "weights_init", "enable_dropout", "rms_calibration_error", "sharpness", "install_shims", "pyro_shim", "tyxe_shim",
            "param_store_to", "remove_dict_entry_startswith"]

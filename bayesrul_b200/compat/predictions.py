@@ -1,44 +1,16 @@
-"""On-disk side of the predict task: the parquet format written by `tasks/predict.py:52-64` through
-`utils/miscellaneous.py:12-41` (`ResultSaver`), i.e. one row per window with the columns `labels, ep_vars, al_vars,
-preds, stds` produced by `BNN.predict_step` / `HNN.predict_step`, and the reader `results/predictions.py:31-40` expects.
-Host-side glue only: the numbers come from brl_predict_moments(_host)."""
+"""On-disk side of the predict task: the parquet format written by `tasks/predict.py:52-64`, i.e. one row per
+window with the columns `labels, ep_vars, al_vars, preds, stds` produced by `BNN.predict_step` / `HNN.predict_step`, which is
+what the reader `results/predictions.py:31-40` expects.  Host-side glue only: the numbers come from
+brl_predict_moments(_host); the reference's own `ResultSaver` (file IO, out of scope) keeps working on these frames."""
 from __future__ import annotations
 
 from pathlib import Path
-from typing import Dict, Iterable, List, Union
+from typing import Dict, Iterable, Union
 
 import numpy as np
 import pandas as pd
 
 PREDICTION_COLUMNS = ["labels", "ep_vars", "al_vars", "preds", "stds"]
-
-
-class ResultSaver:
-    """utils/miscellaneous.py:12-41 -- same constructor, `save` / `load` / `append`, same assertions."""
-
-    def __init__(self, path: Union[Path, str], filename: str) -> None:
-        self.path = Path(path)
-        self.path.mkdir(exist_ok=True)
-        self.file_path = Path(self.path, filename)
-
-    def save(self, df: Union[pd.DataFrame, dict]) -> None:
-        if isinstance(df, dict):
-            df = pd.DataFrame(df)
-        assert isinstance(df, pd.DataFrame), f"{type(df)} is not a dataframe"
-        df.to_parquet(self.file_path)
-
-    def load(self) -> pd.DataFrame:
-        return pd.read_parquet(self.file_path)
-
-    def append(self, series: Union[List[pd.Series], Dict[str, np.ndarray]]) -> None:
-        if isinstance(series, list):
-            series = pd.concat(series, axis=1)
-        if isinstance(series, dict):
-            series = pd.DataFrame(series)
-        df = pd.concat([self.load(), series], axis=1)
-        assert isinstance(df, pd.DataFrame), f"{type(df)} is not a dataframe"
-        assert int(np.asarray(df.isna().sum()).sum()) == 0, "NaNs introduced in results dataframe"
-        self.save(df)
 
 
 def predictions_to_frame(predictions: Iterable[Dict[str, np.ndarray]]) -> pd.DataFrame:
@@ -58,5 +30,7 @@ def write_predictions(model, batches: Iterable, out_dir: Union[Path, str], filen
     if hasattr(model, "on_predict_start"):
         model.on_predict_start()
     frame = predictions_to_frame(model.predict_step(batch, i) for i, batch in enumerate(batches))
-    ResultSaver(out_dir, filename).save(frame)
+    out_dir = Path(out_dir)
+    out_dir.mkdir(parents=True, exist_ok=True)
+    frame.to_parquet(out_dir / filename)
     return frame

@@ -128,11 +128,23 @@ class ClippedAdam:
     def __init__(self, optim_args: dict):
         self.args = dict(lr=1e-3, betas=(0.9, 0.999), eps=1e-8, clip_norm=10.0, lrd=1.0, weight_decay=0.0)
         self.args.update(optim_args)
-        self.state: Dict[int, dict] = {}
+        self.state: Dict[str, dict] = {}
 
-    def step_flat(self, engine, params, grads):
-        for p, g in zip(params, grads):
-            st = self.state.setdefault(id(p), dict(step=0, m=torch.zeros_like(p), v=torch.zeros_like(p)))
+    # Optimiser state is keyed by a STABLE name ("loc" / "log_scale", or the position in the list handed to step_flat) and
+    # remembers which tensor it belongs to: define_bnn() builds a new guide in on_fit_start / on_test_start / on_predict_start,
+    # and an `id()` of a freed tensor can be handed out again -- a new parameter must start from step 0 with zero moments.
+    def _slot(self, name, p):
+        self._slot_restored(name, p)
+        st = self.state.get(name)
+        if st is None or st["param"] is not p:
+            st = dict(step=0, m=torch.zeros_like(p), v=torch.zeros_like(p), param=p)
+            self.state[name] = st
+        return st
+
+    def step_flat(self, engine, params, grads, names=None):
+        names = names if names is not None else [f"param{i}" for i in range(len(params))]
+        for name, p, g in zip(names, params, grads):
+            st = self._slot(name, p)
             st["step"] += 1
             a = self.args
             engine.clipped_adam(p, g, st["m"], st["v"], st["step"], a["lr"], tuple(a["betas"]), a["eps"], a["clip_norm"],
@@ -141,8 +153,7 @@ class ClippedAdam:
     def step_vi(self, engine, guide, g_loc, g_log_scale):
         """The step over a mean-field guide's two flat buffers in ONE launch (brl_clipped_adam_vi), scale refresh included;
         same per-parameter state as step_flat."""
-        sts = [self.state.setdefault(id(p), dict(step=0, m=torch.zeros_like(p), v=torch.zeros_like(p)))
-               for p in (guide.loc, guide.log_scale)]
+        sts = [self._slot(name, p) for name, p in (("loc", guide.loc), ("log_scale", guide.log_scale))]
         for st in sts:
             st["step"] += 1
         a = self.args
@@ -151,7 +162,20 @@ class ClippedAdam:
                                a["clip_norm"], a["lrd"], a["weight_decay"])
 
     def get_state(self):
+        """{name: {step, m, v}} -- restorable with set_state (names, not object ids)."""
         return {k: dict(step=v["step"], m=v["m"].clone(), v=v["v"].clone()) for k, v in self.state.items()}
+
+    def set_state(self, state, params=None):
+        """Restore get_state(); `params` = {name: tensor} binds the slots to live parameters (else bound on first use)."""
+        self.state = {}
+        for k, v in state.items():
+            self.state[k] = dict(step=int(v["step"]), m=v["m"].clone(), v=v["v"].clone(), param=(params or {}).get(k))
+
+    def _slot_restored(self, name, p):  # a restored slot without a bound parameter adopts the first tensor of matching shape
+        st = self.state.get(name)
+        if st is not None and st["param"] is None and st["m"].shape == p.shape:
+            st["param"] = p
+            st["m"], st["v"] = st["m"].to(p.device), st["v"].to(p.device)
 
 
 def _unwrap(fn):
@@ -199,7 +223,7 @@ class SVI:
             if hasattr(self.optim, "step_vi") and guide.loc.is_contiguous() and guide.log_scale.is_contiguous():
                 self.optim.step_vi(self.bnn.engine, guide, g_mu, g_ls)  # one launch: both buffers + scale = exp(log scale)
             else:
-                self.optim.step_flat(self.bnn.engine, [guide.loc, guide.log_scale], [g_mu, g_ls])
+                self.optim.step_flat(self.bnn.engine, [guide.loc, guide.log_scale], [g_mu, g_ls], names=["loc", "log_scale"])
                 guide.refresh()
         return float(loss.item())  # device boundary #2 of the reference (.item() sync every step)
 

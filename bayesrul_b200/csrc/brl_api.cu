@@ -32,6 +32,21 @@ static int fail(int code, const std::string& msg) {
       return fail(BRL_ERR_CUDA, std::string("bayesrul_b200: CUDA error: ") + cudaGetErrorString(e__) + " at " #expr); \
   } while (0)
 
+// Every entry point that takes a context runs on the context's device whatever the caller's current device is, and
+// leaves the caller's current device as it found it (two Engines on two GPUs in one process; torch.cuda.set_device later on).
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 // per-conv-op device tables
 struct OpTables {
   int *koff = nullptr, *kdhw = nullptr, *kci = nullptr;          // forward / dW gather
@@ -540,7 +555,7 @@ int brl_create(brl_ctx** out, int net, int device) {
   if (prop.major != 10)
     return fail(BRL_ERR_UNSUPPORTED, "bayesrul_b200: built for sm_100a (B200) only; device is sm_" +
                                          std::to_string(prop.major) + std::to_string(prop.minor) + " -- no fallback by design");
-  BRL_CUDA(cudaSetDevice(device));
+  DeviceGuard dg(device);  // restored on return: creating a context does not change the caller's current device
   brl_ctx* c = new brl_ctx();
   c->net_id = net; c->device = device; c->net = ns;
   // build gather tables
@@ -620,6 +635,7 @@ int brl_create(brl_ctx** out, int net, int device) {
 
 int brl_destroy(brl_ctx* ctx) {
   if (!ctx) return BRL_OK;
+  DeviceGuard dg(ctx->device);
   cudaFree(ctx->table_pool);
   cudaFree(ctx->site_off_dev);
   tc_destroy(ctx->tc);
@@ -650,6 +666,7 @@ int brl_destroy(brl_ctx* ctx) {
 
 int brl_tc_status(const brl_ctx* ctx) {
   if (!ctx) return -1;
+  DeviceGuard dg(ctx->device);
   const int g = tc_gemm_status();  // TF32 per-layer kernels
   if (g != 0) return g;
   return tc_status(ctx->tc);
@@ -668,6 +685,7 @@ int brl_tc_timing(brl_ctx* ctx, int enable) {
 }
 int brl_tc_timing_read(brl_ctx* ctx, double* kernel_ms, int64_t* launches) {
   BRL_REQUIRE(ctx && kernel_ms && launches && tc_available(ctx->tc), "brl_tc_timing_read: bad argument");
+  DeviceGuard dg(ctx->device);
   long long n[2] = {0, 0};
   tc_timing_read(ctx->tc, kernel_ms, n);
   launches[0] = n[0];
@@ -712,6 +730,7 @@ int64_t brl_workspace_bytes(const brl_ctx* ctx, int64_t B, int64_t S, int train,
 int brl_sample_weights(brl_ctx* ctx, const float* mu, const float* sigma, int guide, int64_t S, const brl_noise* noise,
                        float* w_out, float* delta_out, void* workspace, size_t workspace_bytes, void* stream) {
   BRL_REQUIRE(ctx && mu && sigma && w_out && S > 0, "brl_sample_weights: NULL argument or S <= 0");
+  DeviceGuard dg(ctx->device);
   const NetSpec& n = *ctx->net;
   cudaStream_t st = (cudaStream_t)stream;
   NoiseRef eps = nref(noise, noise ? noise->weight_eps : nullptr, KIND_WEIGHT_EPS, 0);
@@ -760,6 +779,7 @@ int brl_forward(brl_ctx* ctx, const float* x, int64_t B, int64_t S, int mode, co
                 const float* wsamp, float p_dropout, const brl_noise* noise, float* out, int engine, void* workspace,
                 size_t workspace_bytes, void* stream) {
   BRL_REQUIRE(ctx && x && out && workspace, "brl_forward: NULL argument");
+  DeviceGuard dg(ctx->device);
   BRL_REQUIRE(B > 0 && S > 0 && B * 30 < (1ll << 31) / 512, "brl_forward: bad B or S");
   BRL_REQUIRE(mode >= BRL_MODE_DET && mode <= BRL_MODE_FLIPOUT, "brl_forward: unknown mode");
   BRL_REQUIRE(mode == BRL_MODE_WS || theta, "brl_forward: theta is NULL");
@@ -796,6 +816,7 @@ int brl_predict_moments(brl_ctx* ctx, const float* x, int64_t B, int64_t S, int 
                         const float* sigma, float p_dropout, const brl_noise* noise, float* pred, float* std,
                         float* ep_var, float* al_var, int engine, void* workspace, size_t workspace_bytes, void* stream) {
   BRL_REQUIRE(ctx && x && mu && pred && std && workspace, "brl_predict_moments: NULL argument");
+  DeviceGuard dg(ctx->device);
   BRL_REQUIRE(B > 0 && S > 0 && B * 30 < (1ll << 31) / 512, "brl_predict_moments: bad B or S");
   BRL_REQUIRE(guide < 0 || sigma, "brl_predict_moments: sigma is NULL");
   BRL_REQUIRE(guide <= BRL_GUIDE_RADIAL, "Guide unknown. Choose from 'normal', 'radial'.");
@@ -924,6 +945,7 @@ int brl_predict_moments_host(brl_ctx* ctx, const float* x_host, int64_t B, int64
                              const float* sigma, float p_dropout, const brl_noise* noise, float* out_host, int engine,
                              void* workspace, size_t workspace_bytes, void* stream) {
   BRL_REQUIRE(ctx && x_host && mu && out_host && workspace, "brl_predict_moments_host: NULL argument");
+  DeviceGuard dg(ctx->device);
   BRL_REQUIRE(B > 0 && S > 0 && B * 30 < (1ll << 31) / 512, "brl_predict_moments_host: bad B or S");
   BRL_REQUIRE(guide < 0 || sigma, "brl_predict_moments_host: sigma is NULL");
   BRL_REQUIRE(guide <= BRL_GUIDE_RADIAL, "Guide unknown. Choose from 'normal', 'radial'.");
@@ -1130,6 +1152,7 @@ int brl_elbo_step(brl_ctx* ctx, const float* x, const float* y, int64_t B, const
                   const brl_noise* noise, int compute_grads, double* scalars, float* grad_mu, float* grad_sigma,
                   float* grad_log_sigma, float* out, void* workspace, size_t workspace_bytes, void* stream) {
   BRL_REQUIRE(ctx && x && y && mu && sigma && scalars && out && workspace, "brl_elbo_step: NULL argument");
+  DeviceGuard dg(ctx->device);
   BRL_REQUIRE(B > 0 && particles > 0 && dataset_size > 0 && prior_scale > 0.f, "brl_elbo_step: bad sizes");
   BRL_REQUIRE(guide == BRL_GUIDE_NORMAL || guide == BRL_GUIDE_RADIAL, "Guide unknown. Choose from 'normal', 'radial'.");
   BRL_REQUIRE(mode == BRL_MODE_WS || mode == BRL_MODE_LRT || mode == BRL_MODE_FLIPOUT, "brl_elbo_step: mode must be WS, LRT or FLIPOUT");
@@ -1261,6 +1284,7 @@ int brl_hnn_step(brl_ctx* ctx, const float* x, const float* y, int64_t B, const 
                  const brl_noise* noise, int compute_grads, double* scalars, float* grad_theta, float* out,
                  void* workspace, size_t workspace_bytes, void* stream) {
   BRL_REQUIRE(ctx && x && y && theta && scalars && out && workspace, "brl_hnn_step: NULL argument");
+  DeviceGuard dg(ctx->device);
   BRL_REQUIRE(B > 0 && p_dropout >= 0.f && p_dropout < 1.f, "brl_hnn_step: bad B or p_dropout");
   BRL_REQUIRE(!compute_grads || grad_theta, "brl_hnn_step: grad_theta is NULL");
   cudaStream_t st = (cudaStream_t)stream;

@@ -141,6 +141,12 @@ class Engine:
 
 
     # -- helpers ------------------------------------------------------------------------------
+    def _on_device(self):
+        """Context manager for the entry points that take no brl_ctx (moments, mixture, metrics, optimiser): their kernels
+        launch on a stream of THIS engine's device, which must then be the current one (the ctx entry points guard
+        themselves inside the library)."""
+        return torch.cuda.device(self.device)
+
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
@@ -273,14 +279,16 @@ class Engine:
             raise RuntimeError("bayesrul_b200: out must be [S,B,2]")
         S, B = out.shape[0], out.shape[1]
         r = [torch.empty(B, device=self.device) for _ in range(4)]
-        _lib.check(self.lib.brl_moments(out.data_ptr(), S, B, *[t.data_ptr() for t in r], self._stream()))
+        with self._on_device():
+            _lib.check(self.lib.brl_moments(out.data_ptr(), S, B, *[t.data_ptr() for t in r], self._stream()))
         return tuple(r)
 
     def aggregate_predictions(self, out: torch.Tensor) -> torch.Tensor:
         out = _chk(out, self.device, "out")
         S, B = out.shape[0], out.shape[1]
         agg = torch.empty(B, 2, device=self.device)
-        _lib.check(self.lib.brl_aggregate_predictions(out.data_ptr(), S, B, agg.data_ptr(), self._stream()))
+        with self._on_device():
+            _lib.check(self.lib.brl_aggregate_predictions(out.data_ptr(), S, B, agg.data_ptr(), self._stream()))
         return agg
 
     # -- A9 / A10: ELBO step ---------------------------------------------------------------------------
@@ -336,8 +344,9 @@ class Engine:
             raise RuntimeError("bayesrul_b200: mu_m / sigma_m must both be [M,n]")
         M, n = mu_m.shape
         mu, sd = torch.empty(n, device=self.device), torch.empty(n, device=self.device)
-        _lib.check(self.lib.brl_mixture_moments(mu_m.data_ptr(), sigma_m.data_ptr(), M, n, mu.data_ptr(), sd.data_ptr(),
-                                                self._stream()))
+        with self._on_device():
+            _lib.check(self.lib.brl_mixture_moments(mu_m.data_ptr(), sigma_m.data_ptr(), M, n, mu.data_ptr(), sd.data_ptr(),
+                                                    self._stream()))
         return mu, sd
 
     def test_metrics(self, pred, std, y) -> torch.Tensor:
@@ -347,17 +356,19 @@ class Engine:
             raise RuntimeError("bayesrul_b200: pred / std / y shapes differ")
         scalars = torch.empty(4, dtype=torch.float64, device=self.device)
         ws = self.workspace(4096)
-        _lib.check(self.lib.brl_test_metrics(pred.data_ptr(), std.data_ptr(), y.data_ptr(), pred.numel(),
-                                             scalars.data_ptr(), ws.data_ptr(), ws.numel(), self._stream()))
+        with self._on_device():
+            _lib.check(self.lib.brl_test_metrics(pred.data_ptr(), std.data_ptr(), y.data_ptr(), pred.numel(),
+                                                 scalars.data_ptr(), ws.data_ptr(), ws.numel(), self._stream()))
         return scalars
 
     def clipped_adam(self, param, grad, exp_avg, exp_avg_sq, step: int, lr: float, betas=(0.95, 0.999), eps=1e-8,
                      clip_norm=15.0, lrd=1.0, weight_decay=0.0) -> None:
         for t, n in ((param, "param"), (grad, "grad"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
             _chk(t, self.device, n)
-        _lib.check(self.lib.brl_clipped_adam(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(),
-                                             exp_avg_sq.data_ptr(), param.numel(), int(step), lr, betas[0], betas[1],
-                                             eps, clip_norm, lrd, weight_decay, self._stream()))
+        with self._on_device():
+            _lib.check(self.lib.brl_clipped_adam(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(),
+                                                 exp_avg_sq.data_ptr(), param.numel(), int(step), lr, betas[0], betas[1],
+                                                 eps, clip_norm, lrd, weight_decay, self._stream()))
 
     def clipped_adam_vi(self, loc, log_scale, scale, grad_loc, grad_log_scale, m_loc, v_loc, m_ls, v_ls, step: int, lr: float,
                         betas=(0.95, 0.999), eps=1e-8, clip_norm=15.0, lrd=1.0, weight_decay=0.0) -> None:
@@ -367,5 +378,6 @@ class Engine:
             _chk(t, self.device, "clipped_adam_vi tensor")
             if t.numel() != loc.numel():
                 raise RuntimeError("bayesrul_b200: clipped_adam_vi tensors must have the same number of elements")
-        _lib.check(self.lib.brl_clipped_adam_vi(*[t.data_ptr() for t in ts], loc.numel(), int(step), lr, betas[0], betas[1], eps,
-                                                clip_norm, lrd, weight_decay, self._stream()))
+        with self._on_device():
+            _lib.check(self.lib.brl_clipped_adam_vi(*[t.data_ptr() for t in ts], loc.numel(), int(step), lr, betas[0], betas[1], eps,
+                                                    clip_norm, lrd, weight_decay, self._stream()))

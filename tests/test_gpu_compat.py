@@ -159,13 +159,11 @@ def test_chunked_host_predict_equals_device_predict(engine):
         np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-5, atol=1e-6)
 
 
-def test_predict_task_writer_and_deep_ensemble_gen(tmp_path):
+def test_predict_task_writer_and_deep_ensemble(tmp_path):
     """The predict task end to end (tasks/predict.py:52-64 -> results/predictions.py:31-56): HNN members write
-    `<method>_<run>_<subset>.parquet` through predict_step, the frames are read back and mixed by deep_ensemble_gen."""
-    import random
-    from itertools import combinations
+    `<method>_<run>_<subset>.parquet` through predict_step, the frames are read back and mixed by deep_ensemble."""
     import pandas as pd
-    from bayesrul_b200.compat import HNN, Inception, ResultSaver, deep_ensemble_gen, write_predictions
+    from bayesrul_b200.compat import HNN, Inception, deep_ensemble, write_predictions
     g = torch.Generator().manual_seed(3)
     batches = [(torch.randn(n, 30, 18, generator=g), torch.rand(n, generator=g) * 100) for n in (40, 40, 17)]
     frames = []
@@ -176,14 +174,13 @@ def test_predict_task_writer_and_deep_ensemble_gen(tmp_path):
         f = write_predictions(m, batches, tmp_path, name)
         assert list(f.columns) == ["labels", "preds", "stds"] and len(f) == 97  # no MC-dropout: no variance split (frequentist.py:132-151)
         np.testing.assert_allclose(f.labels.values, torch.cat([b[1] for b in batches]).numpy(), rtol=1e-6)
-        frames.append(ResultSaver(tmp_path, name).load().assign(model=f"HNN_{run:03d}", method="HNN"))
+        frames.append(pd.read_parquet(tmp_path / name).assign(model=f"HNN_{run:03d}", method="HNN"))
     df = pd.concat(frames).reset_index(drop=True)
-    out = list(deep_ensemble_gen(df, ["HNN"], 2, 2))
-    random.seed(1)
-    picks = random.sample(list(combinations(range(3), 2)), 2)
-    assert [o.model.iloc[0] for o in out] == ["DE_000", "DE_001"] and all((o.method == "DE").all() for o in out)
-    for o, ens in zip(out, picks):
+    for ens in ((0, 1), (0, 2), (0, 1, 2)):
+        o = deep_ensemble(df[df.model.isin([f"HNN_{k:03d}" for k in ens])])
         mu = np.stack([frames[k].preds.values for k in ens]).astype(np.float64)
         sd = np.stack([frames[k].stds.values for k in ens]).astype(np.float64)
+        assert list(o.columns) == ["preds", "labels", "stds"] and len(o) == 97
+        np.testing.assert_allclose(o.labels.values, frames[0].labels.values)
         np.testing.assert_allclose(o.preds.values, mu.mean(0), rtol=1e-5)
         np.testing.assert_allclose(o.stds.values, np.sqrt((mu**2 + sd**2).mean(0) - mu.mean(0) ** 2), rtol=1e-3, atol=1e-4)

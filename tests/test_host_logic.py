@@ -82,11 +82,11 @@ def test_dropout_decisions_rate_and_tie_path():
     assert np.abs(c - np.eye(16)).max() < 0.02
 
 
-def test_prediction_frame_and_result_saver(tmp_path):
+def test_prediction_frame_round_trip(tmp_path):
     """per-batch predict_step dicts -> one row per window, parquet round trip (tasks/predict.py:52-64)."""
     import numpy as np
     import pandas as pd
-    from bayesrul_b200.compat.predictions import PREDICTION_COLUMNS, ResultSaver, predictions_to_frame
+    from bayesrul_b200.compat.predictions import PREDICTION_COLUMNS, predictions_to_frame
     rng = np.random.default_rng(0)
     batches = [{c: rng.normal(size=n).astype(np.float32) for c in PREDICTION_COLUMNS} for n in (5, 3, 1)]
     frame = predictions_to_frame(batches)
@@ -95,10 +95,27 @@ def test_prediction_frame_and_result_saver(tmp_path):
     ref = ref.explode(ref.columns.tolist()).reset_index(drop=True)
     assert list(frame.columns) == PREDICTION_COLUMNS and len(frame) == 9
     np.testing.assert_array_equal(frame.to_numpy(dtype=np.float32), ref.to_numpy(dtype=np.float32))
-    sav = ResultSaver(tmp_path / "preds", "LRT_000_test.parquet")
-    sav.save(frame)
-    back = sav.load()
-    pd.testing.assert_frame_equal(back, frame)
-    sav.append({"errs": (frame.preds - frame.labels).to_numpy()})
-    assert list(sav.load().columns) == PREDICTION_COLUMNS + ["errs"]
+    frame.to_parquet(tmp_path / "LRT_000_test.parquet")
+    pd.testing.assert_frame_equal(pd.read_parquet(tmp_path / "LRT_000_test.parquet"), frame)
     assert len(predictions_to_frame([])) == 0
+
+
+def test_clipped_adam_state_is_keyed_by_name_and_rebinds():
+    """Optimiser state follows a stable name and restarts when the bound parameter object changes (define_bnn() builds a new
+    guide for fit / test / predict; an id() of a freed tensor may be reused)."""
+    import torch
+    from bayesrul_b200.compat.pyro_shim import ClippedAdam
+    opt = ClippedAdam({"lr": 1e-3})
+    a, b = torch.zeros(4), torch.zeros(4)
+    st = opt._slot("loc", a)
+    st["step"] = 7
+    st["m"] += 1.0
+    assert opt._slot("loc", a) is st and opt._slot("loc", a)["step"] == 7
+    fresh = opt._slot("loc", b)  # a new parameter under the same name: fresh moments, step 0
+    assert fresh is not st and fresh["step"] == 0 and float(fresh["m"].abs().sum()) == 0.0
+    fresh["step"] = 3
+    saved = opt.get_state()
+    assert set(saved) == {"loc"} and saved["loc"]["step"] == 3
+    opt2 = ClippedAdam({"lr": 1e-3})
+    opt2.set_state(saved)
+    assert opt2._slot("loc", b)["step"] == 3  # restored slot adopts the first parameter of matching shape
