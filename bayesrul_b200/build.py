@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libbayesrul_b200.so")
-SOURCES = ["brl_api.cu", "brl_kernels.cu", "brl_gemm.cu", "brl_tc.cu", "brl_tc_gemm.cu", "brl_nets.cpp"]
+SOURCES = ["brl_api.cu", "brl_kernels.cu", "brl_gemm.cu", "brl_tc.cu", "brl_tc_gemm.cu", "brl_tc_train.cu", "brl_nets.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = os.environ.get("BRL_NVCC_EXTRA", "").split() + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"]
 

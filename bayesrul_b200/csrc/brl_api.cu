@@ -13,6 +13,7 @@
 #include "brl_nets.h"
 #include "brl_philox.cuh"
 #include "brl_tc.cuh"
+#include "brl_tc_train.cuh"
 
 using namespace brl;
 
@@ -133,6 +134,9 @@ struct ActBufs {
   float *st_x = nullptr, *st_y = nullptr, *st_out = nullptr, *st_gmu = nullptr, *st_gsig = nullptr, *st_glog = nullptr;
   double* st_scal = nullptr;
   unsigned long long* dyn = nullptr;
+  // level-fused tcgen05 training kernels (Inception conv stack, brl_tc_train.cu): images of one particle lane
+  TtLane tt{};
+  bool has_tt = false;
 };
 constexpr int GRAPH_MAX_PARTICLES = 8;
 
@@ -174,6 +178,11 @@ static void carve_train(const NetSpec& n, Carve& c, long long B, ActBufs& ab) {
   ab.st_glog = c.take<float>(n.P);
   ab.st_scal = c.take<double>(4);
   ab.dyn = c.take<unsigned long long>(4);
+  if (n.id == BRL_NET_INCEPTION) {
+    unsigned char* base = c.take<unsigned char>((long long)tt_lane_bytes(B));
+    if (base) tt_carve(base, B, ab.tt);
+    ab.has_tt = base != nullptr;
+  }
 }
 
 // device {seed, sample0, window0} of the step being captured (nullptr outside a capture): every Philox stream built by
@@ -669,12 +678,14 @@ int brl_tc_status(const brl_ctx* ctx) {
   DeviceGuard dg(ctx->device);
   const int g = tc_gemm_status();  // TF32 per-layer kernels
   if (g != 0) return g;
+  const int t = tt_status();  // level-fused training kernels
+  if (t != 0) return t;
   return tc_status(ctx->tc);
 }
 int brl_gemm_status(void) { return tc_gemm_status(); }
 int brl_set_gemm_backend(brl_ctx* ctx, int backend) {
   BRL_REQUIRE(ctx, "brl_set_gemm_backend: NULL context");
-  BRL_REQUIRE(backend >= 0 && backend <= BRL_GEMM_TC_TF32, "brl_set_gemm_backend: unknown back-end");
+  BRL_REQUIRE(backend >= 0 && backend <= BRL_GEMM_TC_FUSED, "brl_set_gemm_backend: unknown back-end");
   ctx->gemm_backend = backend;
   return BRL_OK;
 }
@@ -1102,12 +1113,39 @@ static int elbo_body(brl_ctx* ctx, const ActBufs* const* lanes, int n_lanes, con
         if (zs != ls) BRL_CUDA(cudaEventRecord(ln.ev_zero, zs));
       }
       FwdArgs fa{x, B, 1, mode, mu, sigma, ab.wsamp, 0.f, &nz, sin_.data(), sout_.data(), outp, compute_grads != 0};
-      run_forward(ctx, ab, fa, ls, l);
+      // level-fused tcgen05 kernels for the ten conv layers (BRL_GEMM_TC_FUSED); the fc layer and the head stay per-layer
+      const bool use_tt = ctx->gemm_backend == BRL_GEMM_TC_FUSED && n.id == BRL_NET_INCEPTION && ab.has_tt &&
+                          (mode == BRL_MODE_LRT || mode == BRL_MODE_FLIPOUT);
+      TtStep ts{};
+      if (use_tt) {
+        ts.x = x; ts.B = B; ts.mode = mode; ts.mu = mu; ts.sigma = sigma; ts.wsamp = ab.wsamp;
+        for (int ly = 0; ly < TT_LAYERS; ++ly) {
+          ts.eps[ly] = nref(&nz, nz.lrt_eps[ly], KIND_LRT_EPS, (unsigned)ly);
+          ts.sgn_in[ly] = sin_[ly]; ts.sgn_out[ly] = sout_[ly];
+          ts.w_off[ly] = n.layers[ly].w_off; ts.b_off[ly] = n.layers[ly].b_off;
+        }
+        const int fc_op = (int)n.ops.size() - 2;
+        ts.feat = ab.act[n.ops[fc_op].in.buf];
+        ts.feat_grad = compute_grads ? ab.grad[n.ops[fc_op].in.buf] : nullptr;
+        ts.g0 = ab.g0; ts.g1 = ab.g1;
+        tt_forward(ab.tt, ts, ls);
+        forward_op(ctx, ab, fa, fc_op, ls, 0);
+        forward_op(ctx, ab, fa, fc_op + 1, ls, 0);
+      } else {
+        run_forward(ctx, ab, fa, ls, l);
+      }
       if (compute_grads && ctx->multi_stream) BRL_CUDA(cudaStreamWaitEvent(ls, ln.ev_zero, 0));
       launch_nll_elbo(outp, y, B, (float)(c_nll / particles), ab0.acc, compute_grads ? ab.grad[n.out_buf] : nullptr, ls);
       if (compute_grads) {
         BwdArgs ba{x, B, mode, mode == BRL_MODE_WS ? ab.wsamp : mu, sigma, ab.wsamp, 0.f, &nz, sin_.data(), sout_.data(), outp, ab.g0, ab.g1};
-        run_backward(ctx, ab, ba, ls, l);
+        if (use_tt) {
+          const int fc_op = (int)n.ops.size() - 2;
+          backward_op(ctx, ab, ba, fc_op + 1, ls, 0, ls, nullptr, nullptr);
+          backward_op(ctx, ab, ba, fc_op, ls, 0, ls, nullptr, nullptr);
+          tt_backward(ab.tt, ts, ls);
+        } else {
+          run_backward(ctx, ab, ba, ls, l);
+        }
       }
     }
     if (nl > 1) {

@@ -1,0 +1,769 @@
+// Level-fused tcgen05 training kernels of the Inception conv stack: the LRT / Flipout forward and backward of the ten conv layers
+// that svi.step runs under `fit_ctxt` (bayesian.py:146-147; tyxe local_reparameterization / flipout).
+//
+// Why "level-fused": a 256-window minibatch is 64 tiles of 4 windows (128 rows = 4 x (30 steps + 2 dead rows)).  A CTA owns ONE conv
+// layer of ONE tile (forward) or of a few tiles (backward): its operands are whole, MMA-addressable IMAGES
+//     activation image of a tile   [8-channel chunk][132 rows][8 x 16 bit]     (2 zero pad rows above / below the 128 tile rows)
+//     weight image of a layer      [tap][8-channel chunk][N][8 x 16 bit]
+// that travel by cp.async.bulk, so there is no im2col gather anywhere: `padding='same'` is a +-16-byte shift of the A
+// descriptor, and the SAME images serve the transposed contractions of the backward pass through MN-major descriptors
+// (tools/ubench/umma_probe.cu pins the descriptor semantics on hardware):
+//     forward           D[row, n]  = sum_c  act[c, row + tap] * W[n, c, tap]      A K-major (act image),   B K-major (weight image)
+//     input gradient    D[row, c]  = sum_n  g[n, row - tap]   * W[n, c, tap]      A K-major (grad image),  B MN-major (weight image^T)
+//     weight gradient   D[c, n]    = sum_r  act[c, r + tap]   * g[n, r]           A MN-major (act image^T), B MN-major (grad image^T)
+// Every layer is a DUAL contraction into two TMEM accumulators:
+//     LRT      mean = a * mu,  var = a^2 * sigma^2,  out = relu(mean + b + eps * sqrt(var + sigma_b^2))        (eps: Philox / injected)
+//     Flipout  mean = a * mu,  pert = (a . s_in) * (W - mu),  out = relu(mean + pert . s_out + b_sampled)
+// The second operand (a^2 or a . s_in) is built in shared memory from the first by the CTA's threads.  The max-pool in front of the
+// two pooled branches is applied by the consumer on its staged input.  Layers of one dependency level run in ONE launch
+// (grid = tiles x layers); activations go from level to level as fp16 images through L2, gradients as bf16 images.
+// Precision: mean path fp16 x fp16 (10-bit mantissa) in the forward pass, everything else bf16 x bf16 (gradients need fp32's
+// exponent range: they carry the 1 / (B * 540) ELBO scale), fp32 accumulation in TMEM.  Stated bound vs the fp32 engine /
+// the oracle: outputs 1e-2, loss 5e-3, gradient cosine > 0.999 (tests/test_gpu_tc_train.py).
+// The 2400 -> 64 fc layer and the head stay on the per-layer engine (fp32), fed by the fp32 feature buffer written here.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdint>
+
+#include "../../include/bayesrul_b200.h"
+#include "brl_gemm_epi.cuh"
+#include "brl_kernels.cuh"
+#include "brl_philox.cuh"
+#include "brl_tc_ptx.cuh"
+#include "brl_tc_train.cuh"
+
+namespace brl {
+
+extern std::atomic<long long> g_launch_count;
+
+namespace {
+
+constexpr int ROWS = 132, CS = ROWS * 16, ROW0 = 2;
+enum { IN_X = 0, IN_XP = 1, IN_M1 = 2, IN_M1P = 3, IN_T2 = 4, IN_T3 = 5 };
+enum { OUT_M1 = 0, OUT_T2 = 1, OUT_T3 = 2, OUT_FEAT = 3 };
+
+struct TtLayer {
+  int layer, in, KC, N, NP, T, out, out_c0;  // out_c0: first chunk of an image output / first channel of a feature output
+  int cin;                                   // real input channels (torch weight [N, cin, T])
+  int w0h, w0b, w1b, w1h, bias, tap_bytes;   // byte offsets inside the weight blob; bytes of one tap's [KC][NP][8] tile
+  int gdst;                                  // gradient image receiving this layer's input gradient (-1: input is x)
+  int roff_per_tile;                         // float offset of this layer's rbuf block inside a tile's 336 * 128 floats
+  long long w_off, b_off;                    // flat parameter offsets
+};
+
+// static description of the ten conv layers (brl_nets.cpp build_inception order)
+struct Table {
+  TtLayer L[TT_LAYERS];
+  int blob_bytes, pack_start[TT_LAYERS + 1];
+};
+const Table& table() {
+  static const Table t = [] {
+    Table tb{};
+    const int in_[10] = {IN_X, IN_X, IN_X, IN_XP, IN_M1, IN_M1, IN_T2, IN_M1, IN_T3, IN_M1P};
+    const int KC[10] = {4, 4, 4, 4, 16, 16, 8, 16, 8, 16};
+    const int N[10] = {27, 27, 27, 27, 16, 64, 16, 64, 16, 32};
+    const int T[10] = {1, 3, 5, 3, 1, 1, 3, 1, 5, 1};
+    const int out[10] = {OUT_M1, OUT_M1, OUT_M1, OUT_M1, OUT_FEAT, OUT_T2, OUT_FEAT, OUT_T3, OUT_FEAT, OUT_FEAT};
+    const int oc0[10] = {0, 4, 8, 12, 0, 0, 16, 0, 32, 48};
+    const int cin[10] = {18, 18, 18, 18, 108, 108, 64, 108, 64, 108};
+    const int gdst[10] = {-1, -1, -1, -1, 0, 1, 4, 2, 5, 3};
+    int off = 0, roff = 0, ps = 0;
+    for (int i = 0; i < 10; ++i) {
+      TtLayer& l = tb.L[i];
+      l.layer = i; l.in = in_[i]; l.KC = KC[i]; l.N = N[i]; l.NP = (N[i] + 15) & ~15; l.T = T[i]; l.out = out[i]; l.out_c0 = oc0[i];
+      l.cin = cin[i]; l.gdst = gdst[i];
+      l.tap_bytes = l.KC * l.NP * 16;
+      const int img = l.T * l.tap_bytes;
+      l.w0h = off; off += img;
+      l.w0b = off; off += img;
+      l.w1b = off; off += img;
+      l.w1h = off; off += img;
+      l.bias = off; off += 2 * 64 * 4;
+      l.roff_per_tile = roff; roff += l.NP * 128;
+      tb.pack_start[i] = ps; ps += l.T * l.KC * 8 * l.NP;
+    }
+    tb.pack_start[10] = ps;
+    tb.blob_bytes = off;
+    return tb;
+  }();
+  return t;
+}
+constexpr int RBUF_PER_TILE = 336 * 128;  // sum of NP over the ten layers x 128 rows
+
+// image channel k of an input -> real channel of the torch weight / sign tensor (-1: padding channel)
+__device__ __forceinline__ int real_ch(int in, int k) {
+  if (in <= IN_XP) return k < 18 ? k : -1;
+  if (in <= IN_M1P) { const int br = k >> 5, j = k & 31; return j < 27 ? br * 27 + j : -1; }
+  return k < 64 ? k : -1;
+}
+struct RowInfo { int t, gw; bool live; };
+__device__ __forceinline__ RowInfo row_info(int rr, int tile, int B) {
+  const int r = rr - ROW0;
+  RowInfo o;
+  o.t = r & 31;
+  o.gw = tile * 4 + (r >> 5);
+  o.live = r >= 0 && r < 128 && o.t < 30 && o.gw < B;
+  return o;
+}
+__device__ __forceinline__ void unpack_h8(const uint4& v, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 t = __half22float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ void unpack_b8(const uint4& v, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ uint4 pack_b8(const float (&f)[8]) {
+  uint4 r;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return r;
+}
+__device__ __forceinline__ uint4 pack_h8(const float (&f)[8]) {
+  return make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
+}
+// kind::f16 instruction descriptor: fp32 D, operand formats (0 fp16, 1 bf16 -- both operands the same: a mixed pair is an
+// illegal instruction on B200), majors (1 = MN-major), M = 128
+__host__ __device__ constexpr uint32_t tt_idesc(int n, int fmt, int a_mn, int b_mn) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// window images: fp32 windows -> fp16 chunk images X and XP = MaxPool1d(3,1,1)(X) (-inf padding), pad rows zero
+// ------------------------------------------------------------------------------------------------
+__global__ void tt_packx_kernel(const float* __restrict__ x, unsigned char* __restrict__ ximg, int B, int ntile) {
+  const long long u = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (u >= (long long)ntile * 3 * ROWS) return;
+  const int tile = (int)(u / (3 * ROWS)), v = (int)(u % (3 * ROWS)), c = v / ROWS, rr = v % ROWS;
+  const RowInfo ri = row_info(rr, tile, B);
+  float f[8], pm[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = pm[j] = 0.f;
+  if (ri.live) {
+    const float* px = x + (long long)ri.gw * 540 + ri.t * 18 + c * 8;
+    const int nf = c < 2 ? 8 : 2;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < nf) {
+        const float v0 = __half2float(__float2half_rn(px[j]));
+        float m = v0;
+        if (ri.t > 0) m = fmaxf(m, __half2float(__float2half_rn(px[j - 18])));
+        if (ri.t < 29) m = fmaxf(m, __half2float(__float2half_rn(px[j + 18])));
+        f[j] = v0;
+        pm[j] = m;
+      }
+  }
+  unsigned char* dst = ximg + ((long long)tile * 6 + c) * CS + rr * 16;
+  *reinterpret_cast<uint4*>(dst) = pack_h8(f);
+  *reinterpret_cast<uint4*>(dst + 3 * CS) = pack_h8(pm);
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight images of one step / particle
+// ------------------------------------------------------------------------------------------------
+struct TtPackArgs {
+  TtLayer L[TT_LAYERS];
+  int start[TT_LAYERS + 1];
+  int mode;
+  const float *mu, *second;  // second: sigma (LRT) or the weight draw (Flipout)
+  unsigned char* blob;
+};
+__global__ void tt_pack_kernel(const TtPackArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < a.start[TT_LAYERS]) {
+    int li = 0;
+    while (i >= a.start[li + 1]) ++li;
+    const TtLayer& l = a.L[li];
+    int j = i - a.start[li];
+    const int n = j % l.NP; j /= l.NP;
+    const int k = j % (l.KC * 8);
+    const int tap = j / (l.KC * 8);
+    const int cr = real_ch(l.in, k);
+    float m = 0.f, s = 0.f;
+    if (n < l.N && cr >= 0) {
+      const long long wi = l.w_off + ((long long)n * l.cin + cr) * l.T + tap;
+      m = a.mu[wi];
+      const float v = a.second[wi];
+      s = a.mode == BRL_MODE_LRT ? v * v : v - m;
+    }
+    const int o = tap * l.tap_bytes + (k >> 3) * (l.NP * 16) + n * 16 + (k & 7) * 2;
+    *reinterpret_cast<__half*>(a.blob + l.w0h + o) = __float2half_rn(m);
+    *reinterpret_cast<__nv_bfloat16*>(a.blob + l.w0b + o) = __float2bfloat16_rn(m);
+    *reinterpret_cast<__nv_bfloat16*>(a.blob + l.w1b + o) = __float2bfloat16_rn(s);
+    *reinterpret_cast<__half*>(a.blob + l.w1h + o) = __float2half_rn(s);
+    return;
+  }
+  const int b = i - a.start[TT_LAYERS];
+  if (b < TT_LAYERS * 64) {
+    const TtLayer& l = a.L[b >> 6];
+    const int n = b & 63;
+    float b0 = 0.f, b1 = 0.f;
+    if (n < l.N) {
+      if (a.mode == BRL_MODE_LRT) { b0 = a.mu[l.b_off + n]; const float sb = a.second[l.b_off + n]; b1 = sb * sb; }
+      else b0 = a.second[l.b_off + n];  // Flipout adds the SAMPLED bias
+    }
+    float* bias = reinterpret_cast<float*>(a.blob + l.bias);
+    bias[n] = b0;
+    bias[64 + n] = b1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward: one CTA = one conv layer of one tile
+// ------------------------------------------------------------------------------------------------
+constexpr int F_A = 0, F_A2 = 16 * CS, F_W0 = 32 * CS, F_W1 = F_W0 + 16384, F_BIAS = F_W1 + 16384, F_BAR = F_BIAS + 512;
+constexpr int F_SMEM = F_BAR + 64;
+
+struct TtFwdArgs {
+  TtLane ln;
+  int B, ntile, nl;
+  TtLayer lay[4];
+  NoiseRef eps[4];
+  const float* sgn_in[4];
+  const float* sgn_out[4];
+  float* feat;
+  int* status;
+};
+
+__device__ __forceinline__ const unsigned char* input_image(const TtLane& ln, int in, int tile) {
+  switch (in) {
+    case IN_X: return ln.ximg + (long long)tile * 6 * CS;
+    case IN_XP: return ln.ximg + (long long)tile * 6 * CS + 3 * CS;
+    case IN_M1: case IN_M1P: return ln.m1 + (long long)tile * 16 * CS;
+    case IN_T2: return ln.t2 + (long long)tile * 8 * CS;
+    default: return ln.t3 + (long long)tile * 8 * CS;
+  }
+}
+__device__ __forceinline__ void bulk_copy_chunked(uint32_t dst, const unsigned char* src, int bytes, uint32_t bar) {
+  for (int o = 0; o < bytes; o += 16384) bulk_g2s(dst + o, src + o, min(16384, bytes - o), bar);
+}
+// MaxPool1d(3,1,1) of a post-ReLU activation image (values >= 0, dead / pad rows are zero, so they act as the -inf padding)
+__device__ __forceinline__ void pool_image(const unsigned char* raw, unsigned char* dst, int KC, int tile, int B, int tid) {
+  for (int idx = tid; idx < KC * ROWS; idx += 128) {
+    const int ch = idx / ROWS, rr = idx - ch * ROWS;
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (row_info(rr, tile, B).live) {
+      const unsigned char* p = raw + ch * CS + rr * 16;
+      o = hmax4(*reinterpret_cast<const uint4*>(p), hmax4(*reinterpret_cast<const uint4*>(p - 16), *reinterpret_cast<const uint4*>(p + 16)));
+    }
+    *reinterpret_cast<uint4*>(dst + ch * CS + rr * 16) = o;
+  }
+}
+// second operand of the dual contraction from the fp16 activation image: bf16(a^2) (LRT) or a * s_in (Flipout; H16: as fp16 --
+// exact -- for the forward pass, whose perturbation GEMM runs fp16 x fp16; bf16 for the backward contractions)
+template <int MODE, bool H16>
+__device__ __forceinline__ void second_operand(const unsigned char* A, unsigned char* A2, unsigned char* Ab, const TtLayer& L,
+                                               const float* sgn_in, int tile, int B, int tid) {
+  for (int idx = tid; idx < L.KC * ROWS; idx += 128) {
+    const int ch = idx / ROWS, rr = idx - ch * ROWS;
+    float f[8], s[8];
+    unpack_h8(*reinterpret_cast<const uint4*>(A + ch * CS + rr * 16), f);
+    if (Ab) *reinterpret_cast<uint4*>(Ab + ch * CS + rr * 16) = pack_b8(f);
+    if (MODE == BRL_MODE_LRT) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] = f[j] * f[j];
+    } else {
+      const RowInfo ri = row_info(rr, tile, B);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int cr = real_ch(L.in, ch * 8 + j);
+        s[j] = (ri.live && cr >= 0) ? f[j] * __ldg(sgn_in + (long long)ri.gw * L.cin + cr) : 0.f;
+      }
+    }
+    *reinterpret_cast<uint4*>(A2 + ch * CS + rr * 16) = H16 ? pack_h8(s) : pack_b8(s);
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128, 1) tt_fwd_kernel(const TtFwdArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const TtLayer& L = a.lay[blockIdx.y];
+  const int tile = blockIdx.x, tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar_ld = sbase + F_BAR, bar_mma = bar_ld + 8;
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + F_BAR + 16);
+  if (tid == 0) {
+    mbar_init(bar_ld, 1);
+    mbar_init(bar_mma, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(smem_u32(tslot), 128);
+  if (L.in <= IN_XP)  // K = 32 for the 18 input features: the 4th chunk is zero
+    for (int i = tid; i < CS / 16; i += 128) reinterpret_cast<uint4*>(smem + F_A + 3 * CS)[i] = make_uint4(0, 0, 0, 0);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tslot;
+  const int ncopy = L.in <= IN_XP ? 3 : L.KC;
+  const int img_bytes = L.T * L.tap_bytes;
+  if (tid == 0) {
+    mbar_expect_tx(bar_ld, ncopy * CS + 2 * img_bytes + 512);
+    bulk_copy_chunked(sbase + (L.in == IN_M1P ? F_A2 : F_A), input_image(a.ln, L.in, tile), ncopy * CS, bar_ld);
+    bulk_copy_chunked(sbase + F_W0, a.ln.blob + L.w0h, img_bytes, bar_ld);
+    bulk_copy_chunked(sbase + F_W1, a.ln.blob + (MODE == BRL_MODE_FLIPOUT ? L.w1h : L.w1b), img_bytes, bar_ld);
+    bulk_g2s(sbase + F_BIAS, a.ln.blob + L.bias, 512, bar_ld);
+  }
+  mbar_wait(bar_ld, 0, a.status, 40);
+  if (L.in == IN_M1P) {  // the pooled branch: pool the staged raw image first
+    pool_image(smem + F_A2, smem + F_A, L.KC, tile, a.B, tid);
+    __syncthreads();
+  }
+  constexpr bool P1H = MODE == BRL_MODE_FLIPOUT;  // perturbation path: fp16 operands (W - mu is far above fp16's subnormals for q_scale >= 1e-4)
+  second_operand<MODE, P1H>(smem + F_A, smem + F_A2, nullptr, L, a.sgn_in[blockIdx.y], tile, a.B, tid);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    if (elect_one()) {
+      const int pad = (L.T - 1) >> 1;
+      for (int tap = 0; tap < L.T; ++tap)
+        for (int ks = 0; ks < L.KC / 2; ++ks) {
+          const uint32_t ao = 2 * ks * CS + (ROW0 + tap - pad) * 16, wo = tap * L.tap_bytes + 2 * ks * L.NP * 16;
+          umma(tmem, umma_desc(sbase + F_A + ao, CS, 128), umma_desc(sbase + F_W0 + wo, L.NP * 16, 128), tt_idesc(L.NP, 0, 0, 0),
+               (tap | ks) != 0);
+          umma(tmem + L.NP, umma_desc(sbase + F_A2 + ao, CS, 128), umma_desc(sbase + F_W1 + wo, L.NP * 16, 128),
+               tt_idesc(L.NP, P1H ? 0 : 1, 0, 0), (tap | ks) != 0);
+        }
+      umma_commit(bar_mma);
+    }
+    __syncwarp();
+  }
+  mbar_wait(bar_mma, 0, a.status, 41);
+  tc_fence_after();
+  // ---- epilogue: thread = tile row
+  const RowInfo ri = row_info(ROW0 + tid, tile, a.B);
+  const uint32_t la = tmem + ((uint32_t)(tid & ~31) << 16);
+  const float* bias = reinterpret_cast<const float*>(smem + F_BIAS);
+  const NoiseRef& nz = a.eps[blockIdx.y];
+  const float* sout = a.sgn_out[blockIdx.y];
+  float* rb = a.ln.rbuf ? a.ln.rbuf + (long long)tile * RBUF_PER_TILE + L.roff_per_tile : nullptr;
+  unsigned char* oimg = L.out == OUT_M1 ? a.ln.m1 + (long long)tile * 16 * CS
+                        : L.out == OUT_T2 ? a.ln.t2 + (long long)tile * 8 * CS
+                        : L.out == OUT_T3 ? a.ln.t3 + (long long)tile * 8 * CS : nullptr;
+  for (int g = 0; g < L.NP / 16; ++g) {
+    float v0[16], v1[16], o[16];
+    tmem_ld16(la + g * 16, v0);
+    tmem_ld16(la + L.NP + g * 16, v1);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int n = g * 16 + j;
+      const bool on = ri.live && n < L.N;
+      float pre;
+      if (MODE == BRL_MODE_LRT) {
+        float var = v1[j] + bias[64 + n];
+        if (var < 0.f) var += fabsf(var) + 1e-6f;
+        const float sd = sqrtf(var);
+        const float e = on ? gnoise_normal(nz, 0, ri.gw, a.B, L.N * 30, n * 30 + ri.t) : 0.f;
+        pre = fmaf(sd, e, v0[j] + bias[n]);
+        if (rb) rb[(long long)n * 128 + tid] = (on && sd > 0.f) ? e / (2.0f * sd) : 0.f;
+      } else {
+        pre = v0[j] + bias[n] + (on ? v1[j] * __ldg(sout + (long long)ri.gw * L.N + n) : 0.f);
+      }
+      o[j] = on ? fmaxf(pre, 0.f) : 0.f;
+    }
+    if (oimg) {
+      unsigned char* dst = oimg + (L.out_c0 + 2 * g) * CS + (ROW0 + tid) * 16;
+      *reinterpret_cast<uint4*>(dst) = pack_h8(reinterpret_cast<float(&)[8]>(o[0]));
+      *reinterpret_cast<uint4*>(dst + CS) = pack_h8(reinterpret_cast<float(&)[8]>(o[8]));
+    } else if (ri.live) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (g * 16 + j < L.N) a.feat[((long long)ri.gw * 80 + L.out_c0 + g * 16 + j) * 30 + ri.t] = o[j];
+    }
+  }
+  if (oimg && tid < 4) {  // the image's pad rows
+    const int pr = tid < 2 ? tid : 128 + tid;
+    for (int c = 0; c < L.NP / 8; ++c) *reinterpret_cast<uint4*>(oimg + (L.out_c0 + c) * CS + pr * 16) = make_uint4(0, 0, 0, 0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward: one CTA = one conv layer of a group of tiles (weight gradients accumulate in TMEM over the group)
+// ------------------------------------------------------------------------------------------------
+constexpr int B_AH = 0, B_AB = 16 * CS, B_A2 = 32 * CS, B_G0 = 48 * CS, B_G1 = 56 * CS, B_W0 = 64 * CS, B_W1 = B_W0 + 16384,
+              B_SUM = B_W1 + 16384, B_BAR = B_SUM + 512;
+constexpr int B_SMEM = B_BAR + 64;
+static_assert(B_SMEM <= 232448, "backward kernel shared memory exceeds the 227 KB opt-in limit");
+
+struct TtBwdArgs {
+  TtLane ln;
+  int B, ntile, nl, tiles_per_cta;
+  TtLayer lay[4];
+  const float* sgn_in[4];
+  const float* sgn_out[4];
+  const float* feat;
+  const float* feat_grad;
+  float *g0, *g1;
+  int* status;
+};
+
+// gradient w.r.t. the layer OUTPUT (post-activation), 8 channels [n0, n0 + 8) of tile row `row`, and the ReLU gate
+template <int MODE>
+__device__ __forceinline__ void output_grad(const TtBwdArgs& a, const TtLayer& L, int tile, int row, const RowInfo& ri, int n0,
+                                            float (&d)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) d[j] = 0.f;
+  if (!ri.live) return;
+  if (L.out == OUT_FEAT) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (n0 + j < L.N) {
+        const long long i = ((long long)ri.gw * 80 + L.out_c0 + n0 + j) * 30 + ri.t;
+        d[j] = a.feat[i] > 0.f ? a.feat_grad[i] : 0.f;
+      }
+    return;
+  }
+  const long long ro = (long long)(ROW0 + row) * 16;
+  float act[8], g[8];
+  if (L.out != OUT_M1) {
+    const int c = n0 >> 3;
+    const unsigned char* ai = (L.out == OUT_T2 ? a.ln.t2 : a.ln.t3) + ((long long)tile * 8 + c) * CS + ro;
+    const unsigned char* gi = a.ln.g[L.out == OUT_T2 ? 4 : 5] + ((long long)tile * 8 + c) * CS + ro;
+    unpack_h8(*reinterpret_cast<const uint4*>(ai), act);
+    unpack_b8(*reinterpret_cast<const uint4*>(gi), g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d[j] = act[j] > 0.f ? g[j] : 0.f;
+    return;
+  }
+  // module-1 output: three direct consumers + the pooled branch (route through MaxPool1d(3,1,1): first maximum wins)
+  const long long co = ((long long)tile * 16 + L.out_c0 + (n0 >> 3)) * CS + ro;
+  float m[5][8], gp[3][8];
+#pragma unroll
+  for (int q = 0; q < 5; ++q) unpack_h8(*reinterpret_cast<const uint4*>(a.ln.m1 + co + (q - 2) * 16), m[q]);
+#pragma unroll
+  for (int q = 0; q < 3; ++q) unpack_b8(*reinterpret_cast<const uint4*>(a.ln.g[3] + co + (q - 1) * 16), gp[q]);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    unpack_b8(*reinterpret_cast<const uint4*>(a.ln.g[k] + co), g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d[j] += g[j];
+  }
+  const int t = ri.t;
+#pragma unroll
+  for (int dq = -1; dq <= 1; ++dq) {  // pooled position q = t + dq; does its window's first maximum sit at t?
+    const int q = t + dq;
+    if (q < 0 || q > 29) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      // window {q-1, q, q+1} clipped to [0, 29]; index into m[] is (position - t + 2)
+      float best = -1.f;
+      int arg = -9;
+#pragma unroll
+      for (int w = -1; w <= 1; ++w) {
+        const int pos = q + w;
+        if (pos < 0 || pos > 29) continue;
+        const float v = m[pos - t + 2][j];
+        if (v > best) { best = v; arg = pos; }
+      }
+      if (arg == t) d[j] += gp[dq + 1][j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) d[j] = m[2][j] > 0.f ? d[j] : 0.f;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128, 1) tt_bwd_kernel(const TtBwdArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const TtLayer& L = a.lay[blockIdx.y];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar_ld = sbase + B_BAR, bar_mma = bar_ld + 8;
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + B_BAR + 16);
+  float* sums = reinterpret_cast<float*>(smem + B_SUM);  // [2][64] bias-gradient partial sums
+  if (tid == 0) {
+    mbar_init(bar_ld, 1);
+    mbar_init(bar_mma, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(smem_u32(tslot), 512);
+  // operand regions start as zeros: chunks a layer does not fill (the 4th chunk of x, M lanes beyond KC) must hold finite values,
+  // and the pad rows of the gradient images stay zero for the whole kernel
+  for (int i = tid; i < B_W0 / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  sums[tid] = 0.f;
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tslot;
+  const bool has_dx = L.gdst >= 0;
+  const int dxw = has_dx ? L.KC * 8 : 0;            // columns of one input-gradient accumulator
+  const uint32_t t_dx0 = tmem, t_dx1 = tmem + dxw, t_dw0 = tmem + 2 * dxw, t_dw1 = t_dw0 + L.T * L.NP;
+  const int ncopy = L.in <= IN_XP ? 3 : L.KC;
+  const int img_bytes = L.T * L.tap_bytes;
+  const int pad = (L.T - 1) >> 1;
+  const int tile0 = blockIdx.x * a.tiles_per_cta, tile1 = min(a.ntile, tile0 + a.tiles_per_cta);
+  uint32_t ph = 0;
+  for (int tile = tile0; tile < tile1; ++tile) {
+    if (tid == 0) {
+      const bool first = tile == tile0;
+      mbar_expect_tx(bar_ld, ncopy * CS + (first ? 2 * img_bytes : 0));
+      bulk_copy_chunked(sbase + (L.in == IN_M1P ? B_AB : B_AH), input_image(a.ln, L.in, tile), ncopy * CS, bar_ld);
+      if (first) {
+        bulk_copy_chunked(sbase + B_W0, a.ln.blob + L.w0b, img_bytes, bar_ld);
+        bulk_copy_chunked(sbase + B_W1, a.ln.blob + L.w1b, img_bytes, bar_ld);
+      }
+    }
+    // ---- gradient operands (global reads only): G0 = d/d(pre-activation), G1 = d/d(variance) or d/d(perturbation); thread = row
+    const RowInfo ri = row_info(ROW0 + tid, tile, a.B);
+    const float* rb = a.ln.rbuf + (long long)tile * RBUF_PER_TILE + L.roff_per_tile;
+    const float* sout = a.sgn_out[blockIdx.y];
+    for (int c = 0; c < L.NP / 8; ++c) {
+      float d[8], d1[8];
+      output_grad<MODE>(a, L, tile, tid, ri, c * 8, d);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int n = c * 8 + j;
+        if (MODE == BRL_MODE_LRT) d1[j] = d[j] * rb[(long long)n * 128 + tid];
+        else d1[j] = (ri.live && n < L.N) ? d[j] * __ldg(sout + (long long)ri.gw * L.N + n) : 0.f;
+      }
+      *reinterpret_cast<uint4*>(smem + B_G0 + c * CS + (ROW0 + tid) * 16) = pack_b8(d);
+      *reinterpret_cast<uint4*>(smem + B_G1 + c * CS + (ROW0 + tid) * 16) = pack_b8(d1);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {  // bias gradients: column sums over the tile's rows
+        const float s0 = warp_sum(d[j]), s1 = warp_sum(d1[j]);
+        if (lane == 0) { atomicAdd(&sums[c * 8 + j], s0); atomicAdd(&sums[64 + c * 8 + j], s1); }
+      }
+    }
+    mbar_wait(bar_ld, ph, a.status, 42);
+    if (L.in == IN_M1P) {
+      pool_image(smem + B_AB, smem + B_AH, L.KC, tile, a.B, tid);
+      __syncthreads();
+    }
+    second_operand<MODE, false>(smem + B_AH, smem + B_A2, smem + B_AB, L, a.sgn_in[blockIdx.y], tile, a.B, tid);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+        if (has_dx)  // D[row, c] += G[row - (tap - pad), n] * W[n, c, tap]: B = the weight image read MN-major
+          for (int tap = 0; tap < L.T; ++tap)
+            for (int ks = 0; ks < L.NP / 16; ++ks) {
+              const uint32_t go = 2 * ks * CS + (ROW0 - (tap - pad)) * 16, wo = tap * L.tap_bytes + ks * 256;
+              umma(t_dx0, umma_desc(sbase + B_G0 + go, CS, 128), umma_desc(sbase + B_W0 + wo, 128, L.NP * 16), tt_idesc(dxw, 1, 0, 1),
+                   (tap | ks) != 0);
+              umma(t_dx1, umma_desc(sbase + B_G1 + go, CS, 128), umma_desc(sbase + B_W1 + wo, 128, L.NP * 16), tt_idesc(dxw, 1, 0, 1),
+                   (tap | ks) != 0);
+            }
+        // D[c, n] += act[c, r + tap - pad] * G[n, r] over the tile's 128 rows: both operands MN-major, accumulated over the group
+        for (int tap = 0; tap < L.T; ++tap)
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint32_t ao = (ROW0 + tap - pad + 16 * ks) * 16, go = (ROW0 + 16 * ks) * 16;
+            const uint32_t acc = (tile != tile0 || ks != 0) ? 1u : 0u;
+            umma(t_dw0 + tap * L.NP, umma_desc(sbase + B_AB + ao, 128, CS), umma_desc(sbase + B_G0 + go, 128, CS), tt_idesc(L.NP, 1, 1, 1), acc);
+            umma(t_dw1 + tap * L.NP, umma_desc(sbase + B_A2 + ao, 128, CS), umma_desc(sbase + B_G1 + go, 128, CS), tt_idesc(L.NP, 1, 1, 1), acc);
+          }
+        umma_commit(bar_mma);
+      }
+      __syncwarp();
+    }
+    mbar_wait(bar_mma, ph, a.status, 43);
+    tc_fence_after();
+    ph ^= 1;
+    if (has_dx) {  // ---- input gradient of this tile -> bf16 image (thread = row)
+      unsigned char* gi = a.ln.g[L.gdst] + (long long)tile * L.KC * CS;
+      const uint32_t la = tmem + ((uint32_t)(tid & ~31) << 16);
+      const float* sin_ = a.sgn_in[blockIdx.y];
+      for (int g = 0; g < dxw / 16; ++g) {
+        float v0[16], v1[16], o[16];
+        tmem_ld16(la + g * 16, v0);
+        tmem_ld16(la + dxw + g * 16, v1);
+        tmem_ld_wait();
+        float av[16];
+        if (MODE == BRL_MODE_LRT) {
+          unpack_h8(*reinterpret_cast<const uint4*>(smem + B_AH + (2 * g) * CS + (ROW0 + tid) * 16), reinterpret_cast<float(&)[8]>(av[0]));
+          unpack_h8(*reinterpret_cast<const uint4*>(smem + B_AH + (2 * g + 1) * CS + (ROW0 + tid) * 16), reinterpret_cast<float(&)[8]>(av[8]));
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float r = 0.f;
+          if (ri.live) {
+            if (MODE == BRL_MODE_LRT) r = fmaf(2.0f * av[j], v1[j], v0[j]);
+            else {
+              const int cr = real_ch(L.in, g * 16 + j);
+              r = cr >= 0 ? fmaf(__ldg(sin_ + (long long)ri.gw * L.cin + cr), v1[j], v0[j]) : 0.f;
+            }
+          }
+          o[j] = r;
+        }
+        unsigned char* dst = gi + (2 * g) * CS + (ROW0 + tid) * 16;
+        *reinterpret_cast<uint4*>(dst) = pack_b8(reinterpret_cast<float(&)[8]>(o[0]));
+        *reinterpret_cast<uint4*>(dst + CS) = pack_b8(reinterpret_cast<float(&)[8]>(o[8]));
+      }
+      if (tid < 4) {
+        const int pr = tid < 2 ? tid : 128 + tid;
+        for (int c = 0; c < L.KC; ++c) *reinterpret_cast<uint4*>(gi + c * CS + pr * 16) = make_uint4(0, 0, 0, 0);
+      }
+    }
+    tc_fence_before();
+    __syncthreads();  // the next tile's copies / operand writes may overwrite what this tile's MMAs and epilogue read
+    tc_fence_after();
+  }
+  // ---- weight gradients of the group: thread = TMEM lane = input channel of the image
+  if (tile0 < tile1) {
+    const int cr = real_ch(L.in, tid);
+    const uint32_t la = tmem + ((uint32_t)(tid & ~31) << 16);
+    for (int tap = 0; tap < L.T; ++tap)
+      for (int g = 0; g < L.NP / 16; ++g) {
+        float v0[16], v1[16];
+        tmem_ld16(la + 2 * dxw + tap * L.NP + g * 16, v0);
+        tmem_ld16(la + 2 * dxw + (L.T + tap) * L.NP + g * 16, v1);
+        tmem_ld_wait();
+        if (cr >= 0) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int n = g * 16 + j;
+            if (n < L.N) {
+              const long long wi = L.w_off + ((long long)n * L.cin + cr) * L.T + tap;
+              atomicAdd(a.g0 + wi, v0[j]);
+              atomicAdd(a.g1 + wi, v1[j]);
+            }
+          }
+        }
+      }
+    if (tid < L.N) {
+      atomicAdd(a.g0 + L.b_off + tid, sums[tid]);
+      atomicAdd(a.g1 + L.b_off + tid, MODE == BRL_MODE_LRT ? sums[64 + tid] : sums[tid]);  // Flipout: the sampled bias (brl_api.cu: gb2)
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+int* g_tt_status = nullptr;
+int* tt_status_word() {
+  if (!g_tt_status) {
+    cudaMalloc(&g_tt_status, sizeof(int));
+    cudaMemset(g_tt_status, 0, sizeof(int));
+  }
+  return g_tt_status;
+}
+inline size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+}  // namespace
+
+int tt_status() {
+  int v = 0;
+  if (g_tt_status) cudaMemcpy(&v, g_tt_status, sizeof(int), cudaMemcpyDeviceToHost);
+  return v;
+}
+
+size_t tt_lane_bytes(long long B) {
+  const size_t nt = (size_t)((B + 3) / 4);
+  return al256(nt * 6 * CS) + al256(nt * 16 * CS) + 2 * al256(nt * 8 * CS) + 4 * al256(nt * 16 * CS) + 2 * al256(nt * 8 * CS) +
+         al256(nt * RBUF_PER_TILE * sizeof(float)) + al256((size_t)table().blob_bytes) + 256;
+}
+void tt_carve(unsigned char* base, long long B, TtLane& ln) {
+  const size_t nt = (size_t)((B + 3) / 4);
+  unsigned char* p = reinterpret_cast<unsigned char*>(al256(reinterpret_cast<size_t>(base)));
+  auto take = [&](size_t bytes) { unsigned char* r = p; p += al256(bytes); return r; };
+  ln.ximg = take(nt * 6 * CS);
+  ln.m1 = take(nt * 16 * CS);
+  ln.t2 = take(nt * 8 * CS);
+  ln.t3 = take(nt * 8 * CS);
+  for (int k = 0; k < 4; ++k) ln.g[k] = take(nt * 16 * CS);
+  ln.g[4] = take(nt * 8 * CS);
+  ln.g[5] = take(nt * 8 * CS);
+  ln.rbuf = reinterpret_cast<float*>(take(nt * RBUF_PER_TILE * sizeof(float)));
+  ln.blob = take((size_t)table().blob_bytes);
+}
+
+static void tt_configure() {
+  static bool done = false;
+  if (done) return;
+  cudaFuncSetAttribute(tt_fwd_kernel<BRL_MODE_LRT>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM);
+  cudaFuncSetAttribute(tt_fwd_kernel<BRL_MODE_FLIPOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM);
+  cudaFuncSetAttribute(tt_bwd_kernel<BRL_MODE_LRT>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM);
+  cudaFuncSetAttribute(tt_bwd_kernel<BRL_MODE_FLIPOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM);
+  done = true;
+}
+static TtLayer layer_of(const TtStep& s, int i) {
+  TtLayer l = table().L[i];
+  l.w_off = s.w_off[i];
+  l.b_off = s.b_off[i];
+  return l;
+}
+
+void tt_forward(const TtLane& ln, const TtStep& s, cudaStream_t st) {
+  tt_configure();
+  const int nt = (int)((s.B + 3) / 4);
+  const Table& tb = table();
+  tt_packx_kernel<<<(unsigned)(((long long)nt * 3 * ROWS + 255) / 256), 256, 0, st>>>(s.x, ln.ximg, (int)s.B, nt);
+  TtPackArgs pa;
+  for (int i = 0; i < TT_LAYERS; ++i) { pa.L[i] = layer_of(s, i); pa.start[i] = tb.pack_start[i]; }
+  pa.start[TT_LAYERS] = tb.pack_start[TT_LAYERS];
+  pa.mode = s.mode; pa.mu = s.mu; pa.second = s.mode == BRL_MODE_LRT ? s.sigma : s.wsamp; pa.blob = ln.blob;
+  tt_pack_kernel<<<(tb.pack_start[TT_LAYERS] + TT_LAYERS * 64 + 255) / 256, 256, 0, st>>>(pa);
+  g_launch_count += 2;
+  static const int levels[3][4] = {{0, 1, 2, 3}, {5, 7, 4, 9}, {6, 8, -1, -1}};
+  for (int lv = 0; lv < 3; ++lv) {
+    TtFwdArgs fa{};
+    fa.ln = ln;
+    if (s.mode != BRL_MODE_LRT) fa.ln.rbuf = nullptr;
+    fa.B = (int)s.B; fa.ntile = nt; fa.feat = s.feat; fa.status = tt_status_word();
+    int nl = 0;
+    for (int k = 0; k < 4; ++k) {
+      const int li = levels[lv][k];
+      if (li < 0) continue;
+      fa.lay[nl] = layer_of(s, li);
+      fa.eps[nl] = s.eps[li];
+      fa.sgn_in[nl] = s.sgn_in[li];
+      fa.sgn_out[nl] = s.sgn_out[li];
+      ++nl;
+    }
+    fa.nl = nl;
+    ++g_launch_count;
+    if (s.mode == BRL_MODE_LRT) tt_fwd_kernel<BRL_MODE_LRT><<<dim3(nt, nl), 128, F_SMEM, st>>>(fa);
+    else tt_fwd_kernel<BRL_MODE_FLIPOUT><<<dim3(nt, nl), 128, F_SMEM, st>>>(fa);
+  }
+}
+
+void tt_backward(const TtLane& ln, const TtStep& s, cudaStream_t st) {
+  tt_configure();
+  const int nt = (int)((s.B + 3) / 4);
+  // reverse dependency levels: {b2b, b3b, b1, b4} need only the fc layer's gradient; {b2a, b3a} need d/dT2, d/dT3;
+  // module 1 needs the four d/dM1 images
+  static const int levels[3][4] = {{6, 8, 4, 9}, {5, 7, -1, -1}, {2, 1, 3, 0}};
+  for (int lv = 0; lv < 3; ++lv) {
+    TtBwdArgs ba{};
+    ba.ln = ln;
+    ba.B = (int)s.B; ba.ntile = nt; ba.feat = s.feat; ba.feat_grad = s.feat_grad; ba.g0 = s.g0; ba.g1 = s.g1; ba.status = tt_status_word();
+    int nl = 0;
+    for (int k = 0; k < 4; ++k) {
+      const int li = levels[lv][k];
+      if (li < 0) continue;
+      ba.lay[nl] = layer_of(s, li);
+      ba.sgn_in[nl] = s.sgn_in[li];
+      ba.sgn_out[nl] = s.sgn_out[li];
+      ++nl;
+    }
+    ba.nl = nl;
+    ba.tiles_per_cta = std::max(1, (nt * nl + 147) / 148);
+    const int ngroups = (nt + ba.tiles_per_cta - 1) / ba.tiles_per_cta;
+    ++g_launch_count;
+    if (s.mode == BRL_MODE_LRT) tt_bwd_kernel<BRL_MODE_LRT><<<dim3(ngroups, nl), 128, B_SMEM, st>>>(ba);
+    else tt_bwd_kernel<BRL_MODE_FLIPOUT><<<dim3(ngroups, nl), 128, B_SMEM, st>>>(ba);
+  }
+}
+
+}  // namespace brl

@@ -115,7 +115,7 @@ class Engine:
     def set_gemm_backend(self, backend: str) -> None:
         """'simt' (fp32 FFMA, parity back-end) or 'tc' (tcgen05 TF32 dual GEMMs) for the per-layer kernels of
         forward(engine='simt') / elbo_step / hnn_step."""
-        _lib.check(self.lib.brl_set_gemm_backend(self.ctx, {"simt": 0, "tc": 7}.get(backend, backend)))
+        _lib.check(self.lib.brl_set_gemm_backend(self.ctx, {"simt": 0, "tc": 7, "fused": 8}.get(backend, backend)))
 
     def set_step_graph(self, enable: bool) -> None:
         """CUDA-graph replay of elbo_step with native noise (on by default; identical results, far less host time)."""

@@ -1,0 +1,116 @@
+"""Level-fused tcgen05 training kernels (brl_set_gemm_backend 'fused': csrc/brl_tc_train.cu) against the oracle.
+
+One svi.step under `fit_ctxt` (bayesian.py:146-147; tyxe local_reparameterization / flipout restated in
+oracle/bnn_oracle.py::forward_lrt / forward_flipout) with the oracle's own noise tensors injected, float64 autograd on the
+oracle side.  Stated bound of this back-end (fp16 / bf16 operands, fp32 accumulation): outputs 1e-2, loss 5e-3, and for the
+likelihood part of the gradient (the analytic KL gradient, identical on both sides, is subtracted so that it cannot mask
+an error) per-site-group cosine > 0.999 and relative L2 error < 3e-2.  The fp32 FFMA back-end stays the 1e-3 parity engine
+(tests/test_gpu_parity.py)."""
+import pytest
+import torch
+
+from oracle import bnn_oracle as O
+from tests.helpers import injected_to_engine, synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+NET = "inception"
+KW = dict(guide="normal", prior_loc=0.0, dataset_size=238150)
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from bayesrul_b200 import Engine
+    e = Engine(NET, DEV)
+    yield e
+    e.set_gemm_backend("simt")
+
+
+def _kl_grads(mu, sg, prior_scale, c):
+    return c * (mu / prior_scale**2), c * (-1.0 / sg + sg / prior_scale**2)
+
+
+def _cos(a, b):
+    return float((a * b).sum() / (a.norm() * b.norm() + 1e-300))
+
+
+def _check_grads(e, got, ref, mu, sg, prior_scale, tag, cos_min=0.999, rel_max=3e-2):
+    c = 1.0 / (238150 * 540.0)
+    kmu, ksg = _kl_grads(mu.double(), sg.double(), prior_scale, c)
+    conv_end = e.info["sites"][20][0]  # sites 0..19 = the ten conv layers (fused kernels); 20..23 = fc + head (per-layer)
+    for name, g, r, k in (("grad_mu", got["grad_mu"], ref["grad_mu"], kmu), ("grad_sigma", got["grad_sigma"], ref["grad_sigma"], ksg)):
+        a = g.double().cpu() - k
+        b = r.double() - k
+        for part, sl in (("conv", slice(0, conv_end)), ("fc+head", slice(conv_end, None)), ("all", slice(None))):
+            cs, rel = _cos(a[sl], b[sl]), float((a[sl] - b[sl]).norm() / (b[sl].norm() + 1e-300))
+            print(f"[{tag}] {name}[{part}]: cosine {cs:.6f}, rel L2 err {rel:.2e}")
+            assert cs > cos_min and rel < rel_max, (tag, name, part, cs, rel)
+        # per conv layer (weights + bias of a layer form one group)
+        for ly in range(10):
+            lo, hi = e.info["sites"][2 * ly][0], e.info["sites"][2 * ly + 2][0]
+            cs = _cos(a[lo:hi], b[lo:hi])
+            assert cs > cos_min - 2e-3, (tag, name, "layer", ly, cs)
+
+
+@pytest.mark.parametrize("mode,particles,sigma,prior_scale", [
+    ("lrt", 1, 0.05, 0.138793), ("lrt", 1, 1.351e-3, 0.138793),
+    ("flipout", 2, 0.05, 0.198768), ("flipout", 2, 2.14e-4, 0.198768)])
+@pytest.mark.parametrize("B", [256, 37])
+def test_fused_elbo_step_vs_oracle(eng, mode, particles, sigma, prior_scale, B):
+    x, y, mu, sg = synth(NET, B, seed=21 + B, sigma=sigma)
+    g = torch.Generator().manual_seed(4)
+    nzs = [O.make_injected_noise(NET, B, mode, g) for _ in range(particles)]
+    kw = dict(mode=mode, prior_scale=prior_scale, **KW)
+    ref = O.elbo_loss_and_grads(NET, x.double(), y.double(), mu.double(), sg.double(),
+                                noises=[O.InjectedNoise({k: v.double() for k, v in n.items()}) for n in nzs], **kw)
+    eng.set_gemm_backend("fused")
+    got = eng.elbo_step(x.to(DEV), y.to(DEV), mu.to(DEV), sg.to(DEV), particles=particles,
+                        noise=injected_to_engine(NET, nzs, B, DEV), **kw)
+    eng.set_gemm_backend("simt")
+    assert eng.tc_status() == 0
+    tag = f"{mode} sigma={sigma} B={B}"
+    sc = got["scalars"].cpu()
+    out_err = ((got["out"].cpu().double() - ref["out"]).abs() / ref["out"].abs().clamp_min(1e-3)).max().item()
+    print(f"\n[{tag}] loss {sc[0].item():.6e} vs {ref['loss'].item():.6e}, nll {sc[1].item():.5e} vs {ref['nll_sum'].item():.5e}, "
+          f"max rel out err {out_err:.2e}")
+    assert abs(sc[0].item() / ref["loss"].item() - 1) < 5e-3
+    assert abs(sc[1].item() / ref["nll_sum"].item() - 1) < 5e-3
+    assert abs(sc[2].item() / ref["kl"].item() - 1) < 1e-4
+    assert out_err < 1e-2
+    # an entry-wise bound on the gradient of a ReLU net under operand rounding is not meaningful (a rounding flips the gate of
+    # the pre-activations next to zero, and one flipped gate moves a unit's gradient by a whole window's contribution); the
+    # direction is.  37 windows average fewer such flips than the 256 of a training minibatch, hence the wider small-batch bound
+    if B >= 256:
+        _check_grads(eng, got, ref, mu, sg, prior_scale, tag)
+    else:
+        _check_grads(eng, got, ref, mu, sg, prior_scale, tag, cos_min=0.995, rel_max=1e-1)
+
+
+@pytest.mark.parametrize("mode,particles", [("lrt", 1), ("flipout", 2)])
+def test_fused_native_noise_matches_fp32_backend(eng, mode, particles):
+    """Native Philox noise: the fused back-end draws the SAME eps / signs / weight noise as the fp32 back-end (same keys), so
+    the two agree to the operand precision; and a graph-replayed step equals the eager one."""
+    from bayesrul_b200 import Noise
+    B = 256
+    x, y, mu, sg = synth(NET, B, seed=5, sigma=0.02)
+    x, y, mu, sg = x.to(DEV), y.to(DEV), mu.to(DEV), sg.to(DEV)
+    kw = dict(mode=mode, prior_scale=0.138793, particles=particles, **KW)
+    eng.set_gemm_backend("simt")
+    ref = eng.elbo_step(x, y, mu, sg, noise=Noise(seed=11), **kw)
+    eng.set_gemm_backend("fused")
+    runs = [eng.elbo_step(x, y, mu, sg, noise=Noise(seed=11), **kw) for _ in range(3)]  # eager, captured, replayed
+    other = eng.elbo_step(x, y, mu, sg, noise=Noise(seed=12), **kw)
+    eng.set_gemm_backend("simt")
+    assert eng.tc_status() == 0
+    got = runs[0]
+    assert abs(got["scalars"][0].item() / ref["scalars"][0].item() - 1) < 5e-3
+    for k in ("grad_mu", "grad_sigma"):
+        cs = _cos(got[k].double(), ref[k].double())
+        assert cs > 0.999, (k, cs)
+    for r in runs[1:]:  # atomics reorder the sums: equal up to fp32 summation order
+        assert torch.allclose(r["scalars"], got["scalars"], rtol=1e-5)
+        for k in ("grad_mu", "grad_sigma"):
+            d = (r[k] - got[k]).abs().max().item() / got[k].abs().max().item()
+            print(f"[{mode}] replay vs eager {k}: max |diff| / max |grad| = {d:.2e}")
+            assert d < 1e-4, (k, d)
+    assert abs(other["scalars"][1].item() - got["scalars"][1].item()) > 0  # a new seed is a new draw (the key is re-read)
