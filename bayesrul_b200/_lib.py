@@ -59,6 +59,7 @@ SIGNATURES = {
     "brl_tc_timing": (_i, [_vp, _i]),
     "brl_tc_timing_read": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(_i64)]),  # double[2], int64[2]
     "brl_tc_trace": (_i, [_vp, _vp]),
+    "brl_tt_trace": (_i, [_vp, _vp]),
     "brl_workspace_bytes": (_i64, [_vp, _i64, _i64, _i, _i]),
     "brl_sample_weights": (_i, [_vp, _vp, _vp, _i, _i64, _np, _vp, _vp, _vp, _sz, _vp]),
     "brl_forward": (_i, [_vp, _vp, _i64, _i64, _i, _vp, _vp, _vp, _f, _np, _vp, _i, _vp, _sz, _vp]),

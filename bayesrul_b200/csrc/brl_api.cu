@@ -289,11 +289,10 @@ static PoolParams pool_params(const NetSpec& n, const OpSpec& op, const ActBufs&
   return p;
 }
 
-static void forward_op(const brl_ctx* ctx, const ActBufs& ab, const FwdArgs& a, size_t oi, cudaStream_t st, int slot) {
+// operator descriptor of a conv / linear op's forward pass (operands, noise, epilogue) and its epilogue kind
+static ConvGemm fwd_gemm(const brl_ctx* ctx, const ActBufs& ab, const FwdArgs& a, size_t oi, int slot, int* epi_out) {
   const NetSpec& n = *ctx->net;
   const OpSpec& op = n.ops[oi];
-  if (op.kind == OP_MAXPOOL3) { launch_maxpool3(pool_params(n, op, ab, a.x, a.B, a.S), st); return; }
-  if (op.kind == OP_AVGPOOL2) { launch_avgpool2(pool_params(n, op, ab, a.x, a.B, a.S), st); return; }
   const LayerSpec& L = n.layers[op.layer];
   ConvGemm p{};
   p.B = (int)a.B; p.P = op.Hout * op.Wout; p.Wrow = op.Wout; p.N = L.cout; p.K = L.cin * L.kh * L.kw; p.S = (int)a.S;
@@ -327,9 +326,20 @@ static void forward_op(const brl_ctx* ctx, const ActBufs& ab, const FwdArgs& a, 
   p.keep = (a.p_dropout > 0.f && L.drop_factor > 0.f) ? 1.0f - a.p_dropout * L.drop_factor : 1.0f;
   p.drop = nref(a.noise, a.noise ? a.noise->drop_mask[op.layer] : nullptr, KIND_DROPOUT, op.layer);
   p.part = ab.part[slot];
+  *epi_out = epi;
+  return p;
+}
+
+static void forward_op(const brl_ctx* ctx, const ActBufs& ab, const FwdArgs& a, size_t oi, cudaStream_t st, int slot) {
+  const NetSpec& n = *ctx->net;
+  const OpSpec& op = n.ops[oi];
+  if (op.kind == OP_MAXPOOL3) { launch_maxpool3(pool_params(n, op, ab, a.x, a.B, a.S), st); return; }
+  if (op.kind == OP_AVGPOOL2) { launch_avgpool2(pool_params(n, op, ab, a.x, a.B, a.S), st); return; }
+  int epi;
+  const ConvGemm p = fwd_gemm(ctx, ab, a, oi, slot, &epi);
   static const int ablate = getenv("BRL_ABLATE") ? atoi(getenv("BRL_ABLATE")) : 0;
   if (ablate & 8) return;
-  if (ctx->gemm_backend & 1) launch_conv_gemm_tc(p, epi, st);
+  if ((ctx->gemm_backend & 1) && ctx->gemm_backend <= BRL_GEMM_TC_TF32) launch_conv_gemm_tc(p, epi, st);
   else launch_conv_gemm(p, epi, st);
 }
 
@@ -375,6 +385,31 @@ struct BwdArgs {
   float *g0, *g1;    // flat gradient accumulators
 };
 
+// backward through the activation / dropout / head of conv op `oi`: gradient of the op output -> compact dpre (+ dvar / dpert)
+static void backward_act(const brl_ctx* ctx, const ActBufs& ab, const BwdArgs& a, int oi, cudaStream_t cs) {
+  const NetSpec& n = *ctx->net;
+  const OpSpec& op = n.ops[oi];
+  const LayerSpec& L = n.layers[op.layer];
+  const int Pout = op.Hout * op.Wout;
+  const bool is_last = op.out_buf == n.out_buf;
+  const float keep = (a.p_dropout > 0.f && L.drop_factor > 0.f) ? 1.0f - a.p_dropout * L.drop_factor : 1.0f;
+  BwdAct ba{};
+  ba.gout = ab.grad[op.out_buf];
+  ba.outv = (is_last && a.out) ? a.out : ab.act[op.out_buf];
+  ba.img_stride = n.bufs[op.out_buf].elems();
+  ba.out_P = n.bufs[op.out_buf].H * n.bufs[op.out_buf].W;
+  ba.co_off = op.co_off; ba.N = L.cout; ba.P = Pout; ba.n_img = a.B; ba.B = (int)a.B;
+  ba.relu = op.relu; ba.head = op.head; ba.inv_keep = 1.0f / keep;
+  ba.dpre = ab.dpre[oi];
+  if (a.mode == BRL_MODE_LRT) {
+    ba.dvar = ab.dsec[oi]; ba.sd = ab.sd[oi];
+    ba.eps = nref(a.noise, a.noise ? a.noise->lrt_eps[op.layer] : nullptr, KIND_LRT_EPS, op.layer);
+  } else if (a.mode == BRL_MODE_FLIPOUT) {
+    ba.dpert = ab.dsec[oi]; ba.sign_out = a.sgn_out[op.layer];
+  }
+  launch_bwd_act(ba, cs);
+}
+
 // expects grad[out_buf] to hold dLoss/d(out) and every other grad buffer zeroed
 // backward of one op on stream `cs` (slot: 0 = the caller's stream, 1.. = side stream): activation backward, input
 // gradient (the critical chain; `ev_dx`, if given, is recorded right behind it) and the weight gradients, which only
@@ -394,24 +429,8 @@ static void backward_op(const brl_ctx* ctx, const ActBufs& ab, const BwdArgs& a,
   }
   const LayerSpec& L = n.layers[op.layer];
   const int Pout = op.Hout * op.Wout;
-  const bool is_last = op.out_buf == n.out_buf;
-  const float keep = (a.p_dropout > 0.f && L.drop_factor > 0.f) ? 1.0f - a.p_dropout * L.drop_factor : 1.0f;
-  BwdAct ba{};
-  ba.gout = ab.grad[op.out_buf];
-  ba.outv = (is_last && a.out) ? a.out : ab.act[op.out_buf];
-  ba.img_stride = n.bufs[op.out_buf].elems();
-  ba.out_P = n.bufs[op.out_buf].H * n.bufs[op.out_buf].W;
-  ba.co_off = op.co_off; ba.N = L.cout; ba.P = Pout; ba.n_img = a.B; ba.B = (int)a.B;
-  ba.relu = op.relu; ba.head = op.head; ba.inv_keep = 1.0f / keep;
-  ba.dpre = ab.dpre[oi];
-  if (a.mode == BRL_MODE_LRT) {
-    ba.dvar = ab.dsec[oi]; ba.sd = ab.sd[oi];
-    ba.eps = nref(a.noise, a.noise ? a.noise->lrt_eps[op.layer] : nullptr, KIND_LRT_EPS, op.layer);
-  } else if (a.mode == BRL_MODE_FLIPOUT) {
-    ba.dpert = ab.dsec[oi]; ba.sign_out = a.sgn_out[op.layer];
-  }
   static const int ablate = getenv("BRL_ABLATE") ? atoi(getenv("BRL_ABLATE")) : 0;  // timing experiments only (wrong results)
-  if (!(ablate & 4)) launch_bwd_act(ba, cs);
+  if (!(ablate & 4)) backward_act(ctx, ab, a, oi, cs);
   if (ws != cs) {  // the weight-gradient stream picks up behind the activation backward
     cudaEventRecord(ev_act, cs);
     cudaStreamWaitEvent(ws, ev_act, 0);
@@ -701,6 +720,11 @@ int brl_tc_timing_read(brl_ctx* ctx, double* kernel_ms, int64_t* launches) {
   tc_timing_read(ctx->tc, kernel_ms, n);
   launches[0] = n[0];
   launches[1] = n[1];
+  return BRL_OK;
+}
+int brl_tt_trace(brl_ctx* ctx, int64_t* device_buf) {
+  BRL_REQUIRE(ctx, "brl_tt_trace: NULL context");
+  tt_trace(reinterpret_cast<long long*>(device_buf));
   return BRL_OK;
 }
 int brl_tc_trace(brl_ctx* ctx, int64_t* device_buf) {
@@ -1124,12 +1148,15 @@ static int elbo_body(brl_ctx* ctx, const ActBufs* const* lanes, int n_lanes, con
           ts.sgn_in[ly] = sin_[ly]; ts.sgn_out[ly] = sout_[ly];
           ts.w_off[ly] = n.layers[ly].w_off; ts.b_off[ly] = n.layers[ly].b_off;
         }
-        const int fc_op = (int)n.ops.size() - 2;
-        ts.feat = ab.act[n.ops[fc_op].in.buf];
-        ts.feat_grad = compute_grads ? ab.grad[n.ops[fc_op].in.buf] : nullptr;
+        const int fc_op = (int)n.ops.size() - 2, fc_layer = n.ops[fc_op].layer;
+        ts.sgn_fc_in = sin_[fc_layer];
+        ts.w_off_fc = n.layers[fc_layer].w_off; ts.b_off_fc = n.layers[fc_layer].b_off;
         ts.g0 = ab.g0; ts.g1 = ab.g1;
         tt_forward(ab.tt, ts, ls);
-        forward_op(ctx, ab, fa, fc_op, ls, 0);
+        int epi;
+        const ConvGemm fc = fwd_gemm(ctx, ab, fa, fc_op, 0, &epi);  // the fc layer: tcgen05 contraction + the per-layer epilogue
+        tt_fc_forward(ab.tt, ts, fc.part, ls);
+        launch_splitk_epilogue(fc, epi, ls);
         forward_op(ctx, ab, fa, fc_op + 1, ls, 0);
       } else {
         run_forward(ctx, ab, fa, ls, l);
@@ -1141,7 +1168,8 @@ static int elbo_body(brl_ctx* ctx, const ActBufs* const* lanes, int n_lanes, con
         if (use_tt) {
           const int fc_op = (int)n.ops.size() - 2;
           backward_op(ctx, ab, ba, fc_op + 1, ls, 0, ls, nullptr, nullptr);
-          backward_op(ctx, ab, ba, fc_op, ls, 0, ls, nullptr, nullptr);
+          backward_act(ctx, ab, ba, fc_op, ls);
+          tt_fc_backward(ab.tt, ts, ab.dpre[fc_op], ab.dsec[fc_op], ls);
           tt_backward(ab.tt, ts, ls);
         } else {
           run_backward(ctx, ab, ba, ls, l);

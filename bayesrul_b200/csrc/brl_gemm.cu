@@ -240,6 +240,20 @@ int conv_gemm_ksplit(const ConvGemm& p) {
   return std::max(1, std::min(p.K / (4 * BK), 296 / ctas));
 }
 
+// the epilogue alone, over partial sums some other kernel has accumulated in p.part ([2][B * P][N]): the fc layer of the level-fused
+// training kernels (brl_tc_train.cu) contracts on the tensor pipe and shares bias / noise / activation handling with this path
+void launch_splitk_epilogue(const ConvGemm& p, int epi, cudaStream_t st) {
+  const long long total = (long long)p.B * p.P * p.N;
+  const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 8);
+  ++g_launch_count;
+  switch (epi) {
+    case EPI_FWD_PLAIN: splitk_epilogue_kernel<false, EPI_FWD_PLAIN><<<grid, 256, 0, st>>>(p); break;
+    case EPI_FWD_LRT: splitk_epilogue_kernel<true, EPI_FWD_LRT><<<grid, 256, 0, st>>>(p); break;
+    case EPI_FWD_FLIPOUT: splitk_epilogue_kernel<true, EPI_FWD_FLIPOUT><<<grid, 256, 0, st>>>(p); break;
+    default: break;
+  }
+}
+
 void launch_conv_gemm(const ConvGemm& p0, int epi, cudaStream_t st) {
   ConvGemm p = p0;
   p.ksplit = conv_gemm_ksplit(p);

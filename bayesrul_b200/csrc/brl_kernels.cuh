@@ -83,6 +83,7 @@ struct ConvGemm {
 constexpr long long SPLITK_SCRATCH_FLOATS = 2ll * 74 * 128 * 32;
 
 void launch_conv_gemm(const ConvGemm& p, int epi, cudaStream_t st);
+void launch_splitk_epilogue(const ConvGemm& p, int epi, cudaStream_t st);  // epilogue over p.part = [2][B * P][N] partial sums
 // same operator on the tensor pipe: tcgen05 kind::tf32 dual GEMM, fp32 accumulation in TMEM (brl_tc_gemm.cu)
 void launch_conv_gemm_tc(const ConvGemm& p, int epi, cudaStream_t st);
 int tc_gemm_status();  // 0 ok, else code of the first mbarrier wait that timed out in a TF32 kernel (synchronises)

@@ -42,6 +42,7 @@ extern std::atomic<long long> g_launch_count;
 namespace {
 
 constexpr int ROWS = 132, CS = ROWS * 16, ROW0 = 2;
+constexpr int NT = 512;  // threads per CTA: 16 warps = 4 TMEM lane quadrants (rows) x 4 column quarters
 enum { IN_X = 0, IN_XP = 1, IN_M1 = 2, IN_M1P = 3, IN_T2 = 4, IN_T3 = 5 };
 enum { OUT_M1 = 0, OUT_T2 = 1, OUT_T3 = 2, OUT_FEAT = 3 };
 
@@ -51,6 +52,8 @@ struct TtLayer {
   int w0h, w0b, w1b, w1h, bias, tap_bytes;   // byte offsets inside the weight blob; bytes of one tap's [KC][NP][8] tile
   int gdst;                                  // gradient image receiving this layer's input gradient (-1: input is x)
   int roff_per_tile;                         // float offset of this layer's rbuf block inside a tile's 336 * 128 floats
+  int poff;                                  // float offset of this layer's weight-gradient partials inside a group's block:
+                                             // [2 paths][N][T][KC * 8 image channels] then [2][64] bias sums
   long long w_off, b_off;                    // flat parameter offsets
 };
 
@@ -58,6 +61,7 @@ struct TtLayer {
 struct Table {
   TtLayer L[TT_LAYERS];
   int blob_bytes, pack_start[TT_LAYERS + 1];
+  int part_floats;  // floats of one group's partial block (all layers)
 };
 const Table& table() {
   static const Table t = [] {
@@ -70,7 +74,7 @@ const Table& table() {
     const int oc0[10] = {0, 4, 8, 12, 0, 0, 16, 0, 32, 48};
     const int cin[10] = {18, 18, 18, 18, 108, 108, 64, 108, 64, 108};
     const int gdst[10] = {-1, -1, -1, -1, 0, 1, 4, 2, 5, 3};
-    int off = 0, roff = 0, ps = 0;
+    int off = 0, roff = 0, ps = 0, po = 0;
     for (int i = 0; i < 10; ++i) {
       TtLayer& l = tb.L[i];
       l.layer = i; l.in = in_[i]; l.KC = KC[i]; l.N = N[i]; l.NP = (N[i] + 15) & ~15; l.T = T[i]; l.out = out[i]; l.out_c0 = oc0[i];
@@ -83,15 +87,25 @@ const Table& table() {
       l.w1h = off; off += img;
       l.bias = off; off += 2 * 64 * 4;
       l.roff_per_tile = roff; roff += l.NP * 128;
+      l.poff = po; po += 2 * l.N * l.T * l.KC * 8 + 128;
       tb.pack_start[i] = ps; ps += l.T * l.KC * 8 * l.NP;
     }
     tb.pack_start[10] = ps;
     tb.blob_bytes = off;
+    tb.part_floats = po;
     return tb;
   }();
   return t;
 }
 constexpr int RBUF_PER_TILE = 336 * 128;  // sum of NP over the ten layers x 128 rows
+// fc layer (2400 -> 64): feature images of a 128-window M-tile, [300 k-chunks][128 windows][8 x 16 bit], k' = t * 80 + c
+// (chunk = t * 10 + c / 8); weight images [300 k-chunks][64 n][8]
+constexpr int FC_KC = 300, FC_CHUNK = 128 * 16, FC_MT_BYTES = FC_KC * FC_CHUNK, FC_WIMG = FC_KC * 64 * 16;
+constexpr int FC_KS = 15, FC_KCS = FC_KC / FC_KS;  // forward: K split over 15 CTAs of 20 chunks (10 MMA k-steps)
+constexpr int FC_NS = 10, FC_NCS = FC_KC / FC_NS;  // input gradient: N' = 2400 in 10 slices of 240 columns (30 chunks)
+__device__ __forceinline__ long long feat_addr(int gw, int t, int c0) {  // 16-byte unit of window gw, step t, channels [c0, c0 + 8)
+  return ((long long)(gw >> 7) * FC_KC + t * 10 + (c0 >> 3)) * FC_CHUNK + (gw & 127) * 16;
+}
 
 // image channel k of an input -> real channel of the torch weight / sign tensor (-1: padding channel)
 __device__ __forceinline__ int real_ch(int in, int k) {
@@ -133,6 +147,14 @@ __device__ __forceinline__ uint4 pack_h8(const float (&f)[8]) {
 __host__ __device__ constexpr uint32_t tt_idesc(int n, int fmt, int a_mn, int b_mn) {
   return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
          ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+// four normals of one Philox block (brl_philox.cuh::normal4 with hardware log / sin / cos)
+__device__ __forceinline__ float4 normal4_fast(const uint4& r) {
+  const float rad0 = sqrtf(-2.0f * __logf(u01(r.x))), rad1 = sqrtf(-2.0f * __logf(u01(r.z)));
+  float s0, c0, s1, c1;
+  __sincosf(6.283185307179586f * u01(r.y), &s0, &c0);
+  __sincosf(6.283185307179586f * u01(r.w), &s1, &c1);
+  return make_float4(rad0 * c0, rad0 * s0, rad1 * c1, rad1 * s1);
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -233,8 +255,9 @@ struct TtFwdArgs {
   NoiseRef eps[4];
   const float* sgn_in[4];
   const float* sgn_out[4];
-  float* feat;
+  const float* sgn_fc_in;  // Flipout: s_in of the fc layer [B, 2400] (the feature producers build its perturbation operand)
   int* status;
+  long long* trace;  // debug: clock64 stamps of CTA (0, y), [4 layers][16] (nullptr = off)
 };
 
 __device__ __forceinline__ const unsigned char* input_image(const TtLane& ln, int in, int tile) {
@@ -251,7 +274,7 @@ __device__ __forceinline__ void bulk_copy_chunked(uint32_t dst, const unsigned c
 }
 // MaxPool1d(3,1,1) of a post-ReLU activation image (values >= 0, dead / pad rows are zero, so they act as the -inf padding)
 __device__ __forceinline__ void pool_image(const unsigned char* raw, unsigned char* dst, int KC, int tile, int B, int tid) {
-  for (int idx = tid; idx < KC * ROWS; idx += 128) {
+  for (int idx = tid; idx < KC * ROWS; idx += NT) {
     const int ch = idx / ROWS, rr = idx - ch * ROWS;
     uint4 o = make_uint4(0, 0, 0, 0);
     if (row_info(rr, tile, B).live) {
@@ -266,7 +289,7 @@ __device__ __forceinline__ void pool_image(const unsigned char* raw, unsigned ch
 template <int MODE, bool H16>
 __device__ __forceinline__ void second_operand(const unsigned char* A, unsigned char* A2, unsigned char* Ab, const TtLayer& L,
                                                const float* sgn_in, int tile, int B, int tid) {
-  for (int idx = tid; idx < L.KC * ROWS; idx += 128) {
+  for (int idx = tid; idx < L.KC * ROWS; idx += NT) {
     const int ch = idx / ROWS, rr = idx - ch * ROWS;
     float f[8], s[8];
     unpack_h8(*reinterpret_cast<const uint4*>(A + ch * CS + rr * 16), f);
@@ -287,10 +310,12 @@ __device__ __forceinline__ void second_operand(const unsigned char* A, unsigned 
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(128, 1) tt_fwd_kernel(const TtFwdArgs a) {
+__global__ void __launch_bounds__(NT, 1) tt_fwd_kernel(const TtFwdArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const TtLayer& L = a.lay[blockIdx.y];
-  const int tile = blockIdx.x, tid = threadIdx.x, warp = tid >> 5;
+  const int tile = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  long long* tr = (a.trace && blockIdx.x == 0 && tid == 0) ? a.trace + blockIdx.y * 16 : nullptr;
+  if (tr) tr[0] = clock64();
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar_ld = sbase + F_BAR, bar_mma = bar_ld + 8;
   uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + F_BAR + 16);
@@ -301,7 +326,7 @@ __global__ void __launch_bounds__(128, 1) tt_fwd_kernel(const TtFwdArgs a) {
   }
   if (warp == 0) tmem_alloc(smem_u32(tslot), 128);
   if (L.in <= IN_XP)  // K = 32 for the 18 input features: the 4th chunk is zero
-    for (int i = tid; i < CS / 16; i += 128) reinterpret_cast<uint4*>(smem + F_A + 3 * CS)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < CS / 16; i += NT) reinterpret_cast<uint4*>(smem + F_A + 3 * CS)[i] = make_uint4(0, 0, 0, 0);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -316,7 +341,9 @@ __global__ void __launch_bounds__(128, 1) tt_fwd_kernel(const TtFwdArgs a) {
     bulk_copy_chunked(sbase + F_W1, a.ln.blob + (MODE == BRL_MODE_FLIPOUT ? L.w1h : L.w1b), img_bytes, bar_ld);
     bulk_g2s(sbase + F_BIAS, a.ln.blob + L.bias, 512, bar_ld);
   }
+  if (tr) tr[1] = clock64();
   mbar_wait(bar_ld, 0, a.status, 40);
+  if (tr) tr[2] = clock64();
   if (L.in == IN_M1P) {  // the pooled branch: pool the staged raw image first
     pool_image(smem + F_A2, smem + F_A, L.KC, tile, a.B, tid);
     __syncthreads();
@@ -326,6 +353,7 @@ __global__ void __launch_bounds__(128, 1) tt_fwd_kernel(const TtFwdArgs a) {
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
+  if (tr) tr[3] = clock64();
   if (warp == 0) {
     tc_fence_after();
     if (elect_one()) {
@@ -344,46 +372,75 @@ __global__ void __launch_bounds__(128, 1) tt_fwd_kernel(const TtFwdArgs a) {
   }
   mbar_wait(bar_mma, 0, a.status, 41);
   tc_fence_after();
-  // ---- epilogue: thread = tile row
-  const RowInfo ri = row_info(ROW0 + tid, tile, a.B);
-  const uint32_t la = tmem + ((uint32_t)(tid & ~31) << 16);
+  if (tr) tr[4] = clock64();
+  // ---- epilogue: thread = tile row (TMEM lane quadrant = warp % 4) x column quarter (warp / 4), eight columns at a time
+  const int row = (warp & 3) * 32 + lane, cq = warp >> 2;
+  const RowInfo ri = row_info(ROW0 + row, tile, a.B);
+  const uint32_t la = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   const float* bias = reinterpret_cast<const float*>(smem + F_BIAS);
   const NoiseRef& nz = a.eps[blockIdx.y];
+  const NoiseKey nk = noise_key(nz);
   const float* sout = a.sgn_out[blockIdx.y];
   float* rb = a.ln.rbuf ? a.ln.rbuf + (long long)tile * RBUF_PER_TILE + L.roff_per_tile : nullptr;
   unsigned char* oimg = L.out == OUT_M1 ? a.ln.m1 + (long long)tile * 16 * CS
                         : L.out == OUT_T2 ? a.ln.t2 + (long long)tile * 8 * CS
                         : L.out == OUT_T3 ? a.ln.t3 + (long long)tile * 8 * CS : nullptr;
-  for (int g = 0; g < L.NP / 16; ++g) {
-    float v0[16], v1[16], o[16];
-    tmem_ld16(la + g * 16, v0);
-    tmem_ld16(la + L.NP + g * 16, v1);
+  // LRT eps of the warp's window (one warp = the 30 steps of one window x 8 channels = elements [240 g, 240 g + 240) of the
+  // layer's stream, i.e. exactly Philox blocks [60 g, 60 g + 60)): every lane draws two blocks = eight normals into a per-warp
+  // scratch (the operand regions are dead once the MMAs have completed) instead of one block per element
+  float* scratch = reinterpret_cast<float*>(smem + F_A) + warp * 256;
+  for (int g = cq; g < L.NP / 8; g += 4) {
+    float v0[8], v1[8], o[8];
+    tmem_ld8(la + g * 8, v0);
+    tmem_ld8(la + L.NP + g * 8, v1);
+    if (MODE == BRL_MODE_LRT && !nz.ptr) {
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int bi = k * 32 + lane;
+        if (bi < 60)
+          *reinterpret_cast<float4*>(scratch + bi * 4) =
+              normal4_fast(philox_block(nk.seed, nz.kind, nz.site, nk.sample0, nk.window0 + ri.gw, (uint32_t)(60 * g + bi)));
+      }
+      __syncwarp();
+    }
     tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int n = g * 16 + j;
+    for (int j = 0; j < 8; ++j) {
+      const int n = g * 8 + j;
       const bool on = ri.live && n < L.N;
       float pre;
       if (MODE == BRL_MODE_LRT) {
         float var = v1[j] + bias[64 + n];
         if (var < 0.f) var += fabsf(var) + 1e-6f;
         const float sd = sqrtf(var);
-        const float e = on ? gnoise_normal(nz, 0, ri.gw, a.B, L.N * 30, n * 30 + ri.t) : 0.f;
+        const float e = !on ? 0.f : nz.ptr ? nz.ptr[(long long)ri.gw * (L.N * 30) + n * 30 + ri.t] : scratch[j * 30 + ri.t];
         pre = fmaf(sd, e, v0[j] + bias[n]);
-        if (rb) rb[(long long)n * 128 + tid] = (on && sd > 0.f) ? e / (2.0f * sd) : 0.f;
+        if (rb) rb[(long long)n * 128 + row] = (on && sd > 0.f) ? e / (2.0f * sd) : 0.f;
       } else {
         pre = v0[j] + bias[n] + (on ? v1[j] * __ldg(sout + (long long)ri.gw * L.N + n) : 0.f);
       }
       o[j] = on ? fmaxf(pre, 0.f) : 0.f;
     }
     if (oimg) {
-      unsigned char* dst = oimg + (L.out_c0 + 2 * g) * CS + (ROW0 + tid) * 16;
-      *reinterpret_cast<uint4*>(dst) = pack_h8(reinterpret_cast<float(&)[8]>(o[0]));
-      *reinterpret_cast<uint4*>(dst + CS) = pack_h8(reinterpret_cast<float(&)[8]>(o[8]));
-    } else if (ri.live) {
+      *reinterpret_cast<uint4*>(oimg + (L.out_c0 + g) * CS + (ROW0 + row) * 16) = pack_h8(o);
+    } else if (ri.live) {  // module-2 output = the fc layer's operands: fp16 features, their bf16 copy and the second operand
+      const int c0 = L.out_c0 + g * 8;
+      const long long fa = feat_addr(ri.gw, ri.t, c0);
+      const uint4 fh = pack_h8(o);
+      float fr[8], f2[8];
+      unpack_h8(fh, fr);
 #pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (g * 16 + j < L.N) a.feat[((long long)ri.gw * 80 + L.out_c0 + g * 16 + j) * 30 + ri.t] = o[j];
+      for (int j = 0; j < 8; ++j)
+        f2[j] = MODE == BRL_MODE_LRT ? fr[j] * fr[j] : fr[j] * __ldg(a.sgn_fc_in + (long long)ri.gw * 2400 + (c0 + j) * 30 + ri.t);
+      *reinterpret_cast<uint4*>(a.ln.fimg + fa) = fh;
+      *reinterpret_cast<uint4*>(a.ln.fbimg + fa) = pack_b8(fr);
+      if (MODE == BRL_MODE_LRT) {
+        *reinterpret_cast<uint4*>(a.ln.f2img + fa) = pack_b8(f2);
+      } else {  // the perturbation GEMM runs fp16 x fp16 in the forward pass (f * s_in is exact in fp16), bf16 in the backward pass
+        *reinterpret_cast<uint4*>(a.ln.f2img + fa) = pack_h8(f2);
+        *reinterpret_cast<uint4*>(a.ln.f2bimg + fa) = pack_b8(f2);
+      }
     }
   }
   if (oimg && tid < 4) {  // the image's pad rows
@@ -392,6 +449,7 @@ __global__ void __launch_bounds__(128, 1) tt_fwd_kernel(const TtFwdArgs a) {
   }
   tc_fence_before();
   __syncthreads();
+  if (tr) tr[5] = clock64();
   if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
@@ -409,10 +467,10 @@ struct TtBwdArgs {
   TtLayer lay[4];
   const float* sgn_in[4];
   const float* sgn_out[4];
-  const float* feat;
-  const float* feat_grad;
   float *g0, *g1;
+  int part_floats;
   int* status;
+  long long* trace;
 };
 
 // gradient w.r.t. the layer OUTPUT (post-activation), 8 channels [n0, n0 + 8) of tile row `row`, and the ReLU gate
@@ -423,12 +481,12 @@ __device__ __forceinline__ void output_grad(const TtBwdArgs& a, const TtLayer& L
   for (int j = 0; j < 8; ++j) d[j] = 0.f;
   if (!ri.live) return;
   if (L.out == OUT_FEAT) {
+    const long long fa = feat_addr(ri.gw, ri.t, L.out_c0 + n0);
+    float f[8], gr[8];
+    unpack_h8(*reinterpret_cast<const uint4*>(a.ln.fimg + fa), f);
+    unpack_b8(*reinterpret_cast<const uint4*>(a.ln.gfimg + fa), gr);
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (n0 + j < L.N) {
-        const long long i = ((long long)ri.gw * 80 + L.out_c0 + n0 + j) * 30 + ri.t;
-        d[j] = a.feat[i] > 0.f ? a.feat_grad[i] : 0.f;
-      }
+    for (int j = 0; j < 8; ++j) d[j] = f[j] > 0.f ? gr[j] : 0.f;
     return;
   }
   const long long ro = (long long)(ROW0 + row) * 16;
@@ -481,10 +539,12 @@ __device__ __forceinline__ void output_grad(const TtBwdArgs& a, const TtLayer& L
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(128, 1) tt_bwd_kernel(const TtBwdArgs a) {
+__global__ void __launch_bounds__(NT, 1) tt_bwd_kernel(const TtBwdArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const TtLayer& L = a.lay[blockIdx.y];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  long long* tr = (a.trace && blockIdx.x == 0 && tid == 0) ? a.trace + blockIdx.y * 16 : nullptr;
+  if (tr) tr[0] = clock64();
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar_ld = sbase + B_BAR, bar_mma = bar_ld + 8;
   uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + B_BAR + 16);
@@ -495,15 +555,21 @@ __global__ void __launch_bounds__(128, 1) tt_bwd_kernel(const TtBwdArgs a) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc(smem_u32(tslot), 512);
-  // operand regions start as zeros: chunks a layer does not fill (the 4th chunk of x, M lanes beyond KC) must hold finite values,
-  // and the pad rows of the gradient images stay zero for the whole kernel
-  for (int i = tid; i < B_W0 / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-  sums[tid] = 0.f;
+  // zeros that must be there: the 4th k-chunk of an x input and the pad rows of the gradient images (they stay zero for the
+  // whole kernel).  Chunks beyond KC are only read as M lanes >= KC * 8 of the weight-gradient MMAs, i.e. accumulator rows that
+  // nobody reads back.
+  for (int i = tid; i < CS / 16; i += NT) reinterpret_cast<uint4*>(smem + B_AH + 3 * CS)[i] = make_uint4(0, 0, 0, 0);
+  if (tid < 64) {  // 16 gradient chunks (G0 | G1 are contiguous) x pad rows {0, 1, 130, 131}
+    const int c = tid >> 2, r4 = tid & 3, pr = r4 < 2 ? r4 : 128 + r4;
+    *reinterpret_cast<uint4*>(smem + B_G0 + c * CS + pr * 16) = make_uint4(0, 0, 0, 0);
+  }
+  if (tid < 128) sums[tid] = 0.f;
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tslot;
+  if (tr) tr[8] = clock64();
   const bool has_dx = L.gdst >= 0;
   const int dxw = has_dx ? L.KC * 8 : 0;            // columns of one input-gradient accumulator
   const uint32_t t_dx0 = tmem, t_dx1 = tmem + dxw, t_dw0 = tmem + 2 * dxw, t_dw1 = t_dw0 + L.T * L.NP;
@@ -522,28 +588,34 @@ __global__ void __launch_bounds__(128, 1) tt_bwd_kernel(const TtBwdArgs a) {
         bulk_copy_chunked(sbase + B_W1, a.ln.blob + L.w1b, img_bytes, bar_ld);
       }
     }
-    // ---- gradient operands (global reads only): G0 = d/d(pre-activation), G1 = d/d(variance) or d/d(perturbation); thread = row
-    const RowInfo ri = row_info(ROW0 + tid, tile, a.B);
+    // ---- gradient operands (global reads only): G0 = d/d(pre-activation), G1 = d/d(variance) or d/d(perturbation);
+    //      thread = row x chunk quarter
+    const int row = (warp & 3) * 32 + lane, cq = warp >> 2;
+    const RowInfo ri = row_info(ROW0 + row, tile, a.B);
     const float* rb = a.ln.rbuf + (long long)tile * RBUF_PER_TILE + L.roff_per_tile;
     const float* sout = a.sgn_out[blockIdx.y];
-    for (int c = 0; c < L.NP / 8; ++c) {
+    for (int c = cq; c < L.NP / 8; c += 4) {
       float d[8], d1[8];
-      output_grad<MODE>(a, L, tile, tid, ri, c * 8, d);
+      output_grad<MODE>(a, L, tile, row, ri, c * 8, d);
+      if (tr && tile == tile0 && c == cq) tr[9] = clock64();
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int n = c * 8 + j;
-        if (MODE == BRL_MODE_LRT) d1[j] = d[j] * rb[(long long)n * 128 + tid];
+        if (MODE == BRL_MODE_LRT) d1[j] = d[j] * rb[(long long)n * 128 + row];
         else d1[j] = (ri.live && n < L.N) ? d[j] * __ldg(sout + (long long)ri.gw * L.N + n) : 0.f;
       }
-      *reinterpret_cast<uint4*>(smem + B_G0 + c * CS + (ROW0 + tid) * 16) = pack_b8(d);
-      *reinterpret_cast<uint4*>(smem + B_G1 + c * CS + (ROW0 + tid) * 16) = pack_b8(d1);
+      *reinterpret_cast<uint4*>(smem + B_G0 + c * CS + (ROW0 + row) * 16) = pack_b8(d);
+      *reinterpret_cast<uint4*>(smem + B_G1 + c * CS + (ROW0 + row) * 16) = pack_b8(d1);
+      if (tr && tile == tile0 && c == cq) tr[10] = clock64();
 #pragma unroll
       for (int j = 0; j < 8; ++j) {  // bias gradients: column sums over the tile's rows
         const float s0 = warp_sum(d[j]), s1 = warp_sum(d1[j]);
         if (lane == 0) { atomicAdd(&sums[c * 8 + j], s0); atomicAdd(&sums[64 + c * 8 + j], s1); }
       }
     }
+    if (tr && tile == tile0) tr[1] = clock64();
     mbar_wait(bar_ld, ph, a.status, 42);
+    if (tr && tile == tile0) tr[2] = clock64();
     if (L.in == IN_M1P) {
       pool_image(smem + B_AB, smem + B_AH, L.KC, tile, a.B, tid);
       __syncthreads();
@@ -552,6 +624,7 @@ __global__ void __launch_bounds__(128, 1) tt_bwd_kernel(const TtBwdArgs a) {
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
+    if (tr && tile == tile0) tr[3] = clock64();
     if (warp == 0) {
       tc_fence_after();
       if (elect_one()) {
@@ -579,35 +652,30 @@ __global__ void __launch_bounds__(128, 1) tt_bwd_kernel(const TtBwdArgs a) {
     mbar_wait(bar_mma, ph, a.status, 43);
     tc_fence_after();
     ph ^= 1;
-    if (has_dx) {  // ---- input gradient of this tile -> bf16 image (thread = row)
+    if (tr && tile == tile0) tr[4] = clock64();
+    if (has_dx) {  // ---- input gradient of this tile -> bf16 image (thread = row x column quarter)
       unsigned char* gi = a.ln.g[L.gdst] + (long long)tile * L.KC * CS;
-      const uint32_t la = tmem + ((uint32_t)(tid & ~31) << 16);
+      const uint32_t la = tmem + ((uint32_t)((warp & 3) * 32) << 16);
       const float* sin_ = a.sgn_in[blockIdx.y];
-      for (int g = 0; g < dxw / 16; ++g) {
-        float v0[16], v1[16], o[16];
-        tmem_ld16(la + g * 16, v0);
-        tmem_ld16(la + dxw + g * 16, v1);
+      for (int g = cq; g < dxw / 8; g += 4) {
+        float v0[8], v1[8], o[8], av[8];
+        tmem_ld8(la + g * 8, v0);
+        tmem_ld8(la + dxw + g * 8, v1);
         tmem_ld_wait();
-        float av[16];
-        if (MODE == BRL_MODE_LRT) {
-          unpack_h8(*reinterpret_cast<const uint4*>(smem + B_AH + (2 * g) * CS + (ROW0 + tid) * 16), reinterpret_cast<float(&)[8]>(av[0]));
-          unpack_h8(*reinterpret_cast<const uint4*>(smem + B_AH + (2 * g + 1) * CS + (ROW0 + tid) * 16), reinterpret_cast<float(&)[8]>(av[8]));
-        }
+        if (MODE == BRL_MODE_LRT) unpack_h8(*reinterpret_cast<const uint4*>(smem + B_AH + g * CS + (ROW0 + row) * 16), av);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < 8; ++j) {
           float r = 0.f;
           if (ri.live) {
             if (MODE == BRL_MODE_LRT) r = fmaf(2.0f * av[j], v1[j], v0[j]);
             else {
-              const int cr = real_ch(L.in, g * 16 + j);
+              const int cr = real_ch(L.in, g * 8 + j);
               r = cr >= 0 ? fmaf(__ldg(sin_ + (long long)ri.gw * L.cin + cr), v1[j], v0[j]) : 0.f;
             }
           }
           o[j] = r;
         }
-        unsigned char* dst = gi + (2 * g) * CS + (ROW0 + tid) * 16;
-        *reinterpret_cast<uint4*>(dst) = pack_b8(reinterpret_cast<float(&)[8]>(o[0]));
-        *reinterpret_cast<uint4*>(dst + CS) = pack_b8(reinterpret_cast<float(&)[8]>(o[8]));
+        *reinterpret_cast<uint4*>(gi + g * CS + (ROW0 + row) * 16) = pack_b8(o);
       }
       if (tid < 4) {
         const int pr = tid < 2 ? tid : 128 + tid;
@@ -617,39 +685,367 @@ __global__ void __launch_bounds__(128, 1) tt_bwd_kernel(const TtBwdArgs a) {
     tc_fence_before();
     __syncthreads();  // the next tile's copies / operand writes may overwrite what this tile's MMAs and epilogue read
     tc_fence_after();
+    if (tr && tile == tile0) tr[5] = clock64();
   }
-  // ---- weight gradients of the group: thread = TMEM lane = input channel of the image
+  // ---- weight gradients of the group: thread = TMEM lane = input channel of the image, (tap, 8 output channels) items spread
+  //      over the column quarters
   if (tile0 < tile1) {
-    const int cr = real_ch(L.in, tid);
-    const uint32_t la = tmem + ((uint32_t)(tid & ~31) << 16);
-    for (int tap = 0; tap < L.T; ++tap)
-      for (int g = 0; g < L.NP / 16; ++g) {
-        float v0[16], v1[16];
-        tmem_ld16(la + 2 * dxw + tap * L.NP + g * 16, v0);
-        tmem_ld16(la + 2 * dxw + (L.T + tap) * L.NP + g * 16, v1);
-        tmem_ld_wait();
-        if (cr >= 0) {
+    const int ch = (warp & 3) * 32 + lane, cq = warp >> 2;
+    const int CH = L.KC * 8;
+    float* part = a.ln.part + (long long)blockIdx.x * a.part_floats + L.poff;
+    const uint32_t la = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const int ng = L.NP / 8;
+    for (int it = cq; it < L.T * ng; it += 4) {
+      const int tap = it / ng, g = it - tap * ng;
+      float v0[8], v1[8];
+      tmem_ld8(la + 2 * dxw + tap * L.NP + g * 8, v0);
+      tmem_ld8(la + 2 * dxw + (L.T + tap) * L.NP + g * 8, v1);
+      tmem_ld_wait();
+      // plain, coalesced stores (lanes = consecutive image channels) into this group's block of partials; tt_reduce_kernel sums
+      // the groups -- 64 CTAs adding to the same 33 k addresses with atomics cost 8 - 13 us per level
+      if (ch < CH) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int n = g * 16 + j;
-            if (n < L.N) {
-              const long long wi = L.w_off + ((long long)n * L.cin + cr) * L.T + tap;
-              atomicAdd(a.g0 + wi, v0[j]);
-              atomicAdd(a.g1 + wi, v1[j]);
-            }
+        for (int j = 0; j < 8; ++j) {
+          const int n = g * 8 + j;
+          if (n < L.N) {
+            part[((long long)n * L.T + tap) * CH + ch] = v0[j];
+            part[(long long)L.N * L.T * CH + ((long long)n * L.T + tap) * CH + ch] = v1[j];
           }
         }
       }
-    if (tid < L.N) {
-      atomicAdd(a.g0 + L.b_off + tid, sums[tid]);
-      atomicAdd(a.g1 + L.b_off + tid, MODE == BRL_MODE_LRT ? sums[64 + tid] : sums[tid]);  // Flipout: the sampled bias (brl_api.cu: gb2)
     }
+    if (tid < 128) part[2ll * L.N * L.T * CH + tid] = sums[tid];
+  }
+  if (tr) tr[6] = clock64();
+  tc_fence_before();
+  __syncthreads();
+  if (tr) tr[7] = clock64();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// fc layer (2400 -> 64) on the tensor pipe: forward (split-K partial sums for the per-layer engine's split-K epilogue, which
+// applies bias / eps * sqrt(var) / sign flips / ReLU exactly as for the fp32 kernels), input gradient, weight gradient
+// ------------------------------------------------------------------------------------------------
+struct TtFcPackArgs {
+  int mode;
+  const float *mu, *second;
+  long long w_off;
+  unsigned char* blob;  // w0h | w0b | w1b | w1h, FC_WIMG bytes each
+};
+__global__ void tt_pack_fc_kernel(const TtFcPackArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 64 * 2400) return;
+  const int n = i / 2400, kp = i - n * 2400, t = kp / 80, c = kp - t * 80;
+  const long long wi = a.w_off + (long long)n * 2400 + c * 30 + t;
+  const float m = a.mu[wi], v = a.second[wi];
+  const float s = a.mode == BRL_MODE_LRT ? v * v : v - m;
+  const int o = (kp >> 3) * 1024 + n * 16 + (kp & 7) * 2;
+  *reinterpret_cast<__half*>(a.blob + o) = __float2half_rn(m);
+  *reinterpret_cast<__nv_bfloat16*>(a.blob + FC_WIMG + o) = __float2bfloat16_rn(m);
+  *reinterpret_cast<__nv_bfloat16*>(a.blob + 2 * FC_WIMG + o) = __float2bfloat16_rn(s);
+  *reinterpret_cast<__half*>(a.blob + 3 * FC_WIMG + o) = __float2half_rn(s);
+}
+
+constexpr int FF_A = 0, FF_A2 = FC_KCS * FC_CHUNK, FF_W0 = 2 * FC_KCS * FC_CHUNK, FF_W1 = FF_W0 + FC_KCS * 1024, FF_BAR = FF_W1 + FC_KCS * 1024;
+constexpr int FF_SMEM = FF_BAR + 64;
+struct TtFcFwdArgs {
+  TtLane ln;
+  int B, mode;
+  float* part;  // [2][B][64] fp32, zeroed: mean-path and second-path sums (brl_gemm.cu split-K scratch layout)
+  int* status;
+};
+__global__ void __launch_bounds__(256, 1) tt_fc_fwd_kernel(const TtFcFwdArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int mt = blockIdx.x, ks = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sbase = smem_u32(smem), bar_ld = sbase + FF_BAR, bar_mma = bar_ld + 8;
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + FF_BAR + 16);
+  if (tid == 0) {
+    mbar_init(bar_ld, 1);
+    mbar_init(bar_mma, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(smem_u32(tslot), 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tslot;
+  if (tid == 0) {
+    const long long ao = ((long long)mt * FC_KC + ks * FC_KCS) * FC_CHUNK;
+    mbar_expect_tx(bar_ld, 2 * FC_KCS * FC_CHUNK + 2 * FC_KCS * 1024);
+    bulk_copy_chunked(sbase + FF_A, a.ln.fimg + ao, FC_KCS * FC_CHUNK, bar_ld);
+    bulk_copy_chunked(sbase + FF_A2, a.ln.f2img + ao, FC_KCS * FC_CHUNK, bar_ld);
+    bulk_copy_chunked(sbase + FF_W0, a.ln.fcblob + (long long)ks * FC_KCS * 1024, FC_KCS * 1024, bar_ld);
+    bulk_copy_chunked(sbase + FF_W1, a.ln.fcblob + (a.mode == BRL_MODE_LRT ? 2 : 3) * (long long)FC_WIMG + (long long)ks * FC_KCS * 1024, FC_KCS * 1024, bar_ld);
+  }
+  mbar_wait(bar_ld, 0, a.status, 44);
+  if (warp == 0) {
+    tc_fence_after();
+    if (elect_one()) {
+      for (int k = 0; k < FC_KCS / 2; ++k) {
+        umma(tmem, umma_desc(sbase + FF_A + 2 * k * FC_CHUNK, FC_CHUNK, 128), umma_desc(sbase + FF_W0 + 2 * k * 1024, 1024, 128),
+             tt_idesc(64, 0, 0, 0), k != 0);
+        umma(tmem + 64, umma_desc(sbase + FF_A2 + 2 * k * FC_CHUNK, FC_CHUNK, 128), umma_desc(sbase + FF_W1 + 2 * k * 1024, 1024, 128),
+             tt_idesc(64, a.mode == BRL_MODE_LRT ? 1 : 0, 0, 0), k != 0);
+      }
+      umma_commit(bar_mma);
+    }
+    __syncwarp();
+  }
+  mbar_wait(bar_mma, 0, a.status, 45);
+  tc_fence_after();
+  const int m = mt * 128 + (warp & 3) * 32 + lane, half = warp >> 2;
+  const uint32_t la = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+#pragma unroll 1
+  for (int g = 0; g < 2; ++g) {
+    float v0[16], v1[16];
+    tmem_ld16(la + half * 32 + g * 16, v0);
+    tmem_ld16(la + 64 + half * 32 + g * 16, v1);
+    tmem_ld_wait();
+    if (m < a.B) {
+      float* p0 = a.part + (long long)m * 64 + half * 32 + g * 16;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        atomicAdd(p0 + j, v0[j]);
+        atomicAdd(p0 + (long long)a.B * 64 + j, v1[j]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+// gradient operands of the fc layer: compact fp32 [B, 64] (bwd_act_kernel) -> bf16 K-major image [8 chunks][128 windows][16 B]
+__device__ __forceinline__ void fc_grad_image(const float* __restrict__ d, unsigned char* img, int mt, int B, int tid, int nthreads) {
+  for (int i = tid; i < 128 * 8; i += nthreads) {
+    const int r = i & 127, c = i >> 7, m = mt * 128 + r;
+    float v[8];
+    if (m < B) {
+      const float4 lo = *reinterpret_cast<const float4*>(d + (long long)m * 64 + c * 8), hi = *reinterpret_cast<const float4*>(d + (long long)m * 64 + c * 8 + 4);
+      v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    }
+    *reinterpret_cast<uint4*>(img + c * FC_CHUNK + r * 16) = pack_b8(v);
+  }
+}
+
+constexpr int FX_G0 = 0, FX_G1 = 8 * FC_CHUNK, FX_W0 = 16 * FC_CHUNK, FX_W1 = FX_W0 + FC_NCS * 1024, FX_BAR = FX_W1 + FC_NCS * 1024;
+constexpr int FX_SMEM = FX_BAR + 64;
+struct TtFcBwdArgs {
+  TtLane ln;
+  int B, nmt, mode;
+  const float *dpre, *dsec;  // [B, 64] fp32
+  const float* sgn_in;       // Flipout [B, 2400]
+  float *g0, *g1;
+  long long w_off, b_off;
+  int* status;
+};
+// d/d(features)[m, k'] = dpre[m, :] * W0[:, k'] + {2 f, s_in}[m, k'] * (dsec[m, :] * W1[:, k'])  -> bf16 image for the level kernels
+template <int MODE>
+__global__ void __launch_bounds__(256, 1) tt_fc_dx_kernel(const TtFcBwdArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int mt = blockIdx.x, ns = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sbase = smem_u32(smem), bar_ld = sbase + FX_BAR, bar_mma = bar_ld + 8;
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + FX_BAR + 16);
+  if (tid == 0) {
+    mbar_init(bar_ld, 1);
+    mbar_init(bar_mma, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(smem_u32(tslot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tslot;
+  if (tid == 0) {
+    mbar_expect_tx(bar_ld, 2 * FC_NCS * 1024);
+    bulk_copy_chunked(sbase + FX_W0, a.ln.fcblob + FC_WIMG + (long long)ns * FC_NCS * 1024, FC_NCS * 1024, bar_ld);
+    bulk_copy_chunked(sbase + FX_W1, a.ln.fcblob + 2 * FC_WIMG + (long long)ns * FC_NCS * 1024, FC_NCS * 1024, bar_ld);
+  }
+  fc_grad_image(a.dpre, smem + FX_G0, mt, a.B, tid, 256);
+  fc_grad_image(a.dsec, smem + FX_G1, mt, a.B, tid, 256);
+  mbar_wait(bar_ld, 0, a.status, 46);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    if (elect_one()) {
+      for (int k = 0; k < 4; ++k) {  // K = 64 output units; B = the weight image read MN-major: [N' = 240 features][K' = 16 units]
+        umma(tmem, umma_desc(sbase + FX_G0 + 2 * k * FC_CHUNK, FC_CHUNK, 128), umma_desc(sbase + FX_W0 + k * 256, 128, 1024),
+             tt_idesc(240, 1, 0, 1), k != 0);
+        umma(tmem + 256, umma_desc(sbase + FX_G1 + 2 * k * FC_CHUNK, FC_CHUNK, 128), umma_desc(sbase + FX_W1 + k * 256, 128, 1024),
+             tt_idesc(240, 1, 0, 1), k != 0);
+      }
+      umma_commit(bar_mma);
+    }
+    __syncwarp();
+  }
+  mbar_wait(bar_mma, 0, a.status, 47);
+  tc_fence_after();
+  const int r = (warp & 3) * 32 + lane, gw = mt * 128 + r, half = warp >> 2;
+  const uint32_t la = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+#pragma unroll 1
+  for (int g = half; g < FC_NCS; g += 2) {
+    float v0[8], v1[8], o[8], f[8];
+    tmem_ld8(la + g * 8, v0);
+    tmem_ld8(la + 256 + g * 8, v1);
+    const int kc = ns * FC_NCS + g, t = kc / 10, c0 = (kc - t * 10) * 8;
+    const long long fa = ((long long)mt * FC_KC + kc) * FC_CHUNK + r * 16;
+    if (MODE == BRL_MODE_LRT) unpack_h8(*reinterpret_cast<const uint4*>(a.ln.fimg + fa), f);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float mul = 0.f;
+      if (gw < a.B) mul = MODE == BRL_MODE_LRT ? 2.0f * f[j] : __ldg(a.sgn_in + (long long)gw * 2400 + (c0 + j) * 30 + t);
+      o[j] = gw < a.B ? fmaf(mul, v1[j], v0[j]) : 0.f;
+    }
+    *reinterpret_cast<uint4*>(a.ln.gfimg + fa) = pack_b8(o);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+constexpr int FW_A = 0, FW_A2 = 16 * FC_CHUNK, FW_G0 = 32 * FC_CHUNK, FW_G1 = 40 * FC_CHUNK, FW_BAR = 48 * FC_CHUNK;
+constexpr int FW_SMEM = FW_BAR + 64;
+// weight gradient: D[k', n] = sum_m F[m, k'] * dpre[m, n] (and the second path), M = 128 features per CTA, K = all windows
+template <int MODE>
+__global__ void __launch_bounds__(256, 1) tt_fc_dw_kernel(const TtFcBwdArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int kt = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sbase = smem_u32(smem), bar_ld = sbase + FW_BAR, bar_mma = bar_ld + 8;
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + FW_BAR + 16);
+  if (tid == 0) {
+    mbar_init(bar_ld, 1);
+    mbar_init(bar_mma, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(smem_u32(tslot), 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tslot;
+  const int nch = min(16, FC_KC - kt * 16);  // the last tile holds 12 chunks: features beyond 2400 are accumulator rows nobody reads
+  uint32_t ph = 0;
+  for (int mt = 0; mt < a.nmt; ++mt) {
+    if (tid == 0) {
+      const long long ao = ((long long)mt * FC_KC + kt * 16) * FC_CHUNK;
+      mbar_expect_tx(bar_ld, 2 * nch * FC_CHUNK);
+      bulk_copy_chunked(sbase + FW_A, a.ln.fbimg + ao, nch * FC_CHUNK, bar_ld);
+      bulk_copy_chunked(sbase + FW_A2, (MODE == BRL_MODE_LRT ? a.ln.f2img : a.ln.f2bimg) + ao, nch * FC_CHUNK, bar_ld);
+    }
+    fc_grad_image(a.dpre, smem + FW_G0, mt, a.B, tid, 256);
+    fc_grad_image(a.dsec, smem + FW_G1, mt, a.B, tid, 256);
+    mbar_wait(bar_ld, ph, a.status, 48);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+        for (int k = 0; k < 8; ++k) {  // 16 windows per k-step; both operands MN-major
+          const uint32_t acc = (mt | k) != 0;
+          umma(tmem, umma_desc(sbase + FW_A + k * 256, 128, FC_CHUNK), umma_desc(sbase + FW_G0 + k * 256, 128, FC_CHUNK),
+               tt_idesc(64, 1, 1, 1), acc);
+          umma(tmem + 64, umma_desc(sbase + FW_A2 + k * 256, 128, FC_CHUNK), umma_desc(sbase + FW_G1 + k * 256, 128, FC_CHUNK),
+               tt_idesc(64, 1, 1, 1), acc);
+        }
+        umma_commit(bar_mma);
+      }
+      __syncwarp();
+    }
+    mbar_wait(bar_mma, ph, a.status, 49);
+    tc_fence_after();
+    ph ^= 1;
+    __syncthreads();
+  }
+  const int kp = kt * 128 + (warp & 3) * 32 + lane, half = warp >> 2;
+  const uint32_t la = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+#pragma unroll 1
+  for (int g = 0; g < 2; ++g) {
+    float v0[16], v1[16];
+    tmem_ld16(la + half * 32 + g * 16, v0);
+    tmem_ld16(la + 64 + half * 32 + g * 16, v1);
+    tmem_ld_wait();
+    if (kp < 2400) {
+      const int t = kp / 80, c = kp - t * 80;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const long long wi = a.w_off + (long long)(half * 32 + g * 16 + j) * 2400 + c * 30 + t;
+        a.g0[wi] = v0[j];
+        a.g1[wi] = v1[j];
+      }
+    }
+  }
+  {  // bias gradients: column sums of the compact gradient tensors, a slice of windows per CTA and per thread group
+    const int n = tid & 63, q = tid >> 6, nsl = gridDim.x * 4, sl = blockIdx.x * 4 + q;
+    const int per = (a.B + nsl - 1) / nsl, m0 = sl * per, m1 = min(a.B, m0 + per);
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll 4
+    for (int m = m0; m < m1; ++m) { s0 += a.dpre[(long long)m * 64 + n]; s1 += a.dsec[(long long)m * 64 + n]; }
+    if (m0 < m1) {
+      atomicAdd(a.g0 + a.b_off + n, s0);
+      atomicAdd(a.g1 + a.b_off + n, MODE == BRL_MODE_LRT ? s1 : s0);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+// weight / bias gradients of the ten conv layers: sum of the groups' partial blocks -> flat gradient accumulators
+struct TtReduceArgs {
+  TtLayer L[TT_LAYERS];
+  int start[TT_LAYERS + 1];  // work items per layer: N * T * CH weights + N biases
+  int ngroups[TT_LAYERS];
+  int part_floats, mode;
+  const float* part;
+  float *g0, *g1;
+};
+constexpr int RED_SPLIT = 8;  // group ranges per output: blockIdx.y; each thread keeps <= 2 x 8 independent loads in flight
+__global__ void tt_reduce_kernel(const TtReduceArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.start[TT_LAYERS]) return;
+  int li = 0;
+  while (i >= a.start[li + 1]) ++li;
+  const TtLayer& l = a.L[li];
+  const int CH = l.KC * 8, nw = l.N * l.T * CH;
+  const int j = i - a.start[li];
+  const int per = (a.ngroups[li] + RED_SPLIT - 1) / RED_SPLIT;
+  const int g_lo = blockIdx.y * per, g_hi = min(a.ngroups[li], g_lo + per);
+  if (g_lo >= g_hi) return;
+  const float* p = a.part + l.poff;
+  float s0 = 0.f, s1 = 0.f;
+  if (j < nw) {
+    const int ch = j % CH, cr = real_ch(l.in, ch);
+    if (cr < 0) return;
+#pragma unroll 8
+    for (int gidx = g_lo; gidx < g_hi; ++gidx) {
+      s0 += p[(long long)gidx * a.part_floats + j];
+      s1 += p[(long long)gidx * a.part_floats + nw + j];
+    }
+    const int nt_ = j / CH, n = nt_ / l.T, tap = nt_ - n * l.T;
+    const long long wi = l.w_off + ((long long)n * l.cin + cr) * l.T + tap;
+    atomicAdd(a.g0 + wi, s0);
+    atomicAdd(a.g1 + wi, s1);
+  } else {
+    const int n = j - nw;
+#pragma unroll 8
+    for (int gidx = g_lo; gidx < g_hi; ++gidx) {
+      s0 += p[(long long)gidx * a.part_floats + 2ll * nw + n];
+      s1 += p[(long long)gidx * a.part_floats + 2ll * nw + 64 + n];
+    }
+    atomicAdd(a.g0 + l.b_off + n, s0);
+    atomicAdd(a.g1 + l.b_off + n, a.mode == BRL_MODE_LRT ? s1 : s0);  // Flipout: the sampled bias (brl_api.cu: gb2)
+  }
+}
+
+long long* g_tt_trace = nullptr;  // debug buffer [6 launches][4 layers][16] (brl_tt_trace)
 int* g_tt_status = nullptr;
 int* tt_status_word() {
   if (!g_tt_status) {
@@ -662,6 +1058,8 @@ inline size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 }  // namespace
 
+void tt_trace(long long* device_buf) { g_tt_trace = device_buf; }
+
 int tt_status() {
   int v = 0;
   if (g_tt_status) cudaMemcpy(&v, g_tt_status, sizeof(int), cudaMemcpyDeviceToHost);
@@ -671,7 +1069,8 @@ int tt_status() {
 size_t tt_lane_bytes(long long B) {
   const size_t nt = (size_t)((B + 3) / 4);
   return al256(nt * 6 * CS) + al256(nt * 16 * CS) + 2 * al256(nt * 8 * CS) + 4 * al256(nt * 16 * CS) + 2 * al256(nt * 8 * CS) +
-         al256(nt * RBUF_PER_TILE * sizeof(float)) + al256((size_t)table().blob_bytes) + 256;
+         al256(nt * RBUF_PER_TILE * sizeof(float)) + al256((size_t)table().blob_bytes) + al256(nt * (size_t)table().part_floats * sizeof(float)) +
+         5 * al256((size_t)((B + 127) / 128) * FC_MT_BYTES) + al256(4 * (size_t)FC_WIMG) + 256;
 }
 void tt_carve(unsigned char* base, long long B, TtLane& ln) {
   const size_t nt = (size_t)((B + 3) / 4);
@@ -686,6 +1085,14 @@ void tt_carve(unsigned char* base, long long B, TtLane& ln) {
   ln.g[5] = take(nt * 8 * CS);
   ln.rbuf = reinterpret_cast<float*>(take(nt * RBUF_PER_TILE * sizeof(float)));
   ln.blob = take((size_t)table().blob_bytes);
+  ln.part = reinterpret_cast<float*>(take(nt * (size_t)table().part_floats * sizeof(float)));  // at most one group per tile
+  const size_t nmt = (size_t)((B + 127) / 128);
+  ln.fimg = take(nmt * FC_MT_BYTES);
+  ln.fbimg = take(nmt * FC_MT_BYTES);
+  ln.f2img = take(nmt * FC_MT_BYTES);
+  ln.f2bimg = take(nmt * FC_MT_BYTES);
+  ln.gfimg = take(nmt * FC_MT_BYTES);
+  ln.fcblob = take(4 * (size_t)FC_WIMG);
 }
 
 static void tt_configure() {
@@ -695,6 +1102,11 @@ static void tt_configure() {
   cudaFuncSetAttribute(tt_fwd_kernel<BRL_MODE_FLIPOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM);
   cudaFuncSetAttribute(tt_bwd_kernel<BRL_MODE_LRT>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM);
   cudaFuncSetAttribute(tt_bwd_kernel<BRL_MODE_FLIPOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM);
+  cudaFuncSetAttribute(tt_fc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM);
+  cudaFuncSetAttribute(tt_fc_dx_kernel<BRL_MODE_LRT>, cudaFuncAttributeMaxDynamicSharedMemorySize, FX_SMEM);
+  cudaFuncSetAttribute(tt_fc_dx_kernel<BRL_MODE_FLIPOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, FX_SMEM);
+  cudaFuncSetAttribute(tt_fc_dw_kernel<BRL_MODE_LRT>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM);
+  cudaFuncSetAttribute(tt_fc_dw_kernel<BRL_MODE_FLIPOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM);
   done = true;
 }
 static TtLayer layer_of(const TtStep& s, int i) {
@@ -714,13 +1126,24 @@ void tt_forward(const TtLane& ln, const TtStep& s, cudaStream_t st) {
   pa.start[TT_LAYERS] = tb.pack_start[TT_LAYERS];
   pa.mode = s.mode; pa.mu = s.mu; pa.second = s.mode == BRL_MODE_LRT ? s.sigma : s.wsamp; pa.blob = ln.blob;
   tt_pack_kernel<<<(tb.pack_start[TT_LAYERS] + TT_LAYERS * 64 + 255) / 256, 256, 0, st>>>(pa);
-  g_launch_count += 2;
+  TtFcPackArgs fp;
+  fp.mode = s.mode; fp.mu = s.mu; fp.second = pa.second; fp.w_off = s.w_off_fc; fp.blob = ln.fcblob;
+  tt_pack_fc_kernel<<<(64 * 2400 + 255) / 256, 256, 0, st>>>(fp);
+  g_launch_count += 3;
+  if (s.B % 128 != 0) {  // windows beyond B of the last 128-window M-tile are K rows of the fc weight-gradient GEMM: they must be zero
+    const size_t last = (size_t)(s.B / 128) * FC_MT_BYTES;
+    cudaMemsetAsync(ln.fbimg + last, 0, FC_MT_BYTES, st);
+    cudaMemsetAsync(ln.f2img + last, 0, FC_MT_BYTES, st);
+    cudaMemsetAsync(ln.f2bimg + last, 0, FC_MT_BYTES, st);
+    cudaMemsetAsync(ln.fimg + last, 0, FC_MT_BYTES, st);
+  }
   static const int levels[3][4] = {{0, 1, 2, 3}, {5, 7, 4, 9}, {6, 8, -1, -1}};
   for (int lv = 0; lv < 3; ++lv) {
     TtFwdArgs fa{};
     fa.ln = ln;
     if (s.mode != BRL_MODE_LRT) fa.ln.rbuf = nullptr;
-    fa.B = (int)s.B; fa.ntile = nt; fa.feat = s.feat; fa.status = tt_status_word();
+    fa.B = (int)s.B; fa.ntile = nt; fa.sgn_fc_in = s.sgn_fc_in; fa.status = tt_status_word();
+    fa.trace = g_tt_trace ? g_tt_trace + lv * 64 : nullptr;
     int nl = 0;
     for (int k = 0; k < 4; ++k) {
       const int li = levels[lv][k];
@@ -733,8 +1156,33 @@ void tt_forward(const TtLane& ln, const TtStep& s, cudaStream_t st) {
     }
     fa.nl = nl;
     ++g_launch_count;
-    if (s.mode == BRL_MODE_LRT) tt_fwd_kernel<BRL_MODE_LRT><<<dim3(nt, nl), 128, F_SMEM, st>>>(fa);
-    else tt_fwd_kernel<BRL_MODE_FLIPOUT><<<dim3(nt, nl), 128, F_SMEM, st>>>(fa);
+    if (s.mode == BRL_MODE_LRT) tt_fwd_kernel<BRL_MODE_LRT><<<dim3(nt, nl), NT, F_SMEM, st>>>(fa);
+    else tt_fwd_kernel<BRL_MODE_FLIPOUT><<<dim3(nt, nl), NT, F_SMEM, st>>>(fa);
+  }
+}
+
+void tt_fc_forward(const TtLane& ln, const TtStep& s, float* part, cudaStream_t st) {
+  tt_configure();
+  const int nmt = (int)((s.B + 127) / 128);
+  cudaMemsetAsync(part, 0, sizeof(float) * 2 * (size_t)s.B * 64, st);
+  TtFcFwdArgs fa{};
+  fa.ln = ln; fa.B = (int)s.B; fa.mode = s.mode; fa.part = part; fa.status = tt_status_word();
+  ++g_launch_count;
+  tt_fc_fwd_kernel<<<dim3(nmt, FC_KS), 256, FF_SMEM, st>>>(fa);
+}
+
+void tt_fc_backward(const TtLane& ln, const TtStep& s, const float* dpre, const float* dsec, cudaStream_t st) {
+  tt_configure();
+  TtFcBwdArgs ba{};
+  ba.ln = ln; ba.B = (int)s.B; ba.nmt = (int)((s.B + 127) / 128); ba.mode = s.mode; ba.dpre = dpre; ba.dsec = dsec;
+  ba.sgn_in = s.sgn_fc_in; ba.g0 = s.g0; ba.g1 = s.g1; ba.w_off = s.w_off_fc; ba.b_off = s.b_off_fc; ba.status = tt_status_word();
+  g_launch_count += 2;
+  if (s.mode == BRL_MODE_LRT) {
+    tt_fc_dx_kernel<BRL_MODE_LRT><<<dim3(ba.nmt, FC_NS), 256, FX_SMEM, st>>>(ba);
+    tt_fc_dw_kernel<BRL_MODE_LRT><<<(FC_KC + 15) / 16, 256, FW_SMEM, st>>>(ba);
+  } else {
+    tt_fc_dx_kernel<BRL_MODE_FLIPOUT><<<dim3(ba.nmt, FC_NS), 256, FX_SMEM, st>>>(ba);
+    tt_fc_dw_kernel<BRL_MODE_FLIPOUT><<<(FC_KC + 15) / 16, 256, FW_SMEM, st>>>(ba);
   }
 }
 
@@ -744,10 +1192,14 @@ void tt_backward(const TtLane& ln, const TtStep& s, cudaStream_t st) {
   // reverse dependency levels: {b2b, b3b, b1, b4} need only the fc layer's gradient; {b2a, b3a} need d/dT2, d/dT3;
   // module 1 needs the four d/dM1 images
   static const int levels[3][4] = {{6, 8, 4, 9}, {5, 7, -1, -1}, {2, 1, 3, 0}};
+  const Table& tb = table();
+  TtReduceArgs ra{};
   for (int lv = 0; lv < 3; ++lv) {
     TtBwdArgs ba{};
     ba.ln = ln;
-    ba.B = (int)s.B; ba.ntile = nt; ba.feat = s.feat; ba.feat_grad = s.feat_grad; ba.g0 = s.g0; ba.g1 = s.g1; ba.status = tt_status_word();
+    ba.part_floats = tb.part_floats;
+    ba.B = (int)s.B; ba.ntile = nt; ba.g0 = s.g0; ba.g1 = s.g1; ba.status = tt_status_word();
+    ba.trace = g_tt_trace ? g_tt_trace + (3 + lv) * 64 : nullptr;
     int nl = 0;
     for (int k = 0; k < 4; ++k) {
       const int li = levels[lv][k];
@@ -760,10 +1212,22 @@ void tt_backward(const TtLane& ln, const TtStep& s, cudaStream_t st) {
     ba.nl = nl;
     ba.tiles_per_cta = std::max(1, (nt * nl + 147) / 148);
     const int ngroups = (nt + ba.tiles_per_cta - 1) / ba.tiles_per_cta;
+    for (int k = 0; k < 4; ++k)
+      if (levels[lv][k] >= 0) ra.ngroups[levels[lv][k]] = ngroups;
     ++g_launch_count;
-    if (s.mode == BRL_MODE_LRT) tt_bwd_kernel<BRL_MODE_LRT><<<dim3(ngroups, nl), 128, B_SMEM, st>>>(ba);
-    else tt_bwd_kernel<BRL_MODE_FLIPOUT><<<dim3(ngroups, nl), 128, B_SMEM, st>>>(ba);
+    if (s.mode == BRL_MODE_LRT) tt_bwd_kernel<BRL_MODE_LRT><<<dim3(ngroups, nl), NT, B_SMEM, st>>>(ba);
+    else tt_bwd_kernel<BRL_MODE_FLIPOUT><<<dim3(ngroups, nl), NT, B_SMEM, st>>>(ba);
   }
+  int tot = 0;
+  for (int i = 0; i < TT_LAYERS; ++i) {
+    ra.L[i] = layer_of(s, i);
+    ra.start[i] = tot;
+    tot += ra.L[i].N * ra.L[i].T * ra.L[i].KC * 8 + ra.L[i].N;
+  }
+  ra.start[TT_LAYERS] = tot;
+  ra.part_floats = tb.part_floats; ra.mode = s.mode; ra.part = ln.part; ra.g0 = s.g0; ra.g1 = s.g1;
+  ++g_launch_count;
+  tt_reduce_kernel<<<dim3((tot + 255) / 256, RED_SPLIT), 256, 0, st>>>(ra);
 }
 
 }  // namespace brl

@@ -20,6 +20,14 @@ struct TtLane {
   unsigned char* g[6];   // bf16 gradient images: [0..2] d/dM1 from b1 / b2a / b3a, [3] d/dMaxPool(M1) from b4, [4] d/dT2, [5] d/dT3
   float* rbuf;           // LRT: eps / (2 sd) of every conv layer output, [layer][ntile][NP][128 rows]
   unsigned char* blob;   // weight images of this step / particle
+  float* part;           // weight-gradient partials of the backward CTA groups: [group][layer blocks] (tt_reduce_kernel sums them)
+  // fc layer operands, per 128-window M-tile [300 k-chunks][128 windows][16 B], k' = t * 80 + c:
+  unsigned char* fimg;   // fp16 module-2 output (features)
+  unsigned char* fbimg;  // the same in bf16 (A operand of the weight-gradient GEMM)
+  unsigned char* f2img;  // second operand of the forward GEMM: bf16 f^2 (LRT) or fp16 f * s_in (Flipout)
+  unsigned char* f2bimg; // Flipout: bf16 f * s_in (A operand of the perturbation-path weight gradient)
+  unsigned char* gfimg;  // bf16 gradient w.r.t. the features (written by the fc input-gradient kernel)
+  unsigned char* fcblob; // fc weight images [300][64][8]: fp16 mu | bf16 mu | bf16 sigma^2 or (W - mu) | fp16 of the same
 };
 size_t tt_lane_bytes(long long B);
 void tt_carve(unsigned char* base, long long B, TtLane& ln);
@@ -34,16 +42,24 @@ struct TtStep {
   NoiseRef eps[TT_LAYERS];          // LRT eps streams (injected tensor [B, N*30] or Philox)
   const float* sgn_in[TT_LAYERS];   // Flipout [B, Cin]
   const float* sgn_out[TT_LAYERS];  // Flipout [B, Cout]
-  float* feat;           // fp32 [B,80,30]: module-2 output = input buffer of the fc layer (per-layer engine)
-  const float* feat_grad;  // fp32 [B,80,30]: its gradient (written by the fc layer's backward)
+  const float* sgn_fc_in;  // Flipout: s_in of the fc layer [B, 2400]
+  long long w_off_fc, b_off_fc;
   float* g0;             // flat gradient accumulators [P] (brl_kernels.cuh: Finalize): mean path / variance or perturbation path
   float* g1;
   long long w_off[TT_LAYERS], b_off[TT_LAYERS];
 };
-// forward: x -> feat (+ the activation / eps images the backward pass re-reads); 5 launches
+// forward of the ten conv layers: x -> feature images (+ the activation / eps images the backward pass re-reads); 6 launches
 void tt_forward(const TtLane& ln, const TtStep& s, cudaStream_t st);
-// backward: feat_grad -> g0 / g1 of the ten conv layers (atomic accumulation: the buffers must be zeroed); 3 launches
+// fc layer GEMMs on the tensor pipe.  Forward: both contractions as split-K partial sums into `part` ([2][B][64] fp32, the
+// split-K scratch layout of brl_gemm.cu) -- the per-layer engine's split-K epilogue then applies bias / eps * sqrt(var) / signs /
+// ReLU.  Backward: dpre / dsec = compact [B, 64] gradients (bwd_act_kernel) -> feature-gradient image + g0 / g1 of the fc layer.
+void tt_fc_forward(const TtLane& ln, const TtStep& s, float* part, cudaStream_t st);
+void tt_fc_backward(const TtLane& ln, const TtStep& s, const float* dpre, const float* dsec, cudaStream_t st);
+// backward: feature-gradient image -> g0 / g1 of the ten conv layers (accumulated: the buffers must be zeroed); 4 launches
 void tt_backward(const TtLane& ln, const TtStep& s, cudaStream_t st);
+// debug: device buffer int64[6 launches][4 layers][16] receiving clock64 stamps of CTA (0, layer) of the three forward and three
+// backward level launches (nullptr = off)
+void tt_trace(long long* device_buf);
 int tt_status();  // 0 ok; else the code of the first bounded mbarrier wait that timed out (synchronises)
 
 }  // namespace brl

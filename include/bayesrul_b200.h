@@ -132,6 +132,10 @@ int brl_tc_timing_read(brl_ctx* ctx, double kernel_ms[2], int64_t launches[2]);
 /* Debug: device buffer (int64[>= 16*128], or NULL to switch off) into which CTA 0 of tc_conv_kernel writes
  * clock64() time stamps of its issuer / epilogue warps for its first 16 work items. */
 int brl_tc_trace(brl_ctx* ctx, int64_t* device_buf);
+/* Debug: device buffer int64[6 * 4 * 16] (or NULL to switch off) into which CTA (0, layer) of the three forward and the three
+ * backward level launches of the BRL_GEMM_TC_FUSED training kernels write clock64() stamps of their phases
+ * (start, copies issued, copies landed, operands built, MMAs done, epilogue done, ...). */
+int brl_tt_trace(brl_ctx* ctx, int64_t* device_buf);
 
 /* ---- guide: weight sampler (replaces AutoNormal.forward / AutoRadial.forward,
  *      guides/radial.py:31-41,124-144; 24 pyro.sample sites per draw) ------------------- */
