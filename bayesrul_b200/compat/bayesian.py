@@ -65,12 +65,13 @@ class BNN(_Base):
 
     def __init__(self, net, optimizer, pretrain_epochs, mc_samples_train: int, mc_samples_eval: int, dataset_size: int,
                  fit_context: str, prior_loc: float, prior_scale: float, guide: str, q_scale: float, device=None,
-                 engine: str = "simt"):
+                 engine: str = "simt", train_backend: str = "auto"):
         super().__init__()
         pyro.clear_param_store()
-        self.save_hyperparameters(logger=False, ignore=["net", "device", "engine"])
+        self.save_hyperparameters(logger=False, ignore=["net", "device", "engine", "train_backend"])
         self.net = net
         self._engine_kind = engine
+        self._train_backend = train_backend
         if device is not None:
             self._device = torch.device(device)
             self.net.to(self._device)
@@ -98,7 +99,8 @@ class BNN(_Base):
             guide_kwargs["init_loc_fn"] = tyxe.guides.PretrainedInitializer.from_net(self.net)
         guide = partial(guide_base, **guide_kwargs)
         self.net.to(self.device)
-        self.bnn = tyxe.VariationalBNN(self.net, prior, likelihood, guide, engine=self._engine_kind)
+        self.bnn = tyxe.VariationalBNN(self.net, prior, likelihood, guide, engine=self._engine_kind,
+                                       train_backend=self._train_backend)
 
     def on_fit_start(self) -> None:  # bayesian.py:100-132
         self.define_bnn()

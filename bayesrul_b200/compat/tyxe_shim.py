@@ -112,13 +112,18 @@ class guides:  # namespace mirror of tyxe.guides
 class VariationalBNN:
     """tyxe.bnn.VariationalBNN(net, prior, likelihood, guide_builder)."""
 
-    def __init__(self, net, prior: IIDPrior, likelihood: HeteroskedasticGaussian, net_guide_builder, engine="simt"):
+    def __init__(self, net, prior: IIDPrior, likelihood: HeteroskedasticGaussian, net_guide_builder, engine="simt",
+                 train_backend="auto"):
         self.net, self.prior, self.likelihood = net, prior, likelihood
         try:
             self.net_guide = net_guide_builder(net, prior=prior)
         except TypeError:
             self.net_guide = net_guide_builder(net)
         self.engine_kind = engine
+        # kernels of the ELBO step: "auto" = the level-fused tcgen05 kernels where they exist (Inception under LRT / Flipout:
+        # fp16 / bf16 operands, loss 5e-3, gradient cosine > 0.999), else the fp32 FFMA kernels; "simt" = always the fp32 parity
+        # back-end (rtol 1e-3 against the oracle); "fused" / "tc" force a back-end
+        self.train_backend = train_backend
         self.seed = int(torch.initial_seed() % (2**62))
         self._step = 0
         self._last_kl = None
@@ -157,6 +162,10 @@ class VariationalBNN:
         ctx = active_context()
         mode = ctx if (ctx and g.family == "normal") else "ws"
         N = self.likelihood.dataset_size
+        be = self.train_backend
+        if be == "auto":
+            be = "fused" if (getattr(self.net, "kind", "") == "inception" and mode in ("lrt", "flipout")) else "simt"
+        self.engine.set_gemm_backend(be)
         res = self.engine.elbo_step(x.contiguous(), y.reshape(-1).contiguous(), g.loc, g.scale, mode=mode, guide=g.family,
                                     particles=particles, prior_loc=self.prior.loc, prior_scale=self.prior.scale,
                                     dataset_size=N, noise=self._noise(), compute_grads=grads)

@@ -22,26 +22,29 @@ def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
     return start, start + base + (1 if rank < rem else 0)
 
 
-def merge_moments(parts: Sequence[Tuple[int, torch.Tensor, torch.Tensor, torch.Tensor]]):
-    """Chan merge of per-shard predictive moments.  parts = [(n_r, pred_r, ep_var_r (unbiased), al_var_r)].
+def merge_moments(parts: Sequence[Tuple[object, torch.Tensor, torch.Tensor, torch.Tensor]]):
+    """Chan merge of per-shard predictive moments.  parts = [(n_r, pred_r, ep_var_r (unbiased), al_var_r)]; n_r is a Python
+    number or a tensor (0-dim or broadcastable to pred_r: nothing is read back to the host).
     Returns (pred, std, ep_var, al_var) identical to reducing all samples at once (bayesian.py:212-215)."""
-    n = sum(p[0] for p in parts)
-    mean = sum(p[0] * p[1].double() for p in parts) / n
-    m2 = sum((p[2].double() * (p[0] - 1) if p[0] > 1 else torch.zeros_like(mean)) + p[0] * (p[1].double() - mean) ** 2
-             for p in parts)
-    al = sum(p[0] * p[3].double() for p in parts) / n
-    ep = m2 / (n - 1) if n > 1 else torch.full_like(mean, float("nan"))
+    ns = [p[0].double() if isinstance(p[0], torch.Tensor) else float(p[0]) for p in parts]
+    n = sum(ns)
+    mean = sum(k * p[1].double() for k, p in zip(ns, parts)) / n
+    m2 = sum(p[2].double().nan_to_num(0.0) * (k - 1) + k * (p[1].double() - mean) ** 2 for k, p in zip(ns, parts))
+    al = sum(k * p[3].double() for k, p in zip(ns, parts)) / n
+    ep = m2 / (n - 1)  # n == 1: 0 / 0 = NaN, like loc.var(0) of a single sample
     dt = parts[0][1].dtype
     return mean.to(dt), (al + ep).sqrt().to(dt), ep.to(dt), al.to(dt)
 
 
 def all_gather_moments(n_local: int, pred, ep_var, al_var, group=None):
-    """Moment merge across ranks that each hold a different subset of MC samples of the SAME windows."""
+    """Moment merge across ranks that each hold a different subset of MC samples of the SAME windows: one all-gather of
+    [4, B] per rank, Chan merge on the device (no host synchronisation)."""
     world = dist.get_world_size(group)
     packed = torch.stack([torch.full_like(pred, float(n_local)), pred, ep_var.nan_to_num(0.0), al_var])
-    bufs = [torch.empty_like(packed) for _ in range(world)]
-    dist.all_gather(bufs, packed, group=group)
-    return merge_moments([(int(b[0, 0].item()), b[1], b[2], b[3]) for b in bufs])
+    flat = torch.empty((world * packed.shape[0],) + tuple(packed.shape[1:]), dtype=packed.dtype, device=packed.device)
+    dist.all_gather_into_tensor(flat, packed, group=group)  # rank-major concatenation along dim 0
+    bufs = flat.view((world,) + tuple(packed.shape))
+    return merge_moments([(bufs[r, 0], bufs[r, 1], bufs[r, 2], bufs[r, 3]) for r in range(world)])
 
 
 def mixture_across_ranks(mu_local: torch.Tensor, sigma_local: torch.Tensor, group=None):
@@ -55,17 +58,21 @@ def mixture_across_ranks(mu_local: torch.Tensor, sigma_local: torch.Tensor, grou
 
 
 def allreduce_elbo_grads(res: dict, group=None) -> dict:
-    """Average the ELBO step outputs of data-parallel ranks with one flat all-reduce.  Each rank computed its
-    loss with plate scale N/B_r, so the mean over ranks is the global-batch gradient (KL is rank-replicated)."""
-    world = dist.get_world_size(group)
-    gm, gl, gs = res["grad_mu"], res["grad_log_sigma"], res["grad_sigma"]
-    flat = torch.cat([gm, gl, gs, res["scalars"].to(gm.dtype)])
-    dist.all_reduce(flat, group=group)
-    flat /= world
-    P = gm.numel()
+    """Average the ELBO step outputs of data-parallel ranks with ONE collective over the step's flat result buffer
+    [grad_mu | grad_log_sigma | loss, nll, kl, mse] (Engine.elbo_step: res["flat"]); grad_sigma is not reduced (the optimiser
+    steps log sigma).  Each rank computed its loss with plate scale N/B_r, so the mean over ranks is the global-batch
+    gradient (the KL term is rank-replicated); NCCL's AVG folds the 1 / world in."""
+    flat = res["flat"]
+    P = res["grad_mu"].numel()
+    flat[2 * P: 2 * P + 4].copy_(res["scalars"])  # float64 -> the fp32 tail of the reduced range
+    red = flat[: 2 * P + 4]
+    if dist.get_backend(group) == "nccl":
+        dist.all_reduce(red, op=dist.ReduceOp.AVG, group=group)
+    else:  # gloo (CPU tests) has no AVG
+        dist.all_reduce(red, group=group)
+        red /= dist.get_world_size(group)
     out = dict(res)
-    out["grad_mu"], out["grad_log_sigma"], out["grad_sigma"] = flat[:P], flat[P:2 * P], flat[2 * P:3 * P]
-    out["scalars"] = flat[3 * P:].double()
+    out["scalars"] = flat[2 * P: 2 * P + 4].double()
     return out
 
 

@@ -309,7 +309,10 @@ class Engine:
             mode = "ws"
         scalars = torch.empty(4, dtype=torch.float64, device=self.device)
         out = torch.empty(particles, B, 2, device=self.device)
-        g = [torch.empty(self.P, device=self.device) for _ in range(3)] if compute_grads else [None] * 3
+        # ONE flat fp32 buffer [grad_mu | grad_log_sigma | 4 scalars | grad_sigma]: data-parallel ranks all-reduce its first
+        # 2 P + 4 floats in a single collective (dist.allreduce_elbo_grads) -- no concatenation, no slicing copies
+        flat = torch.empty(3 * self.P + 4, device=self.device) if compute_grads else None
+        g = [flat[: self.P], flat[2 * self.P + 4:], flat[self.P: 2 * self.P]] if compute_grads else [None] * 3
         ws = self._ws_for(B, 2 if particles > 1 else 1, True, "simt")  # S >= 2: room for two particles side by side
         nz, keep = self._noise(noise)
         p = lambda t: t.data_ptr() if t is not None else None
@@ -318,7 +321,7 @@ class Engine:
                                           float(prior_scale), int(dataset_size), nz, int(compute_grads),
                                           scalars.data_ptr(), p(g[0]), p(g[1]), p(g[2]), out.data_ptr(), ws.data_ptr(),
                                           ws.numel(), self._stream()))
-        return dict(scalars=scalars, grad_mu=g[0], grad_sigma=g[1], grad_log_sigma=g[2], out=out)
+        return dict(scalars=scalars, grad_mu=g[0], grad_sigma=g[1], grad_log_sigma=g[2], out=out, flat=flat)
 
     # -- A13: HNN step -----------------------------------------------------------------------------------
     def hnn_step(self, x, y, theta, p_dropout: float = 0.0, noise: Optional[Noise] = None, compute_grads: bool = True):

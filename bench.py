@@ -10,9 +10,12 @@ per MC sample, bayesian.py:235-249) + the predictive-moment reduction.
 A "step" = one such batch; `value` = window x samples / s with inputs resident in HBM; `e2e` = the
 same through BNN.predict_step -> brl_predict_moments_host with pinned HOST inputs and host results.
 Riding along: "train" (one whole svi.step of the LRT / Flipout experiments at B=256 per GPU: ELBO
-forward + backward + ClippedAdam, + the NCCL all-reduce at N > 1), "mcd_predict" (configs[1]),
-"radial_sweep" (configs[3], MC samples sharded over the ranks + moment merge), "deep_ensemble"
-(configs[4]).  One process per GPU; windows are sharded across ranks, no data-path collective in the
+forward + backward + ClippedAdam, + the NCCL all-reduce at N > 1; level-fused tcgen05 kernels, with
+the fp32 and TF32 per-layer back-ends and the CPU port beside them), "mcd_predict" (configs[1]),
+"flipout_predict" (configs[2]: q_scale 2.14e-4, S=20), "radial_sweep" (configs[3], MC samples sharded
+over the ranks + moment merge), "deep_ensemble" (five members as one launch) and "deep_ensemble_full"
+(configs[4] at its stated scale: 1M windows, 5 members + LRT BNN at S=1000, members / samples sharded
+over the ranks, NCCL moment merges inside the timed region).  One process per GPU; windows are sharded across ranks, no data-path collective in the
 headline (weak scaling).  Only the JSON line is written to stdout.
 """
 import argparse
@@ -152,8 +155,9 @@ def cpu_predict_rate(n_windows, n_samples, threads):
     return n_windows * run_small / dt, dt
 
 
-def cpu_train_rate(mode, particles, q, prior_scale, threads, steps=3):
-    """Oracle port of one ELBO step (forward + autograd backward) on the host cores, B = 256."""
+def cpu_train_rate(mode, particles, q, prior_scale, threads, steps=10, warmup=3):
+    """Oracle port of one ELBO step (forward + autograd backward) on the host cores, B = 256: `warmup` untimed steps, then
+    the MEDIAN of `steps` timed ones."""
     from oracle import bnn_oracle as O
 
     torch.set_num_threads(threads)
@@ -167,11 +171,14 @@ def cpu_train_rate(mode, particles, q, prior_scale, threads, steps=3):
         nz = [O.InjectedNoise(O.make_injected_noise(NET, B_TRAIN, mode, g)) for _ in range(particles)]
         return O.elbo_loss_and_grads(NET, x, y, mu, sg, noises=nz, **kw)
 
-    step()
-    t0 = time.perf_counter()
-    for _ in range(steps):
+    for _ in range(warmup):
         step()
-    dt = (time.perf_counter() - t0) / steps
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+    dt = statistics.median(ts)
     return B_TRAIN / dt, dt
 
 
@@ -189,7 +196,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    nb, ns = B_PRED, 2
+    nb, ns = B_PRED, 10
     for _ in range(max(1, min(args.warmup, 1))):
         cpu_predict_rate(nb // 4, 2, threads)
     t = 0.0
@@ -222,6 +229,7 @@ def main():
     ap.add_argument("--engine", default=os.environ.get("BRL_ENGINE", "auto"))
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--no-full", action="store_true", help="skip the 1M-window configs[4] pass (about 5 s at one GPU)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -300,7 +308,7 @@ def main():
                      f"{units_per_step * args.steps // conv_launches} window-samples per launch (average of {conv_launches} launches) / "
                      f"{conv_ms / conv_launches:.3f} ms per launch (CUDA events on the launch stream inside the timed region); "
                      f"kernel share of the step {conv_ms / (t_local * 1e3):.2f}; whole step incl. fc/pack/sampler/moments = {step_tf:.1f} TFLOP/s; "
-                     f"peak = sustained bf16 cuBLAS of {pk['src']} MEASURED_PEAKS.json; traffic = ncu dram read+write per launch "
+                     f"peak = BURST bf16 cuBLAS of {pk['src']} MEASURED_PEAKS.json (the kernel is event-timed per launch); traffic = ncu dram read+write per launch "
                      f"(profiles/conv_traffic.json)")
         # second kernel: [128 windows x 2400] x [2400 x 64] + head; bound by the read of the fp16 feature tensor
         fc_bytes = units_per_step * args.steps * 4800.0
@@ -310,7 +318,7 @@ def main():
     else:
         achieved_tf = step_tf
         roof_note = (f"fp32 SIMT engine: algorithmic GEMM FLOPs of the whole step ({F_FWD} per window-sample) / step time; "
-                     f"peak = sustained bf16 cuBLAS of {pk['src']} MEASURED_PEAKS.json")
+                     f"peak = burst bf16 cuBLAS of {pk['src']} MEASURED_PEAKS.json")
 
     # ---- e2e: BNN.predict_step through the reference-facing class, pinned host inputs, host results
     net = Inception(30, 18)
@@ -339,9 +347,10 @@ def main():
         xt, yt = xt.to(device), yt.to(device)
         from bayesrul_b200.dist import allreduce_elbo_grads
         NT = 40
+        pk_t = peaks()
         for mode, particles, q, ps, lr in (("lrt", 1, 1.351e-3, 0.138793, 1.0e-3), ("flipout", 2, 2.14e-4, 0.198768, 1.0e-3)):
             # one svi.step of the reference (bayesian.py:147): ELBO forward + backward, then pyro's ClippedAdam on (loc, log scale)
-            # (conf/model/bnn.yaml:6-10); data-parallel ranks average the flat gradient with ONE NCCL all-reduce first
+            # (conf/model/bnn.yaml:6-10); data-parallel ranks average the step's flat result buffer with ONE NCCL all-reduce first
             P = mu.numel()
             par = {"mu": mu.clone(), "ls": torch.full_like(mu, float(torch.log(torch.tensor(q)))), "sg": torch.full_like(mu, q)}
             opt = {k: torch.zeros(P, device=device) for k in ("m_mu", "v_mu", "m_ls", "v_ls")}
@@ -353,35 +362,43 @@ def main():
                                   prior_scale=ps, dataset_size=N_DATASET, noise=Noise(seed=5000 + st["i"], window0=rank * B_TRAIN))
                 if dist is not None:
                     r = allreduce_elbo_grads(r)
-                eng.clipped_adam_vi(par["mu"], par["ls"], par["sg"], r["grad_mu"].contiguous(), r["grad_log_sigma"].contiguous(),
+                eng.clipped_adam_vi(par["mu"], par["ls"], par["sg"], r["grad_mu"], r["grad_log_sigma"],
                                     opt["m_mu"], opt["v_mu"], opt["m_ls"], opt["v_ls"], st["i"], lr, (0.95, 0.999), 1e-8, 15.0)
 
             res = {}
-            # fp32 FFMA kernels / tcgen05 TF32 dual-GEMM kernels (same operators) / TF32 forward + input-gradient kernels with the
-            # fp32 dual weight-gradient kernel (bit mask of brl_set_gemm_backend: 1 forward, 2 input gradient, 4 weight gradient)
-            for backend, mask in (("simt", 0), ("tc", 7), ("mixed", 3)):
-                eng.set_gemm_backend(mask)
+            # level-fused tcgen05 kernels (fp16 / bf16 operands: the default of compat.BNN) / fp32 FFMA parity kernels /
+            # per-layer tcgen05 TF32 dual GEMMs (brl_set_gemm_backend: 8 / 0 / 7)
+            l0t = lib.brl_launch_count()
+            for backend in ("fused", "simt", "tc"):
+                eng.set_gemm_backend(backend)
                 res[backend] = max_over_ranks(timed_steps(train_step, NT, 6, flush_buf, dist), dist, device)
-            eng.set_gemm_backend("simt")
+            eng.set_gemm_backend("fused")
             eng.set_step_graph(False)  # the same step without the CUDA-graph replay (eager launches), for the record
             t_eager = max_over_ranks(timed_steps(train_step, NT, 3, flush_buf, dist), dist, device)
             eng.set_step_graph(True)
-            best = min(res, key=res.get)
-            tt = res[best]
+            eng.set_gemm_backend("simt")
+            tt = res["fused"]
             flops = F_TRAIN_LRT * particles * B_TRAIN  # 13 036 416 per window per particle
+            ach = flops / (tt / NT) / 1e12
             train[mode] = {"windows_per_s": world * B_TRAIN * NT / tt, "ms_per_step": 1e3 * tt / NT, "batch_per_gpu": B_TRAIN,
-                           "particles": particles,
-                           "gemm_backend": {"simt": "fp32 FFMA", "tc": "tcgen05 TF32", "mixed": "tcgen05 TF32 forward + dX, fp32 FFMA dW"}[best],
-                           "ms_per_step_by_backend": {"simt_fp32": 1e3 * res["simt"] / NT, "tc_tf32": 1e3 * res["tc"] / NT,
-                                                      "tc_tf32_fwd_dx+simt_dw": 1e3 * res["mixed"] / NT},
-                           "ms_per_step_eager_simt": 1e3 * t_eager / NT,
-                           "achieved_tflops": flops / (tt / NT) / 1e12,
+                           "particles": particles, "gemm_backend": "level-fused tcgen05 (fp16 / bf16 operands, fp32 accumulate)",
+                           "ms_per_step_by_backend": {"fused_tcgen05": 1e3 * res["fused"] / NT, "simt_fp32": 1e3 * res["simt"] / NT,
+                                                      "per_layer_tcgen05_tf32": 1e3 * res["tc"] / NT},
+                           "ms_per_step_eager_fused": 1e3 * t_eager / NT,
+                           "roofline": {"bound": "tensor", "achieved": ach, "peak": pk_t["tf_burst"], "unit": "TFLOP/s",
+                                        "frac": ach / pk_t["tf_burst"], "traffic": None, "kernel": "svi.step (whole step)",
+                                        "note": f"{F_TRAIN_LRT} algorithmic GEMM FLOPs per window-particle x {particles} x {B_TRAIN} windows / "
+                                                "step time; a 256-window minibatch is 3.3 GFLOP -- the step is a chain of ~25 latency-bound "
+                                                "launches, not tensor-pipe throughput (profiles/r02_ncu_train_fused.txt); peak = burst bf16 "
+                                                f"cuBLAS of {pk_t['src']} MEASURED_PEAKS.json"},
                            "includes": "ELBO forward + backward + KL + gradient finalisation (CUDA-graph replay) + ClippedAdam on (loc, log scale)"
-                                       + (f" + NCCL all-reduce of the flat gradient over {world} ranks" if dist is not None else "")}
+                                       + (f" + ONE NCCL all-reduce (AVG) of the step's flat result buffer over {world} ranks" if dist is not None else "")}
             if world == 1 and not args.no_cpu:
                 v, dt = cpu_train_rate(mode, particles, q, ps, os.cpu_count() or 1)
                 train[mode]["cpu_windows_per_s"] = v
                 train[mode]["cpu_ms_per_step"] = 1e3 * dt
+                train[mode]["cpu_sample"] = "oracle port, 3 warm-up + 10 timed steps, median"
+                train[mode]["speedup_vs_cpu_port"] = train[mode]["windows_per_s"] / v
 
         # the frequentist twin (configs[1] / [4] train their HNNs with it): HNN.step (frequentist.py:39-48: forward with dropout,
         # gaussian_nll_loss, backward) + Adam on the flat parameter buffer (brl_clipped_adam with the clip disabled)
@@ -394,8 +411,7 @@ def main():
             r = eng.hnn_step(xt, yt, th, p_dropout=0.241437, noise=Noise(seed=7000 + hs["i"], window0=rank * B_TRAIN))
             g = r["grad"]
             if dist is not None:
-                dist.all_reduce(g)
-                g /= world
+                dist.all_reduce(g, op=dist.ReduceOp.AVG)  # NCCL folds the 1 / world in
             eng.clipped_adam(th, g, hm, hv, hs["i"], 1e-3, (0.9, 0.999), 1e-8, 1e30)
 
         th_t = max_over_ranks(timed_steps(hnn_train_step, NT, 6, flush_buf, dist), dist, device)
@@ -418,6 +434,19 @@ def main():
         tm = max_over_ranks(timed_steps(mcd_step, 3, 2, flush_buf, dist), dist, device)
         mcd = {"window_samples_per_s": world * units_per_step * 3 / tm, "ms_per_step": 1e3 * tm / 3, "p_dropout": 0.241437,
                "masks": S_PRED, "noise": "in-kernel Philox masks (fused)"}
+
+    # ---- configs[2], prediction half: the Flipout experiment's BNN (ncmapss_fo.yaml:17-25: q_scale 2.14e-4, S = 20 weight samples;
+    #      outside fit_ctxt the predictive path is plain weight sampling)
+    fo_pred = {}
+    if not args.no_train:
+        sg_fo = torch.full_like(mu, 2.14e-4)
+
+        def fo_step(i=0):
+            eng.predict_moments(xs[i % n_rot], mu, sg_fo, S=20, guide="normal", noise=Noise(seed=6060, window0=rank * B_PRED), engine=engine)
+
+        tf = max_over_ranks(timed_steps(fo_step, 5, 3, flush_buf, dist), dist, device)
+        fo_pred = {"window_samples_per_s": world * B_PRED * 20 * 5 / tf, "ms_per_step": 1e3 * tf / 5, "mc_samples": 20, "q_scale": 2.14e-4,
+                   "windows_per_step_per_gpu": B_PRED}
 
     # ---- configs[3]: Radial BNN (ncmapss_rad: q_scale 1.241e-3), MC-sample sweep, the S samples SHARDED across the ranks
     #      (every rank sees the same windows; per-window (n, mean, M2, sum sigma^2) merged with one all-gather + Chan's formula)
@@ -457,6 +486,55 @@ def main():
         deepens = {"window_members_per_s": world * B_PRED * 5 * 5 / td, "ms_per_step": 1e3 * td / 5, "members": 5,
                    "windows_per_step_per_gpu": B_PRED}
 
+    # ---- configs[4] at its stated scale: 1 000 000 windows, deep ensemble of 5 HNN members + the LRT-trained BNN at S = 1000.
+    #      Members and MC samples are SHARDED over the ranks (every rank sees all windows); per window chunk the ranks merge
+    #      their per-window moments with one NCCL all-gather (BNN: Chan merge) and one all-reduce (ensemble mixture) inside
+    #      the timed region.  One timed pass (+ one warm-up chunk): 1.005e9 window-(samples + members) per pass.
+    de_full = {}
+    if not args.no_train and not args.no_full:
+        from bayesrul_b200.dist import all_gather_moments, mixture_across_ranks, shard_range
+        n_full, S_full, chunk = 1_000_000, 1000, 100_000
+        gdev = torch.Generator(device=device).manual_seed(31337)
+        s_lo, s_hi = shard_range(S_full, rank, world)
+        m_lo, m_hi = shard_range(5, rank, world)
+        res_full = {}
+
+        def full_chunk(xc, c):
+            m = eng.predict_moments(xc, mu, sigma, S=s_hi - s_lo, guide="normal", noise=Noise(seed=99, sample0=s_lo), engine=engine)
+            if m_hi > m_lo:
+                o = eng.forward(xc, "ws", wsamp=members[m_lo:m_hi].contiguous(), S=m_hi - m_lo, engine=engine)
+                mu_m, sd_m = o[:, :, 0].contiguous(), o[:, :, 1].contiguous()
+            else:
+                mu_m = sd_m = torch.zeros(0, xc.shape[0], device=device)
+            if dist is not None:
+                m = all_gather_moments(s_hi - s_lo, m[0], m[2], m[3])
+                de = mixture_across_ranks(mu_m, sd_m)
+            else:
+                de = eng.mixture_moments(mu_m, sd_m)
+            res_full[c] = (m[0], m[1], de[0], de[1])
+
+        xw = torch.randn(chunk, 30, 18, device=device, generator=gdev)
+        full_chunk(xw[:10_000].contiguous(), -1)  # warm-up (workspace growth, graph-free path)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_full = 0.0
+        for c in range(n_full // chunk):
+            xw = torch.randn(chunk, 30, 18, device=device, generator=gdev)  # the chunk's windows, resident before the clock starts
+            ev0.record()
+            full_chunk(xw, c)
+            ev1.record()
+            torch.cuda.synchronize()
+            t_full += ev0.elapsed_time(ev1) / 1e3
+        t_full = max_over_ranks(t_full, dist, device)
+        units = n_full * (S_full + 5)
+        de_full = {"window_units_per_s": units / t_full, "seconds_per_pass": t_full, "windows": n_full, "bnn_mc_samples": S_full,
+                   "members": 5, "window_chunk": chunk,
+                   "sharding": f"MC samples {S_full} and members 5 over {world} rank(s); per chunk one all-gather of [4, {chunk}] moments + "
+                               "one all-reduce of the mixture sums" if dist is not None else "single rank: no collective",
+                   "unit": "window x (BNN samples + ensemble members) / s"}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -470,18 +548,19 @@ def main():
         "clocks": clocks, "gpu_launches": int(launches_timed),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "bayesrul_b200.compat.BNN.predict_step -> brl_predict_moments_host (pinned host batch -> host results)"},
-        "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": pk["tf_sust"], "unit": "TFLOP/s",
-                     "frac": achieved_tf / pk["tf_sust"], "traffic": traffic, "kernel": "tc_conv_kernel" if engine == "tc" else "step",
+        "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": pk["tf_burst"], "unit": "TFLOP/s",
+                     "frac": achieved_tf / pk["tf_burst"], "traffic": traffic, "kernel": "tc_conv_kernel" if engine == "tc" else "step",
                      "ms_per_launch": conv_ms / max(conv_launches, 1), "share_of_step": conv_ms / (t_local * 1e3) if conv_launches else None,
                      "note": roof_note, "other_kernels": kernels},
-        "train": train, "mcd_predict": mcd, "radial_sweep": radial, "deep_ensemble": deepens,
+        "train": train, "mcd_predict": mcd, "flipout_predict": fo_pred, "radial_sweep": radial, "deep_ensemble": deepens,
+        "deep_ensemble_full": de_full,
     }
     if world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
         cpu_predict_rate(1000, 2, threads)  # warm-up
-        v, dt = cpu_predict_rate(B_PRED, 10, threads)
+        v, dt = cpu_predict_rate(B_PRED, 25, threads)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": f"{B_PRED} windows x 10 of the {S_PRED} MC samples ({dt:.1f} s), plain-PyTorch "
+                                "sample": f"{B_PRED} windows x 25 of the {S_PRED} MC samples ({dt:.1f} s), plain-PyTorch "
                                           f"restatement on torch {torch.__version__} CPU"}
     os.write(json_fd, (json.dumps(line) + "\n").encode())
     if dist is not None:

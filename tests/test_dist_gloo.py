@@ -57,6 +57,9 @@ def _worker(rank, world, port, q):
     nzr = {k: v[a:b] for k, v in nz.items()}
     part = O.elbo_loss_and_grads(net, x[a:b], y[a:b], mu0, sg0, noises=[O.InjectedNoise(nzr)], **kw)
     part["scalars"] = torch.stack([part["loss"], part["nll_sum"], part["kl"], torch.zeros(())])
+    P = mu0.numel()  # the engine's flat result buffer: [grad_mu | grad_log_sigma | 4 scalars | grad_sigma] (Engine.elbo_step)
+    flat = torch.cat([part["grad_mu"], part["grad_log_sigma"], torch.zeros(4, dtype=torch.float64), part["grad_sigma"]])
+    part.update(flat=flat, grad_mu=flat[:P], grad_log_sigma=flat[P:2 * P], grad_sigma=flat[2 * P + 4:])
     red = D.allreduce_elbo_grads(part)
     ok = ok and torch.allclose(red["grad_mu"], full["grad_mu"], rtol=1e-9, atol=1e-14)
     ok = ok and torch.allclose(red["grad_log_sigma"], full["grad_log_sigma"], rtol=1e-9, atol=1e-14)

@@ -59,11 +59,13 @@ def test_bnn_training_loop_and_checkpoint(fit_context, guide, particles):
     assert torch.allclose(m2.bnn.net_guide.scale, m.bnn.net_guide.scale)
 
 
-def test_bnn_step_matches_oracle_semantics():
-    """svi.step's return value is the scaled loss of SURVEY A.6 (checked with the oracle on the same Philox draw)."""
+@pytest.mark.parametrize("train_backend,tol", [("simt", 2e-3), ("auto", 5e-3)])
+def test_bnn_step_matches_oracle_semantics(train_backend, tol):
+    """svi.step's return value is the scaled loss of SURVEY A.6 (checked with the oracle on the same Philox draw), on the fp32
+    parity back-end and on the default one ("auto": the level-fused tcgen05 kernels for Inception under LRT)."""
     from bayesrul_b200.compat import BNN, Inception
     torch.manual_seed(7)
-    m = BNN(Inception(30, 18), None, 5, 1, 8, 238150, "lrt", 0.0, 0.138793, "normal", 0.02, device=DEV)
+    m = BNN(Inception(30, 18), None, 5, 1, 8, 238150, "lrt", 0.0, 0.138793, "normal", 0.02, device=DEV, train_backend=train_backend)
     m.on_fit_start()
     x, y = _batch(64, 3)
     g = m.bnn.net_guide
@@ -74,7 +76,7 @@ def test_bnn_step_matches_oracle_semantics():
         loss = m.svi.step(x, y.unsqueeze(-1))
     ref, _ = O.elbo_loss("inception", x.cpu(), y.cpu(), mu, sg, mode="lrt", guide="normal", prior_loc=0.0,
                          prior_scale=0.138793, dataset_size=238150, noises=[O.PhiloxNoise("inception", seed)])
-    assert abs(loss / ref.item() - 1) < 2e-3
+    assert abs(loss / ref.item() - 1) < tol
 
 
 def test_hnn_train_and_mc_dropout_predict():
