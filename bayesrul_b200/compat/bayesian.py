@@ -16,11 +16,9 @@ from functools import partial
 from types import SimpleNamespace
 
 import torch
-import torch.nn.functional as F
 
 from . import pyro_shim as pyro
 from . import tyxe_shim as tyxe
-from .metrics import rms_calibration_error, sharpness
 from .nets import weights_init
 from .radial import AutoRadial
 
@@ -123,9 +121,8 @@ class BNN(_Base):
             output = self._agg(self.svi.last["out"], self.hparams.mc_samples_train)
             loc, scale = output[:, 0], output[:, 1]
             kl = float(self.svi.last["scalars"][2].item())
-        mse = F.mse_loss(y.squeeze(), loc.squeeze()).item()
-        rmsce = rms_calibration_error(loc, scale, y.squeeze())
-        sharp = sharpness(scale)
+        m = self.bnn.engine.step_metrics(loc, scale, y)  # mse, sharpness, rmsce (+ nll, mace) in one fused pass (N3)
+        mse, sharp, rmsce = m[1].item(), m[2].float(), m[3].float()
         self.log("mse/train", mse, on_step=False, on_epoch=True)
         self.log("elbo/train", elbo, on_step=False, on_epoch=True)
         self.log("kl/train", kl, on_step=False, on_epoch=True)
@@ -142,13 +139,13 @@ class BNN(_Base):
         if output.dim() == 3:
             output = output[0]
         loc, scale = output[:, 0], output[:, 1]
-        mse = F.mse_loss(y.squeeze(), loc)
+        m = self.bnn.engine.step_metrics(loc, scale, y)
         self.log("elbo/val", elbo)
-        self.log("mse/val", mse)
+        self.log("mse/val", m[1].float())
         self.log("kl/val", kl)
         self.log("likelihood/val", elbo - kl)
-        self.log("rmsce/val", rms_calibration_error(loc, scale, y.squeeze()))
-        self.log("sharp/val", sharpness(scale))
+        self.log("rmsce/val", m[3].float())
+        self.log("sharp/val", m[2].float())
 
     def on_test_start(self) -> None:
         self.define_bnn()
@@ -157,7 +154,7 @@ class BNN(_Base):
     def test_step(self, batch, batch_idx):  # bayesian.py:203-225
         (x, y) = batch[0].to(self.device, non_blocking=True), batch[1].to(self.device, non_blocking=True)
         loc, scale, _, _ = self.bnn.predict_moments(x, self.hparams.mc_samples_eval)
-        m = self.bnn.engine.test_metrics(loc, scale, y.contiguous())  # nll, mse, sharpness, rmsce in one pass
+        m = self.bnn.engine.step_metrics(loc, scale, y)  # nll, mse, sharpness, rmsce (+ mace) in one pass
         self.log("nll/test", m[0])
         self.log("mse/test", m[1])
         self.log("rmsce/test", m[3])

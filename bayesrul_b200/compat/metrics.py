@@ -1,5 +1,7 @@
-"""Online metrics logged every step (reference: bayesrul/results/metrics.py:210-274).  Small torch
-reductions on device; the fused one-pass version is Engine.test_metrics (brl_test_metrics)."""
+"""Online metrics logged every step (reference: bayesrul/results/metrics.py:210-297), as free functions with the
+reference's signatures (torch on whatever device the tensors live on): the function-level mirror and the comparison
+target of the tests.  The wrappers (compat.BNN / compat.HNN) do NOT call these per step: they log from
+Engine.step_metrics (brl_step_metrics: nll, mse, sharpness, rmsce, mace from one fused pass + a 100-bin histogram)."""
 import torch
 from torch import Tensor
 

@@ -1449,6 +1449,15 @@ int brl_test_metrics(const float* pred, const float* std, const float* y, int64_
   return BRL_OK;
 }
 
+int brl_step_metrics(const float* pred, const float* std, const float* y, int64_t nn, double* scalars, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  BRL_REQUIRE(pred && std && y && scalars && workspace && nn > 0, "brl_step_metrics: bad argument");
+  if (workspace_bytes < 1024) return fail(BRL_ERR_WORKSPACE, "brl_step_metrics: workspace must be >= 1024 bytes");
+  launch_test_metrics(pred, std, y, nn, scalars, (unsigned int*)workspace, (cudaStream_t)stream, 5);
+  BRL_CUDA(cudaGetLastError());
+  return BRL_OK;
+}
+
 int brl_clipped_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t nn, int64_t step, float lr,
                      float beta1, float beta2, float eps, float clip_norm, float lrd, float weight_decay, void* stream) {
   BRL_REQUIRE(param && grad && exp_avg && exp_avg_sq && nn > 0 && step >= 1, "brl_clipped_adam: bad argument");

@@ -563,28 +563,30 @@ __global__ void test_metrics_acc_kernel(const float* __restrict__ pred, const fl
   for (int i = threadIdx.x; i < 100; i += blockDim.x)
     if (sh[i]) atomicAdd(hist + i, sh[i]);
 }
-__global__ void test_metrics_final_kernel(const double* acc, const unsigned int* hist, long long n, double* scalars) {
+__global__ void test_metrics_final_kernel(const double* acc, const unsigned int* hist, long long n, double* scalars, int nscal) {
   if (threadIdx.x != 0) return;
   scalars[0] = acc[0] / (double)n;
   scalars[1] = acc[1] / (double)n;
   scalars[2] = sqrt(acc[2] / (double)n);
-  double cum = 0.0, sq = 0.0;
+  double cum = 0.0, sq = 0.0, ab = 0.0;
   for (int j = 0; j < 100; ++j) {
     cum += hist[j];
     const double e = (double)j / 99.0 - cum / (double)n;
     sq += e * e;
+    ab += fabs(e);
   }
   scalars[3] = sqrt(sq / 100.0);
+  if (nscal > 4) scalars[4] = ab / 100.0;  // mean absolute calibration error (results/metrics.py:277-297)
 }
 void launch_test_metrics(const float* pred, const float* std, const float* y, long long n, double* scalars,
-                         unsigned int* hist, cudaStream_t st) {
+                         unsigned int* hist, cudaStream_t st, int nscal) {
   // workspace layout: hist[100] u32 followed (at +512 B) by acc[3] doubles
   double* acc = reinterpret_cast<double*>(reinterpret_cast<char*>(hist) + 512);
   cudaMemsetAsync(hist, 0, 512 + 3 * sizeof(double), st);
   ++g_launch_count;
   test_metrics_acc_kernel<<<(unsigned)min((n + 255) / 256, (long long)148 * 4), 256, 0, st>>>(pred, std, y, n, acc, hist);
   ++g_launch_count;
-  test_metrics_final_kernel<<<1, 32, 0, st>>>(acc, hist, n, scalars);
+  test_metrics_final_kernel<<<1, 32, 0, st>>>(acc, hist, n, scalars, nscal);
 }
 
 // ------------------------------------------------------------------------------------------------

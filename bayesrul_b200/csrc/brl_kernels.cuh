@@ -189,7 +189,7 @@ void launch_aggregate(const float* out, long long S, long long B, float* agg, cu
 void launch_mixture(const float* mu_m, const float* sd_m, long long M, long long n, float* mu, float* sd,
                     cudaStream_t st);
 void launch_test_metrics(const float* pred, const float* std, const float* y, long long n, double* scalars,
-                         unsigned int* hist, cudaStream_t st);
+                         unsigned int* hist, cudaStream_t st, int nscal = 4);
 void launch_clipped_adam(float* p, const float* g, float* m, float* v, long long n, float step_size, float b1,
                          float b2, float eps, float clip, float wd, cudaStream_t st);
 void launch_clipped_adam_vi(float* loc, float* ls, float* scale, const float* g_loc, const float* g_ls, float* m_loc, float* v_loc,

@@ -364,6 +364,20 @@ class Engine:
                                                  scalars.data_ptr(), ws.data_ptr(), ws.numel(), self._stream()))
         return scalars
 
+    def step_metrics(self, pred, std, y) -> torch.Tensor:
+        """device float64[5]: gaussian_nll, mse, sharpness, rmsce, mace -- every scalar a training / validation / test step
+        logs (bayesian.py:158-166; results/metrics.py:210-297) from one fused pass."""
+        pred, std, y = (_chk(t.reshape(-1), self.device, n) for t, n in ((pred, "pred"), (std, "std"), (y, "y")))
+        if not (pred.shape == std.shape == y.shape):
+            raise RuntimeError("bayesrul_b200: pred / std / y shapes differ")
+        scalars = torch.empty(5, dtype=torch.float64, device=self.device)
+        if getattr(self, "_metrics_ws", None) is None:
+            self._metrics_ws = torch.empty(4096, dtype=torch.uint8, device=self.device)  # its own scratch: survives workspace growth
+        with self._on_device():
+            _lib.check(self.lib.brl_step_metrics(pred.data_ptr(), std.data_ptr(), y.data_ptr(), pred.numel(), scalars.data_ptr(),
+                                                 self._metrics_ws.data_ptr(), self._metrics_ws.numel(), self._stream()))
+        return scalars
+
     def clipped_adam(self, param, grad, exp_avg, exp_avg_sq, step: int, lr: float, betas=(0.95, 0.999), eps=1e-8,
                      clip_norm=15.0, lrd=1.0, weight_decay=0.0) -> None:
         for t, n in ((param, "param"), (grad, "grad"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):

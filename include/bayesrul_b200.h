@@ -215,6 +215,13 @@ int brl_mixture_moments(const float* mu_m, const float* sigma_m, int64_t M, int6
 int brl_test_metrics(const float* pred, const float* std, const float* y, int64_t n, double* scalars,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- the scalars logged every training / validation / test step (bayesian.py:158-166,187-197; frequentist.py:50-58,94-110):
+ *      device double[5] = {gaussian_nll_loss(pred,y,std^2), mse_loss, sharpness, rms_calibration_error, mean_absolute_calibration_error}
+ *      (results/metrics.py:210-213,255-274,277-297; 100 bins, prop_type "interval") from ONE pass over the batch + a
+ *      100-bin coverage histogram, instead of ~30 small torch launches per step */
+int brl_step_metrics(const float* pred, const float* std, const float* y, int64_t n, double* scalars,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- fused ClippedAdam over a flat buffer (pyro.optim.ClippedAdam, conf/model/bnn.yaml:6-10) */
 int brl_clipped_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                      int64_t step, float lr, float beta1, float beta2, float eps, float clip_norm,

@@ -234,6 +234,24 @@ def test_hnn_step_vs_oracle(engines, net, p):
 
 
 # ----------------------------------------------------------------------------- small reductions / optimiser
+@pytest.mark.parametrize("n", [100, 256, 10000])
+def test_step_metrics_vs_reference_formulas(engines, n):
+    """N3: brl_step_metrics = {gaussian_nll, mse, sharpness, rmsce, mace} of results/metrics.py:210-297 (restated in torch by
+    compat.metrics / the oracle) at the batch sizes of a train step (100 / 256) and of a test batch (10 000)."""
+    from bayesrul_b200.compat import metrics as M
+    e = engines["inception"]
+    g = torch.Generator().manual_seed(60 + n)
+    y = torch.rand(n, generator=g) * 100
+    std = torch.rand(n, generator=g) * 20 + 0.5
+    pred = y + torch.randn(n, generator=g) * std * 1.3  # mildly over-confident predictions: a non-trivial calibration curve
+    sc = e.step_metrics(pred.to(DEV), std.to(DEV), y.to(DEV)).cpu()
+    want = [torch.nn.functional.gaussian_nll_loss(pred, y, std**2).item(), torch.nn.functional.mse_loss(pred, y).item(),
+            M.sharpness(std).item(), O.rms_calibration_error(pred.double(), std.double(), y.double()).item(),
+            M.mean_absolute_calibration_error(pred.double(), std.double(), y.double()).item()]
+    for k, (a, b) in enumerate(zip(sc.tolist(), want)):
+        assert abs(a - b) <= 2e-3 * abs(b) + 2.0 / n, (k, sc, want)  # one residual on a bin edge moves a proportion by 1 / n
+
+
 def test_test_metrics_and_adam(engines):
     e = engines["inception"]
     g = torch.Generator().manual_seed(6)
