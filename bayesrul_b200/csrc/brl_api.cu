@@ -1152,7 +1152,8 @@ static int elbo_body(brl_ctx* ctx, const ActBufs* const* lanes, int n_lanes, con
         ts.sgn_fc_in = sin_[fc_layer];
         ts.w_off_fc = n.layers[fc_layer].w_off; ts.b_off_fc = n.layers[fc_layer].b_off;
         ts.g0 = ab.g0; ts.g1 = ab.g1;
-        tt_forward(ab.tt, ts, ls);
+        const TtSide tsd{ln.side[0], ln.ev_fork, ln.ev_join[0]};
+        tt_forward(ab.tt, ts, ls, tsd);
         int epi;
         const ConvGemm fc = fwd_gemm(ctx, ab, fa, fc_op, 0, &epi);  // the fc layer: tcgen05 contraction + the per-layer epilogue
         tt_fc_forward(ab.tt, ts, fc.part, ls);
@@ -1167,10 +1168,14 @@ static int elbo_body(brl_ctx* ctx, const ActBufs* const* lanes, int n_lanes, con
         BwdArgs ba{x, B, mode, mode == BRL_MODE_WS ? ab.wsamp : mu, sigma, ab.wsamp, 0.f, &nz, sin_.data(), sout_.data(), outp, ab.g0, ab.g1};
         if (use_tt) {
           const int fc_op = (int)n.ops.size() - 2;
-          backward_op(ctx, ab, ba, fc_op + 1, ls, 0, ls, nullptr, nullptr);
+          const TtSide tsd{ln.side[0], ln.ev_fork, ln.ev_join[0]};
+          // head: its weight gradient trails on a second side stream, joined before the finalisation
+          backward_op(ctx, ab, ba, fc_op + 1, ls, 0, ln.side[1], ln.ev_op[0], nullptr);
+          BRL_CUDA(cudaEventRecord(ln.ev_join[1], ln.side[1]));
           backward_act(ctx, ab, ba, fc_op, ls);
-          tt_fc_backward(ab.tt, ts, ab.dpre[fc_op], ab.dsec[fc_op], ls);
-          tt_backward(ab.tt, ts, ls);
+          tt_fc_backward(ab.tt, ts, ab.dpre[fc_op], ab.dsec[fc_op], ls, tsd);
+          tt_backward(ab.tt, ts, ls, tsd);
+          BRL_CUDA(cudaStreamWaitEvent(ls, ln.ev_join[1], 0));
         } else {
           run_backward(ctx, ab, ba, ls, l);
         }

@@ -1116,19 +1116,22 @@ static TtLayer layer_of(const TtStep& s, int i) {
   return l;
 }
 
-void tt_forward(const TtLane& ln, const TtStep& s, cudaStream_t st) {
+void tt_forward(const TtLane& ln, const TtStep& s, cudaStream_t st, const TtSide& sd) {
   tt_configure();
   const int nt = (int)((s.B + 3) / 4);
   const Table& tb = table();
+  cudaEventRecord(sd.fork, st);  // the parameters (and a Flipout weight draw) are complete on `st` here
+  cudaStreamWaitEvent(sd.side, sd.fork, 0);
   tt_packx_kernel<<<(unsigned)(((long long)nt * 3 * ROWS + 255) / 256), 256, 0, st>>>(s.x, ln.ximg, (int)s.B, nt);
   TtPackArgs pa;
   for (int i = 0; i < TT_LAYERS; ++i) { pa.L[i] = layer_of(s, i); pa.start[i] = tb.pack_start[i]; }
   pa.start[TT_LAYERS] = tb.pack_start[TT_LAYERS];
   pa.mode = s.mode; pa.mu = s.mu; pa.second = s.mode == BRL_MODE_LRT ? s.sigma : s.wsamp; pa.blob = ln.blob;
-  tt_pack_kernel<<<(tb.pack_start[TT_LAYERS] + TT_LAYERS * 64 + 255) / 256, 256, 0, st>>>(pa);
+  tt_pack_kernel<<<(tb.pack_start[TT_LAYERS] + TT_LAYERS * 64 + 255) / 256, 256, 0, sd.side>>>(pa);
   TtFcPackArgs fp;
   fp.mode = s.mode; fp.mu = s.mu; fp.second = pa.second; fp.w_off = s.w_off_fc; fp.blob = ln.fcblob;
-  tt_pack_fc_kernel<<<(64 * 2400 + 255) / 256, 256, 0, st>>>(fp);
+  tt_pack_fc_kernel<<<(64 * 2400 + 255) / 256, 256, 0, sd.side>>>(fp);
+  cudaEventRecord(sd.join, sd.side);
   g_launch_count += 3;
   if (s.B % 128 != 0) {  // windows beyond B of the last 128-window M-tile are K rows of the fc weight-gradient GEMM: they must be zero
     const size_t last = (size_t)(s.B / 128) * FC_MT_BYTES;
@@ -1137,6 +1140,7 @@ void tt_forward(const TtLane& ln, const TtStep& s, cudaStream_t st) {
     cudaMemsetAsync(ln.f2bimg + last, 0, FC_MT_BYTES, st);
     cudaMemsetAsync(ln.fimg + last, 0, FC_MT_BYTES, st);
   }
+  cudaStreamWaitEvent(st, sd.join, 0);  // weight images ready
   static const int levels[3][4] = {{0, 1, 2, 3}, {5, 7, 4, 9}, {6, 8, -1, -1}};
   for (int lv = 0; lv < 3; ++lv) {
     TtFwdArgs fa{};
@@ -1171,22 +1175,27 @@ void tt_fc_forward(const TtLane& ln, const TtStep& s, float* part, cudaStream_t 
   tt_fc_fwd_kernel<<<dim3(nmt, FC_KS), 256, FF_SMEM, st>>>(fa);
 }
 
-void tt_fc_backward(const TtLane& ln, const TtStep& s, const float* dpre, const float* dsec, cudaStream_t st) {
+void tt_fc_backward(const TtLane& ln, const TtStep& s, const float* dpre, const float* dsec, cudaStream_t st, const TtSide& sd) {
   tt_configure();
   TtFcBwdArgs ba{};
   ba.ln = ln; ba.B = (int)s.B; ba.nmt = (int)((s.B + 127) / 128); ba.mode = s.mode; ba.dpre = dpre; ba.dsec = dsec;
   ba.sgn_in = s.sgn_fc_in; ba.g0 = s.g0; ba.g1 = s.g1; ba.w_off = s.w_off_fc; ba.b_off = s.b_off_fc; ba.status = tt_status_word();
   g_launch_count += 2;
+  // the weight gradient needs nothing downstream of it until the finalisation: it leaves the critical chain for the side stream
+  // (joined at the end of tt_backward)
+  cudaEventRecord(sd.fork, st);
+  cudaStreamWaitEvent(sd.side, sd.fork, 0);
   if (s.mode == BRL_MODE_LRT) {
     tt_fc_dx_kernel<BRL_MODE_LRT><<<dim3(ba.nmt, FC_NS), 256, FX_SMEM, st>>>(ba);
-    tt_fc_dw_kernel<BRL_MODE_LRT><<<(FC_KC + 15) / 16, 256, FW_SMEM, st>>>(ba);
+    tt_fc_dw_kernel<BRL_MODE_LRT><<<(FC_KC + 15) / 16, 256, FW_SMEM, sd.side>>>(ba);
   } else {
     tt_fc_dx_kernel<BRL_MODE_FLIPOUT><<<dim3(ba.nmt, FC_NS), 256, FX_SMEM, st>>>(ba);
-    tt_fc_dw_kernel<BRL_MODE_FLIPOUT><<<(FC_KC + 15) / 16, 256, FW_SMEM, st>>>(ba);
+    tt_fc_dw_kernel<BRL_MODE_FLIPOUT><<<(FC_KC + 15) / 16, 256, FW_SMEM, sd.side>>>(ba);
   }
+  cudaEventRecord(sd.join, sd.side);
 }
 
-void tt_backward(const TtLane& ln, const TtStep& s, cudaStream_t st) {
+void tt_backward(const TtLane& ln, const TtStep& s, cudaStream_t st, const TtSide& sd) {
   tt_configure();
   const int nt = (int)((s.B + 3) / 4);
   // reverse dependency levels: {b2b, b3b, b1, b4} need only the fc layer's gradient; {b2a, b3a} need d/dT2, d/dT3;
@@ -1228,6 +1237,7 @@ void tt_backward(const TtLane& ln, const TtStep& s, cudaStream_t st) {
   ra.part_floats = tb.part_floats; ra.mode = s.mode; ra.part = ln.part; ra.g0 = s.g0; ra.g1 = s.g1;
   ++g_launch_count;
   tt_reduce_kernel<<<dim3((tot + 255) / 256, RED_SPLIT), 256, 0, st>>>(ra);
+  cudaStreamWaitEvent(st, sd.join, 0);  // the fc weight gradient (tt_fc_backward) is part of what the caller finalises next
 }
 
 }  // namespace brl

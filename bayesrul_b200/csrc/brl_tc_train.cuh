@@ -49,14 +49,17 @@ struct TtStep {
   long long w_off[TT_LAYERS], b_off[TT_LAYERS];
 };
 // forward of the ten conv layers: x -> feature images (+ the activation / eps images the backward pass re-reads); 6 launches
-void tt_forward(const TtLane& ln, const TtStep& s, cudaStream_t st);
+// side stream + two events of the calling lane: independent kernels of a step (weight packing next to the window packing, the fc
+// weight gradient next to the conv backward chain) fork to `side` and join back; all of it is stream-capturable
+struct TtSide { cudaStream_t side; cudaEvent_t fork, join; };
+void tt_forward(const TtLane& ln, const TtStep& s, cudaStream_t st, const TtSide& sd);
 // fc layer GEMMs on the tensor pipe.  Forward: both contractions as split-K partial sums into `part` ([2][B][64] fp32, the
 // split-K scratch layout of brl_gemm.cu) -- the per-layer engine's split-K epilogue then applies bias / eps * sqrt(var) / signs /
 // ReLU.  Backward: dpre / dsec = compact [B, 64] gradients (bwd_act_kernel) -> feature-gradient image + g0 / g1 of the fc layer.
 void tt_fc_forward(const TtLane& ln, const TtStep& s, float* part, cudaStream_t st);
-void tt_fc_backward(const TtLane& ln, const TtStep& s, const float* dpre, const float* dsec, cudaStream_t st);
+void tt_fc_backward(const TtLane& ln, const TtStep& s, const float* dpre, const float* dsec, cudaStream_t st, const TtSide& sd);
 // backward: feature-gradient image -> g0 / g1 of the ten conv layers (accumulated: the buffers must be zeroed); 4 launches
-void tt_backward(const TtLane& ln, const TtStep& s, cudaStream_t st);
+void tt_backward(const TtLane& ln, const TtStep& s, cudaStream_t st, const TtSide& sd);
 // debug: device buffer int64[6 launches][4 layers][16] receiving clock64 stamps of CTA (0, layer) of the three forward and three
 // backward level launches (nullptr = off)
 void tt_trace(long long* device_buf);

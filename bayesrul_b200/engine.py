@@ -367,7 +367,7 @@ class Engine:
     def step_metrics(self, pred, std, y) -> torch.Tensor:
         """device float64[5]: gaussian_nll, mse, sharpness, rmsce, mace -- every scalar a training / validation / test step
         logs (bayesian.py:158-166; results/metrics.py:210-297) from one fused pass."""
-        pred, std, y = (_chk(t.reshape(-1), self.device, n) for t, n in ((pred, "pred"), (std, "std"), (y, "y")))
+        pred, std, y = (_chk(t.reshape(-1).contiguous(), self.device, n) for t, n in ((pred, "pred"), (std, "std"), (y, "y")))
         if not (pred.shape == std.shape == y.shape):
             raise RuntimeError("bayesrul_b200: pred / std / y shapes differ")
         scalars = torch.empty(5, dtype=torch.float64, device=self.device)

@@ -448,28 +448,47 @@ def main():
         fo_pred = {"window_samples_per_s": world * B_PRED * 20 * 5 / tf, "ms_per_step": 1e3 * tf / 5, "mc_samples": 20, "q_scale": 2.14e-4,
                    "windows_per_step_per_gpu": B_PRED}
 
-    # ---- configs[3]: Radial BNN (ncmapss_rad: q_scale 1.241e-3), MC-sample sweep, the S samples SHARDED across the ranks
-    #      (every rank sees the same windows; per-window (n, mean, M2, sum sigma^2) merged with one all-gather + Chan's formula)
+    # ---- configs[3]: Radial BNN (ncmapss_rad: q_scale 1.241e-3), MC-sample sweep over a FIXED batch of windows, sharded 2-D:
+    #      the ranks form a (window shards) x (sample shards) grid; MC samples are split only while every rank keeps >= 16 of them
+    #      (a fused launch wants tens of samples: S = 10 over 8 ranks would leave 1 - 2 per launch), the remaining factor of the
+    #      world splits the windows.  Ranks that share a window shard merge their per-window (n, mean, M2, sum sigma^2) with one
+    #      all-gather + Chan's formula inside the timed region.
     radial = {}
     if not args.no_train:
-        from bayesrul_b200.dist import all_gather_moments, shard_range
+        from bayesrul_b200.dist import merge_moments, shard_range
         sg_rad = torch.full_like(mu, 1.241e-3)
         x_rad = synth(B_PRED, seed=4242)[0].to(device)  # the same windows on every rank
         for S_tot in (10, 100, 1000):
-            s_lo, s_hi = shard_range(S_tot, rank, world)
+            ss = 1
+            while ss * 2 <= world and world % (ss * 2) == 0 and S_tot // (ss * 2) >= 16:
+                ss *= 2
+            wsh = world // ss
+            wi, si = rank // ss, rank % ss
+            w_lo, w_hi = shard_range(B_PRED, wi, wsh)
+            s_lo, s_hi = shard_range(S_tot, si, ss)
+            xr = x_rad[w_lo:w_hi].contiguous()
 
             def rad_step(i=0):
-                m = eng.predict_moments(x_rad, mu, sg_rad, S=s_hi - s_lo, guide="radial", noise=Noise(seed=777, sample0=s_lo), engine=engine)
-                if dist is not None:
-                    m = all_gather_moments(s_hi - s_lo, m[0], m[2], m[3])
+                m = eng.predict_moments(xr, mu, sg_rad, S=s_hi - s_lo, guide="radial", noise=Noise(seed=777, sample0=s_lo, window0=w_lo),
+                                        engine=engine)
+                if ss > 1:  # one all-gather over the world ([4, windows of a shard], padded to the largest shard); merge my row of the grid
+                    nmax = -(-B_PRED // wsh)
+                    packed = torch.zeros(4, nmax, device=device)
+                    packed[0, : w_hi - w_lo] = float(s_hi - s_lo)
+                    packed[1, : w_hi - w_lo], packed[2, : w_hi - w_lo], packed[3, : w_hi - w_lo] = m[0], m[2].nan_to_num(0.0), m[3]
+                    allp = torch.empty(world * 4, nmax, device=device)
+                    dist.all_gather_into_tensor(allp, packed)
+                    allp = allp.view(world, 4, nmax)[wi * ss:(wi + 1) * ss, :, : w_hi - w_lo]
+                    m = merge_moments([(allp[r, 0], allp[r, 1], allp[r, 2], allp[r, 3]) for r in range(ss)])
                 outs["rad"] = m
 
             nrep = 3
             tr = max_over_ranks(timed_steps(rad_step, nrep, 2, flush_buf, dist), dist, device)
             radial[f"S={S_tot}"] = {"window_samples_per_s": B_PRED * S_tot * nrep / tr, "ms_per_step": 1e3 * tr / nrep,
-                                    "samples_per_rank": s_hi - s_lo}
-        radial["note"] = (f"{B_PRED} windows, AutoRadial guide (eps/||eps||*r sampler, two-phase norm), samples sharded over {world} rank(s)"
-                          + (", NCCL all-gather of the per-window moments + Chan merge inside the timed region" if dist is not None else ""))
+                                    "samples_per_rank": s_hi - s_lo, "windows_per_rank": w_hi - w_lo, "grid": f"{wsh} window x {ss} sample shards"}
+        radial["note"] = (f"{B_PRED} windows in total (strong scaling), AutoRadial guide (eps/||eps||*r sampler, two-phase norm), "
+                          f"{world} rank(s) as a window x sample grid"
+                          + ("; NCCL all-gather of the per-window moments + Chan merge inside the timed region where samples are split" if dist is not None else ""))
 
     # ---- configs[4]: deep ensemble of 5 HNN members (deterministic heteroscedastic nets) + mixture moments (deepens.py:21-24);
     #      windows sharded across the ranks like the headline workload
