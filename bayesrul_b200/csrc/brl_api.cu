@@ -1124,22 +1124,25 @@ static int elbo_body(brl_ctx* ctx, const ActBufs* const* lanes, int n_lanes, con
       }
       float* outp = out + (long long)pt * B * 2;
       const brl_ctx::Lane& ln = ctx->lanes[l];
+      // level-fused tcgen05 kernels (BRL_GEMM_TC_FUSED): ten conv layers + the fc layer on the tensor pipe, the rest of the net
+      // (fc epilogue, head, likelihood, their backward) in one tail kernel
+      const bool use_tt = ctx->gemm_backend == BRL_GEMM_TC_FUSED && n.id == BRL_NET_INCEPTION && ab.has_tt &&
+                          (mode == BRL_MODE_LRT || mode == BRL_MODE_FLIPOUT);
       if (compute_grads) {  // a dozen memsets: on a side stream underneath the forward pass, joined before the NLL
         cudaStream_t zs = ctx->multi_stream ? ln.zero : ls;
         if (zs != ls) {
           BRL_CUDA(cudaEventRecord(ln.ev_zero, ls));
           BRL_CUDA(cudaStreamWaitEvent(zs, ln.ev_zero, 0));
         }
-        int rc = zero_grads(n, ab, B, zs);
-        if (rc) return rc;
+        if (!use_tt) {  // the fused back-end keeps its gradients in bf16 images that are written, not accumulated
+          int rc = zero_grads(n, ab, B, zs);
+          if (rc) return rc;
+        }
         BRL_CUDA(cudaMemsetAsync(ab.g0, 0, sizeof(float) * n.P, zs));
         BRL_CUDA(cudaMemsetAsync(ab.g1, 0, sizeof(float) * n.P, zs));
         if (zs != ls) BRL_CUDA(cudaEventRecord(ln.ev_zero, zs));
       }
       FwdArgs fa{x, B, 1, mode, mu, sigma, ab.wsamp, 0.f, &nz, sin_.data(), sout_.data(), outp, compute_grads != 0};
-      // level-fused tcgen05 kernels for the ten conv layers (BRL_GEMM_TC_FUSED); the fc layer and the head stay per-layer
-      const bool use_tt = ctx->gemm_backend == BRL_GEMM_TC_FUSED && n.id == BRL_NET_INCEPTION && ab.has_tt &&
-                          (mode == BRL_MODE_LRT || mode == BRL_MODE_FLIPOUT);
       TtStep ts{};
       if (use_tt) {
         ts.x = x; ts.B = B; ts.mode = mode; ts.mu = mu; ts.sigma = sigma; ts.wsamp = ab.wsamp;
@@ -1154,28 +1157,31 @@ static int elbo_body(brl_ctx* ctx, const ActBufs* const* lanes, int n_lanes, con
         ts.g0 = ab.g0; ts.g1 = ab.g1;
         const TtSide tsd{ln.side[0], ln.ev_fork, ln.ev_join[0]};
         tt_forward(ab.tt, ts, ls, tsd);
-        int epi;
-        const ConvGemm fc = fwd_gemm(ctx, ab, fa, fc_op, 0, &epi);  // the fc layer: tcgen05 contraction + the per-layer epilogue
-        tt_fc_forward(ab.tt, ts, fc.part, ls);
-        launch_splitk_epilogue(fc, epi, ls);
-        forward_op(ctx, ab, fa, fc_op + 1, ls, 0);
+        tt_fc_forward(ab.tt, ts, ab.part[0], ls);
       } else {
         run_forward(ctx, ab, fa, ls, l);
       }
       if (compute_grads && ctx->multi_stream) BRL_CUDA(cudaStreamWaitEvent(ls, ln.ev_zero, 0));
-      launch_nll_elbo(outp, y, B, (float)(c_nll / particles), ab0.acc, compute_grads ? ab.grad[n.out_buf] : nullptr, ls);
+      if (use_tt) {
+        const int fc_op = (int)n.ops.size() - 2, fc_layer = n.ops[fc_op].layer, hd_layer = n.ops[fc_op + 1].layer;
+        TtTail tl{};
+        tl.part = ab.part[0]; tl.y = y; tl.gscale = (float)(c_nll / particles); tl.compute_grads = compute_grads;
+        tl.acc = ab0.acc; tl.out = outp; tl.dpre = ab.dpre[fc_op]; tl.dsec = ab.dsec[fc_op];
+        tl.eps_fc = nref(&nz, nz.lrt_eps[fc_layer], KIND_LRT_EPS, (unsigned)fc_layer);
+        tl.eps_head = nref(&nz, nz.lrt_eps[hd_layer], KIND_LRT_EPS, (unsigned)hd_layer);
+        tl.sout_fc = sout_[fc_layer]; tl.sin_head = sin_[hd_layer]; tl.sout_head = sout_[hd_layer];
+        tl.hw_off = n.layers[hd_layer].w_off; tl.hb_off = n.layers[hd_layer].b_off;
+        tt_tail(ts, tl, ls);
+      } else {
+        launch_nll_elbo(outp, y, B, (float)(c_nll / particles), ab0.acc, compute_grads ? ab.grad[n.out_buf] : nullptr, ls);
+      }
       if (compute_grads) {
         BwdArgs ba{x, B, mode, mode == BRL_MODE_WS ? ab.wsamp : mu, sigma, ab.wsamp, 0.f, &nz, sin_.data(), sout_.data(), outp, ab.g0, ab.g1};
         if (use_tt) {
           const int fc_op = (int)n.ops.size() - 2;
           const TtSide tsd{ln.side[0], ln.ev_fork, ln.ev_join[0]};
-          // head: its weight gradient trails on a second side stream, joined before the finalisation
-          backward_op(ctx, ab, ba, fc_op + 1, ls, 0, ln.side[1], ln.ev_op[0], nullptr);
-          BRL_CUDA(cudaEventRecord(ln.ev_join[1], ln.side[1]));
-          backward_act(ctx, ab, ba, fc_op, ls);
           tt_fc_backward(ab.tt, ts, ab.dpre[fc_op], ab.dsec[fc_op], ls, tsd);
           tt_backward(ab.tt, ts, ls, tsd);
-          BRL_CUDA(cudaStreamWaitEvent(ls, ln.ev_join[1], 0));
         } else {
           run_backward(ctx, ab, ba, ls, l);
         }

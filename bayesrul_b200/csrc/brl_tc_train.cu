@@ -998,6 +998,187 @@ __global__ void __launch_bounds__(256, 1) tt_fc_dw_kernel(const TtFcBwdArgs a) {
   if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// tail of the net in ONE launch: fc epilogue (bias, eps * sqrt(var) / sign flips, ReLU) -> head 64 -> 2 (dual) -> softplus +
+// Threshold(1e-9) -> ELBO likelihood (second softplus, bayesian.py:73-76) and its gradient -> head backward (input and weight
+// gradients) -> activation backward of the fc layer (the compact dpre / dsec tensors of tt_fc_backward).  It replaces eight
+// per-layer launches (split-K epilogue, head GEMM, NLL, two activation-backward, head dX / dW) of 3 - 11 us each; the arithmetic
+// is that of brl_gemm_epi.cuh / nll_elbo_kernel / bwd_act_kernel, one warp per window, lane = hidden units {lane, lane + 32}.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double tt_block_sum(double v) {  // valid in thread 0
+  __shared__ double red[32];
+  __syncthreads();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    v = threadIdx.x < (blockDim.x + 31) / 32 ? red[threadIdx.x] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  }
+  return v;
+}
+struct TtTailArgs {
+  int B, mode, compute_grads;
+  const float* part;           // [2][B][64] fc partial sums (mean path, second path)
+  const float *fc_b0, *fc_b1;  // LRT: mu_b, sigma_b of the fc layer; Flipout: fc_b0 = sampled bias
+  const float *hw0, *hw1;      // head weights [2][64]: LRT mu, sigma; Flipout mu, sampled W
+  const float *hb0, *hb1;      // head bias [2]:      LRT mu_b, sigma_b; Flipout hb0 = sampled bias
+  NoiseRef eps_fc, eps_head;   // LRT
+  const float *sout_fc, *sin_head, *sout_head;  // Flipout [B,64], [B,64], [B,2]
+  const float* y;
+  float gscale;
+  double* acc;                 // [0] += nll, [1] += squared error
+  float* out;                  // [B,2]
+  float *dpre, *dsec;          // [B,64] compact gradients of the fc layer's pre-activation / second path
+  float *g0, *g1;              // flat gradient accumulators (head layer: atomics)
+  long long hw_off, hb_off;
+};
+template <int MODE>
+__global__ void __launch_bounds__(256) tt_tail_kernel(const TtTailArgs a) {
+  __shared__ float sg[2][2][64 + 1];  // [path][output][hidden unit | bias] head weight-gradient partials of the CTA
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 2 * 2 * 65; i += 256) (&sg[0][0][0])[i] = 0.f;
+  __syncthreads();
+  float w0[2][2], w1[2][2];  // head weights of this lane's two hidden units: [output][unit]
+#pragma unroll
+  for (int o = 0; o < 2; ++o)
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int k = lane + 32 * u;
+      const float m = a.hw0[o * 64 + k], v = a.hw1[o * 64 + k];
+      w0[o][u] = m;
+      w1[o][u] = MODE == BRL_MODE_LRT ? v * v : v - m;
+    }
+  float gw0[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, gw1[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, gb0[2] = {0.f, 0.f}, gb1[2] = {0.f, 0.f};
+  double nll = 0.0, se = 0.0;
+  const int nwarps = gridDim.x * 8;
+  for (int m = blockIdx.x * 8 + warp; m < a.B; m += nwarps) {
+    // ---- fc epilogue
+    float h[2], sd[2], ef[2], sgn_in[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int k = lane + 32 * u;
+      const float a0 = a.part[(long long)m * 64 + k], a1 = a.part[((long long)a.B + m) * 64 + k];
+      float pre;
+      if (MODE == BRL_MODE_LRT) {
+        const float sb = a.fc_b1[k];
+        float var = fmaf(sb, sb, a1);
+        if (var < 0.f) var += fabsf(var) + 1e-6f;
+        sd[u] = sqrtf(var);
+        ef[u] = gnoise_normal(a.eps_fc, 0, m, a.B, 64, k);
+        pre = fmaf(sd[u], ef[u], a0 + a.fc_b0[k]);
+        sgn_in[u] = 0.f;
+      } else {
+        ef[u] = a.sout_fc[(long long)m * 64 + k];
+        pre = a0 + a1 * ef[u] + a.fc_b0[k];
+        sd[u] = 0.f;
+        sgn_in[u] = a.sin_head[(long long)m * 64 + k];
+      }
+      h[u] = fmaxf(pre, 0.f);
+    }
+    // ---- head: two outputs x two paths, reduced over the 64 hidden units
+    float p0[2], p1[2];
+#pragma unroll
+    for (int o = 0; o < 2; ++o) {
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        s0 = fmaf(h[u], w0[o][u], s0);
+        s1 = fmaf(MODE == BRL_MODE_LRT ? h[u] * h[u] : h[u] * sgn_in[u], w1[o][u], s1);
+      }
+      p0[o] = warp_sum(s0);
+      p1[o] = warp_sum(s1);
+    }
+    float outv[2], sdo[2], eo[2];
+#pragma unroll
+    for (int o = 0; o < 2; ++o) {
+      float v;
+      if (MODE == BRL_MODE_LRT) {
+        const float sb = a.hb1[o];
+        float var = fmaf(sb, sb, p1[o]);
+        if (var < 0.f) var += fabsf(var) + 1e-6f;
+        sdo[o] = sqrtf(var);
+        eo[o] = gnoise_normal(a.eps_head, 0, m, a.B, 2, o);
+        v = fmaf(sdo[o], eo[o], p0[o] + a.hb0[o]);
+      } else {
+        eo[o] = a.sout_head[(long long)m * 2 + o];
+        sdo[o] = 0.f;
+        v = p0[o] + p1[o] * eo[o] + a.hb0[o];
+      }
+      v = v > 20.0f ? v : log1pf(expf(v));
+      outv[o] = v > 1e-9f ? v : 1e-9f;
+    }
+    if (lane == 0) *reinterpret_cast<float2*>(a.out + 2ll * m) = make_float2(outv[0], outv[1]);
+    // ---- likelihood and its gradient w.r.t. the two outputs
+    const float loc = outv[0], sc = outv[1];
+    const float s = sc > 20.0f ? sc : log1pf(expf(sc));
+    const float dy = a.y[m] - loc, r = dy / s;
+    if (lane == 0) {
+      nll += 0.5 * (double)r * r + (double)logf(s) + 0.9189385332046727;
+      se += (double)dy * dy;
+    }
+    if (!a.compute_grads) continue;
+    const float sig = sc > 20.0f ? 1.0f : 1.0f / (1.0f + expf(-sc));
+    const float go[2] = {-r / s * a.gscale, (1.0f - r * r) / s * sig * a.gscale};
+    // ---- head backward
+    float d[2], d1[2];
+#pragma unroll
+    for (int o = 0; o < 2; ++o) {
+      d[o] = outv[o] > 1e-9f ? go[o] * (1.0f - expf(-outv[o])) : 0.f;
+      d1[o] = MODE == BRL_MODE_LRT ? (sdo[o] > 0.f ? d[o] * eo[o] / (2.0f * sdo[o]) : 0.f) : d[o] * eo[o];
+      gb0[o] += d[o];
+      gb1[o] += MODE == BRL_MODE_LRT ? d1[o] : d[o];
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int k = lane + 32 * u;
+      const float x1 = MODE == BRL_MODE_LRT ? h[u] * h[u] : h[u] * sgn_in[u];
+      float dh0 = 0.f, dh1 = 0.f;
+#pragma unroll
+      for (int o = 0; o < 2; ++o) {
+        gw0[o][u] = fmaf(d[o], h[u], gw0[o][u]);
+        gw1[o][u] = fmaf(d1[o], x1, gw1[o][u]);
+        dh0 = fmaf(d[o], w0[o][u], dh0);
+        dh1 = fmaf(d1[o], w1[o][u], dh1);
+      }
+      const float dh = MODE == BRL_MODE_LRT ? fmaf(2.0f * h[u], dh1, dh0) : fmaf(sgn_in[u], dh1, dh0);
+      // ---- activation backward of the fc layer
+      const float dp = h[u] > 0.f ? dh : 0.f;
+      a.dpre[(long long)m * 64 + k] = dp;
+      a.dsec[(long long)m * 64 + k] = MODE == BRL_MODE_LRT ? (sd[u] > 0.f ? dp * ef[u] / (2.0f * sd[u]) : 0.f) : dp * ef[u];
+    }
+  }
+  // ---- reductions: likelihood sums (lane 0 of every warp holds its windows'), head weight gradients
+  nll = tt_block_sum(nll);
+  se = tt_block_sum(se);
+  if (tid == 0) {
+    atomicAdd(a.acc + 0, nll);
+    atomicAdd(a.acc + 1, se);
+  }
+  if (!a.compute_grads) return;
+#pragma unroll
+  for (int o = 0; o < 2; ++o) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      atomicAdd(&sg[0][o][lane + 32 * u], gw0[o][u]);
+      atomicAdd(&sg[1][o][lane + 32 * u], gw1[o][u]);
+    }
+    if (lane == 0) {  // d[o] is warp-uniform: one lane carries the bias gradient
+      atomicAdd(&sg[0][o][64], gb0[o]);
+      atomicAdd(&sg[1][o][64], gb1[o]);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < 2 * 2 * 65; i += 256) {
+    const int path = i / 130, r = i - path * 130, o = r / 65, k = r - o * 65;
+    float* g = path ? a.g1 : a.g0;
+    atomicAdd(g + (k < 64 ? a.hw_off + o * 64 + k : a.hb_off + o), sg[path][o][k]);
+  }
+}
+
 // weight / bias gradients of the ten conv layers: sum of the groups' partial blocks -> flat gradient accumulators
 struct TtReduceArgs {
   TtLayer L[TT_LAYERS];
@@ -1173,6 +1354,24 @@ void tt_fc_forward(const TtLane& ln, const TtStep& s, float* part, cudaStream_t 
   fa.ln = ln; fa.B = (int)s.B; fa.mode = s.mode; fa.part = part; fa.status = tt_status_word();
   ++g_launch_count;
   tt_fc_fwd_kernel<<<dim3(nmt, FC_KS), 256, FF_SMEM, st>>>(fa);
+}
+
+void tt_tail(const TtStep& s, const TtTail& t, cudaStream_t st) {
+  TtTailArgs a{};
+  a.B = (int)s.B; a.mode = s.mode; a.compute_grads = t.compute_grads;
+  a.part = t.part;
+  const bool lrt = s.mode == BRL_MODE_LRT;
+  a.fc_b0 = (lrt ? s.mu : s.wsamp) + s.b_off_fc; a.fc_b1 = lrt ? s.sigma + s.b_off_fc : nullptr;
+  a.hw0 = s.mu + t.hw_off; a.hw1 = (lrt ? s.sigma : s.wsamp) + t.hw_off;
+  a.hb0 = (lrt ? s.mu : s.wsamp) + t.hb_off; a.hb1 = lrt ? s.sigma + t.hb_off : nullptr;
+  a.eps_fc = t.eps_fc; a.eps_head = t.eps_head;
+  a.sout_fc = t.sout_fc; a.sin_head = t.sin_head; a.sout_head = t.sout_head;
+  a.y = t.y; a.gscale = t.gscale; a.acc = t.acc; a.out = t.out; a.dpre = t.dpre; a.dsec = t.dsec;
+  a.g0 = s.g0; a.g1 = s.g1; a.hw_off = t.hw_off; a.hb_off = t.hb_off;
+  const int grid = (int)std::min<long long>((s.B + 7) / 8, 148);
+  ++g_launch_count;
+  if (lrt) tt_tail_kernel<BRL_MODE_LRT><<<grid, 256, 0, st>>>(a);
+  else tt_tail_kernel<BRL_MODE_FLIPOUT><<<grid, 256, 0, st>>>(a);
 }
 
 void tt_fc_backward(const TtLane& ln, const TtStep& s, const float* dpre, const float* dsec, cudaStream_t st, const TtSide& sd) {

@@ -58,6 +58,22 @@ void tt_forward(const TtLane& ln, const TtStep& s, cudaStream_t st, const TtSide
 // ReLU.  Backward: dpre / dsec = compact [B, 64] gradients (bwd_act_kernel) -> feature-gradient image + g0 / g1 of the fc layer.
 void tt_fc_forward(const TtLane& ln, const TtStep& s, float* part, cudaStream_t st);
 void tt_fc_backward(const TtLane& ln, const TtStep& s, const float* dpre, const float* dsec, cudaStream_t st, const TtSide& sd);
+// Everything between the fc GEMM and the fc layer's backward GEMMs in ONE launch: fc epilogue over `part`, head forward, softplus /
+// threshold, ELBO likelihood (+ its sums in acc[0..1]), head backward (its weight gradients into g0 / g1) and the fc layer's
+// activation backward (dpre / dsec, compact [B, 64]).
+struct TtTail {
+  const float* part;
+  const float* y;
+  float gscale;           // c_nll / particles (launch_nll_elbo)
+  int compute_grads;
+  double* acc;
+  float* out;             // [B,2]
+  float *dpre, *dsec;
+  NoiseRef eps_fc, eps_head;
+  const float *sout_fc, *sin_head, *sout_head;
+  long long hw_off, hb_off;  // flat offsets of the head layer's weight / bias
+};
+void tt_tail(const TtStep& s, const TtTail& t, cudaStream_t st);
 // backward: feature-gradient image -> g0 / g1 of the ten conv layers (accumulated: the buffers must be zeroed); 4 launches
 void tt_backward(const TtLane& ln, const TtStep& s, cudaStream_t st, const TtSide& sd);
 // debug: device buffer int64[6 launches][4 layers][16] receiving clock64 stamps of CTA (0, layer) of the three forward and three
