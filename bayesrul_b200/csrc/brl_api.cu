@@ -1111,7 +1111,7 @@ static int elbo_body(brl_ctx* ctx, const ActBufs* const* lanes, int n_lanes, con
         jobs.start[0] = 0;
         auto add = [&](float* dst, int C, unsigned kind, unsigned site) {
           jobs.dst[jobs.n] = dst; jobs.C[jobs.n] = C; jobs.kind[jobs.n] = kind; jobs.site[jobs.n] = site;
-          jobs.start[jobs.n + 1] = jobs.start[jobs.n] + B * C;
+          jobs.start[jobs.n + 1] = jobs.start[jobs.n] + B * ((C + 3) / 4);  // work items: one Philox block = four channels
           ++jobs.n;
         };
         for (size_t ly = 0; ly < n.layers.size(); ++ly) {

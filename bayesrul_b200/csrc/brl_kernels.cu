@@ -284,9 +284,16 @@ __global__ void gen_signs_multi_kernel(const SignJobs jobs, long long B, NoiseRe
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int j = 0;
     while (j + 1 < jobs.n && i >= jobs.start[j + 1]) ++j;
+    // one work item = one Philox block = the signs of four consecutive channels of a window (element c: block c >> 2, lane c & 3,
+    // the keying of philox_sign)
     const long long e = i - jobs.start[j];
-    const int C = jobs.C[j], c = (int)(e % C), b = (int)(e / C);
-    jobs.dst[j][e] = philox_sign(k.seed, jobs.kind[j], jobs.site[j], k.sample0, k.window0 + b, c);
+    const int C = jobs.C[j], Q = (C + 3) >> 2, q = (int)(e % Q), b = (int)(e / Q);
+    const uint4 r = philox_block(k.seed, jobs.kind[j], jobs.site[j], k.sample0, k.window0 + b, (uint32_t)q);
+    float* d = jobs.dst[j] + (long long)b * C + 4 * q;
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int l = 0; l < 4; ++l)
+      if (4 * q + l < C) d[l] = (w[l] >> 31) ? -1.0f : 1.0f;
   }
 }
 void launch_gen_signs_multi(const SignJobs& jobs, long long B, NoiseRef base, cudaStream_t st) {

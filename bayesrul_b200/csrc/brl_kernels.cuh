@@ -155,7 +155,7 @@ struct SignJobs {
   float* dst[32];
   int C[32];
   unsigned int kind[32], site[32];
-  long long start[33];  // element offsets of the jobs in the launch's index space
+  long long start[33];  // offsets of the jobs in the launch's index space (work item = four consecutive channels of a window)
   int n;
 };
 void launch_gen_signs_multi(const SignJobs& jobs, long long B, NoiseRef base, cudaStream_t st);
