@@ -1127,7 +1127,8 @@ static int elbo_body(brl_ctx* ctx, const ActBufs* const* lanes, int n_lanes, con
       // level-fused tcgen05 kernels (BRL_GEMM_TC_FUSED): ten conv layers + the fc layer on the tensor pipe, the rest of the net
       // (fc epilogue, head, likelihood, their backward) in one tail kernel
       const bool use_tt = ctx->gemm_backend == BRL_GEMM_TC_FUSED && n.id == BRL_NET_INCEPTION && ab.has_tt &&
-                          (mode == BRL_MODE_LRT || mode == BRL_MODE_FLIPOUT);
+                          (mode == BRL_MODE_LRT || mode == BRL_MODE_FLIPOUT) &&
+                          2 * B * 64 <= SPLITK_SCRATCH_FLOATS;  // fc partial sums live in the split-K scratch (B <= 4736), else per-layer
       if (compute_grads) {  // a dozen memsets: on a side stream underneath the forward pass, joined before the NLL
         cudaStream_t zs = ctx->multi_stream ? ln.zero : ls;
         if (zs != ls) {

@@ -115,3 +115,27 @@ def test_fused_native_noise_matches_fp32_backend(eng, mode, particles):
             print(f"[{mode}] replay vs eager {k}: max |diff| / max |grad| = {d:.2e}")
             assert d < 1e-4, (k, d)
     assert abs(other["scalars"][1].item() - got["scalars"][1].item()) > 0  # a new seed is a new draw (the key is re-read)
+
+
+@pytest.mark.parametrize("B", [1, 5, 129, 1000])
+def test_fused_batch_sizes_match_fp32_backend(eng, B):
+    """Ragged tiles (B not a multiple of 4), ragged fc M-tiles (not a multiple of 128) and several weight-gradient tiles per CTA
+    (B = 1000: 250 tiles over <= 148 CTA groups): native noise, so the fp32 back-end draws the same numbers."""
+    from bayesrul_b200 import Noise
+    x, y, mu, sg = synth(NET, B, seed=100 + B, sigma=0.01)
+    x, y, mu, sg = x.to(DEV), y.to(DEV), mu.to(DEV), sg.to(DEV)
+    for mode, particles in (("lrt", 1), ("flipout", 2)):
+        kw = dict(mode=mode, prior_scale=0.138793, particles=particles, **KW)
+        eng.set_gemm_backend("simt")
+        ref = eng.elbo_step(x, y, mu, sg, noise=Noise(seed=3), **kw)
+        eng.set_gemm_backend("fused")
+        got = eng.elbo_step(x, y, mu, sg, noise=Noise(seed=3), **kw)
+        eng.set_gemm_backend("simt")
+        assert eng.tc_status() == 0
+        assert abs(got["scalars"][0].item() / ref["scalars"][0].item() - 1) < 5e-3, (mode, B)
+        assert torch.allclose(got["out"], ref["out"], rtol=1e-2, atol=1e-3), (mode, B)
+        c = 1.0 / (238150 * 540.0)
+        kmu, ksg = _kl_grads(mu.double().cpu(), sg.double().cpu(), 0.138793, c)
+        for k, kk in (("grad_mu", kmu), ("grad_sigma", ksg)):
+            cs = _cos(got[k].double().cpu() - kk, ref[k].double().cpu() - kk)
+            assert cs > (0.999 if B >= 129 else 0.98), (mode, B, k, cs)
