@@ -407,8 +407,20 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) tc_conv_kernel(const ConvArgs
           unsigned char* dst = reg + R_M1 + (brA * 4 + h * 2) * CS + rowoff;
           *reinterpret_cast<uint4*>(dst) = lo;
           *reinterpret_cast<uint4*>(dst + CS) = hi;
+#ifdef BRL_POOL_SHFL
           *reinterpret_cast<uint4*>(dst + R_M1P) = pool3x4(lo, lane);  // R_M1P - R_M1 == 16 chunks
           *reinterpret_cast<uint4*>(dst + R_M1P + CS) = pool3x4(hi, lane);
+#else
+          // MaxPool1d(3,1,1) through shared memory: the neighbouring rows of a window are the neighbouring lanes' stores of the
+          // two lines above (same warp: visible after __syncwarp); the rows next to a window (dead rows 30 / 31, pad rows) hold
+          // zeros at all times, which is the -inf padding for values >= 0.  Four 16-byte loads instead of sixteen shuffles.
+          __syncwarp();
+          const uint4 z4 = make_uint4(0, 0, 0, 0);
+          const uint4 plo = hmax4(lo, hmax4(*reinterpret_cast<const uint4*>(dst - 16), *reinterpret_cast<const uint4*>(dst + 16)));
+          const uint4 phi = hmax4(hi, hmax4(*reinterpret_cast<const uint4*>(dst + CS - 16), *reinterpret_cast<const uint4*>(dst + CS + 16)));
+          *reinterpret_cast<uint4*>(dst + R_M1P) = t < 30 ? plo : z4;  // R_M1P - R_M1 == 16 chunks
+          *reinterpret_cast<uint4*>(dst + R_M1P + CS) = t < 30 ? phi : z4;
+#endif
         }
         arrive_ready(BAR_READY_A, k);
         tr(it, 2 + 3 * k);
