@@ -34,12 +34,15 @@ class _FusedStepLoss(torch.autograd.Function):
 
 
 class HNN(_Base):
-    def __init__(self, net, optimizer, mc_samples: int, p_dropout, device=None, engine: str = "simt"):
+    def __init__(self, net, optimizer, mc_samples: int, p_dropout, device=None, engine: str = "simt", train_backend: str = "auto"):
         super().__init__()
-        self.save_hyperparameters(logger=False, ignore=["net", "device", "engine"])
+        self.save_hyperparameters(logger=False, ignore=["net", "device", "engine", "train_backend"])
         self.net = net
         self.net.apply(weights_init)
         self._engine_kind = engine
+        # kernels of HNN.step: "auto" = the level-fused tcgen05 kernels for the Inception net (fp16 / bf16 operands: loss 5e-3,
+        # gradient cosine > 0.999 of the fp32 oracle), the fp32 FFMA kernels for the other nets; "simt" forces the fp32 parity back-end
+        self._train_backend = train_backend
         self._it = 0
         if device is not None:
             self._device = torch.device(device)
@@ -65,6 +68,10 @@ class HNN(_Base):
             return output[:, 0], output[:, 1]
         train = phase == "train"
         p = float(self.net.dropout) if (train or getattr(self.net, "mc_dropout", False)) else 0.0
+        be = self._train_backend
+        if be == "auto":
+            be = "fused" if getattr(self.net, "kind", "") == "inception" else "simt"
+        self.net.engine().set_gemm_backend(be)
         res = self.net.engine().hnn_step(x.contiguous(), y.contiguous(), self.net.flat(), p, self._noise(), compute_grads=train)
         loss = res["scalars"][0].float()
         if train:  # the returned loss carries a grad_fn whose backward writes the fused step's gradient into param.grad

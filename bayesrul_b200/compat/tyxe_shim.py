@@ -120,8 +120,8 @@ class VariationalBNN:
         except TypeError:
             self.net_guide = net_guide_builder(net)
         self.engine_kind = engine
-        # kernels of the ELBO step: "auto" = the level-fused tcgen05 kernels where they exist (Inception under LRT / Flipout:
-        # fp16 / bf16 operands, loss 5e-3, gradient cosine > 0.999), else the fp32 FFMA kernels; "simt" = always the fp32 parity
+        # kernels of the ELBO step: "auto" = the level-fused tcgen05 kernels where they exist (Inception: LRT, Flipout and the
+        # weight-sampling ELBO; fp16 / bf16 operands, loss 5e-3, gradient cosine > 0.999), else the fp32 FFMA kernels; "simt" = always the fp32 parity
         # back-end (rtol 1e-3 against the oracle); "fused" / "tc" force a back-end
         self.train_backend = train_backend
         self.seed = int(torch.initial_seed() % (2**62))
@@ -164,7 +164,7 @@ class VariationalBNN:
         N = self.likelihood.dataset_size
         be = self.train_backend
         if be == "auto":
-            be = "fused" if (getattr(self.net, "kind", "") == "inception" and mode in ("lrt", "flipout")) else "simt"
+            be = "fused" if getattr(self.net, "kind", "") == "inception" else "simt"  # lrt / flipout / weight sampling (radial)
         self.engine.set_gemm_backend(be)
         res = self.engine.elbo_step(x.contiguous(), y.reshape(-1).contiguous(), g.loc, g.scale, mode=mode, guide=g.family,
                                     particles=particles, prior_loc=self.prior.loc, prior_scale=self.prior.scale,

@@ -1127,7 +1127,7 @@ static int elbo_body(brl_ctx* ctx, const ActBufs* const* lanes, int n_lanes, con
       // level-fused tcgen05 kernels (BRL_GEMM_TC_FUSED): ten conv layers + the fc layer on the tensor pipe, the rest of the net
       // (fc epilogue, head, likelihood, their backward) in one tail kernel
       const bool use_tt = ctx->gemm_backend == BRL_GEMM_TC_FUSED && n.id == BRL_NET_INCEPTION && ab.has_tt &&
-                          (mode == BRL_MODE_LRT || mode == BRL_MODE_FLIPOUT) &&
+                          (mode == BRL_MODE_LRT || mode == BRL_MODE_FLIPOUT || mode == BRL_MODE_WS) &&
                           2 * B * 64 <= SPLITK_SCRATCH_FLOATS;  // fc partial sums live in the split-K scratch (B <= 4736), else per-layer
       if (compute_grads) {  // a dozen memsets: on a side stream underneath the forward pass, joined before the NLL
         cudaStream_t zs = ctx->multi_stream ? ln.zero : ls;
@@ -1146,9 +1146,11 @@ static int elbo_body(brl_ctx* ctx, const ActBufs* const* lanes, int n_lanes, con
       FwdArgs fa{x, B, 1, mode, mu, sigma, ab.wsamp, 0.f, &nz, sin_.data(), sout_.data(), outp, compute_grads != 0};
       TtStep ts{};
       if (use_tt) {
-        ts.x = x; ts.B = B; ts.mode = mode; ts.mu = mu; ts.sigma = sigma; ts.wsamp = ab.wsamp;
+        // weight-sampling ELBO (radial guide / no fit context): ONE contraction with the particle's weight draw
+        ts.x = x; ts.B = B; ts.mode = mode; ts.mu = mode == BRL_MODE_WS ? ab.wsamp : mu; ts.sigma = sigma; ts.wsamp = ab.wsamp;
         for (int ly = 0; ly < TT_LAYERS; ++ly) {
           ts.eps[ly] = nref(&nz, nz.lrt_eps[ly], KIND_LRT_EPS, (unsigned)ly);
+          ts.keep[ly] = 1.0f;
           ts.sgn_in[ly] = sin_[ly]; ts.sgn_out[ly] = sout_[ly];
           ts.w_off[ly] = n.layers[ly].w_off; ts.b_off[ly] = n.layers[ly].b_off;
         }
@@ -1341,6 +1343,38 @@ static int hnn_body(brl_ctx* ctx, const ActBufs& ab, const float* x, const float
                     const brl_noise* noise, int compute_grads, double* scalars, float* grad_theta, float* out, cudaStream_t st) {
   const NetSpec& n = *ctx->net;
   brl_noise nz = noise_at_sample(n, noise, 0, B);
+  if (ctx->gemm_backend == BRL_GEMM_TC_FUSED && n.id == BRL_NET_INCEPTION && ab.has_tt && 2 * B * 64 <= SPLITK_SCRATCH_FLOATS) {
+    // level-fused tcgen05 kernels, one contraction with the deterministic weights; dropout masks in the epilogues
+    const brl_ctx::Lane& ln = ctx->lanes[0];
+    const int fc_op = (int)n.ops.size() - 2, fc_layer = n.ops[fc_op].layer, hd_layer = n.ops[fc_op + 1].layer;
+    auto keep_of = [&](int ly) { return (p_dropout > 0.f && n.layers[ly].drop_factor > 0.f) ? 1.0f - p_dropout * n.layers[ly].drop_factor : 1.0f; };
+    TtStep ts{};
+    ts.x = x; ts.B = B; ts.mode = BRL_MODE_DET; ts.mu = theta;
+    for (int ly = 0; ly < TT_LAYERS; ++ly) {
+      ts.drop[ly] = nref(&nz, nz.drop_mask[ly], KIND_DROPOUT, (unsigned)ly);
+      ts.keep[ly] = keep_of(ly);
+      ts.w_off[ly] = n.layers[ly].w_off; ts.b_off[ly] = n.layers[ly].b_off;
+    }
+    ts.w_off_fc = n.layers[fc_layer].w_off; ts.b_off_fc = n.layers[fc_layer].b_off;
+    ts.g0 = grad_theta; ts.g1 = nullptr;
+    const TtSide tsd{ln.side[0], ln.ev_fork, ln.ev_join[0]};
+    BRL_CUDA(cudaMemsetAsync(scalars, 0, 2 * sizeof(double), st));
+    if (compute_grads) BRL_CUDA(cudaMemsetAsync(grad_theta, 0, sizeof(float) * n.P, st));
+    tt_forward(ab.tt, ts, st, tsd);
+    tt_fc_forward(ab.tt, ts, ab.part[0], st);
+    TtTail tl{};
+    tl.part = ab.part[0]; tl.y = y; tl.gscale = 0.f; tl.compute_grads = compute_grads; tl.acc = scalars; tl.out = out;
+    tl.dpre = ab.dpre[fc_op]; tl.dsec = ab.dsec[fc_op];
+    tl.hw_off = n.layers[hd_layer].w_off; tl.hb_off = n.layers[hd_layer].b_off;
+    tl.loss_kind = 1; tl.keep_fc = keep_of(fc_layer); tl.drop_fc = nref(&nz, nz.drop_mask[fc_layer], KIND_DROPOUT, (unsigned)fc_layer);
+    tt_tail(ts, tl, st);
+    if (compute_grads) {
+      tt_fc_backward(ab.tt, ts, ab.dpre[fc_op], ab.dsec[fc_op], st, tsd);
+      tt_backward(ab.tt, ts, st, tsd);
+    }
+    BRL_CUDA(cudaGetLastError());
+    return BRL_OK;
+  }
   FwdArgs fa{x, B, 1, BRL_MODE_DET, theta, nullptr, nullptr, p_dropout, &nz, nullptr, nullptr, out, false};
   run_forward(ctx, ab, fa, st);
   BRL_CUDA(cudaMemsetAsync(scalars, 0, 2 * sizeof(double), st));

@@ -42,6 +42,7 @@ extern std::atomic<long long> g_launch_count;
 namespace {
 
 constexpr int ROWS = 132, CS = ROWS * 16, ROW0 = 2;
+constexpr int TT_PLAIN = 0;  // single contraction: deterministic weights (HNN / MC-dropout) or one weight draw (weight-sampling ELBO)
 constexpr int NT = 512;  // threads per CTA: 16 warps = 4 TMEM lane quadrants (rows) x 4 column quarters
 enum { IN_X = 0, IN_XP = 1, IN_M1 = 2, IN_M1P = 3, IN_T2 = 4, IN_T3 = 5 };
 enum { OUT_M1 = 0, OUT_T2 = 1, OUT_T3 = 2, OUT_FEAT = 3 };
@@ -242,7 +243,7 @@ __global__ void tt_pack_kernel(const TtPackArgs a) {
       const long long wi = l.w_off + ((long long)n * l.cin + cr) * l.T + tap;
       m = a.mu[wi];
       const float v = a.second[wi];
-      s = a.mode == BRL_MODE_LRT ? v * v : v - m;
+      s = a.mode == BRL_MODE_LRT ? v * v : a.mode == BRL_MODE_FLIPOUT ? v - m : 0.f;
     }
     const int o = tap * l.tap_bytes + (k >> 3) * (l.NP * 16) + n * 16 + (k & 7) * 2;
     *reinterpret_cast<__half*>(a.blob + l.w0h + o) = __float2half_rn(m);
@@ -258,7 +259,8 @@ __global__ void tt_pack_kernel(const TtPackArgs a) {
     float b0 = 0.f, b1 = 0.f;
     if (n < l.N) {
       if (a.mode == BRL_MODE_LRT) { b0 = a.mu[l.b_off + n]; const float sb = a.second[l.b_off + n]; b1 = sb * sb; }
-      else b0 = a.second[l.b_off + n];  // Flipout adds the SAMPLED bias
+      else if (a.mode == BRL_MODE_FLIPOUT) b0 = a.second[l.b_off + n];  // Flipout adds the SAMPLED bias
+      else b0 = a.mu[l.b_off + n];
     }
     float* bias = reinterpret_cast<float*>(a.blob + l.bias);
     bias[n] = b0;
@@ -280,6 +282,8 @@ struct TtFwdArgs {
   const float* sgn_in[4];
   const float* sgn_out[4];
   const float* sgn_fc_in;  // Flipout: s_in of the fc layer [B, 2400] (the feature producers build its perturbation operand)
+  NoiseRef drop[4];        // PLAIN mode: dropout site behind the layer (injected masks [B, N, 30] or Philox)
+  float keep[4];           // its keep probability (1 = no dropout site / dropout off)
   int* status;
   long long* trace;  // debug: clock64 stamps of CTA (0, y), [4 layers][16] (nullptr = off)
 };
@@ -318,6 +322,7 @@ __device__ __forceinline__ void second_operand(const unsigned char* A, unsigned 
     float f[8], s[8];
     unpack_h8(*reinterpret_cast<const uint4*>(A + ch * CS + rr * 16), f);
     if (Ab) *reinterpret_cast<uint4*>(Ab + ch * CS + rr * 16) = pack_b8(f);
+    if (MODE == TT_PLAIN) continue;  // single contraction: only the bf16 copy is needed (backward pass)
     if (MODE == BRL_MODE_LRT) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) s[j] = f[j] * f[j];
@@ -359,10 +364,10 @@ __global__ void __launch_bounds__(NT, 1) tt_fwd_kernel(const TtFwdArgs a) {
   const int ncopy = L.in <= IN_XP ? 3 : L.KC;
   const int img_bytes = L.T * L.tap_bytes;
   if (tid == 0) {
-    mbar_expect_tx(bar_ld, ncopy * CS + 2 * img_bytes + 512);
+    mbar_expect_tx(bar_ld, ncopy * CS + (MODE == TT_PLAIN ? 1 : 2) * img_bytes + 512);
     bulk_copy_chunked(sbase + (L.in == IN_M1P ? F_A2 : F_A), input_image(a.ln, L.in, tile), ncopy * CS, bar_ld);
     bulk_copy_chunked(sbase + F_W0, a.ln.blob + L.w0h, img_bytes, bar_ld);
-    bulk_copy_chunked(sbase + F_W1, a.ln.blob + (MODE == BRL_MODE_FLIPOUT ? L.w1h : L.w1b), img_bytes, bar_ld);
+    if (MODE != TT_PLAIN) bulk_copy_chunked(sbase + F_W1, a.ln.blob + (MODE == BRL_MODE_FLIPOUT ? L.w1h : L.w1b), img_bytes, bar_ld);
     bulk_g2s(sbase + F_BIAS, a.ln.blob + L.bias, 512, bar_ld);
   }
   if (tr) tr[1] = clock64();
@@ -373,7 +378,7 @@ __global__ void __launch_bounds__(NT, 1) tt_fwd_kernel(const TtFwdArgs a) {
     __syncthreads();
   }
   constexpr bool P1H = MODE == BRL_MODE_FLIPOUT;  // perturbation path: fp16 operands (W - mu is far above fp16's subnormals for q_scale >= 1e-4)
-  second_operand<MODE, P1H>(smem + F_A, smem + F_A2, nullptr, L, a.sgn_in[blockIdx.y], tile, a.B, tid);
+  if (MODE != TT_PLAIN) second_operand<MODE, P1H>(smem + F_A, smem + F_A2, nullptr, L, a.sgn_in[blockIdx.y], tile, a.B, tid);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -387,8 +392,9 @@ __global__ void __launch_bounds__(NT, 1) tt_fwd_kernel(const TtFwdArgs a) {
           const uint32_t ao = 2 * ks * CS + (ROW0 + tap - pad) * 16, wo = tap * L.tap_bytes + 2 * ks * L.NP * 16;
           umma(tmem, umma_desc(sbase + F_A + ao, CS, 128), umma_desc(sbase + F_W0 + wo, L.NP * 16, 128), tt_idesc(L.NP, 0, 0, 0),
                (tap | ks) != 0);
-          umma(tmem + L.NP, umma_desc(sbase + F_A2 + ao, CS, 128), umma_desc(sbase + F_W1 + wo, L.NP * 16, 128),
-               tt_idesc(L.NP, P1H ? 0 : 1, 0, 0), (tap | ks) != 0);
+          if (MODE != TT_PLAIN)
+            umma(tmem + L.NP, umma_desc(sbase + F_A2 + ao, CS, 128), umma_desc(sbase + F_W1 + wo, L.NP * 16, 128),
+                 tt_idesc(L.NP, P1H ? 0 : 1, 0, 0), (tap | ks) != 0);
         }
       umma_commit(bar_mma);
     }
@@ -416,7 +422,15 @@ __global__ void __launch_bounds__(NT, 1) tt_fwd_kernel(const TtFwdArgs a) {
   for (int g = cq; g < L.NP / 8; g += 4) {
     float v0[8], v1[8], o[8];
     tmem_ld8(la + g * 8, v0);
-    tmem_ld8(la + L.NP + g * 8, v1);
+    if (MODE != TT_PLAIN) tmem_ld8(la + L.NP + g * 8, v1);
+    KeepBits kb = {};
+    const float keep = MODE == TT_PLAIN ? a.keep[blockIdx.y] : 1.0f;
+    const uint32_t e0 = (uint32_t)ri.t * (uint32_t)((L.N + 15) & ~15) + (uint32_t)(g * 8);  // dropout element order: position-major
+    if (MODE == TT_PLAIN && keep < 1.0f && !a.drop[blockIdx.y].ptr) {  // 8 of the 16 keep decisions of one Philox block
+      const NoiseRef& dz = a.drop[blockIdx.y];
+      const NoiseKey dk = noise_key(dz);
+      kb = keep_bits(philox_block_mask(dk.seed, dz.kind, dz.site, dk.sample0, dk.window0 + ri.gw, e0 >> 4), keep_threshold(keep));
+    }
     if (MODE == BRL_MODE_LRT && !nz.ptr) {
       __syncwarp();
 #pragma unroll
@@ -441,10 +455,17 @@ __global__ void __launch_bounds__(NT, 1) tt_fwd_kernel(const TtFwdArgs a) {
         const float e = !on ? 0.f : nz.ptr ? nz.ptr[(long long)ri.gw * (L.N * 30) + n * 30 + ri.t] : scratch[j * 30 + ri.t];
         pre = fmaf(sd, e, v0[j] + bias[n]);
         if (rb) rb[(long long)n * 128 + row] = (on && sd > 0.f) ? e / (2.0f * sd) : 0.f;
-      } else {
+      } else if (MODE == BRL_MODE_FLIPOUT) {
         pre = v0[j] + bias[n] + (on ? v1[j] * __ldg(sout + (long long)ri.gw * L.N + n) : 0.f);
+      } else {
+        pre = v0[j] + bias[n];
       }
       o[j] = on ? fmaxf(pre, 0.f) : 0.f;
+      if (MODE == TT_PLAIN && keep < 1.0f && on) {  // dropout site behind the ReLU (inception.py:48-52,119-123)
+        const NoiseRef& dz = a.drop[blockIdx.y];
+        const bool kp = dz.ptr ? dz.ptr[((long long)ri.gw * L.N + n) * 30 + ri.t] != 0.f : keep_at(kb, (e0 & 15u) + j);
+        o[j] = kp ? o[j] / keep : 0.f;
+      }
     }
     if (oimg) {
       *reinterpret_cast<uint4*>(oimg + (L.out_c0 + g) * CS + (ROW0 + row) * 16) = pack_h8(o);
@@ -456,12 +477,13 @@ __global__ void __launch_bounds__(NT, 1) tt_fwd_kernel(const TtFwdArgs a) {
       unpack_h8(fh, fr);
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        f2[j] = MODE == BRL_MODE_LRT ? fr[j] * fr[j] : fr[j] * __ldg(a.sgn_fc_in + (long long)ri.gw * 2400 + (c0 + j) * 30 + ri.t);
+        f2[j] = MODE == BRL_MODE_LRT ? fr[j] * fr[j]
+                : MODE == BRL_MODE_FLIPOUT ? fr[j] * __ldg(a.sgn_fc_in + (long long)ri.gw * 2400 + (c0 + j) * 30 + ri.t) : 0.f;
       *reinterpret_cast<uint4*>(a.ln.fimg + fa) = fh;
       *reinterpret_cast<uint4*>(a.ln.fbimg + fa) = pack_b8(fr);
       if (MODE == BRL_MODE_LRT) {
         *reinterpret_cast<uint4*>(a.ln.f2img + fa) = pack_b8(f2);
-      } else {  // the perturbation GEMM runs fp16 x fp16 in the forward pass (f * s_in is exact in fp16), bf16 in the backward pass
+      } else if (MODE == BRL_MODE_FLIPOUT) {  // the perturbation GEMM runs fp16 x fp16 in the forward pass (f * s_in is exact in fp16), bf16 in the backward pass
         *reinterpret_cast<uint4*>(a.ln.f2img + fa) = pack_h8(f2);
         *reinterpret_cast<uint4*>(a.ln.f2bimg + fa) = pack_b8(f2);
       }
@@ -492,6 +514,7 @@ struct TtBwdArgs {
   const float* sgn_in[4];
   const float* sgn_out[4];
   float *g0, *g1;
+  float keep[4];  // PLAIN mode: keep probability of the dropout site behind each layer (1 = none)
   int part_floats;
   int* status;
   long long* trace;
@@ -605,11 +628,11 @@ __global__ void __launch_bounds__(NT, 1) tt_bwd_kernel(const TtBwdArgs a) {
   for (int tile = tile0; tile < tile1; ++tile) {
     if (tid == 0) {
       const bool first = tile == tile0;
-      mbar_expect_tx(bar_ld, ncopy * CS + (first ? 2 * img_bytes : 0));
+      mbar_expect_tx(bar_ld, ncopy * CS + (first ? (MODE == TT_PLAIN ? 1 : 2) * img_bytes : 0));
       bulk_copy_chunked(sbase + (L.in == IN_M1P ? B_AB : B_AH), input_image(a.ln, L.in, tile), ncopy * CS, bar_ld);
       if (first) {
         bulk_copy_chunked(sbase + B_W0, a.ln.blob + L.w0b, img_bytes, bar_ld);
-        bulk_copy_chunked(sbase + B_W1, a.ln.blob + L.w1b, img_bytes, bar_ld);
+        if (MODE != TT_PLAIN) bulk_copy_chunked(sbase + B_W1, a.ln.blob + L.w1b, img_bytes, bar_ld);
       }
     }
     // ---- gradient operands (global reads only): G0 = d/d(pre-activation), G1 = d/d(variance) or d/d(perturbation);
@@ -621,18 +644,24 @@ __global__ void __launch_bounds__(NT, 1) tt_bwd_kernel(const TtBwdArgs a) {
     for (int c = cq; c < L.NP / 8; c += 4) {
       float d[8], d1[8];
       output_grad<MODE>(a, L, tile, row, ri, c * 8, d);
+      if (MODE == TT_PLAIN && a.keep[blockIdx.y] < 1.0f) {  // dropout behind the ReLU: the stored activation a * m / keep gates, 1 / keep scales
+        const float ik = 1.0f / a.keep[blockIdx.y];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] *= ik;
+      }
       if (tr && tile == tile0 && c == cq) tr[9] = clock64();
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int n = c * 8 + j;
         if (MODE == BRL_MODE_LRT) d1[j] = d[j] * rb[(long long)n * 128 + row];
-        else d1[j] = (ri.live && n < L.N) ? d[j] * __ldg(sout + (long long)ri.gw * L.N + n) : 0.f;
+        else if (MODE == BRL_MODE_FLIPOUT) d1[j] = (ri.live && n < L.N) ? d[j] * __ldg(sout + (long long)ri.gw * L.N + n) : 0.f;
+        else d1[j] = 0.f;
       }
       *reinterpret_cast<uint4*>(smem + B_G0 + c * CS + (ROW0 + row) * 16) = pack_b8(d);
-      *reinterpret_cast<uint4*>(smem + B_G1 + c * CS + (ROW0 + row) * 16) = pack_b8(d1);
+      if (MODE != TT_PLAIN) *reinterpret_cast<uint4*>(smem + B_G1 + c * CS + (ROW0 + row) * 16) = pack_b8(d1);
       if (tr && tile == tile0 && c == cq) tr[10] = clock64();
       {  // bias gradients: column sums over the tile's rows (lane 4 j holds channel j's)
-        const float s0 = warp_sum8(d, lane), s1 = warp_sum8(d1, lane);
+        const float s0 = warp_sum8(d, lane), s1 = MODE == TT_PLAIN ? 0.f : warp_sum8(d1, lane);
         if ((lane & 3) == 0) { atomicAdd(&sums[c * 8 + (lane >> 2)], s0); atomicAdd(&sums[64 + c * 8 + (lane >> 2)], s1); }
       }
     }
@@ -657,8 +686,9 @@ __global__ void __launch_bounds__(NT, 1) tt_bwd_kernel(const TtBwdArgs a) {
               const uint32_t go = 2 * ks * CS + (ROW0 - (tap - pad)) * 16, wo = tap * L.tap_bytes + ks * 256;
               umma(t_dx0, umma_desc(sbase + B_G0 + go, CS, 128), umma_desc(sbase + B_W0 + wo, 128, L.NP * 16), tt_idesc(dxw, 1, 0, 1),
                    (tap | ks) != 0);
-              umma(t_dx1, umma_desc(sbase + B_G1 + go, CS, 128), umma_desc(sbase + B_W1 + wo, 128, L.NP * 16), tt_idesc(dxw, 1, 0, 1),
-                   (tap | ks) != 0);
+              if (MODE != TT_PLAIN)
+                umma(t_dx1, umma_desc(sbase + B_G1 + go, CS, 128), umma_desc(sbase + B_W1 + wo, 128, L.NP * 16), tt_idesc(dxw, 1, 0, 1),
+                     (tap | ks) != 0);
             }
         // D[c, n] += act[c, r + tap - pad] * G[n, r] over the tile's 128 rows: both operands MN-major, accumulated over the group
         for (int tap = 0; tap < L.T; ++tap)
@@ -666,7 +696,8 @@ __global__ void __launch_bounds__(NT, 1) tt_bwd_kernel(const TtBwdArgs a) {
             const uint32_t ao = (ROW0 + tap - pad + 16 * ks) * 16, go = (ROW0 + 16 * ks) * 16;
             const uint32_t acc = (tile != tile0 || ks != 0) ? 1u : 0u;
             umma(t_dw0 + tap * L.NP, umma_desc(sbase + B_AB + ao, 128, CS), umma_desc(sbase + B_G0 + go, 128, CS), tt_idesc(L.NP, 1, 1, 1), acc);
-            umma(t_dw1 + tap * L.NP, umma_desc(sbase + B_A2 + ao, 128, CS), umma_desc(sbase + B_G1 + go, 128, CS), tt_idesc(L.NP, 1, 1, 1), acc);
+            if (MODE != TT_PLAIN)
+              umma(t_dw1 + tap * L.NP, umma_desc(sbase + B_A2 + ao, 128, CS), umma_desc(sbase + B_G1 + go, 128, CS), tt_idesc(L.NP, 1, 1, 1), acc);
           }
         umma_commit(bar_mma);
       }
@@ -683,7 +714,7 @@ __global__ void __launch_bounds__(NT, 1) tt_bwd_kernel(const TtBwdArgs a) {
       for (int g = cq; g < dxw / 8; g += 4) {
         float v0[8], v1[8], o[8], av[8];
         tmem_ld8(la + g * 8, v0);
-        tmem_ld8(la + dxw + g * 8, v1);
+        if (MODE != TT_PLAIN) tmem_ld8(la + dxw + g * 8, v1);
         tmem_ld_wait();
         if (MODE == BRL_MODE_LRT) unpack_h8(*reinterpret_cast<const uint4*>(smem + B_AH + g * CS + (ROW0 + row) * 16), av);
 #pragma unroll
@@ -691,10 +722,10 @@ __global__ void __launch_bounds__(NT, 1) tt_bwd_kernel(const TtBwdArgs a) {
           float r = 0.f;
           if (ri.live) {
             if (MODE == BRL_MODE_LRT) r = fmaf(2.0f * av[j], v1[j], v0[j]);
-            else {
+            else if (MODE == BRL_MODE_FLIPOUT) {
               const int cr = real_ch(L.in, g * 8 + j);
               r = cr >= 0 ? fmaf(__ldg(sin_ + (long long)ri.gw * L.cin + cr), v1[j], v0[j]) : 0.f;
-            }
+            } else r = v0[j];
           }
           o[j] = r;
         }
@@ -722,7 +753,7 @@ __global__ void __launch_bounds__(NT, 1) tt_bwd_kernel(const TtBwdArgs a) {
       const int tap = it / ng, g = it - tap * ng;
       float v0[8], v1[8];
       tmem_ld8(la + 2 * dxw + tap * L.NP + g * 8, v0);
-      tmem_ld8(la + 2 * dxw + (L.T + tap) * L.NP + g * 8, v1);
+      if (MODE != TT_PLAIN) tmem_ld8(la + 2 * dxw + (L.T + tap) * L.NP + g * 8, v1);
       tmem_ld_wait();
       // plain, coalesced stores (lanes = consecutive image channels) into this group's block of partials; tt_reduce_kernel sums
       // the groups -- 64 CTAs adding to the same 33 k addresses with atomics cost 8 - 13 us per level
@@ -732,7 +763,7 @@ __global__ void __launch_bounds__(NT, 1) tt_bwd_kernel(const TtBwdArgs a) {
           const int n = g * 8 + j;
           if (n < L.N) {
             part[((long long)n * L.T + tap) * CH + ch] = v0[j];
-            part[(long long)L.N * L.T * CH + ((long long)n * L.T + tap) * CH + ch] = v1[j];
+            if (MODE != TT_PLAIN) part[(long long)L.N * L.T * CH + ((long long)n * L.T + tap) * CH + ch] = v1[j];
           }
         }
       }
@@ -763,7 +794,7 @@ __global__ void tt_pack_fc_kernel(const TtFcPackArgs a) {
   const int n = i / 2400, kp = i - n * 2400, t = kp / 80, c = kp - t * 80;
   const long long wi = a.w_off + (long long)n * 2400 + c * 30 + t;
   const float m = a.mu[wi], v = a.second[wi];
-  const float s = a.mode == BRL_MODE_LRT ? v * v : v - m;
+  const float s = a.mode == BRL_MODE_LRT ? v * v : a.mode == BRL_MODE_FLIPOUT ? v - m : 0.f;
   const int o = (kp >> 3) * 1024 + n * 16 + (kp & 7) * 2;
   *reinterpret_cast<__half*>(a.blob + o) = __float2half_rn(m);
   *reinterpret_cast<__nv_bfloat16*>(a.blob + FC_WIMG + o) = __float2bfloat16_rn(m);
@@ -796,11 +827,12 @@ __global__ void __launch_bounds__(256, 1) tt_fc_fwd_kernel(const TtFcFwdArgs a) 
   const uint32_t tmem = *tslot;
   if (tid == 0) {
     const long long ao = ((long long)mt * FC_KC + ks * FC_KCS) * FC_CHUNK;
-    mbar_expect_tx(bar_ld, 2 * FC_KCS * FC_CHUNK + 2 * FC_KCS * 1024);
+    const bool dual = a.mode == BRL_MODE_LRT || a.mode == BRL_MODE_FLIPOUT;
+    mbar_expect_tx(bar_ld, (dual ? 2 : 1) * (FC_KCS * FC_CHUNK + FC_KCS * 1024));
     bulk_copy_chunked(sbase + FF_A, a.ln.fimg + ao, FC_KCS * FC_CHUNK, bar_ld);
-    bulk_copy_chunked(sbase + FF_A2, a.ln.f2img + ao, FC_KCS * FC_CHUNK, bar_ld);
     bulk_copy_chunked(sbase + FF_W0, a.ln.fcblob + (long long)ks * FC_KCS * 1024, FC_KCS * 1024, bar_ld);
-    bulk_copy_chunked(sbase + FF_W1, a.ln.fcblob + (a.mode == BRL_MODE_LRT ? 2 : 3) * (long long)FC_WIMG + (long long)ks * FC_KCS * 1024, FC_KCS * 1024, bar_ld);
+    if (dual) bulk_copy_chunked(sbase + FF_A2, a.ln.f2img + ao, FC_KCS * FC_CHUNK, bar_ld);
+    if (dual) bulk_copy_chunked(sbase + FF_W1, a.ln.fcblob + (a.mode == BRL_MODE_LRT ? 2 : 3) * (long long)FC_WIMG + (long long)ks * FC_KCS * 1024, FC_KCS * 1024, bar_ld);
   }
   mbar_wait(bar_ld, 0, a.status, 44);
   if (warp == 0) {
@@ -809,8 +841,9 @@ __global__ void __launch_bounds__(256, 1) tt_fc_fwd_kernel(const TtFcFwdArgs a) 
       for (int k = 0; k < FC_KCS / 2; ++k) {
         umma(tmem, umma_desc(sbase + FF_A + 2 * k * FC_CHUNK, FC_CHUNK, 128), umma_desc(sbase + FF_W0 + 2 * k * 1024, 1024, 128),
              tt_idesc(64, 0, 0, 0), k != 0);
-        umma(tmem + 64, umma_desc(sbase + FF_A2 + 2 * k * FC_CHUNK, FC_CHUNK, 128), umma_desc(sbase + FF_W1 + 2 * k * 1024, 1024, 128),
-             tt_idesc(64, a.mode == BRL_MODE_LRT ? 1 : 0, 0, 0), k != 0);
+        if (a.mode == BRL_MODE_LRT || a.mode == BRL_MODE_FLIPOUT)
+          umma(tmem + 64, umma_desc(sbase + FF_A2 + 2 * k * FC_CHUNK, FC_CHUNK, 128), umma_desc(sbase + FF_W1 + 2 * k * 1024, 1024, 128),
+               tt_idesc(64, a.mode == BRL_MODE_LRT ? 1 : 0, 0, 0), k != 0);
       }
       umma_commit(bar_mma);
     }
@@ -822,16 +855,17 @@ __global__ void __launch_bounds__(256, 1) tt_fc_fwd_kernel(const TtFcFwdArgs a) 
   const uint32_t la = tmem + ((uint32_t)((warp & 3) * 32) << 16);
 #pragma unroll 1
   for (int g = 0; g < 2; ++g) {
+    const bool dual = a.mode == BRL_MODE_LRT || a.mode == BRL_MODE_FLIPOUT;
     float v0[16], v1[16];
     tmem_ld16(la + half * 32 + g * 16, v0);
-    tmem_ld16(la + 64 + half * 32 + g * 16, v1);
+    if (dual) tmem_ld16(la + 64 + half * 32 + g * 16, v1);
     tmem_ld_wait();
     if (m < a.B) {
       float* p0 = a.part + (long long)m * 64 + half * 32 + g * 16;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         atomicAdd(p0 + j, v0[j]);
-        atomicAdd(p0 + (long long)a.B * 64 + j, v1[j]);
+        if (dual) atomicAdd(p0 + (long long)a.B * 64 + j, v1[j]);
       }
     }
   }
@@ -885,12 +919,12 @@ __global__ void __launch_bounds__(256, 1) tt_fc_dx_kernel(const TtFcBwdArgs a) {
   tc_fence_after();
   const uint32_t tmem = *tslot;
   if (tid == 0) {
-    mbar_expect_tx(bar_ld, 2 * FC_NCS * 1024);
+    mbar_expect_tx(bar_ld, (MODE == TT_PLAIN ? 1 : 2) * FC_NCS * 1024);
     bulk_copy_chunked(sbase + FX_W0, a.ln.fcblob + FC_WIMG + (long long)ns * FC_NCS * 1024, FC_NCS * 1024, bar_ld);
-    bulk_copy_chunked(sbase + FX_W1, a.ln.fcblob + 2 * FC_WIMG + (long long)ns * FC_NCS * 1024, FC_NCS * 1024, bar_ld);
+    if (MODE != TT_PLAIN) bulk_copy_chunked(sbase + FX_W1, a.ln.fcblob + 2 * FC_WIMG + (long long)ns * FC_NCS * 1024, FC_NCS * 1024, bar_ld);
   }
   fc_grad_image(a.dpre, smem + FX_G0, mt, a.B, tid, 256);
-  fc_grad_image(a.dsec, smem + FX_G1, mt, a.B, tid, 256);
+  if (MODE != TT_PLAIN) fc_grad_image(a.dsec, smem + FX_G1, mt, a.B, tid, 256);
   mbar_wait(bar_ld, 0, a.status, 46);
   fence_async_smem();
   tc_fence_before();
@@ -901,8 +935,9 @@ __global__ void __launch_bounds__(256, 1) tt_fc_dx_kernel(const TtFcBwdArgs a) {
       for (int k = 0; k < 4; ++k) {  // K = 64 output units; B = the weight image read MN-major: [N' = 240 features][K' = 16 units]
         umma(tmem, umma_desc(sbase + FX_G0 + 2 * k * FC_CHUNK, FC_CHUNK, 128), umma_desc(sbase + FX_W0 + k * 256, 128, 1024),
              tt_idesc(240, 1, 0, 1), k != 0);
-        umma(tmem + 256, umma_desc(sbase + FX_G1 + 2 * k * FC_CHUNK, FC_CHUNK, 128), umma_desc(sbase + FX_W1 + k * 256, 128, 1024),
-             tt_idesc(240, 1, 0, 1), k != 0);
+        if (MODE != TT_PLAIN)
+          umma(tmem + 256, umma_desc(sbase + FX_G1 + 2 * k * FC_CHUNK, FC_CHUNK, 128), umma_desc(sbase + FX_W1 + k * 256, 128, 1024),
+               tt_idesc(240, 1, 0, 1), k != 0);
       }
       umma_commit(bar_mma);
     }
@@ -916,15 +951,16 @@ __global__ void __launch_bounds__(256, 1) tt_fc_dx_kernel(const TtFcBwdArgs a) {
   for (int g = half; g < FC_NCS; g += 2) {
     float v0[8], v1[8], o[8], f[8];
     tmem_ld8(la + g * 8, v0);
-    tmem_ld8(la + 256 + g * 8, v1);
+    if (MODE != TT_PLAIN) tmem_ld8(la + 256 + g * 8, v1);
     const int kc = ns * FC_NCS + g, t = kc / 10, c0 = (kc - t * 10) * 8;
     const long long fa = ((long long)mt * FC_KC + kc) * FC_CHUNK + r * 16;
     // LRT: the factor is 2 f.  Flipout: s_in, read back as the sign of the perturbation operand f * s_in (f >= 0 behind the ReLU;
     // where f == 0 the consumer masks this gradient anyway) -- one coalesced 16-byte load instead of eight strided sign loads
-    unpack_h8(*reinterpret_cast<const uint4*>((MODE == BRL_MODE_LRT ? a.ln.fimg : a.ln.f2img) + fa), f);
+    if (MODE != TT_PLAIN) unpack_h8(*reinterpret_cast<const uint4*>((MODE == BRL_MODE_LRT ? a.ln.fimg : a.ln.f2img) + fa), f);
     tmem_ld_wait();
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
+      if (MODE == TT_PLAIN) { o[j] = gw < a.B ? v0[j] : 0.f; continue; }
       const float mul = MODE == BRL_MODE_LRT ? 2.0f * f[j] : (signbit(f[j]) ? -1.0f : 1.0f);
       o[j] = gw < a.B ? fmaf(mul, v1[j], v0[j]) : 0.f;
     }
@@ -959,12 +995,12 @@ __global__ void __launch_bounds__(256, 1) tt_fc_dw_kernel(const TtFcBwdArgs a) {
   for (int mt = 0; mt < a.nmt; ++mt) {
     if (tid == 0) {
       const long long ao = ((long long)mt * FC_KC + kt * 16) * FC_CHUNK;
-      mbar_expect_tx(bar_ld, 2 * nch * FC_CHUNK);
+      mbar_expect_tx(bar_ld, (MODE == TT_PLAIN ? 1 : 2) * nch * FC_CHUNK);
       bulk_copy_chunked(sbase + FW_A, a.ln.fbimg + ao, nch * FC_CHUNK, bar_ld);
-      bulk_copy_chunked(sbase + FW_A2, (MODE == BRL_MODE_LRT ? a.ln.f2img : a.ln.f2bimg) + ao, nch * FC_CHUNK, bar_ld);
+      if (MODE != TT_PLAIN) bulk_copy_chunked(sbase + FW_A2, (MODE == BRL_MODE_LRT ? a.ln.f2img : a.ln.f2bimg) + ao, nch * FC_CHUNK, bar_ld);
     }
     fc_grad_image(a.dpre, smem + FW_G0, mt, a.B, tid, 256);
-    fc_grad_image(a.dsec, smem + FW_G1, mt, a.B, tid, 256);
+    if (MODE != TT_PLAIN) fc_grad_image(a.dsec, smem + FW_G1, mt, a.B, tid, 256);
     mbar_wait(bar_ld, ph, a.status, 48);
     fence_async_smem();
     tc_fence_before();
@@ -976,8 +1012,9 @@ __global__ void __launch_bounds__(256, 1) tt_fc_dw_kernel(const TtFcBwdArgs a) {
           const uint32_t acc = (mt | k) != 0;
           umma(tmem, umma_desc(sbase + FW_A + k * 256, 128, FC_CHUNK), umma_desc(sbase + FW_G0 + k * 256, 128, FC_CHUNK),
                tt_idesc(64, 1, 1, 1), acc);
-          umma(tmem + 64, umma_desc(sbase + FW_A2 + k * 256, 128, FC_CHUNK), umma_desc(sbase + FW_G1 + k * 256, 128, FC_CHUNK),
-               tt_idesc(64, 1, 1, 1), acc);
+          if (MODE != TT_PLAIN)
+            umma(tmem + 64, umma_desc(sbase + FW_A2 + k * 256, 128, FC_CHUNK), umma_desc(sbase + FW_G1 + k * 256, 128, FC_CHUNK),
+                 tt_idesc(64, 1, 1, 1), acc);
         }
         umma_commit(bar_mma);
       }
@@ -994,7 +1031,7 @@ __global__ void __launch_bounds__(256, 1) tt_fc_dw_kernel(const TtFcBwdArgs a) {
   for (int g = 0; g < 2; ++g) {
     float v0[16], v1[16];
     tmem_ld16(la + half * 32 + g * 16, v0);
-    tmem_ld16(la + 64 + half * 32 + g * 16, v1);
+    if (MODE != TT_PLAIN) tmem_ld16(la + 64 + half * 32 + g * 16, v1);
     tmem_ld_wait();
     if (kp < 2400) {
       const int t = kp / 80, c = kp - t * 80;
@@ -1002,7 +1039,7 @@ __global__ void __launch_bounds__(256, 1) tt_fc_dw_kernel(const TtFcBwdArgs a) {
       for (int j = 0; j < 16; ++j) {
         const long long wi = a.w_off + (long long)(half * 32 + g * 16 + j) * 2400 + c * 30 + t;
         a.g0[wi] = v0[j];
-        a.g1[wi] = v1[j];
+        if (MODE != TT_PLAIN) a.g1[wi] = v1[j];
       }
     }
   }
@@ -1011,10 +1048,13 @@ __global__ void __launch_bounds__(256, 1) tt_fc_dw_kernel(const TtFcBwdArgs a) {
     const int per = (a.B + nsl - 1) / nsl, m0 = sl * per, m1 = min(a.B, m0 + per);
     float s0 = 0.f, s1 = 0.f;
 #pragma unroll 4
-    for (int m = m0; m < m1; ++m) { s0 += a.dpre[(long long)m * 64 + n]; s1 += a.dsec[(long long)m * 64 + n]; }
+    for (int m = m0; m < m1; ++m) {
+      s0 += a.dpre[(long long)m * 64 + n];
+      if (MODE != TT_PLAIN) s1 += a.dsec[(long long)m * 64 + n];
+    }
     if (m0 < m1) {
       atomicAdd(a.g0 + a.b_off + n, s0);
-      atomicAdd(a.g1 + a.b_off + n, MODE == BRL_MODE_LRT ? s1 : s0);
+      if (MODE != TT_PLAIN) atomicAdd(a.g1 + a.b_off + n, MODE == BRL_MODE_LRT ? s1 : s0);
     }
   }
   tc_fence_before();
@@ -1059,6 +1099,10 @@ struct TtTailArgs {
   float *dpre, *dsec;          // [B,64] compact gradients of the fc layer's pre-activation / second path
   float *g0, *g1;              // flat gradient accumulators (head layer: atomics)
   long long hw_off, hb_off;
+  // PLAIN mode (one contraction: HNN / MC-dropout step, weight-sampling ELBO): fc_b0 / hw0 / hb0 are the weights in use
+  int loss_kind;               // 0: ELBO likelihood (second softplus, sums in acc); 1: F.gaussian_nll_loss (frequentist.py:39-48, means in acc)
+  float keep_fc;               // keep probability of the dropout site behind the fc layer (1 = none)
+  NoiseRef drop_fc;            // its masks: injected [B, 64] or Philox
 };
 template <int MODE>
 __global__ void __launch_bounds__(256) tt_tail_kernel(const TtTailArgs a) {
@@ -1072,7 +1116,7 @@ __global__ void __launch_bounds__(256) tt_tail_kernel(const TtTailArgs a) {
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const int k = lane + 32 * u;
-      const float m = a.hw0[o * 64 + k], v = a.hw1[o * 64 + k];
+      const float m = a.hw0[o * 64 + k], v = MODE == TT_PLAIN ? 0.f : a.hw1[o * 64 + k];
       w0[o][u] = m;
       w1[o][u] = MODE == BRL_MODE_LRT ? v * v : v - m;
     }
@@ -1085,9 +1129,12 @@ __global__ void __launch_bounds__(256) tt_tail_kernel(const TtTailArgs a) {
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const int k = lane + 32 * u;
-      const float a0 = a.part[(long long)m * 64 + k], a1 = a.part[((long long)a.B + m) * 64 + k];
+      const float a0 = a.part[(long long)m * 64 + k], a1 = MODE == TT_PLAIN ? 0.f : a.part[((long long)a.B + m) * 64 + k];
       float pre;
-      if (MODE == BRL_MODE_LRT) {
+      if (MODE == TT_PLAIN) {
+        pre = a0 + a.fc_b0[k];
+        sd[u] = ef[u] = sgn_in[u] = 0.f;
+      } else if (MODE == BRL_MODE_LRT) {
         const float sb = a.fc_b1[k];
         float var = fmaf(sb, sb, a1);
         if (var < 0.f) var += fabsf(var) + 1e-6f;
@@ -1102,6 +1149,15 @@ __global__ void __launch_bounds__(256) tt_tail_kernel(const TtTailArgs a) {
         sgn_in[u] = a.sin_head[(long long)m * 64 + k];
       }
       h[u] = fmaxf(pre, 0.f);
+      if (MODE == TT_PLAIN && a.keep_fc < 1.0f) {  // dropout behind the fc layer's ReLU (inception.py:204-206)
+        bool kp;
+        if (a.drop_fc.ptr) kp = a.drop_fc.ptr[(long long)m * 64 + k] != 0.f;
+        else {
+          const NoiseKey dk = noise_key(a.drop_fc);
+          kp = philox_keep(dk.seed, a.drop_fc.kind, a.drop_fc.site, dk.sample0, dk.window0 + m, 64, 0, k, a.keep_fc);
+        }
+        h[u] = kp ? h[u] / a.keep_fc : 0.f;
+      }
     }
     // ---- head: two outputs x two paths, reduced over the 64 hidden units
     float p0[2], p1[2];
@@ -1111,16 +1167,19 @@ __global__ void __launch_bounds__(256) tt_tail_kernel(const TtTailArgs a) {
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         s0 = fmaf(h[u], w0[o][u], s0);
-        s1 = fmaf(MODE == BRL_MODE_LRT ? h[u] * h[u] : h[u] * sgn_in[u], w1[o][u], s1);
+        if (MODE != TT_PLAIN) s1 = fmaf(MODE == BRL_MODE_LRT ? h[u] * h[u] : h[u] * sgn_in[u], w1[o][u], s1);
       }
       p0[o] = warp_sum(s0);
-      p1[o] = warp_sum(s1);
+      p1[o] = MODE == TT_PLAIN ? 0.f : warp_sum(s1);
     }
     float outv[2], sdo[2], eo[2];
 #pragma unroll
     for (int o = 0; o < 2; ++o) {
       float v;
-      if (MODE == BRL_MODE_LRT) {
+      if (MODE == TT_PLAIN) {
+        v = p0[o] + a.hb0[o];
+        sdo[o] = eo[o] = 0.f;
+      } else if (MODE == BRL_MODE_LRT) {
         const float sb = a.hb1[o];
         float var = fmaf(sb, sb, p1[o]);
         if (var < 0.f) var += fabsf(var) + 1e-6f;
@@ -1138,21 +1197,33 @@ __global__ void __launch_bounds__(256) tt_tail_kernel(const TtTailArgs a) {
     if (lane == 0) *reinterpret_cast<float2*>(a.out + 2ll * m) = make_float2(outv[0], outv[1]);
     // ---- likelihood and its gradient w.r.t. the two outputs
     const float loc = outv[0], sc = outv[1];
-    const float s = sc > 20.0f ? sc : log1pf(expf(sc));
-    const float dy = a.y[m] - loc, r = dy / s;
-    if (lane == 0) {
-      nll += 0.5 * (double)r * r + (double)logf(s) + 0.9189385332046727;
-      se += (double)dy * dy;
+    float go[2];
+    if (MODE == TT_PLAIN && a.loss_kind == 1) {  // F.gaussian_nll_loss(loc, y, scale^2): eps clamp 1e-6 on the variance, mean reduction
+      const float var0 = sc * sc, var = fmaxf(var0, 1e-6f), dl = loc - a.y[m], invB = 1.0f / (float)a.B;
+      if (lane == 0) {
+        nll += 0.5 * ((double)logf(var) + (double)dl * dl / var);
+        se += (double)dl * dl;
+      }
+      go[0] = dl / var * invB;
+      go[1] = var0 > 1e-6f ? 0.5f * (1.0f / var - dl * dl / (var * var)) * 2.0f * sc * invB : 0.f;
+    } else {
+      const float s = sc > 20.0f ? sc : log1pf(expf(sc));
+      const float dy = a.y[m] - loc, r = dy / s;
+      if (lane == 0) {
+        nll += 0.5 * (double)r * r + (double)logf(s) + 0.9189385332046727;
+        se += (double)dy * dy;
+      }
+      const float sig = sc > 20.0f ? 1.0f : 1.0f / (1.0f + expf(-sc));
+      go[0] = -r / s * a.gscale;
+      go[1] = (1.0f - r * r) / s * sig * a.gscale;
     }
     if (!a.compute_grads) continue;
-    const float sig = sc > 20.0f ? 1.0f : 1.0f / (1.0f + expf(-sc));
-    const float go[2] = {-r / s * a.gscale, (1.0f - r * r) / s * sig * a.gscale};
     // ---- head backward
     float d[2], d1[2];
 #pragma unroll
     for (int o = 0; o < 2; ++o) {
       d[o] = outv[o] > 1e-9f ? go[o] * (1.0f - expf(-outv[o])) : 0.f;
-      d1[o] = MODE == BRL_MODE_LRT ? (sdo[o] > 0.f ? d[o] * eo[o] / (2.0f * sdo[o]) : 0.f) : d[o] * eo[o];
+      d1[o] = MODE == TT_PLAIN ? 0.f : MODE == BRL_MODE_LRT ? (sdo[o] > 0.f ? d[o] * eo[o] / (2.0f * sdo[o]) : 0.f) : d[o] * eo[o];
       gb0[o] += d[o];
       gb1[o] += MODE == BRL_MODE_LRT ? d1[o] : d[o];
     }
@@ -1168,19 +1239,20 @@ __global__ void __launch_bounds__(256) tt_tail_kernel(const TtTailArgs a) {
         dh0 = fmaf(d[o], w0[o][u], dh0);
         dh1 = fmaf(d1[o], w1[o][u], dh1);
       }
-      const float dh = MODE == BRL_MODE_LRT ? fmaf(2.0f * h[u], dh1, dh0) : fmaf(sgn_in[u], dh1, dh0);
-      // ---- activation backward of the fc layer
-      const float dp = h[u] > 0.f ? dh : 0.f;
+      const float dh = MODE == TT_PLAIN ? dh0 : MODE == BRL_MODE_LRT ? fmaf(2.0f * h[u], dh1, dh0) : fmaf(sgn_in[u], dh1, dh0);
+      // ---- activation backward of the fc layer (with dropout the stored activation is a * m / keep: it gates, 1 / keep scales)
+      const float dp = h[u] > 0.f ? (MODE == TT_PLAIN ? dh / a.keep_fc : dh) : 0.f;
       a.dpre[(long long)m * 64 + k] = dp;
-      a.dsec[(long long)m * 64 + k] = MODE == BRL_MODE_LRT ? (sd[u] > 0.f ? dp * ef[u] / (2.0f * sd[u]) : 0.f) : dp * ef[u];
+      if (MODE != TT_PLAIN) a.dsec[(long long)m * 64 + k] = MODE == BRL_MODE_LRT ? (sd[u] > 0.f ? dp * ef[u] / (2.0f * sd[u]) : 0.f) : dp * ef[u];
     }
   }
   // ---- reductions: likelihood sums (lane 0 of every warp holds its windows'), head weight gradients
   nll = tt_block_sum(nll);
   se = tt_block_sum(se);
   if (tid == 0) {
-    atomicAdd(a.acc + 0, nll);
-    atomicAdd(a.acc + 1, se);
+    const double sc_ = (MODE == TT_PLAIN && a.loss_kind == 1) ? 1.0 / (double)a.B : 1.0;  // HNN: means (nll_hnn_kernel)
+    atomicAdd(a.acc + 0, nll * sc_);
+    atomicAdd(a.acc + 1, se * sc_);
   }
   if (!a.compute_grads) return;
 #pragma unroll
@@ -1196,7 +1268,7 @@ __global__ void __launch_bounds__(256) tt_tail_kernel(const TtTailArgs a) {
     }
   }
   __syncthreads();
-  for (int i = tid; i < 2 * 2 * 65; i += 256) {
+  for (int i = tid; i < (MODE == TT_PLAIN ? 1 : 2) * 2 * 65; i += 256) {
     const int path = i / 130, r = i - path * 130, o = r / 65, k = r - o * 65;
     float* g = path ? a.g1 : a.g0;
     atomicAdd(g + (k < 64 ? a.hw_off + o * 64 + k : a.hb_off + o), sg[path][o][k]);
@@ -1225,6 +1297,7 @@ __global__ void tt_reduce_kernel(const TtReduceArgs a) {
   const int g_lo = blockIdx.y * per, g_hi = min(a.ngroups[li], g_lo + per);
   if (g_lo >= g_hi) return;
   const float* p = a.part + l.poff;
+  const bool dual = a.mode == BRL_MODE_LRT || a.mode == BRL_MODE_FLIPOUT;
   float s0 = 0.f, s1 = 0.f;
   if (j < nw) {
     const int ch = j % CH, cr = real_ch(l.in, ch);
@@ -1232,21 +1305,21 @@ __global__ void tt_reduce_kernel(const TtReduceArgs a) {
 #pragma unroll 8
     for (int gidx = g_lo; gidx < g_hi; ++gidx) {
       s0 += p[(long long)gidx * a.part_floats + j];
-      s1 += p[(long long)gidx * a.part_floats + nw + j];
+      if (dual) s1 += p[(long long)gidx * a.part_floats + nw + j];
     }
     const int nt_ = j / CH, n = nt_ / l.T, tap = nt_ - n * l.T;
     const long long wi = l.w_off + ((long long)n * l.cin + cr) * l.T + tap;
     atomicAdd(a.g0 + wi, s0);
-    atomicAdd(a.g1 + wi, s1);
+    if (dual) atomicAdd(a.g1 + wi, s1);
   } else {
     const int n = j - nw;
 #pragma unroll 8
     for (int gidx = g_lo; gidx < g_hi; ++gidx) {
       s0 += p[(long long)gidx * a.part_floats + 2ll * nw + n];
-      s1 += p[(long long)gidx * a.part_floats + 2ll * nw + 64 + n];
+      if (dual) s1 += p[(long long)gidx * a.part_floats + 2ll * nw + 64 + n];
     }
     atomicAdd(a.g0 + l.b_off + n, s0);
-    atomicAdd(a.g1 + l.b_off + n, a.mode == BRL_MODE_LRT ? s1 : s0);  // Flipout: the sampled bias (brl_api.cu: gb2)
+    if (dual) atomicAdd(a.g1 + l.b_off + n, a.mode == BRL_MODE_LRT ? s1 : s0);  // Flipout: the sampled bias (brl_api.cu: gb2)
   }
 }
 
@@ -1305,6 +1378,10 @@ static void tt_configure() {
   if (done) return;
   cudaFuncSetAttribute(tt_fwd_kernel<BRL_MODE_LRT>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM);
   cudaFuncSetAttribute(tt_fwd_kernel<BRL_MODE_FLIPOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM);
+  cudaFuncSetAttribute(tt_fwd_kernel<TT_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM);
+  cudaFuncSetAttribute(tt_bwd_kernel<TT_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM);
+  cudaFuncSetAttribute(tt_fc_dx_kernel<TT_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, FX_SMEM);
+  cudaFuncSetAttribute(tt_fc_dw_kernel<TT_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM);
   cudaFuncSetAttribute(tt_bwd_kernel<BRL_MODE_LRT>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM);
   cudaFuncSetAttribute(tt_bwd_kernel<BRL_MODE_FLIPOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM);
   cudaFuncSetAttribute(tt_fc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM);
@@ -1331,7 +1408,7 @@ void tt_forward(const TtLane& ln, const TtStep& s, cudaStream_t st, const TtSide
   TtPackArgs pa;
   for (int i = 0; i < TT_LAYERS; ++i) { pa.L[i] = layer_of(s, i); pa.start[i] = tb.pack_start[i]; }
   pa.start[TT_LAYERS] = tb.pack_start[TT_LAYERS];
-  pa.mode = s.mode; pa.mu = s.mu; pa.second = s.mode == BRL_MODE_LRT ? s.sigma : s.wsamp; pa.blob = ln.blob;
+  pa.mode = s.mode; pa.mu = s.mu; pa.second = s.mode == BRL_MODE_LRT ? s.sigma : s.mode == BRL_MODE_FLIPOUT ? s.wsamp : s.mu; pa.blob = ln.blob;
   tt_pack_kernel<<<(tb.pack_start[TT_LAYERS] + TT_LAYERS * 64 + 255) / 256, 256, 0, sd.side>>>(pa);
   TtFcPackArgs fp;
   fp.mode = s.mode; fp.mu = s.mu; fp.second = pa.second; fp.w_off = s.w_off_fc; fp.blob = ln.fcblob;
@@ -1361,12 +1438,15 @@ void tt_forward(const TtLane& ln, const TtStep& s, cudaStream_t st, const TtSide
       fa.eps[nl] = s.eps[li];
       fa.sgn_in[nl] = s.sgn_in[li];
       fa.sgn_out[nl] = s.sgn_out[li];
+      fa.drop[nl] = s.drop[li];
+      fa.keep[nl] = s.keep[li];
       ++nl;
     }
     fa.nl = nl;
     ++g_launch_count;
     if (s.mode == BRL_MODE_LRT) tt_fwd_kernel<BRL_MODE_LRT><<<dim3(nt, nl), NT, F_SMEM, st>>>(fa);
-    else tt_fwd_kernel<BRL_MODE_FLIPOUT><<<dim3(nt, nl), NT, F_SMEM, st>>>(fa);
+    else if (s.mode == BRL_MODE_FLIPOUT) tt_fwd_kernel<BRL_MODE_FLIPOUT><<<dim3(nt, nl), NT, F_SMEM, st>>>(fa);
+    else tt_fwd_kernel<TT_PLAIN><<<dim3(nt, nl), NT, F_SMEM, st>>>(fa);
   }
 }
 
@@ -1384,10 +1464,11 @@ void tt_tail(const TtStep& s, const TtTail& t, cudaStream_t st) {
   TtTailArgs a{};
   a.B = (int)s.B; a.mode = s.mode; a.compute_grads = t.compute_grads;
   a.part = t.part;
-  const bool lrt = s.mode == BRL_MODE_LRT;
-  a.fc_b0 = (lrt ? s.mu : s.wsamp) + s.b_off_fc; a.fc_b1 = lrt ? s.sigma + s.b_off_fc : nullptr;
-  a.hw0 = s.mu + t.hw_off; a.hw1 = (lrt ? s.sigma : s.wsamp) + t.hw_off;
-  a.hb0 = (lrt ? s.mu : s.wsamp) + t.hb_off; a.hb1 = lrt ? s.sigma + t.hb_off : nullptr;
+  const bool lrt = s.mode == BRL_MODE_LRT, plain = s.mode != BRL_MODE_LRT && s.mode != BRL_MODE_FLIPOUT;
+  a.fc_b0 = ((lrt || plain) ? s.mu : s.wsamp) + s.b_off_fc; a.fc_b1 = lrt ? s.sigma + s.b_off_fc : nullptr;
+  a.hw0 = s.mu + t.hw_off; a.hw1 = plain ? nullptr : (lrt ? s.sigma : s.wsamp) + t.hw_off;
+  a.hb0 = ((lrt || plain) ? s.mu : s.wsamp) + t.hb_off; a.hb1 = lrt ? s.sigma + t.hb_off : nullptr;
+  a.loss_kind = t.loss_kind; a.keep_fc = t.keep_fc; a.drop_fc = t.drop_fc;
   a.eps_fc = t.eps_fc; a.eps_head = t.eps_head;
   a.sout_fc = t.sout_fc; a.sin_head = t.sin_head; a.sout_head = t.sout_head;
   a.y = t.y; a.gscale = t.gscale; a.acc = t.acc; a.out = t.out; a.dpre = t.dpre; a.dsec = t.dsec;
@@ -1395,6 +1476,7 @@ void tt_tail(const TtStep& s, const TtTail& t, cudaStream_t st) {
   const int grid = (int)std::min<long long>((s.B + 7) / 8, 148);
   ++g_launch_count;
   if (lrt) tt_tail_kernel<BRL_MODE_LRT><<<grid, 256, 0, st>>>(a);
+  else if (plain) tt_tail_kernel<TT_PLAIN><<<grid, 256, 0, st>>>(a);
   else tt_tail_kernel<BRL_MODE_FLIPOUT><<<grid, 256, 0, st>>>(a);
 }
 
@@ -1411,6 +1493,9 @@ void tt_fc_backward(const TtLane& ln, const TtStep& s, const float* dpre, const 
   if (s.mode == BRL_MODE_LRT) {
     tt_fc_dx_kernel<BRL_MODE_LRT><<<dim3(ba.nmt, FC_NS), 256, FX_SMEM, st>>>(ba);
     tt_fc_dw_kernel<BRL_MODE_LRT><<<(FC_KC + 15) / 16, 256, FW_SMEM, sd.side>>>(ba);
+  } else if (s.mode != BRL_MODE_FLIPOUT) {
+    tt_fc_dx_kernel<TT_PLAIN><<<dim3(ba.nmt, FC_NS), 256, FX_SMEM, st>>>(ba);
+    tt_fc_dw_kernel<TT_PLAIN><<<(FC_KC + 15) / 16, 256, FW_SMEM, sd.side>>>(ba);
   } else {
     tt_fc_dx_kernel<BRL_MODE_FLIPOUT><<<dim3(ba.nmt, FC_NS), 256, FX_SMEM, st>>>(ba);
     tt_fc_dw_kernel<BRL_MODE_FLIPOUT><<<(FC_KC + 15) / 16, 256, FW_SMEM, sd.side>>>(ba);
@@ -1439,6 +1524,7 @@ void tt_backward(const TtLane& ln, const TtStep& s, cudaStream_t st, const TtSid
       ba.lay[nl] = layer_of(s, li);
       ba.sgn_in[nl] = s.sgn_in[li];
       ba.sgn_out[nl] = s.sgn_out[li];
+      ba.keep[nl] = s.keep[li];
       ++nl;
     }
     ba.nl = nl;
@@ -1448,7 +1534,8 @@ void tt_backward(const TtLane& ln, const TtStep& s, cudaStream_t st, const TtSid
       if (levels[lv][k] >= 0) ra.ngroups[levels[lv][k]] = ngroups;
     ++g_launch_count;
     if (s.mode == BRL_MODE_LRT) tt_bwd_kernel<BRL_MODE_LRT><<<dim3(ngroups, nl), NT, B_SMEM, st>>>(ba);
-    else tt_bwd_kernel<BRL_MODE_FLIPOUT><<<dim3(ngroups, nl), NT, B_SMEM, st>>>(ba);
+    else if (s.mode == BRL_MODE_FLIPOUT) tt_bwd_kernel<BRL_MODE_FLIPOUT><<<dim3(ngroups, nl), NT, B_SMEM, st>>>(ba);
+    else tt_bwd_kernel<TT_PLAIN><<<dim3(ngroups, nl), NT, B_SMEM, st>>>(ba);
   }
   int tot = 0;
   for (int i = 0; i < TT_LAYERS; ++i) {

@@ -35,13 +35,16 @@ void tt_carve(unsigned char* base, long long B, TtLane& ln);
 struct TtStep {
   const float* x;        // [B,30,18]
   long long B;
-  int mode;              // BRL_MODE_LRT or BRL_MODE_FLIPOUT
+  int mode;              // BRL_MODE_LRT / BRL_MODE_FLIPOUT (dual contraction) or BRL_MODE_DET / BRL_MODE_WS (one contraction with the
+                         // weights `mu`: the HNN / MC-dropout step, the weight-sampling ELBO of the radial guide)
   const float* mu;       // [P]
   const float* sigma;    // [P]  (LRT)
   const float* wsamp;    // [P]  (Flipout: the particle's weight draw)
   NoiseRef eps[TT_LAYERS];          // LRT eps streams (injected tensor [B, N*30] or Philox)
   const float* sgn_in[TT_LAYERS];   // Flipout [B, Cin]
   const float* sgn_out[TT_LAYERS];  // Flipout [B, Cout]
+  NoiseRef drop[TT_LAYERS];         // single-contraction modes: dropout site behind each conv layer (masks [B, N, 30] or Philox)
+  float keep[TT_LAYERS];            // its keep probability (1 = no site / dropout off)
   const float* sgn_fc_in;  // Flipout: s_in of the fc layer [B, 2400]
   long long w_off_fc, b_off_fc;
   float* g0;             // flat gradient accumulators [P] (brl_kernels.cuh: Finalize): mean path / variance or perturbation path
@@ -72,6 +75,9 @@ struct TtTail {
   NoiseRef eps_fc, eps_head;
   const float *sout_fc, *sin_head, *sout_head;
   long long hw_off, hb_off;  // flat offsets of the head layer's weight / bias
+  int loss_kind = 0;         // single-contraction modes: 0 ELBO likelihood, 1 F.gaussian_nll_loss (HNN step)
+  float keep_fc = 1.0f;      // dropout site behind the fc layer
+  NoiseRef drop_fc{};
 };
 void tt_tail(const TtStep& s, const TtTail& t, cudaStream_t st);
 // backward: feature-gradient image -> g0 / g1 of the ten conv layers (accumulated: the buffers must be zeroed); 4 launches

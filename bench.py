@@ -414,13 +414,18 @@ def main():
                 dist.all_reduce(g, op=dist.ReduceOp.AVG)  # NCCL folds the 1 / world in
             eng.clipped_adam(th, g, hm, hv, hs["i"], 1e-3, (0.9, 0.999), 1e-8, 1e30)
 
+        eng.set_gemm_backend("simt")
+        th_s = max_over_ranks(timed_steps(hnn_train_step, NT, 6, flush_buf, dist), dist, device)
+        eng.set_gemm_backend("fused")
         th_t = max_over_ranks(timed_steps(hnn_train_step, NT, 6, flush_buf, dist), dist, device)
         eng.set_step_graph(False)
         th_e = max_over_ranks(timed_steps(hnn_train_step, NT, 3, flush_buf, dist), dist, device)
         eng.set_step_graph(True)
+        eng.set_gemm_backend("simt")
         train["hnn_mcd"] = {"windows_per_s": world * B_TRAIN * NT / th_t, "ms_per_step": 1e3 * th_t / NT, "batch_per_gpu": B_TRAIN,
-                            "p_dropout": 0.241437, "ms_per_step_eager": 1e3 * th_e / NT, "gemm_backend": "fp32 FFMA",
-                            "ms_per_step_by_backend": {"simt_fp32": 1e3 * th_t / NT},
+                            "p_dropout": 0.241437, "ms_per_step_eager": 1e3 * th_e / NT,
+                            "gemm_backend": "level-fused tcgen05 (fp16 / bf16 operands, fp32 accumulate)",
+                            "ms_per_step_by_backend": {"fused_tcgen05": 1e3 * th_t / NT, "simt_fp32": 1e3 * th_s / NT},
                             "includes": "HNN.step forward (fused dropout masks) + gaussian_nll_loss + backward (CUDA-graph replay) + Adam"
                                         + (f" + NCCL all-reduce over {world} ranks" if dist is not None else "")}
 

@@ -58,7 +58,8 @@ extern "C" {
 #define BRL_GEMM_TC_TF32 7   /* tcgen05 kind::tf32 dual GEMMs, fp32 accumulation in TMEM (stated bound 5e-3 vs fp32);
                               * bit mask: 1 forward, 2 input-gradient, 4 weight-gradient kernels (partial masks: debugging) */
 
-#define BRL_GEMM_TC_FUSED 8  /* Inception, LRT / Flipout ELBO steps: the ten conv layers run as LEVEL-FUSED tcgen05 kernels (one CTA
+#define BRL_GEMM_TC_FUSED 8  /* Inception: brl_elbo_step (LRT / Flipout / weight sampling) and brl_hnn_step (dropout masks in the epilogues)
+                              * run the ten conv layers and the fc layer as LEVEL-FUSED tcgen05 kernels (one CTA
                               * per layer per 4-window tile; operands are bulk-copied activation / weight images, taps are
                               * descriptor shifts, the backward contractions read the same images through MN-major descriptors;
                               * fp16 / bf16 operands, fp32 accumulation: outputs 1e-2, loss 5e-3, gradient cosine > 0.999);

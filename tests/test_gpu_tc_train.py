@@ -139,3 +139,62 @@ def test_fused_batch_sizes_match_fp32_backend(eng, B):
         for k, kk in (("grad_mu", kmu), ("grad_sigma", ksg)):
             cs = _cos(got[k].double().cpu() - kk, ref[k].double().cpu() - kk)
             assert cs > (0.999 if B >= 129 else 0.98), (mode, B, k, cs)
+
+
+@pytest.mark.parametrize("guide", ["normal", "radial"])
+@pytest.mark.parametrize("B", [256, 33])
+def test_fused_weight_sampling_elbo_vs_oracle(eng, guide, B):
+    """Weight-sampling ELBO (no fit context / the radial guide's Trace_ELBO, bayesian.py:81-83,105-109) on the fused back-end:
+    one contraction per layer with the particle's weight draw."""
+    sigma = 0.03
+    x, y, mu, sg = synth(NET, B, seed=70 + B, sigma=sigma)
+    g = torch.Generator().manual_seed(8)
+    nzs = [O.make_injected_noise(NET, B, "radial" if guide == "radial" else "ws", g)]
+    kw = dict(mode="ws", guide=guide, prior_loc=0.0, prior_scale=0.138793, dataset_size=238150)
+    ref = O.elbo_loss_and_grads(NET, x.double(), y.double(), mu.double(), sg.double(),
+                                noises=[O.InjectedNoise({k: v.double() for k, v in n.items()}) for n in nzs], **kw)
+    eng.set_gemm_backend("fused")
+    got = eng.elbo_step(x.to(DEV), y.to(DEV), mu.to(DEV), sg.to(DEV), particles=1, noise=injected_to_engine(NET, nzs, B, DEV), **kw)
+    eng.set_gemm_backend("simt")
+    assert eng.tc_status() == 0
+    sc = got["scalars"].cpu()
+    assert abs(sc[0].item() / ref["loss"].item() - 1) < 5e-3
+    assert abs(sc[1].item() / ref["nll_sum"].item() - 1) < 5e-3
+    out_err = ((got["out"].cpu().double() - ref["out"]).abs() / ref["out"].abs().clamp_min(1e-3)).max().item()
+    assert out_err < 1e-2, out_err
+    cmin = 0.999 if B >= 256 else 0.99
+    cs = _cos(got["grad_mu"].double().cpu(), ref["grad_mu"])  # the KL part of grad_mu is tiny next to the likelihood part here
+    print(f"\n[ws {guide} B={B}] loss {sc[0].item():.6e} vs {ref['loss'].item():.6e}, out err {out_err:.2e}, grad_mu cosine {cs:.6f}")
+    assert cs > cmin, cs
+
+
+@pytest.mark.parametrize("p", [0.0, 0.241437])
+@pytest.mark.parametrize("B", [256, 29])
+def test_fused_hnn_step_vs_oracle(eng, p, B):
+    """HNN.step (frequentist.py:39-48: forward with the dropout sites, F.gaussian_nll_loss, backward) on the fused back-end with the
+    oracle's own keep masks injected."""
+    x, y, mu, _ = synth(NET, B, seed=31 + B)
+    g = torch.Generator().manual_seed(5)
+    nz = O.make_injected_noise(NET, B, "det", g, p_dropout=p)
+    th = mu.double().requires_grad_(True)
+    loss, out = O.hnn_loss(NET, x.double(), y.double(), th, p, O.InjectedNoise({k: v.double() for k, v in nz.items()}))
+    (gref,) = torch.autograd.grad(loss, th)
+    eng.set_gemm_backend("fused")
+    got = eng.hnn_step(x.to(DEV), y.to(DEV), mu.to(DEV), p, injected_to_engine(NET, [nz], B, DEV) if p > 0 else None)
+    # native masks: same draws as the fp32 back-end, and graph replay == eager
+    from bayesrul_b200 import Noise
+    xd, yd, mud = x.to(DEV), y.to(DEV), mu.to(DEV)
+    runs = [eng.hnn_step(xd, yd, mud, p, Noise(seed=9)) for _ in range(3)]
+    eng.set_gemm_backend("simt")
+    simt = eng.hnn_step(xd, yd, mud, p, Noise(seed=9))
+    assert eng.tc_status() == 0
+    assert abs(got["scalars"][0].item() / loss.item() - 1) < 5e-3
+    out_err = ((got["out"].cpu().double() - out.detach()).abs() / out.detach().abs().clamp_min(1e-3)).max().item()
+    cs = _cos(got["grad"].double().cpu(), gref)
+    print(f"\n[hnn p={p} B={B}] loss {got['scalars'][0].item():.6e} vs {loss.item():.6e}, out err {out_err:.2e}, grad cosine {cs:.6f}")
+    assert out_err < 1e-2
+    assert cs > (0.999 if B >= 256 else 0.99)
+    assert abs(runs[0]["scalars"][0].item() / simt["scalars"][0].item() - 1) < 5e-3
+    assert _cos(runs[0]["grad"].double(), simt["grad"].double()) > 0.999
+    for r in runs[1:]:
+        assert torch.allclose(r["scalars"], runs[0]["scalars"], rtol=1e-5)
