@@ -12,9 +12,15 @@ for k in r.get("other_kernels", []):
     print(f"  {k['kernel']}: {k['achieved']:.0f} / {k['peak']:.0f} {k['unit']} = {k['frac']:.3f}, {k['ms_per_launch']:.3f} ms/launch")
 for m, v in d.get("train", {}).items():
     print(f"  train {m}: {v['ms_per_step']:.3f} ms/step = {v['windows_per_s'] / 1e3:.0f} k windows/s [{v['gemm_backend']}] {v['ms_per_step_by_backend']} "
-          f"eager {v.get('ms_per_step_eager_simt', v.get('ms_per_step_eager'))} cpu {v.get('cpu_windows_per_s')}")
+          f"eager {v.get('ms_per_step_eager_fused', v.get('ms_per_step_eager_simt', v.get('ms_per_step_eager')))} cpu {v.get('cpu_windows_per_s')}"
+          + (f" ({v['speedup_vs_cpu_port']:.0f}x)" if v.get("speedup_vs_cpu_port") else ""))
 if d.get("mcd_predict"):
     print(f"  mcd {d['mcd_predict']['window_samples_per_s'] / 1e6:.1f} M")
+if d.get("flipout_predict"):
+    print(f"  flipout predict (S=20) {d['flipout_predict']['window_samples_per_s'] / 1e6:.1f} M")
+if d.get("deep_ensemble_full"):
+    f = d["deep_ensemble_full"]
+    print(f"  configs[4] at scale: {f['window_units_per_s'] / 1e6:.1f} M window-units/s, {f['seconds_per_pass']:.2f} s per pass of 1M windows x (1000 + 5)")
 if d.get("radial_sweep"):
     print("  radial", {k: round(v["window_samples_per_s"] / 1e6, 1) for k, v in d["radial_sweep"].items() if k != "note"})
 if d.get("deep_ensemble"):
