@@ -102,8 +102,8 @@ constexpr int RBUF_PER_TILE = 336 * 128;  // sum of NP over the ten layers x 128
 // fc layer (2400 -> 64): feature images of a 128-window M-tile, [300 k-chunks][128 windows][8 x 16 bit], k' = t * 80 + c
 // (chunk = t * 10 + c / 8); weight images [300 k-chunks][64 n][8]
 constexpr int FC_KC = 300, FC_CHUNK = 128 * 16, FC_MT_BYTES = FC_KC * FC_CHUNK, FC_WIMG = FC_KC * 64 * 16;
-constexpr int FC_KS = 15, FC_KCS = FC_KC / FC_KS;  // forward: K split over 15 CTAs of 20 chunks (10 MMA k-steps)
-constexpr int FC_NS = 10, FC_NCS = FC_KC / FC_NS;  // input gradient: N' = 2400 in 10 slices of 240 columns (30 chunks)
+constexpr int FC_KS = 30, FC_KCS = FC_KC / FC_KS;  // forward: K split over 30 CTAs of 10 chunks (5 MMA k-steps) per M-tile
+constexpr int FC_NS = 25, FC_NCS = FC_KC / FC_NS;  // input gradient: N' = 2400 in 25 slices of 96 columns (12 chunks) per M-tile
 __device__ __forceinline__ long long feat_addr(int gw, int t, int c0) {  // 16-byte unit of window gw, step t, channels [c0, c0 + 8)
   return ((long long)(gw >> 7) * FC_KC + t * 10 + (c0 >> 3)) * FC_CHUNK + (gw & 127) * 16;
 }
@@ -932,12 +932,12 @@ __global__ void __launch_bounds__(256, 1) tt_fc_dx_kernel(const TtFcBwdArgs a) {
   if (warp == 0) {
     tc_fence_after();
     if (elect_one()) {
-      for (int k = 0; k < 4; ++k) {  // K = 64 output units; B = the weight image read MN-major: [N' = 240 features][K' = 16 units]
+      for (int k = 0; k < 4; ++k) {  // K = 64 output units; B = the weight image read MN-major: [N' = FC_NCS * 8 features][K' = 16 units]
         umma(tmem, umma_desc(sbase + FX_G0 + 2 * k * FC_CHUNK, FC_CHUNK, 128), umma_desc(sbase + FX_W0 + k * 256, 128, 1024),
-             tt_idesc(240, 1, 0, 1), k != 0);
+             tt_idesc(FC_NCS * 8, 1, 0, 1), k != 0);
         if (MODE != TT_PLAIN)
           umma(tmem + 256, umma_desc(sbase + FX_G1 + 2 * k * FC_CHUNK, FC_CHUNK, 128), umma_desc(sbase + FX_W1 + k * 256, 128, 1024),
-               tt_idesc(240, 1, 0, 1), k != 0);
+               tt_idesc(FC_NCS * 8, 1, 0, 1), k != 0);
       }
       umma_commit(bar_mma);
     }
@@ -1324,13 +1324,21 @@ __global__ void tt_reduce_kernel(const TtReduceArgs a) {
 }
 
 long long* g_tt_trace = nullptr;  // debug buffer [6 launches][4 layers][16] (brl_tt_trace)
-int* g_tt_status = nullptr;
+// per-device state (function attributes and the time-out word live in a device's context: one process may drive several GPUs)
+constexpr int TT_MAX_DEV = 64;
+int* g_tt_status[TT_MAX_DEV] = {};
+int tt_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return d < 0 || d >= TT_MAX_DEV ? 0 : d;
+}
 int* tt_status_word() {
-  if (!g_tt_status) {
-    cudaMalloc(&g_tt_status, sizeof(int));
-    cudaMemset(g_tt_status, 0, sizeof(int));
+  const int d = tt_device();
+  if (!g_tt_status[d]) {
+    cudaMalloc(&g_tt_status[d], sizeof(int));
+    cudaMemset(g_tt_status[d], 0, sizeof(int));
   }
-  return g_tt_status;
+  return g_tt_status[d];
 }
 inline size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
 
@@ -1338,9 +1346,10 @@ inline size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 void tt_trace(long long* device_buf) { g_tt_trace = device_buf; }
 
-int tt_status() {
+int tt_status() {  // of the current device
   int v = 0;
-  if (g_tt_status) cudaMemcpy(&v, g_tt_status, sizeof(int), cudaMemcpyDeviceToHost);
+  const int d = tt_device();
+  if (g_tt_status[d]) cudaMemcpy(&v, g_tt_status[d], sizeof(int), cudaMemcpyDeviceToHost);
   return v;
 }
 
@@ -1374,7 +1383,8 @@ void tt_carve(unsigned char* base, long long B, TtLane& ln) {
 }
 
 static void tt_configure() {
-  static bool done = false;
+  static bool done_dev[TT_MAX_DEV] = {};
+  bool& done = done_dev[tt_device()];
   if (done) return;
   cudaFuncSetAttribute(tt_fwd_kernel<BRL_MODE_LRT>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM);
   cudaFuncSetAttribute(tt_fwd_kernel<BRL_MODE_FLIPOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM);
