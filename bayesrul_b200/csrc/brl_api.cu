@@ -1515,6 +1515,20 @@ int brl_clipped_adam(float* param, const float* grad, float* exp_avg, float* exp
   return BRL_OK;
 }
 
+int brl_clipped_adam_vi_scaled(float* loc, float* log_scale, float* scale, const float* grad_loc, const float* grad_log_scale,
+                               float* m_loc, float* v_loc, float* m_log_scale, float* v_log_scale, int64_t nn, int64_t step, float lr,
+                               float beta1, float beta2, float eps, float clip_norm, float lrd, float weight_decay, float grad_scale,
+                               void* stream) {
+  BRL_REQUIRE(loc && log_scale && scale && grad_loc && grad_log_scale && m_loc && v_loc && m_log_scale && v_log_scale && nn > 0 && step >= 1,
+              "brl_clipped_adam_vi_scaled: bad argument");
+  const double lr_t = (double)lr * std::pow((double)lrd, (double)step);
+  const double bc1 = 1.0 - std::pow((double)beta1, (double)step), bc2 = 1.0 - std::pow((double)beta2, (double)step);
+  launch_clipped_adam_vi(loc, log_scale, scale, grad_loc, grad_log_scale, m_loc, v_loc, m_log_scale, v_log_scale, nn,
+                         (float)(lr_t * std::sqrt(bc2) / bc1), beta1, beta2, eps, clip_norm, weight_decay, (cudaStream_t)stream, grad_scale);
+  BRL_CUDA(cudaGetLastError());
+  return BRL_OK;
+}
+
 int brl_clipped_adam_vi(float* loc, float* log_scale, float* scale, const float* grad_loc, const float* grad_log_scale,
                         float* m_loc, float* v_loc, float* m_log_scale, float* v_log_scale, int64_t nn, int64_t step, float lr,
                         float beta1, float beta2, float eps, float clip_norm, float lrd, float weight_decay, void* stream) {

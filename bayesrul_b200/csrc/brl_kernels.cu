@@ -618,10 +618,10 @@ __global__ void clipped_adam_kernel(float* __restrict__ p, const float* __restri
 __global__ void clipped_adam_vi_kernel(float* __restrict__ loc, float* __restrict__ ls, float* __restrict__ scale,
                                        const float* __restrict__ g_loc, const float* __restrict__ g_ls, float* __restrict__ m_loc,
                                        float* __restrict__ v_loc, float* __restrict__ m_ls, float* __restrict__ v_ls, long long n,
-                                       float step_size, float b1, float b2, float eps, float clip, float wd) {
+                                       float step_size, float b1, float b2, float eps, float clip, float wd, float gscale) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     {
-      float gr = fminf(fmaxf(g_loc[i], -clip), clip);
+      float gr = fminf(fmaxf(g_loc[i] * gscale, -clip), clip);
       const float pi = loc[i];
       if (wd != 0.f) gr = fmaf(wd, pi, gr);
       const float mi = b1 * m_loc[i] + (1.f - b1) * gr, vi = b2 * v_loc[i] + (1.f - b2) * gr * gr;
@@ -630,7 +630,7 @@ __global__ void clipped_adam_vi_kernel(float* __restrict__ loc, float* __restric
       loc[i] = pi - step_size * mi / (sqrtf(vi) + eps);
     }
     {
-      float gr = fminf(fmaxf(g_ls[i], -clip), clip);
+      float gr = fminf(fmaxf(g_ls[i] * gscale, -clip), clip);
       const float pi = ls[i];
       if (wd != 0.f) gr = fmaf(wd, pi, gr);
       const float mi = b1 * m_ls[i] + (1.f - b1) * gr, vi = b2 * v_ls[i] + (1.f - b2) * gr * gr;
@@ -644,10 +644,11 @@ __global__ void clipped_adam_vi_kernel(float* __restrict__ loc, float* __restric
 }
 void launch_clipped_adam_vi(float* loc, float* ls, float* scale, const float* g_loc, const float* g_ls, float* m_loc, float* v_loc,
                             float* m_ls, float* v_ls, long long n, float step_size, float b1, float b2, float eps, float clip, float wd,
-                            cudaStream_t st) {
+                            cudaStream_t st, float gscale) {
   ++g_launch_count;
   clipped_adam_vi_kernel<<<(unsigned)min((n + 255) / 256, (long long)148 * 8), 256, 0, st>>>(loc, ls, scale, g_loc, g_ls, m_loc, v_loc,
-                                                                                            m_ls, v_ls, n, step_size, b1, b2, eps, clip, wd);
+                                                                                            m_ls, v_ls, n, step_size, b1, b2, eps, clip, wd,
+                                                                                            gscale);
 }
 void launch_clipped_adam(float* p, const float* g, float* m, float* v, long long n, float step_size, float b1,
                          float b2, float eps, float clip, float wd, cudaStream_t st) {

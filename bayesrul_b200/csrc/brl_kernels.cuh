@@ -194,6 +194,6 @@ void launch_clipped_adam(float* p, const float* g, float* m, float* v, long long
                          float b2, float eps, float clip, float wd, cudaStream_t st);
 void launch_clipped_adam_vi(float* loc, float* ls, float* scale, const float* g_loc, const float* g_ls, float* m_loc, float* v_loc,
                             float* m_ls, float* v_ls, long long n, float step_size, float b1, float b2, float eps, float clip, float wd,
-                            cudaStream_t st);
+                            cudaStream_t st, float gscale = 1.0f);  // gscale: multiplies the gradients first (1 / world after a SUM all-reduce)
 
 }  // namespace brl

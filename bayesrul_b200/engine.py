@@ -294,7 +294,7 @@ class Engine:
     # -- A9 / A10: ELBO step ---------------------------------------------------------------------------
     def elbo_step(self, x, y, mu, sigma, *, mode: str = "lrt", guide: str = "normal", particles: int = 1,
                   prior_loc: float = 0.0, prior_scale: float = 1.0, dataset_size: int, noise: Optional[Noise] = None,
-                  compute_grads: bool = True):
+                  compute_grads: bool = True, out_flat: Optional[torch.Tensor] = None):
         """One `svi.step` worth of work.  Returns dict(scalars[4] (device, float64: loss, nll_sum, kl, mse),
         grad_mu, grad_sigma, grad_log_sigma, out [particles,B,2])."""
         x = self._x(x)
@@ -311,8 +311,17 @@ class Engine:
         out = torch.empty(particles, B, 2, device=self.device)
         # ONE flat fp32 buffer [grad_mu | grad_log_sigma | 4 scalars | grad_sigma]: data-parallel ranks all-reduce its first
         # 2 P + 4 floats in a single collective (dist.allreduce_elbo_grads) -- no concatenation, no slicing copies
-        flat = torch.empty(3 * self.P + 4, device=self.device) if compute_grads else None
-        g = [flat[: self.P], flat[2 * self.P + 4:], flat[self.P: 2 * self.P]] if compute_grads else [None] * 3
+        # (`out_flat`: a caller-owned buffer of >= 2 P + 4 floats for the reduced part, e.g. symmetric memory of
+        # dist.FlatGradAllReduce; grad_sigma then lives in its own tensor)
+        flat, g = None, [None] * 3
+        if compute_grads and out_flat is not None:
+            flat = _chk(out_flat, self.device, "out_flat")
+            if flat.numel() < 2 * self.P + 4:
+                raise RuntimeError("bayesrul_b200: out_flat needs at least 2 P + 4 floats")
+            g = [flat[: self.P], torch.empty(self.P, device=self.device), flat[self.P: 2 * self.P]]
+        elif compute_grads:
+            flat = torch.empty(3 * self.P + 4, device=self.device)
+            g = [flat[: self.P], flat[2 * self.P + 4:], flat[self.P: 2 * self.P]]
         ws = self._ws_for(B, 2 if particles > 1 else 1, True, "simt")  # S >= 2: room for two particles side by side
         nz, keep = self._noise(noise)
         p = lambda t: t.data_ptr() if t is not None else None
@@ -388,13 +397,18 @@ class Engine:
                                                  eps, clip_norm, lrd, weight_decay, self._stream()))
 
     def clipped_adam_vi(self, loc, log_scale, scale, grad_loc, grad_log_scale, m_loc, v_loc, m_ls, v_ls, step: int, lr: float,
-                        betas=(0.95, 0.999), eps=1e-8, clip_norm=15.0, lrd=1.0, weight_decay=0.0) -> None:
-        """One launch: ClippedAdam on `loc` and on `log_scale`, then scale = exp(log_scale) (all in place)."""
+                        betas=(0.95, 0.999), eps=1e-8, clip_norm=15.0, lrd=1.0, weight_decay=0.0, grad_scale: float = 1.0) -> None:
+        """One launch: ClippedAdam on `loc` and on `log_scale`, then scale = exp(log_scale) (all in place).  grad_scale multiplies
+        the gradients before the clamp (1 / world after a SUM all-reduce)."""
         ts = (loc, log_scale, scale, grad_loc, grad_log_scale, m_loc, v_loc, m_ls, v_ls)
         for t in ts:
             _chk(t, self.device, "clipped_adam_vi tensor")
             if t.numel() != loc.numel():
                 raise RuntimeError("bayesrul_b200: clipped_adam_vi tensors must have the same number of elements")
         with self._on_device():
-            _lib.check(self.lib.brl_clipped_adam_vi(*[t.data_ptr() for t in ts], loc.numel(), int(step), lr, betas[0], betas[1], eps,
-                                                    clip_norm, lrd, weight_decay, self._stream()))
+            if grad_scale != 1.0:
+                _lib.check(self.lib.brl_clipped_adam_vi_scaled(*[t.data_ptr() for t in ts], loc.numel(), int(step), lr, betas[0], betas[1],
+                                                               eps, clip_norm, lrd, weight_decay, float(grad_scale), self._stream()))
+            else:
+                _lib.check(self.lib.brl_clipped_adam_vi(*[t.data_ptr() for t in ts], loc.numel(), int(step), lr, betas[0], betas[1], eps,
+                                                        clip_norm, lrd, weight_decay, self._stream()))

@@ -345,7 +345,8 @@ def main():
     if not args.no_train:
         xt, yt = synth(B_TRAIN, seed=777 + rank)
         xt, yt = xt.to(device), yt.to(device)
-        from bayesrul_b200.dist import allreduce_elbo_grads
+        from bayesrul_b200.dist import FlatGradAllReduce
+        reducer = FlatGradAllReduce(mu.numel(), device) if dist is not None else None  # NVLS multimem all-reduce when available
         NT = 40
         pk_t = peaks()
         for mode, particles, q, ps, lr in (("lrt", 1, 1.351e-3, 0.138793, 1.0e-3), ("flipout", 2, 2.14e-4, 0.198768, 1.0e-3)):
@@ -359,11 +360,14 @@ def main():
             def train_step(i=0):
                 st["i"] += 1
                 r = eng.elbo_step(xt, yt, par["mu"], par["sg"], mode=mode, guide="normal", particles=particles, prior_loc=0.0,
-                                  prior_scale=ps, dataset_size=N_DATASET, noise=Noise(seed=5000 + st["i"], window0=rank * B_TRAIN))
-                if dist is not None:
-                    r = allreduce_elbo_grads(r)
+                                  prior_scale=ps, dataset_size=N_DATASET, noise=Noise(seed=5000 + st["i"], window0=rank * B_TRAIN),
+                                  out_flat=reducer.flat if reducer is not None else None)
+                gs = 1.0
+                if reducer is not None:
+                    r = reducer.reduce(r)
+                    gs = reducer.grad_scale
                 eng.clipped_adam_vi(par["mu"], par["ls"], par["sg"], r["grad_mu"], r["grad_log_sigma"],
-                                    opt["m_mu"], opt["v_mu"], opt["m_ls"], opt["v_ls"], st["i"], lr, (0.95, 0.999), 1e-8, 15.0)
+                                    opt["m_mu"], opt["v_mu"], opt["m_ls"], opt["v_ls"], st["i"], lr, (0.95, 0.999), 1e-8, 15.0, grad_scale=gs)
 
             res = {}
             # level-fused tcgen05 kernels (fp16 / bf16 operands: the default of compat.BNN) / fp32 FFMA parity kernels /
@@ -392,7 +396,7 @@ def main():
                                                 "launches, not tensor-pipe throughput (profiles/r02_ncu_train_fused.txt); peak = burst bf16 "
                                                 f"cuBLAS of {pk_t['src']} MEASURED_PEAKS.json"},
                            "includes": "ELBO forward + backward + KL + gradient finalisation (CUDA-graph replay) + ClippedAdam on (loc, log scale)"
-                                       + (f" + ONE NCCL all-reduce (AVG) of the step's flat result buffer over {world} ranks" if dist is not None else "")}
+                                       + (f" + ONE all-reduce of the step's flat result buffer over {world} ranks ({reducer.mode})" if dist is not None else "")}
             if world == 1 and not args.no_cpu:
                 v, dt = cpu_train_rate(mode, particles, q, ps, os.cpu_count() or 1)
                 train[mode]["cpu_windows_per_s"] = v

@@ -234,6 +234,13 @@ int brl_clipped_adam_vi(float* loc, float* log_scale, float* scale, const float*
                         float* m_loc, float* v_loc, float* m_log_scale, float* v_log_scale, int64_t n, int64_t step, float lr,
                         float beta1, float beta2, float eps, float clip_norm, float lrd, float weight_decay, void* stream);
 
+/* the same with the gradients multiplied by grad_scale first (before the clamp): 1 / world_size after a SUM all-reduce of the
+ * data-parallel ranks' gradients (the NVLS multimem all-reduce of dist.FlatGradAllReduce has no AVG), so no separate scaling launch */
+int brl_clipped_adam_vi_scaled(float* loc, float* log_scale, float* scale, const float* grad_loc, const float* grad_log_scale,
+                               float* m_loc, float* v_loc, float* m_log_scale, float* v_log_scale, int64_t n, int64_t step, float lr,
+                               float beta1, float beta2, float eps, float clip_norm, float lrd, float weight_decay, float grad_scale,
+                               void* stream);
+
 #ifdef __cplusplus
 }
 #endif
