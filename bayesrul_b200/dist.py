@@ -86,10 +86,12 @@ class FlatGradAllReduce:
     The multimem kernel SUMS: `grad_scale` (1 / world) is what the optimiser must multiply the gradients with
     (`Engine.clipped_adam_vi(..., grad_scale=reducer.grad_scale)`), the scalars are scaled here."""
 
-    def __init__(self, P: int, device, group=None, prefer_symm: bool = True):
+    def __init__(self, P: int, device, group=None, prefer_symm: bool = True, numel: int = 0):
+        """numel > 0: a plain buffer of that many floats instead of the ELBO layout (e.g. the HNN step's [P] gradient: use
+        `reduce_flat()`)."""
         self.P, self.group = P, group
         self.world = dist.get_world_size(group)
-        n = 2 * P + 4
+        n = numel if numel > 0 else 2 * P + 4
         n_pad = (n + 7) // 8 * 8
         self.mode, self.grad_scale = "nccl", 1.0
         self.flat = None
@@ -109,6 +111,16 @@ class FlatGradAllReduce:
                 self.flat = None
         if self.flat is None:
             self.flat = torch.zeros(n_pad, device=device)
+
+    def reduce_flat(self) -> float:
+        """All-reduce self.flat in place; returns the factor that turns its content into the mean over the ranks."""
+        if self.world == 1:
+            return 1.0
+        if self.mode == "multimem":
+            torch.ops.symm_mem.multimem_all_reduce_(self.flat, "sum", self._group_name)
+        else:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
+        return self.grad_scale
 
     def reduce(self, res: dict) -> dict:
         """res = Engine.elbo_step(..., out_flat=self.flat).  Returns res with rank-averaged scalars; the gradients in

@@ -333,14 +333,17 @@ class Engine:
         return dict(scalars=scalars, grad_mu=g[0], grad_sigma=g[1], grad_log_sigma=g[2], out=out, flat=flat)
 
     # -- A13: HNN step -----------------------------------------------------------------------------------
-    def hnn_step(self, x, y, theta, p_dropout: float = 0.0, noise: Optional[Noise] = None, compute_grads: bool = True):
+    def hnn_step(self, x, y, theta, p_dropout: float = 0.0, noise: Optional[Noise] = None, compute_grads: bool = True,
+                 out_grad: Optional[torch.Tensor] = None):
         x = self._x(x)
         B = x.shape[0]
         y = _chk(y, self.device, "y")
         theta = self._theta(theta, "theta")
         scalars = torch.empty(2, dtype=torch.float64, device=self.device)
         out = torch.empty(B, 2, device=self.device)
-        grad = torch.empty(self.P, device=self.device) if compute_grads else None
+        grad = None
+        if compute_grads:  # out_grad: a caller-owned buffer of >= P floats (e.g. dist.FlatGradAllReduce(...).flat)
+            grad = _chk(out_grad, self.device, "out_grad")[: self.P] if out_grad is not None else torch.empty(self.P, device=self.device)
         ws = self._ws_for(B, 1, True, "simt")
         nz, keep = self._noise(noise)
         _lib.check(self.lib.brl_hnn_step(self.ctx, x.data_ptr(), y.data_ptr(), B, theta.data_ptr(), float(p_dropout), nz,

@@ -410,12 +410,15 @@ def main():
         hm, hv = torch.zeros_like(th), torch.zeros_like(th)
         hs = {"i": 0}
 
+        hred = FlatGradAllReduce(0, device, numel=mu.numel()) if dist is not None else None
+
         def hnn_train_step(i=0):
             hs["i"] += 1
-            r = eng.hnn_step(xt, yt, th, p_dropout=0.241437, noise=Noise(seed=7000 + hs["i"], window0=rank * B_TRAIN))
+            r = eng.hnn_step(xt, yt, th, p_dropout=0.241437, noise=Noise(seed=7000 + hs["i"], window0=rank * B_TRAIN),
+                             out_grad=hred.flat if hred is not None else None)
             g = r["grad"]
-            if dist is not None:
-                dist.all_reduce(g, op=dist.ReduceOp.AVG)  # NCCL folds the 1 / world in
+            if hred is not None and hred.reduce_flat() != 1.0:
+                g = g * hred.grad_scale  # SUM (multimem) -> mean; NCCL's AVG needs nothing
             eng.clipped_adam(th, g, hm, hv, hs["i"], 1e-3, (0.9, 0.999), 1e-8, 1e30)
 
         eng.set_gemm_backend("simt")
