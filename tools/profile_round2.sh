@@ -19,6 +19,6 @@ for mode in lrt flipout; do
   BRL_NO_GRAPH=1 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -c 400 --csv \
     --log-file gpurun_out/launches_train_fused_${mode}_${tag}.csv python tools/profile_train.py $mode 3 fused > gpurun_out/ncu_tfl_${mode}_${tag}.log 2>&1
 done
-BRL_NO_GRAPH=1 ncu --set full --clock-control none --import-source on -k regex:tt_ -s 22 -c 12 -o gpurun_out/prof_train_fused_${tag} -f \
+BRL_NO_GRAPH=1 ncu --set full --clock-control none --import-source on -k regex:tt_ -s 28 -c 14 -o gpurun_out/prof_train_fused_${tag} -f \
   python tools/profile_train.py lrt 3 fused > gpurun_out/ncu_tf_${tag}.log 2>&1
 ls -la gpurun_out/*${tag}*
