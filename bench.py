@@ -589,9 +589,9 @@ def main():
     if world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
         cpu_predict_rate(1000, 2, threads)  # warm-up
-        v, dt = cpu_predict_rate(B_PRED, 25, threads)
+        v, dt = cpu_predict_rate(B_PRED, S_PRED, threads)  # one whole step of the workload: ~11 s on the 16-core GPU box
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": f"{B_PRED} windows x 25 of the {S_PRED} MC samples ({dt:.1f} s), plain-PyTorch "
+                                "sample": f"{B_PRED} windows x all {S_PRED} MC samples = one step ({dt:.1f} s), plain-PyTorch "
                                           f"restatement on torch {torch.__version__} CPU"}
     os.write(json_fd, (json.dumps(line) + "\n").encode())
     if dist is not None:
