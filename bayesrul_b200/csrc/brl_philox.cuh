@@ -3,19 +3,22 @@
 //   key     = (seed lo32, seed hi32)
 //   counter = (element >> 2, global window index, global MC sample index, kind << 24 | layer/site)
 // and element e takes lane (e & 3) of its block.  Normals are Box-Muller on lanes (0,1) and (2,3).
-// Dropout keep-decisions: SIXTEEN per block, 16-bit resolution.  Element order is position-major,
+// Dropout keep-decisions: SIXTEEN per block, 14-bit resolution.  Element order is position-major,
 //   e = position * roundup16(C) + channel,  block = e >> 4,  decision bi = (e & 12) | {0, 2, 1, 3}[e & 3] of the block
 // (the middle two of every four are swapped so that the two 16-bit lanes of one SIMD compare are two ADJACENT channels,
 // i.e. one packed half2 of the fused kernel is masked with a single AND), so the 8 / 16 consecutive channels one
 // epilogue thread owns at its position share one Philox block.  With B[0..15] the
-// bytes of the block (little-endian words x, y, z, w), decision bi compares the 16-bit number
-//   u = B[(bi + 1) & 15] << 8 | B[bi]      with      T = min(ceil(keep * 2^16 - 0.5), 65535)   (keep iff u < T),
-// i.e. the sixteen overlapping 16-bit windows of the 128 bits: every decision has exactly the 16-bit marginal T / 2^16, and
-// two neighbouring decisions share only the byte that is the LOW byte of one of them (their covariance is < 2^-8 of a
-// Bernoulli variance; tests/test_host_logic.py bounds the empirical correlations).  All sixteen come out of eight
-// two-lane SIMD compares, branch-free.  (Eight independent 16-bit decisions per block made MC-dropout Philox-bound.)
+// bytes of the block (little-endian words x, y, z, w), decision bi compares the 14-bit number
+//   u = (B[(bi + 1) & 15] << 8 | B[bi]) & 0x3FFF      with      T = min(ceil(keep * 2^14 - 0.5), 16383)   (keep iff u < T),
+// i.e. the low 14 bits of the sixteen overlapping 16-bit windows of the 128 bits: every decision has exactly the 14-bit marginal
+// T / 2^14 (|T / 2^14 - keep| <= 2^-14), and two neighbouring decisions share only bits that are the LOW byte of one of them (their
+// covariance is < 2^-8 of a Bernoulli variance; tests/test_host_logic.py bounds the empirical correlations).  A 14-bit number is the bit
+// pattern of a non-negative finite fp16 (exponent < 16) whose float order is its integer order, so two decisions are ONE packed-half
+// compare with a mask result (HSET2) behind one AND: eight pairs per block, branch-free.  (Round 1 compared 16-bit lanes with the
+// emulated integer SIMD compare -- six ALU-pipe instructions per pair, which made the MC-dropout epilogue ALU-pipe-bound.)
 #pragma once
 #include <cstdint>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 namespace brl {
@@ -93,21 +96,25 @@ __device__ __forceinline__ float philox_uniform(uint64_t seed, uint32_t kind, ui
   return u01(lane_of(r, elem & 3u));
 }
 
-// integer threshold of a keep probability: u < T  <=>  (u + 0.5) * 2^-16 < keep   (u a 16-bit number)
+// integer threshold of a keep probability: u < T  <=>  (u + 0.5) * 2^-14 < keep   (u a 14-bit number)
 __host__ __device__ __forceinline__ uint32_t keep_threshold(float keep) {
-  const uint32_t t = (uint32_t)ceilf(keep * 65536.0f - 0.5f);
-  return t > 65535u ? 65535u : t;
+  const uint32_t t = (uint32_t)ceilf(keep * 16384.0f - 0.5f);
+  return t > 16383u ? 16383u : t;
 }
 // all sixteen decisions of block r: ev[i] / od[i] hold decisions 4i, 4i+2 / 4i+1, 4i+3 as all-ones 16-bit lanes
 struct KeepBits { uint32_t ev[4], od[4]; };
+__device__ __forceinline__ uint32_t keep_lt2(uint32_t w, uint32_t T2) {  // both 16-bit lanes: (lane & 0x3FFF) < T ? 0xFFFF : 0
+  const uint32_t h = w & 0x3FFF3FFFu;
+  return __hlt2_mask(*reinterpret_cast<const __half2*>(&h), *reinterpret_cast<const __half2*>(&T2));
+}
 __device__ __forceinline__ KeepBits keep_bits(const uint4& r, uint32_t T) {
   const uint32_t T2 = T | (T << 16);
   KeepBits k;
-  k.ev[0] = __vcmpltu2(r.x, T2); k.ev[1] = __vcmpltu2(r.y, T2); k.ev[2] = __vcmpltu2(r.z, T2); k.ev[3] = __vcmpltu2(r.w, T2);
-  k.od[0] = __vcmpltu2(__funnelshift_r(r.x, r.y, 8), T2);
-  k.od[1] = __vcmpltu2(__funnelshift_r(r.y, r.z, 8), T2);
-  k.od[2] = __vcmpltu2(__funnelshift_r(r.z, r.w, 8), T2);
-  k.od[3] = __vcmpltu2(__funnelshift_r(r.w, r.x, 8), T2);
+  k.ev[0] = keep_lt2(r.x, T2); k.ev[1] = keep_lt2(r.y, T2); k.ev[2] = keep_lt2(r.z, T2); k.ev[3] = keep_lt2(r.w, T2);
+  k.od[0] = keep_lt2(__funnelshift_r(r.x, r.y, 8), T2);
+  k.od[1] = keep_lt2(__funnelshift_r(r.y, r.z, 8), T2);
+  k.od[2] = keep_lt2(__funnelshift_r(r.z, r.w, 8), T2);
+  k.od[3] = keep_lt2(__funnelshift_r(r.w, r.x, 8), T2);
   return k;
 }
 // all-ones / all-zeros 16-bit lanes for the channel pair (2p, 2p + 1) of the block's sixteen channels, p = 0..7: channels

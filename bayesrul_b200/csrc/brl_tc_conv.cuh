@@ -96,7 +96,7 @@ __device__ __forceinline__ void act_injected(float (&v)[N], const float* bias, b
   }
 }
 // Native dropout masks work on the PACKED halves: the 1 / keep scale is applied in fp32 before the ReLU-and-pack convert
-// (relu(v * c) == relu(v) * c for c > 0), the keep decisions of a channel pair are the two 16-bit lanes of one SIMD
+// (relu(v * c) == relu(v) * c for c > 0), the keep decisions of a channel pair are the two 16-bit lanes of one packed-half
 // compare (brl_philox.cuh: keep_pair), so a pair is masked by ONE `and`.  One Philox block per 16 channels; N = 8 uses the
 // half of the block selected by ch0 (the neighbouring thread uses the other half).  Channels >= nvalid (zero columns and
 // conv1's constant-1 column that carries the next module's biases) are neither scaled nor masked.

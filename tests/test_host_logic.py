@@ -73,7 +73,7 @@ def test_dropout_decisions_rate_and_tie_path():
     r = O._philox_block(1234, O.KIND_DROPOUT, 3, 0, np.zeros(n, dtype=np.int64), blk, rounds=7)
     for keep in (0.93964075, 0.758563, 0.5, 240.5 / 256.0):
         T = O.keep_threshold(keep)
-        assert abs(T / 65536.0 - keep) <= 1.0 / 65536.0
+        assert abs(T / 16384.0 - keep) <= 1.0 / 16384.0
         rate = np.mean([O.keep_decisions(r, np.full(n, bi, dtype=np.uint32), keep).mean() for bi in range(16)])
         assert abs(rate - keep) < 4.0 * np.sqrt(keep * (1 - keep) / (16 * n)), (keep, rate)
     # decisions of the 16 byte positions are (empirically) uncorrelated
