@@ -1026,11 +1026,11 @@ int brl_predict_moments_host(brl_ctx* ctx, const float* x_host, int64_t B, int64
       if (guide == BRL_GUIDE_NORMAL) launch_sample_normal(mu, sigma, n.P, sw, eps, h.wsamp, nullptr, st);
       else launch_sample_radial(mu, sigma, n.P, sw, ctx->site_off_dev, nsites, ctx->max_site, eps,
                                 nref(&nz, nz.radial_r, KIND_RADIAL_R, 0), h.norms, h.wsamp, nullptr, st);
-      const char* err = tc_pack_weights(ctx->tc, h.wsamp, n.P, sw, h.images + s0 * (long long)tc_weight_image_bytes(), st);
+      const char* err = tc_pack_weights(ctx->tc, h.wsamp, n.P, sw, h.images + s0 * (long long)tc_weight_image_bytes(), p_dropout, st);
       if (err) return fail(BRL_ERR_UNSUPPORTED, err);
     }
   } else {
-    const char* err = tc_pack_weights(ctx->tc, mu, 0, 1, h.images, st);
+    const char* err = tc_pack_weights(ctx->tc, mu, 0, 1, h.images, p_dropout, st);
     if (err) return fail(BRL_ERR_UNSUPPORTED, err);
   }
   // ---- chunks of windows x sub-chunks of samples

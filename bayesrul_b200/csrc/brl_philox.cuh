@@ -107,8 +107,7 @@ __device__ __forceinline__ uint32_t keep_lt2(uint32_t w, uint32_t T2) {  // both
   const uint32_t h = w & 0x3FFF3FFFu;
   return __hlt2_mask(*reinterpret_cast<const __half2*>(&h), *reinterpret_cast<const __half2*>(&T2));
 }
-__device__ __forceinline__ KeepBits keep_bits(const uint4& r, uint32_t T) {
-  const uint32_t T2 = T | (T << 16);
+__device__ __forceinline__ KeepBits keep_bits_packed(const uint4& r, uint32_t T2) {  // T2 = T | T << 16
   KeepBits k;
   k.ev[0] = keep_lt2(r.x, T2); k.ev[1] = keep_lt2(r.y, T2); k.ev[2] = keep_lt2(r.z, T2); k.ev[3] = keep_lt2(r.w, T2);
   k.od[0] = keep_lt2(__funnelshift_r(r.x, r.y, 8), T2);
@@ -117,6 +116,7 @@ __device__ __forceinline__ KeepBits keep_bits(const uint4& r, uint32_t T) {
   k.od[3] = keep_lt2(__funnelshift_r(r.w, r.x, 8), T2);
   return k;
 }
+__device__ __forceinline__ KeepBits keep_bits(const uint4& r, uint32_t T) { return keep_bits_packed(r, T | (T << 16)); }
 // all-ones / all-zeros 16-bit lanes for the channel pair (2p, 2p + 1) of the block's sixteen channels, p = 0..7: channels
 // 4i, 4i+1 take decisions 4i, 4i+2 (the lanes of ev[i]); channels 4i+2, 4i+3 take decisions 4i+1, 4i+3 (the lanes of od[i])
 __device__ __forceinline__ uint32_t keep_pair(const KeepBits& k, uint32_t p) {

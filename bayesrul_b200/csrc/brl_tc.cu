@@ -97,6 +97,9 @@ struct PackArgs {
   long long w_stride;  // P, or 0 when the weights are shared by all samples
   unsigned char* blob;
   long long off[12][2];
+  // inverted dropout's 1 / keep of the sites behind module 1 and module 2 (MC-dropout: 1 / (1 - p / 4), else 1), folded into the
+  // weights that read those activations: the module-2 1x1 convs and the fc layer (their bias entries are not scaled)
+  float inv4;
 };
 
 __device__ __forceinline__ void put_h(unsigned char* img, int byte_off, float v) {
@@ -142,7 +145,7 @@ __global__ void tc_pack_kernel(const PackArgs a) {
     const int co = n < 16 ? n : n < 80 ? n - 16 : n - 80;
     const int grp = k >> 5, c = k & 31;
     float v = 0.f;
-    if (c < 27) v = w[a.off[layer][0] + (long long)co * 108 + grp * 27 + c];
+    if (c < 27) v = a.inv4 * w[a.off[layer][0] + (long long)co * 108 + grp * 27 + c];
     else if (k == 27) v = w[a.off[layer][1] + co];  // bias on M1's constant channel
     put_h(blob, WI_B1 + (k >> 3) * (144 * 16) + n * 16 + (k & 7) * 2, v);
     return;
@@ -151,7 +154,7 @@ __global__ void tc_pack_kernel(const PackArgs a) {
   if (j < N_B4) {
     const int n = j / 128, k = j % 128, grp = k >> 5, c = k & 31;
     float v = 0.f;
-    if (c < 27) v = w[a.off[9][0] + (long long)n * 108 + grp * 27 + c];
+    if (c < 27) v = a.inv4 * w[a.off[9][0] + (long long)n * 108 + grp * 27 + c];
     else if (k == 27) v = w[a.off[9][1] + n];
     put_h(blob, WI_B4 + (k >> 3) * 512 + n * 16 + (k & 7) * 2, v);
     return;
@@ -185,7 +188,7 @@ __global__ void tc_pack_kernel(const PackArgs a) {
     float v = 0.f;
     if (kp < 2400) {
       const int cb = kp / 240, r = kp % 240, t = r >> 3, c = cb * 8 + (r & 7);
-      v = w[a.off[10][0] + (long long)n * 2400 + c * 30 + t];
+      v = a.inv4 * w[a.off[10][0] + (long long)n * 2400 + c * 30 + t];
     }
     put_h(blob, BLOB_FC + (kp >> 3) * 1024 + n * 16 + (kp & 7) * 2, v);
     return;
@@ -413,11 +416,13 @@ size_t tc_workspace_bytes(const TcState* s, long long B, long long S) {
 
 size_t tc_weight_image_bytes() { return BLOB_BYTES; }
 
+static float inv_keep4(float p_dropout) { return p_dropout > 0.f ? 1.0f / (1.0f - p_dropout * 0.25f) : 1.0f; }
+
 const char* tc_pack_weights(TcState* st, const float* weights, long long w_sample_stride, long long n, unsigned char* images,
-                            cudaStream_t stream) {
+                            float p_dropout, cudaStream_t stream) {
   if (!tc_available(st)) return "bayesrul_b200: tensor-core engine is implemented for the Inception net only";
   PackArgs pa;
-  pa.w = weights; pa.w_stride = w_sample_stride; pa.blob = images;
+  pa.w = weights; pa.w_stride = w_sample_stride; pa.blob = images; pa.inv4 = inv_keep4(p_dropout);
   for (int l = 0; l < 12; ++l) { pa.off[l][0] = st->loff[l][0]; pa.off[l][1] = st->loff[l][1]; }
   tc_pack_kernel<<<dim3((PACK_THREADS_TOTAL + 255) / 256, (unsigned)n), 256, 0, stream>>>(pa);
   count_launch(1);
@@ -444,7 +449,7 @@ const char* tc_forward(TcState* st, const float* x, long long B, long long S, co
     blob = const_cast<unsigned char*>(prepacked);
   } else {
     PackArgs pa;
-    pa.w = weights; pa.w_stride = w_sample_stride; pa.blob = blob;
+    pa.w = weights; pa.w_stride = w_sample_stride; pa.blob = blob; pa.inv4 = inv_keep4(p_dropout);
     for (int l = 0; l < 12; ++l) { pa.off[l][0] = st->loff[l][0]; pa.off[l][1] = st->loff[l][1]; }
     tc_pack_kernel<<<dim3((PACK_THREADS_TOTAL + 255) / 256, (unsigned)nblob), 256, 0, stream>>>(pa);
     count_launch(1);
@@ -465,6 +470,17 @@ const char* tc_forward(TcState* st, const float* x, long long B, long long S, co
   ca.B = (int)B; ca.S = (int)S; ca.ntile4 = (int)nt4; ca.ntile128 = (int)nt128;
   ca.keep4 = drop ? 1.0f - p_dropout * 0.25f : 1.0f;
   for (int l = 0; l < 12; ++l) ca.drop[l] = nr(l);
+  {  // key of the native dropout masks (brl_tc_conv.cuh: philox7_rk)
+    const unsigned long long seed = noise ? noise->seed : 0ull;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 7; ++r) { ca.rk[2 * r] = k0; ca.rk[2 * r + 1] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+    ca.sample0 = noise ? (uint32_t)noise->sample0 : 0u;
+    ca.window0 = noise ? (uint32_t)noise->window0 : 0u;
+    ca.inj_mask = 0u;
+    ca.keepT2 = keep_threshold(ca.keep4) * 0x10001u;
+    for (int l = 0; l < 12; ++l)
+      if (ca.drop[l].ptr) ca.inj_mask |= 1u << l;
+  }
   ca.status = st->status;
   ca.trace = st->trace;
   const long long items = S * ((nt4 + 1) / 2);

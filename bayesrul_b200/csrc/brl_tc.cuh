@@ -23,7 +23,9 @@ const char* tc_forward(TcState*, const float* x, long long B, long long S, const
                        float p_dropout, const brl_noise* noise, float* out, void* ws, size_t ws_bytes, bool pack_x,
                        cudaStream_t st, const unsigned char* prepacked = nullptr);
 size_t tc_weight_image_bytes();  // bytes of one sample's fp16 weight image
-// fp32 weights [n, P] (or one shared [P] vector: n = 1) -> n fp16 weight images at `images` (tc_weight_image_bytes() apart)
+// fp32 weights [n, P] (or one shared [P] vector: n = 1) -> n fp16 weight images at `images` (tc_weight_image_bytes() apart).
+// The images depend on p_dropout (inverted dropout's 1 / keep is folded into the weights behind a dropout site): pass the value
+// the images will be used with in tc_forward.
 const char* tc_pack_weights(TcState*, const float* weights, long long w_sample_stride, long long n, unsigned char* images,
-                            cudaStream_t st);
+                            float p_dropout, cudaStream_t st);
 }  // namespace brl

@@ -34,6 +34,12 @@ struct ConvArgs {
   int B, S, ntile4, ntile128;
   float keep4;                // dropout keep of the branch sites (1 = off)
   NoiseRef drop[12];
+  // native dropout masks: the seven Philox round keys (the same for every thread: they ride in the kernel parameters, i.e. the
+  // constant bank, instead of being re-derived by two adds per round per block), the sample / window origin of the key and
+  // one bit per site that has an injected mask instead
+  uint32_t rk[14];
+  uint32_t sample0, window0, inj_mask;
+  uint32_t keepT2;            // keep_threshold(keep4) in both 16-bit lanes
   int* status;
   long long* trace;  // debug: CTA 0 time stamps, [16 items][64 slots] (nullptr = off)
 };
@@ -81,37 +87,44 @@ __device__ __forceinline__ void act_plain(float (&v)[N], const float* bias) {
   for (int j = 0; j < N; ++j) v[j] = fmaxf(BIAS ? v[j] + bias[j] : v[j], 0.f);
 }
 // Injected dropout masks (parity tests): ReLU (+bias) and the mask of site `layer` on N fp32 accumulator columns = channels
-// ch0.. of a site with `nvalid` channels, at time step t
+// ch0.. of a site with `nvalid` channels, at time step t.  The 1 / keep scale of inverted dropout is NOT applied here: it is folded
+// into the weights of the layer that reads the activation (tc_pack_kernel), where it costs nothing.
 template <bool BIAS, int N>
 __device__ __forceinline__ void act_injected(float (&v)[N], const float* bias, bool live, const ConvArgs& a, int layer, int s, int gw,
                                              int t, int ch0, int nvalid) {
 #pragma unroll
   for (int j = 0; j < N; ++j) v[j] = fmaxf(BIAS ? v[j] + bias[j] : v[j], 0.f);
   if (live) {
-    const float inv = 1.0f / a.keep4;
     const float* m = a.drop[layer].ptr + ((long long)s * a.B + gw) * (nvalid * 30) + t;
 #pragma unroll
     for (int j = 0; j < N; ++j)
-      if (ch0 + j < nvalid) v[j] = m[(ch0 + j) * 30] != 0.f ? v[j] * inv : 0.f;
+      if (ch0 + j < nvalid) v[j] = m[(ch0 + j) * 30] != 0.f ? v[j] : 0.f;
   }
 }
-// Native dropout masks work on the PACKED halves: the 1 / keep scale is applied in fp32 before the ReLU-and-pack convert
-// (relu(v * c) == relu(v) * c for c > 0), the keep decisions of a channel pair are the two 16-bit lanes of one packed-half
-// compare (brl_philox.cuh: keep_pair), so a pair is masked by ONE `and`.  One Philox block per 16 channels; N = 8 uses the
-// half of the block selected by ch0 (the neighbouring thread uses the other half).  Channels >= nvalid (zero columns and
-// conv1's constant-1 column that carries the next module's biases) are neither scaled nor masked.
+// Philox4x32-7 with the round keys read from the kernel parameters (bit-identical to brl_philox.cuh: philox_block_mask)
+__device__ __forceinline__ uint4 philox7_rk(const ConvArgs& a, uint32_t block, uint32_t window, uint32_t sample, uint32_t site) {
+  uint4 c = make_uint4(block, window, sample, (KIND_DROPOUT << 24) | site);
+#pragma unroll
+  for (int r = 0; r < 7; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ a.rk[2 * r], lo1, hi0 ^ c.w ^ a.rk[2 * r + 1], lo0);
+  }
+  return c;
+}
+// Native dropout masks work on the PACKED halves: the keep decisions of a channel pair are the two 16-bit lanes of one packed-half
+// compare (brl_philox.cuh: keep_pair), so a pair is masked by ONE `and` behind the ReLU-and-pack convert.  One Philox block per 16
+// channels; N = 8 uses the half of the block selected by ch0 (the neighbouring thread uses the other half).  Channels >= nvalid
+// (zero columns and conv1's constant-1 column that carries the next module's biases) are not masked.  No 1 / keep scale (see above).
 template <bool BIAS, int N>
 __device__ __forceinline__ void act_drop_packed(float (&v)[N], const float* bias, bool live, const ConvArgs& a, int layer, int s, int gw,
                                                 int t, int ch0, int nvalid, uint32_t (&h)[N / 2]) {
-  const NoiseRef& nz = a.drop[layer];
-  const float inv = 1.0f / a.keep4;
+  if (BIAS) {
 #pragma unroll
-  for (int j = 0; j < N; ++j) {
-    if (BIAS) v[j] += bias[j];
-    if (ch0 + j < nvalid) v[j] *= inv;
+    for (int j = 0; j < N; ++j) v[j] += bias[j];
   }
   const uint32_t e0 = (uint32_t)t * (uint32_t)((nvalid + 15) & ~15) + (uint32_t)ch0;
-  KeepBits kb = keep_bits(philox_block_mask(nz.seed, nz.kind, nz.site, nz.sample0 + s, nz.window0 + gw, e0 >> 4), keep_threshold(a.keep4));
+  KeepBits kb = keep_bits_packed(philox7_rk(a, e0 >> 4, a.window0 + gw, a.sample0 + s, (uint32_t)layer), a.keepT2);
   if (N < 16 && (e0 & 8u)) {  // upper half of the block (warp-uniform): channel pairs 4..7 move to 0..3
     kb.ev[0] = kb.ev[2]; kb.ev[1] = kb.ev[3]; kb.od[0] = kb.od[2]; kb.od[1] = kb.od[3];
   }
@@ -154,7 +167,7 @@ template <bool DROP>
 __device__ __forceinline__ void finish16(float (&v)[16], bool live, const ConvArgs& a, int layer, int s, int gw, int t,
                                          int ch0, int nvalid, uint4& lo, uint4& hi) {
   if (DROP) {
-    if (a.drop[layer].ptr) {
+    if ((a.inj_mask >> layer) & 1u) {
       act_injected<false, 16>(v, nullptr, live, a, layer, s, gw, t, ch0, nvalid);
       lo = pack8(v, live);
       hi = pack8(v + 8, live);
@@ -503,7 +516,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) tc_conv_kernel(const ConvArgs
         tc_fence_before();
         if (DROP) {
           uint4 o4;
-          if (!a.drop[q < 2 ? 6 : 8].ptr) {
+          if (!((a.inj_mask >> (q < 2 ? 6 : 8)) & 1u)) {
             uint32_t h[4];
             act_drop_packed<true, 8>(out, sbias + 304 + q * 8, live, a, q < 2 ? 6 : 8, s, gw, t, (q & 1) * 8, 16, h);
             o4 = make_uint4(h[0], h[1], h[2], h[3]);
