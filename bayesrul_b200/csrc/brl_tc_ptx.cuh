@@ -9,7 +9,10 @@ namespace brl {
 // waits suspend in hardware (time hint) instead of spinning: a spinning issuer / loader warp steals issue slots from the
 // epilogue warps of its scheduler.  SPIN_LIMIT x hint bounds a wait to ~1.3 s before it reports a protocol time-out.
 constexpr uint32_t SPIN_LIMIT = 1u << 16;
-constexpr uint32_t WAIT_HINT_NS = 20000u;
+#ifndef BRL_WAIT_HINT_NS
+#define BRL_WAIT_HINT_NS 20000u
+#endif
+constexpr uint32_t WAIT_HINT_NS = BRL_WAIT_HINT_NS;
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
