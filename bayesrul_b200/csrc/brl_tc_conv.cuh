@@ -116,7 +116,8 @@ __device__ __forceinline__ uint4 philox7_rk(const ConvArgs& a, uint32_t block, u
 // compare (brl_philox.cuh: keep_pair), so a pair is masked by ONE `and` behind the ReLU-and-pack convert.  One Philox block per 16
 // channels; N = 8 uses the half of the block selected by ch0 (the neighbouring thread uses the other half).  Channels >= nvalid
 // (zero columns and conv1's constant-1 column that carries the next module's biases) are not masked.  No 1 / keep scale (see above).
-template <bool BIAS, int N>
+// ALLVALID: every channel ch0 .. ch0 + N - 1 is a real channel of the site (module-2 sites), so the nvalid tests fold away.
+template <bool BIAS, int N, bool ALLVALID = false>
 __device__ __forceinline__ void act_drop_packed(float (&v)[N], const float* bias, bool live, const ConvArgs& a, int layer, int s, int gw,
                                                 int t, int ch0, int nvalid, uint32_t (&h)[N / 2]) {
   if (BIAS) {
@@ -124,16 +125,20 @@ __device__ __forceinline__ void act_drop_packed(float (&v)[N], const float* bias
     for (int j = 0; j < N; ++j) v[j] += bias[j];
   }
   const uint32_t e0 = (uint32_t)t * (uint32_t)((nvalid + 15) & ~15) + (uint32_t)ch0;
-  KeepBits kb = keep_bits_packed(philox7_rk(a, e0 >> 4, a.window0 + gw, a.sample0 + s, (uint32_t)layer), a.keepT2);
+  // dead rows (time steps 30 / 31, windows >= B) must store zeros: with threshold 0 every decision is "drop"; the channels >= nvalid that
+  // the masks below force to "keep" are exact zeros in a dead row anyway (no input, no tap shift reaches conv1's constant column)
+  KeepBits kb = keep_bits_packed(philox7_rk(a, e0 >> 4, a.window0 + gw, a.sample0 + s, (uint32_t)layer), live ? a.keepT2 : 0u);
   if (N < 16 && (e0 & 8u)) {  // upper half of the block (warp-uniform): channel pairs 4..7 move to 0..3
     kb.ev[0] = kb.ev[2]; kb.ev[1] = kb.ev[3]; kb.od[0] = kb.od[2]; kb.od[1] = kb.od[3];
   }
 #pragma unroll
   for (int p = 0; p < N / 2; ++p) {
     uint32_t m = keep_pair(kb, p);
-    if (ch0 + 2 * p + 1 >= nvalid) m |= 0xFFFF0000u;
-    if (ch0 + 2 * p >= nvalid) m = 0xFFFFFFFFu;
-    h[p] = live ? (pack_relu_h2(v[2 * p], v[2 * p + 1]) & m) : 0u;
+    if (!ALLVALID) {
+      if (ch0 + 2 * p + 1 >= nvalid) m |= 0xFFFF0000u;
+      if (ch0 + 2 * p >= nvalid) m = 0xFFFFFFFFu;
+    }
+    h[p] = pack_relu_h2(v[2 * p], v[2 * p + 1]) & m;
   }
 }
 __device__ __forceinline__ uint4 pack8(const float* v, bool live) {
@@ -163,7 +168,7 @@ __device__ __forceinline__ uint4 relu_pack8(const float* v, bool live) {
   return make_uint4(r[0], r[1], r[2], r[3]);
 }
 // 16 accumulator columns -> two 16-byte fp16 chunks (ReLU, optional dropout of site `layer`)
-template <bool DROP>
+template <bool DROP, bool ALLVALID = false>
 __device__ __forceinline__ void finish16(float (&v)[16], bool live, const ConvArgs& a, int layer, int s, int gw, int t,
                                          int ch0, int nvalid, uint4& lo, uint4& hi) {
   if (DROP) {
@@ -173,7 +178,7 @@ __device__ __forceinline__ void finish16(float (&v)[16], bool live, const ConvAr
       hi = pack8(v + 8, live);
     } else {
       uint32_t h[8];
-      act_drop_packed<false, 16>(v, nullptr, live, a, layer, s, gw, t, ch0, nvalid, h);
+      act_drop_packed<false, 16, ALLVALID>(v, nullptr, live, a, layer, s, gw, t, ch0, nvalid, h);
       lo = make_uint4(h[0], h[1], h[2], h[3]);
       hi = make_uint4(h[4], h[5], h[6], h[7]);
     }
@@ -474,7 +479,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) tc_conv_kernel(const ConvArgs
         arrive_ready(BAR_READY_B, k);  // every TMEM column this thread needs is in registers: phase C may start now
         if (q < 3) {
           uint4 lo, hi;
-          finish16<DROP>(acc[2], live, a, q == 0 ? 4 : 9, s, gw, t, q == 2 ? 16 : 0, q == 0 ? 16 : 32, lo, hi);
+          finish16<DROP, true>(acc[2], live, a, q == 0 ? 4 : 9, s, gw, t, q == 2 ? 16 : 0, q == 0 ? 16 : 32, lo, hi);
           const int fc = q == 0 ? 0 : q == 1 ? 6 : 8;
           if (BRL_FEAT_LIVE(live)) {
             st_global_cs(frow + fc * 480, lo);
@@ -518,7 +523,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) tc_conv_kernel(const ConvArgs
           uint4 o4;
           if (!((a.inj_mask >> (q < 2 ? 6 : 8)) & 1u)) {
             uint32_t h[4];
-            act_drop_packed<true, 8>(out, sbias + 304 + q * 8, live, a, q < 2 ? 6 : 8, s, gw, t, (q & 1) * 8, 16, h);
+            act_drop_packed<true, 8, true>(out, sbias + 304 + q * 8, live, a, q < 2 ? 6 : 8, s, gw, t, (q & 1) * 8, 16, h);
             o4 = make_uint4(h[0], h[1], h[2], h[3]);
           } else {
             act_injected<true, 8>(out, sbias + 304 + q * 8, live, a, q < 2 ? 6 : 8, s, gw, t, (q & 1) * 8, 16);
