@@ -207,13 +207,14 @@ class SVI:
         res = self.bnn._elbo(x, y, particles=self.loss.num_particles, analytic_kl=self.loss.analytic_kl, grads=grads)
         self.last = res
         sc = res["scalars"]
+        # (device scalar, host factor): the factor is applied AFTER the .item() read -- a device multiply would be one more launch
+        # on the critical path of every step
         if self.no_obs:  # unscaled KL (A.6 svi_no_obs)
-            return res, sc[2] * self.guide_scale
-        ref_c = res["c"]
-        return res, sc[0] * (self.model_scale / ref_c)
+            return res, sc[2], float(self.guide_scale)
+        return res, sc[0], float(self.model_scale / res["c"])
 
     def step(self, x, y=None) -> float:
-        res, loss = self._run(x, y, True)
+        res, loss, factor = self._run(x, y, True)
         k = self.model_scale / res["c"]
         g_mu, g_ls = res["grad_mu"], res["grad_log_sigma"]
         if k != 1.0:
@@ -225,10 +226,10 @@ class SVI:
             else:
                 self.optim.step_flat(self.bnn.engine, [guide.loc, guide.log_scale], [g_mu, g_ls], names=["loc", "log_scale"])
                 guide.refresh()
-        return float(loss.item())  # device boundary #2 of the reference (.item() sync every step)
+        return float(loss.item()) * factor  # device boundary #2 of the reference (.item() sync every step)
 
     def evaluate_loss(self, x, y=None) -> float:
         if y is None and self.no_obs and self.bnn._last_kl is not None:
             return float(self.bnn._last_kl.item())  # KL does not depend on the batch for analytic KL
-        res, loss = self._run(x, y if y is not None else torch.zeros(x.shape[0], device=x.device), False)
-        return float(loss.item())
+        res, loss, factor = self._run(x, y if y is not None else torch.zeros(x.shape[0], device=x.device), False)
+        return float(loss.item()) * factor
