@@ -392,7 +392,7 @@ def main():
                            "roofline": {"bound": "tensor", "achieved": ach, "peak": pk_t["tf_burst"], "unit": "TFLOP/s",
                                         "frac": ach / pk_t["tf_burst"], "traffic": None, "kernel": "svi.step (whole step)",
                                         "note": f"{F_TRAIN_LRT} algorithmic GEMM FLOPs per window-particle x {particles} x {B_TRAIN} windows / "
-                                                "step time; a 256-window minibatch is 3.3 GFLOP -- the step is a chain of ~25 latency-bound "
+                                                "step time; a 256-window minibatch is 3.3 GFLOP -- the step is a chain of 16 latency-bound "
                                                 "launches, not tensor-pipe throughput (profiles/r02_ncu_train_fused.txt); peak = burst bf16 "
                                                 f"cuBLAS of {pk_t['src']} MEASURED_PEAKS.json"},
                            "includes": "ELBO forward + backward + KL + gradient finalisation (CUDA-graph replay) + ClippedAdam on (loc, log scale)"
