@@ -442,7 +442,23 @@ __global__ void moments_update_kernel(const float* __restrict__ out, long long S
   for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
     float n = 0.f, mean = 0.f, m2 = 0.f, s2 = 0.f;
     if (!first) { n = state[b]; mean = state[B + b]; m2 = state[2 * B + b]; s2 = state[3 * B + b]; }
-    for (long long s = 0; s < S; ++s) {
+    // the loads do not depend on the Welford chain: batches of 16 are issued ahead of it (the loop was one DRAM round trip per MC
+    // sample: 52 us for S = 100); the arithmetic and its order are unchanged
+    long long s = 0;
+    for (; s + 16 <= S; s += 16) {
+      float2 o[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) o[u] = __ldcs(reinterpret_cast<const float2*>(out + ((s + u) * B + b) * 2));
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        n += 1.f;
+        const float d = o[u].x - mean;
+        mean += d / n;
+        m2 = fmaf(d, o[u].x - mean, m2);
+        s2 = fmaf(o[u].y, o[u].y, s2);
+      }
+    }
+    for (; s < S; ++s) {
       const float2 o = *reinterpret_cast<const float2*>(out + (s * B + b) * 2);
       n += 1.f;
       const float d = o.x - mean;
