@@ -964,8 +964,11 @@ static bool host_carve(const brl_ctx* ctx, Carve& c, long long B, long long S, i
 
 int64_t brl_workspace_bytes_host(const brl_ctx* ctx, int64_t B, int64_t S, int engine) {
   if (!ctx || B <= 0 || S <= 0) return BRL_ERR_INVALID;
-  if (engine != BRL_ENGINE_TC_FP16 || !tc_available(ctx->tc))
-    return brl_workspace_bytes(ctx, B, std::min<int64_t>(S, 16), 0, BRL_ENGINE_SIMT_FP32) + (B * 540 + 4 * B) * (int64_t)sizeof(float) + 1024;
+  if (engine != BRL_ENGINE_TC_FP16 || !tc_host_pipeline(ctx->tc)) {
+    const bool tc = engine == BRL_ENGINE_TC_FP16 && tc_available(ctx->tc);  // (Linear net: one copy, then the device entry point)
+    return brl_workspace_bytes(ctx, B, std::min<int64_t>(S, tc ? 128 : 16), 0, tc ? BRL_ENGINE_TC_FP16 : BRL_ENGINE_SIMT_FP32) +
+           (B * 540 + 4 * B) * (int64_t)sizeof(float) + 1024;
+  }
   size_t need = 0;
   for (int native = 0; native < 2; ++native) {  // injected noise runs as ONE window chunk (larger per-chunk buffers): size for both
     Carve c(nullptr, 0);
@@ -987,15 +990,16 @@ int brl_predict_moments_host(brl_ctx* ctx, const float* x_host, int64_t B, int64
   cudaStream_t st = (cudaStream_t)stream;
   const NetSpec& n = *ctx->net;
   const size_t xbytes = sizeof(float) * (size_t)B * 540;
-  if (engine != BRL_ENGINE_TC_FP16 || !tc_available(ctx->tc)) {
-    // per-layer engine: one copy, then the device entry point on the rest of the workspace
+  if (engine != BRL_ENGINE_TC_FP16 || !tc_host_pipeline(ctx->tc)) {
+    // per-layer engine (or the Linear net's tensor-core engine): one copy, then the device entry point on the rest of the workspace
+    const int dev_engine = (engine == BRL_ENGINE_TC_FP16 && tc_available(ctx->tc)) ? BRL_ENGINE_TC_FP16 : BRL_ENGINE_SIMT_FP32;
     Carve c(workspace, workspace_bytes);
     float* x_dev = c.take<float>(B * 540);
     float* res = c.take<float>(4 * B);
     if (!c.ok) return fail(BRL_ERR_WORKSPACE, "brl_predict_moments_host: workspace too small");
     BRL_CUDA(cudaMemcpyAsync(x_dev, x_host, xbytes, cudaMemcpyHostToDevice, st));
     int rc = brl_predict_moments(ctx, x_dev, B, S, guide, mu, sigma, p_dropout, noise, res, res + B, res + 2 * B, res + 3 * B,
-                                 BRL_ENGINE_SIMT_FP32, (char*)workspace + c.used, workspace_bytes - c.used, stream);
+                                 dev_engine, (char*)workspace + c.used, workspace_bytes - c.used, stream);
     if (rc) return rc;
     BRL_CUDA(cudaMemcpyAsync(out_host, res, sizeof(float) * 4 * B, cudaMemcpyDeviceToHost, st));
     return BRL_OK;

@@ -342,6 +342,8 @@ __global__ void __launch_bounds__(192, 1) tc_fc_kernel(const FcArgs a, const __g
   if (warp == 1) tmem_dealloc(tmem, 128);
 }
 
+#include "brl_tc_linear.cuh"
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -350,9 +352,9 @@ TcState* tc_create(int net) {
   st->net = net;
   st->status = nullptr;
   st->sm_count = 148;
-  if (net != BRL_NET_INCEPTION) return st;
+  if (net != BRL_NET_INCEPTION && net != BRL_NET_LINEAR) return st;
   const NetSpec& n = get_net(net);
-  for (int l = 0; l < 12; ++l) { st->loff[l][0] = n.layers[l].w_off; st->loff[l][1] = n.layers[l].b_off; }
+  for (int l = 0; l < (net == BRL_NET_LINEAR ? 5 : 12); ++l) { st->loff[l][0] = n.layers[l].w_off; st->loff[l][1] = n.layers[l].b_off; }
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&st->sm_count, cudaDevAttrMultiProcessorCount, dev);
@@ -362,6 +364,7 @@ TcState* tc_create(int net) {
   cudaFuncSetAttribute(tc_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM);
   cudaFuncSetAttribute(tc_fc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM);
   cudaFuncSetAttribute(tc_fc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM);
+  cudaFuncSetAttribute(tcl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lin::SMEM);
   return st;
 }
 void tc_destroy(TcState* s) {
@@ -403,13 +406,16 @@ static void tc_time_end(TcState* st, int k, cudaStream_t stream) {
   if (st->timing) cudaEventRecord(st->evs[k][st->ev_used[k]++].second, stream);
 }
 void tc_trace(TcState* s, long long* buf) { s->trace = buf; }
-bool tc_available(const TcState* s) { return s && s->net == BRL_NET_INCEPTION && s->status != nullptr; }
+bool tc_available(const TcState* s) { return s && (s->net == BRL_NET_INCEPTION || s->net == BRL_NET_LINEAR) && s->status != nullptr; }
+bool tc_host_pipeline(const TcState* s) { return tc_available(s) && s->net == BRL_NET_INCEPTION; }
 int tc_status(const TcState* s) {
   int v = -1;
   if (s && s->status) cudaMemcpy(&v, s->status, sizeof(int), cudaMemcpyDeviceToHost);
   return v;
 }
 size_t tc_workspace_bytes(const TcState* s, long long B, long long S) {
+  if (s && s->net == BRL_NET_LINEAR)  // fp16 window matrix | weight images
+    return (size_t)(((B + 127) / 128) * 128 * lin::KX * 2 + S * (long long)lin::IMG_BYTES + 2048);
   const long long nt128 = (B + 127) / 128, npair = ((B + 3) / 4 + 1) / 2;
   return (size_t)(S * (long long)BLOB_BYTES + S * nt128 * 128 * FEAT_ROW_BYTES + 2 * npair * XIMG_TILE_BYTES + 2048);
 }
@@ -420,7 +426,7 @@ static float inv_keep4(float p_dropout) { return p_dropout > 0.f ? 1.0f / (1.0f 
 
 const char* tc_pack_weights(TcState* st, const float* weights, long long w_sample_stride, long long n, unsigned char* images,
                             float p_dropout, cudaStream_t stream) {
-  if (!tc_available(st)) return "bayesrul_b200: tensor-core engine is implemented for the Inception net only";
+  if (!tc_host_pipeline(st)) return "bayesrul_b200: prepacked weight images are implemented for the Inception net only";
   PackArgs pa;
   pa.w = weights; pa.w_stride = w_sample_stride; pa.blob = images; pa.inv4 = inv_keep4(p_dropout);
   for (int l = 0; l < 12; ++l) { pa.off[l][0] = st->loff[l][0]; pa.off[l][1] = st->loff[l][1]; }
@@ -429,11 +435,66 @@ const char* tc_pack_weights(TcState* st, const float* weights, long long w_sampl
   return nullptr;
 }
 
+typedef CUresult (*TmaEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// resolved through the runtime so that the library carries no link-time dependency on libcuda.so
+static TmaEncodeFn tma_encode_fn() {
+  static TmaEncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return nullptr;
+    encode = reinterpret_cast<TmaEncodeFn>(fn);
+  }
+  return encode;
+}
+
+// Linear net: windows -> fp16 matrix, weights -> fp16 images, one persistent launch (brl_tc_linear.cuh)
+static const char* tcl_forward(TcState* st, const float* x, long long B, long long S, const float* weights, long long w_sample_stride,
+                               float p_dropout, float* out, void* ws, bool pack_x, cudaStream_t stream) {
+  if (p_dropout > 0.f) return "bayesrul_b200: the Linear net's tensor-core engine has no dropout path (use engine 'simt')";
+  const long long nt128 = (B + 127) / 128, Bpad = nt128 * 128;
+  unsigned char* x16 = reinterpret_cast<unsigned char*>(ws);
+  unsigned char* img = x16 + ((Bpad * lin::KX * 2 + 255) / 256) * 256;
+  if (pack_x) {
+    tcl_packx_kernel<<<(unsigned)((Bpad * (lin::KX / 8) + 255) / 256), 256, 0, stream>>>(x, x16, (int)B, (int)Bpad);
+    count_launch(1);
+  }
+  LinPackArgs pa;
+  pa.w = weights; pa.w_stride = w_sample_stride; pa.img = img;
+  for (int l = 0; l < 5; ++l) { pa.w_off[l] = st->loff[l][0]; pa.b_off[l] = st->loff[l][1]; }
+  const long long nimg = w_sample_stride ? S : 1;
+  tcl_pack_kernel<<<dim3((lin::IMG_HALVES + lin::TAIL_FLOATS + 255) / 256, (unsigned)nimg), 256, 0, stream>>>(pa);
+  CUtensorMap xmap;
+  {
+    TmaEncodeFn encode = tma_encode_fn();
+    if (!encode) return "bayesrul_b200: cuTensorMapEncodeTiled is not available from this driver";
+    const cuuint64_t gdim[2] = {(cuuint64_t)lin::KX, (cuuint64_t)Bpad};
+    const cuuint64_t gstr[1] = {(cuuint64_t)lin::KX * 2};
+    const cuuint32_t box[2] = {64, 128};
+    const cuuint32_t estr[2] = {1, 1};
+    if (encode(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, x16, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return "bayesrul_b200: cuTensorMapEncodeTiled failed for the window matrix";
+  }
+  LinArgs la;
+  la.img = img; la.img_stride = w_sample_stride ? lin::IMG_BYTES : 0; la.out = out;
+  la.B = (int)B; la.S = (int)S; la.ntile128 = (int)nt128; la.status = st->status;
+  const int grid = (int)std::min<long long>(st->sm_count, S * nt128);
+  tcl_kernel<<<grid, 128, lin::SMEM, stream>>>(la, xmap);
+  count_launch(2);
+  return nullptr;
+}
+
 const char* tc_forward(TcState* st, const float* x, long long B, long long S, const float* weights, long long w_sample_stride,
                        float p_dropout, const brl_noise* noise, float* out, void* ws, size_t ws_bytes, bool pack_x,
                        cudaStream_t stream, const unsigned char* prepacked) {
-  if (!tc_available(st)) return "bayesrul_b200: tensor-core engine is implemented for the Inception net only";
+  if (!tc_available(st)) return "bayesrul_b200: tensor-core engine is implemented for the Inception and Linear nets only";
   if (ws_bytes < tc_workspace_bytes(st, B, S)) return "bayesrul_b200: workspace too small for the tensor-core engine";
+  if (st->net == BRL_NET_LINEAR) {
+    if (prepacked) return "bayesrul_b200: prepacked weight images are implemented for the Inception net only";
+    return tcl_forward(st, x, B, S, weights, w_sample_stride, p_dropout, out, ws, pack_x, stream);
+  }
   const long long nt128 = (B + 127) / 128, nt4 = (B + 3) / 4;
   // workspace: window images (independent of S, so later sample chunks of a batch find them again) | blobs | features
   const int ntx = (int)((nt4 + 1) / 2 * 2);
@@ -505,18 +566,8 @@ const char* tc_forward(TcState* st, const float* x, long long B, long long S, co
     const cuuint64_t gstr[1] = {FEAT_ROW_BYTES};
     const cuuint32_t box[2] = {FC_BK, 128};
     const cuuint32_t estr[2] = {1, 1};
-    // resolved through the runtime so that the library carries no link-time dependency on libcuda.so (it must load, and
-    // export every symbol, on a machine without a driver)
-    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static EncodeFn encode = nullptr;
-    if (!encode) {
-      void* fn = nullptr;
-      cudaDriverEntryPointQueryResult qres;
-      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
-        return "bayesrul_b200: cuTensorMapEncodeTiled is not available from this driver";
-      encode = reinterpret_cast<EncodeFn>(fn);
-    }
+    TmaEncodeFn encode = tma_encode_fn();  // (no link-time dependency on libcuda.so: the library must load without a driver)
+    if (!encode) return "bayesrul_b200: cuTensorMapEncodeTiled is not available from this driver";
     const CUresult r = encode(&fmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, feat, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return "bayesrul_b200: cuTensorMapEncodeTiled failed for the feature tensor";

@@ -9,7 +9,8 @@ namespace brl {
 struct TcState;
 TcState* tc_create(int net);
 void tc_destroy(TcState*);
-bool tc_available(const TcState*);
+bool tc_available(const TcState*);      // Inception: fused conv + fc kernels; Linear: brl_tc_linear.cuh
+bool tc_host_pipeline(const TcState*);  // chunked host-batch pipeline with prepacked weight images (Inception only)
 int tc_status(const TcState*);  // 0 ok; else the code of the first mbarrier wait that timed out (synchronises)
 void tc_timing(TcState*, bool enable);
 void tc_timing_read(TcState*, double ms[2], long long launches[2]);  // [conv, fc]; synchronises the recorded events

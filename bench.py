@@ -517,6 +517,28 @@ def main():
         deepens = {"window_members_per_s": world * B_PRED * 5 * 5 / td, "ms_per_step": 1e3 * td / 5, "members": 5,
                    "windows_per_step_per_gpu": B_PRED}
 
+    # ---- the two nets no shipped config selects (nets/conv.py:47-61 Conv-D3, nets/linear.py:44-55 Linear): weight-sampling predict on the
+    #      per-layer engines (fp32 FFMA and tcgen05 TF32 GEMMs), S = 20, for the record
+    other_nets = {}
+    if not args.no_train and world == 1:
+        from bayesrul_b200 import Engine as _Engine
+        for net_name in ("conv", "linear"):
+            en = _Engine(net_name, device)
+            mu_n = init_flat_params(net_name, 12345).to(device)
+            sg_n = torch.full_like(mu_n, CFG["q_scale"])
+            rec = {}
+            for be in ("simt", "tc"):
+                en.set_gemm_backend(be)
+
+                def on_step(i=0):
+                    outs["on"] = en.predict_moments(xs[i % n_rot], mu_n, sg_n, S=20, guide="normal", noise=Noise(seed=9000 + i), engine="simt")
+
+                t_on = timed_steps(on_step, 3, 2, flush_buf, None)
+                rec[{"simt": "fp32_ffma", "tc": "per_layer_tcgen05_tf32"}[be]] = B_PRED * 20 * 3 / t_on
+            en.set_gemm_backend("simt")
+            other_nets[net_name] = {"window_samples_per_s": rec, "mc_samples": 20, "windows_per_step": B_PRED, "params": int(mu_n.numel())}
+            del en
+
     # ---- configs[4] at its stated scale: 1 000 000 windows, deep ensemble of 5 HNN members + the LRT-trained BNN at S = 1000.
     #      Members and MC samples are SHARDED over the ranks (every rank sees all windows); per window chunk the ranks merge
     #      their per-window moments with one NCCL all-gather (BNN: Chan merge) and one all-reduce (ensemble mixture) inside
@@ -584,6 +606,7 @@ def main():
                      "ms_per_launch": conv_ms / max(conv_launches, 1), "share_of_step": conv_ms / (t_local * 1e3) if conv_launches else None,
                      "note": roof_note, "other_kernels": kernels},
         "train": train, "mcd_predict": mcd, "flipout_predict": fo_pred, "radial_sweep": radial, "deep_ensemble": deepens,
+        "other_nets_predict": other_nets,
         "deep_ensemble_full": de_full,
     }
     if world == 1 and not args.no_cpu:

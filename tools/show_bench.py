@@ -27,3 +27,6 @@ if d.get("deep_ensemble"):
     print(f"  deep ensemble {d['deep_ensemble']['window_members_per_s'] / 1e6:.1f} M window-members/s ({d['deep_ensemble']['ms_per_step']:.3f} ms)")
 if d.get("cpu_baseline"):
     print(f"  cpu baseline {d['cpu_baseline']['value']:.0f} ({d['cpu_baseline']['cores']} cores): {d['cpu_baseline']['sample']}")
+if d.get("other_nets_predict"):
+    print("  other nets (S=20 predict, M window-samples/s):",
+          {n: {k: round(v / 1e6, 1) for k, v in r["window_samples_per_s"].items()} for n, r in d["other_nets_predict"].items()})
