@@ -126,12 +126,12 @@ __global__ void __launch_bounds__(128, 1) tcl_kernel(const LinArgs a, const __gr
     const int row0 = tile * 128;
 
     // one layer's copies and MMAs (thread 0): k-blocks of 64 through the two-stage ring, the first two copies may already be in flight
-    auto load = [&](bool tma_a, int kb, const unsigned char* wsrc, int wbytes) {
+    auto load = [&](bool tma_a, int kb, const unsigned char* wsrc, int wbytes, int xrow = -1) {
       const uint32_t st = ld_cnt & 1u;
       if (ld_cnt >= 2) ok = mbar_wait(bar_empty + 8 * st, ((ld_cnt - 2) >> 1) & 1u, a.status, 20) && ok;  // the MMAs that read the stage
       const uint32_t dst = sbase + st * STAGE_BYTES;
       mbar_expect_tx(bar_full + 8 * st, (tma_a ? STAGE_A : 0) + wbytes);
-      if (tma_a) tma_load_2d(dst, &xmap, kb * 64, row0, bar_full + 8 * st);
+      if (tma_a) tma_load_2d(dst, &xmap, kb * 64, xrow >= 0 ? xrow : row0, bar_full + 8 * st);
       bulk_g2s(dst + STAGE_A, wsrc + (long long)kb * wbytes, wbytes, bar_full + 8 * st);
       ++ld_cnt;
     };
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(128, 1) tcl_kernel(const LinArgs a, const __gr
       __syncthreads();
     };
 
-    if (tid == 0) run_layer(true, NKB1, 0u, N1, img + L_W1, KB1_BYTES, 0u, 0);
+    if (tid == 0) run_layer(true, NKB1, 0u, N1, img + L_W1, KB1_BYTES, 0u, it == beg ? 0 : 2);  // (first two copies: end of the previous item)
     layer_done();
     if (tid == 0) { load(false, 0, img + L_W2, KB2_BYTES); load(false, 1, img + L_W2, KB2_BYTES); }  // underneath the epilogue
     store_act(0u, N1, tail + T_B1, smem + S_H1);
@@ -194,6 +194,12 @@ __global__ void __launch_bounds__(128, 1) tcl_kernel(const LinArgs a, const __gr
     publish();
     if (tid == 0) { tc_fence_after(); run_layer(false, 2, sbase + S_H1, N4, img + L_W4, KB4_BYTES, 0u, 2); }
     layer_done();
+    if (tid == 0 && it + 1 < end) {  // the ring is idle from here on: the next item's first two fc1 k-blocks travel underneath the head
+      const int s2 = (int)((it + 1) / a.ntile128), tile2 = (int)((it + 1) % a.ntile128);
+      const unsigned char* img2 = a.img + (long long)s2 * a.img_stride;
+      load(true, 0, img2 + L_W1, KB1_BYTES, tile2 * 128);
+      load(true, 1, img2 + L_W1, KB1_BYTES, tile2 * 128);
+    }
     // fc4 epilogue + head 32 -> 2 + softplus + Threshold(1e-9, 1e-9)
     {
       float o0 = __ldg(tail + T_B5), o1 = __ldg(tail + T_B5 + 1);

@@ -518,7 +518,7 @@ def main():
                    "windows_per_step_per_gpu": B_PRED}
 
     # ---- the two nets no shipped config selects (nets/conv.py:47-61 Conv-D3, nets/linear.py:44-55 Linear): weight-sampling predict on the
-    #      per-layer engines (fp32 FFMA and tcgen05 TF32 GEMMs), S = 20, for the record
+    #      per-layer engines (fp32 FFMA and tcgen05 TF32 GEMMs) and, for the Linear net, on its fused tcgen05 engine
     other_nets = {}
     if not args.no_train and world == 1:
         from bayesrul_b200 import Engine as _Engine
@@ -536,6 +536,13 @@ def main():
                 t_on = timed_steps(on_step, 3, 2, flush_buf, None)
                 rec[{"simt": "fp32_ffma", "tc": "per_layer_tcgen05_tf32"}[be]] = B_PRED * 20 * 3 / t_on
             en.set_gemm_backend("simt")
+            if en.has_tc():  # Linear: the fused fp16 tcgen05 engine (csrc/brl_tc_linear.cuh), at the headline's S as well
+
+                def on_tc(i=0, S=20):
+                    outs["on"] = en.predict_moments(xs[i % n_rot], mu_n, sg_n, S=S, guide="normal", noise=Noise(seed=9100 + i), engine="tc")
+
+                rec["fused_tcgen05_fp16"] = B_PRED * 20 * 3 / timed_steps(on_tc, 3, 2, flush_buf, None)
+                rec[f"fused_tcgen05_fp16_S{S_PRED}"] = B_PRED * S_PRED * 3 / timed_steps(lambda i=0: on_tc(i, S_PRED), 3, 2, flush_buf, None)
             other_nets[net_name] = {"window_samples_per_s": rec, "mc_samples": 20, "windows_per_step": B_PRED, "params": int(mu_n.numel())}
             del en
 
