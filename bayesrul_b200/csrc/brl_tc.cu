@@ -343,6 +343,7 @@ __global__ void __launch_bounds__(192, 1) tc_fc_kernel(const FcArgs a, const __g
 }
 
 #include "brl_tc_linear.cuh"
+#include "brl_tc_convd3.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // host side
@@ -352,9 +353,8 @@ TcState* tc_create(int net) {
   st->net = net;
   st->status = nullptr;
   st->sm_count = 148;
-  if (net != BRL_NET_INCEPTION && net != BRL_NET_LINEAR) return st;
   const NetSpec& n = get_net(net);
-  for (int l = 0; l < (net == BRL_NET_LINEAR ? 5 : 12); ++l) { st->loff[l][0] = n.layers[l].w_off; st->loff[l][1] = n.layers[l].b_off; }
+  for (int l = 0; l < (net == BRL_NET_LINEAR ? 5 : net == BRL_NET_CONV ? 4 : 12); ++l) { st->loff[l][0] = n.layers[l].w_off; st->loff[l][1] = n.layers[l].b_off; }
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&st->sm_count, cudaDevAttrMultiProcessorCount, dev);
@@ -365,6 +365,7 @@ TcState* tc_create(int net) {
   cudaFuncSetAttribute(tc_fc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM);
   cudaFuncSetAttribute(tc_fc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM);
   cudaFuncSetAttribute(tcl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lin::SMEM);
+  cudaFuncSetAttribute(tcc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cd3::SMEM);
   return st;
 }
 void tc_destroy(TcState* s) {
@@ -406,7 +407,7 @@ static void tc_time_end(TcState* st, int k, cudaStream_t stream) {
   if (st->timing) cudaEventRecord(st->evs[k][st->ev_used[k]++].second, stream);
 }
 void tc_trace(TcState* s, long long* buf) { s->trace = buf; }
-bool tc_available(const TcState* s) { return s && (s->net == BRL_NET_INCEPTION || s->net == BRL_NET_LINEAR) && s->status != nullptr; }
+bool tc_available(const TcState* s) { return s && s->status != nullptr; }  // all three nets (the status word exists: sm_100 context)
 bool tc_host_pipeline(const TcState* s) { return tc_available(s) && s->net == BRL_NET_INCEPTION; }
 int tc_status(const TcState* s) {
   int v = -1;
@@ -416,6 +417,8 @@ int tc_status(const TcState* s) {
 size_t tc_workspace_bytes(const TcState* s, long long B, long long S) {
   if (s && s->net == BRL_NET_LINEAR)  // fp16 window matrix | weight images
     return (size_t)(((B + 127) / 128) * 128 * lin::KX * 2 + S * (long long)lin::IMG_BYTES + 2048);
+  if (s && s->net == BRL_NET_CONV)  // per-tile window images | weight images
+    return (size_t)(((B + 3) / 4) * (long long)cd3::XQ_BYTES + S * (long long)cd3::IMG_BYTES + 2048);
   const long long nt128 = (B + 127) / 128, npair = ((B + 3) / 4 + 1) / 2;
   return (size_t)(S * (long long)BLOB_BYTES + S * nt128 * 128 * FEAT_ROW_BYTES + 2 * npair * XIMG_TILE_BYTES + 2048);
 }
@@ -486,14 +489,43 @@ static const char* tcl_forward(TcState* st, const float* x, long long B, long lo
   return nullptr;
 }
 
+// Conv-D3 net: windows -> per-tile fp16 images, weights -> fp16 images, one persistent launch (brl_tc_convd3.cuh)
+static const char* tcc_forward(TcState* st, const float* x, long long B, long long S, const float* weights, long long w_sample_stride,
+                               float p_dropout, float* out, void* ws, bool pack_x, cudaStream_t stream) {
+  if (p_dropout > 0.f) return "bayesrul_b200: the Conv-D3 net's tensor-core engine has no dropout path (use engine 'simt')";
+  const long long ntile = (B + 3) / 4;
+  unsigned char* ximg = reinterpret_cast<unsigned char*>(ws);
+  unsigned char* img = ximg + ((ntile * cd3::XQ_BYTES + 255) / 256) * 256;
+  if (pack_x) {
+    tcc_packx_kernel<<<(unsigned)((ntile * 20 * ROWS + 255) / 256), 256, 0, stream>>>(x, ximg, (int)B, (int)ntile);
+    count_launch(1);
+  }
+  Cd3PackArgs pa;
+  pa.w = weights; pa.w_stride = w_sample_stride; pa.img = img;
+  for (int l = 0; l < 4; ++l) { pa.w_off[l] = st->loff[l][0]; pa.b_off[l] = st->loff[l][1]; }
+  const long long nimg = w_sample_stride ? S : 1;
+  tcc_pack_kernel<<<dim3((cd3::IMG_HALVES + cd3::TAIL_FLOATS + 255) / 256, (unsigned)nimg), 256, 0, stream>>>(pa);
+  Cd3Args ca;
+  ca.ximg = ximg; ca.img = img; ca.img_stride = w_sample_stride ? cd3::IMG_BYTES : 0; ca.out = out;
+  ca.B = (int)B; ca.S = (int)S; ca.ntile = (int)ntile; ca.status = st->status;
+  const int grid = (int)std::min<long long>(2ll * st->sm_count, S * ntile);
+  tcc_kernel<<<grid, 128, cd3::SMEM, stream>>>(ca);
+  count_launch(2);
+  return nullptr;
+}
+
 const char* tc_forward(TcState* st, const float* x, long long B, long long S, const float* weights, long long w_sample_stride,
                        float p_dropout, const brl_noise* noise, float* out, void* ws, size_t ws_bytes, bool pack_x,
                        cudaStream_t stream, const unsigned char* prepacked) {
-  if (!tc_available(st)) return "bayesrul_b200: tensor-core engine is implemented for the Inception and Linear nets only";
+  if (!tc_available(st)) return "bayesrul_b200: tensor-core engine unavailable (no sm_100 context)";
   if (ws_bytes < tc_workspace_bytes(st, B, S)) return "bayesrul_b200: workspace too small for the tensor-core engine";
   if (st->net == BRL_NET_LINEAR) {
     if (prepacked) return "bayesrul_b200: prepacked weight images are implemented for the Inception net only";
     return tcl_forward(st, x, B, S, weights, w_sample_stride, p_dropout, out, ws, pack_x, stream);
+  }
+  if (st->net == BRL_NET_CONV) {
+    if (prepacked) return "bayesrul_b200: prepacked weight images are implemented for the Inception net only";
+    return tcc_forward(st, x, B, S, weights, w_sample_stride, p_dropout, out, ws, pack_x, stream);
   }
   const long long nt128 = (B + 127) / 128, nt4 = (B + 3) / 4;
   // workspace: window images (independent of S, so later sample chunks of a batch find them again) | blobs | features

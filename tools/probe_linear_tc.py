@@ -1,4 +1,4 @@
-"""Linear net, weight-sampling predict (B = 10 000 x S = 100, q_scale 1.351e-3): tcgen05 engine vs the per-layer engines."""
+"""Linear (default) or Conv-D3 net (argv[1] = conv), weight-sampling predict (B = 10 000 x S = 100, q_scale 1.351e-3): tcgen05 engine vs the per-layer engines."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -6,10 +6,11 @@ from bayesrul_b200 import Engine, Noise
 from bayesrul_b200.compat.nets import init_flat_params
 
 dev = torch.device("cuda", 0)
-e = Engine("linear", dev)
+net = sys.argv[1] if len(sys.argv) > 1 else "linear"
+e = Engine(net, dev)
 B, S = 10000, 100
 x = torch.randn(B, 30, 18, device=dev)
-mu = init_flat_params("linear", 12345).to(dev)
+mu = init_flat_params(net, 12345).to(dev)
 sg = torch.full_like(mu, 1.351e-3)
 for engine, be in (("tc", "simt"), ("simt", "simt"), ("simt", "tc")):
     e.set_gemm_backend(be)
