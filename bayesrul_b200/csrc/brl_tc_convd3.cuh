@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(128, 2) tcc_kernel(const Cd3Args a) {
   const long long beg = per * blockIdx.x, end = min(total, beg + per);
   uint32_t fph = 0, dph = 0;
   int s_loaded = -1;
-  bool ok = true;
+  bool ok = true, prefetched = false;
   const uint32_t xs = sbase + S_X, a3 = sbase + S_A3, ws = sbase + S_W;
 
   auto layer_done = [&]() {
@@ -147,10 +147,12 @@ __global__ void __launch_bounds__(128, 2) tcc_kernel(const Cd3Args a) {
   for (long long it = beg; it < end && ok; ++it) {
     const int s = (int)(it / a.ntile), tile = (int)(it % a.ntile);
     if (tid == 0) {  // window image of the tile (+ the weight image when the MC sample changes), then conv1
-      const bool neww = s != s_loaded;
-      mbar_expect_tx(bar_full, XQ_BYTES + (neww ? IMG_BYTES : 0));
-      cd3_bulk(xs, a.ximg + (long long)tile * XQ_BYTES, XQ_BYTES, bar_full);
-      if (neww) cd3_bulk(ws, a.img + (long long)s * a.img_stride, IMG_BYTES, bar_full);
+      if (!prefetched) {
+        const bool neww = s != s_loaded;
+        mbar_expect_tx(bar_full, XQ_BYTES + (neww ? IMG_BYTES : 0));
+        cd3_bulk(xs, a.ximg + (long long)tile * XQ_BYTES, XQ_BYTES, bar_full);
+        if (neww) cd3_bulk(ws, a.img + (long long)s * a.img_stride, IMG_BYTES, bar_full);
+      }
       ok = mbar_wait(bar_full, fph, a.status, 30) && ok;
       tc_fence_after();
       for (int t = 0; t < 10; ++t)
@@ -192,6 +194,14 @@ __global__ void __launch_bounds__(128, 2) tcc_kernel(const Cd3Args a) {
       umma_commit(bar_done);
     }
     layer_done();
+    // conv2's MMAs were the last readers of the window / conv2 image: the next tile's window image travels underneath the rest of this
+    // tile (same MC sample only: the weight image is still in use)
+    prefetched = false;
+    if (tid == 0 && it + 1 < end && (int)((it + 1) / a.ntile) == s) {
+      mbar_expect_tx(bar_full, XQ_BYTES);
+      cd3_bulk(xs, a.ximg + (long long)((it + 1) % a.ntile) * XQ_BYTES, XQ_BYTES, bar_full);
+      prefetched = true;
+    }
     {  // conv2 epilogue: bias, ReLU, AvgPool((2,1)) over rows (2 j, 2 j + 1), j < 12 -> conv3's A image row j of the window
       float v[2][16];
       tmem_ld16(lane_base + 160, v[0]);

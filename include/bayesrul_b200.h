@@ -51,7 +51,7 @@ extern "C" {
 
 /* arithmetic back-ends of the forward pass */
 #define BRL_ENGINE_SIMT_FP32 0 /* fp32 FFMA implicit-GEMM kernels: the parity engine (rtol 1e-3 vs oracle) */
-#define BRL_ENGINE_TC_FP16 1   /* tcgen05 / TMEM kernels, fp16 operands (10-bit mantissa) + fp32 accumulate: Inception and Linear nets */
+#define BRL_ENGINE_TC_FP16 1   /* tcgen05 / TMEM kernels, fp16 operands (10-bit mantissa) + fp32 accumulate (every net; dropout: Inception only) */
 
 /* contraction back-ends of the per-layer kernels (every net, every mode, forward + backward) */
 #define BRL_GEMM_SIMT_FP32 0 /* fp32 FFMA implicit GEMMs: the parity back-end (rtol 1e-3 vs oracle) */
