@@ -497,7 +497,7 @@ static const char* tcc_forward(TcState* st, const float* x, long long B, long lo
   unsigned char* ximg = reinterpret_cast<unsigned char*>(ws);
   unsigned char* img = ximg + ((ntile * cd3::XQ_BYTES + 255) / 256) * 256;
   if (pack_x) {
-    tcc_packx_kernel<<<(unsigned)((ntile * 20 * ROWS + 255) / 256), 256, 0, stream>>>(x, ximg, (int)B, (int)ntile);
+    tcc_packx_kernel<<<(unsigned)((ntile * 6 * ROWS + 255) / 256), 256, 0, stream>>>(x, ximg, (int)B, (int)ntile);
     count_launch(1);
   }
   Cd3PackArgs pa;
