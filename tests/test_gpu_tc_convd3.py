@@ -75,3 +75,22 @@ def test_convd3_tc_rejects_dropout(eng):
     x, _, mu, _ = synth("conv", 8, seed=1)
     with pytest.raises(RuntimeError, match="dropout"):
         eng.forward(x.to(DEV), "det", theta=mu.to(DEV), S=2, p_dropout=0.2, engine="tc")
+
+
+def test_convd3_tc_full_size_shard_invariance(eng):
+    """B = 10 000 x S = 100 (the headline workload's size): the result of a window does not depend on how the batch is sharded (a weight
+    draw has no window index, every tile row is computed independently) -- bit-exact, ragged split -- and the moments are finite."""
+    from bayesrul_b200 import Noise
+    B, S = 10000, 100
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, 30, 18, generator=g).to(DEV)
+    mu = O.init_params("conv", 1).to(DEV)
+    sg = torch.full_like(mu, 1.351e-3)
+    full = eng.predict_moments(x, mu, sg, S=S, noise=Noise(seed=21), engine="tc")
+    cut = 1003
+    parts = [eng.predict_moments(x[a:b].contiguous(), mu, sg, S=S, noise=Noise(seed=21, window0=a), engine="tc") for a, b in ((0, cut), (cut, B))]
+    assert eng.tc_status() == 0
+    for i in range(4):
+        assert torch.isfinite(full[i]).all()
+        assert torch.equal(torch.cat([p[i] for p in parts]), full[i]), i
+    assert (full[1] > 0).all() and (full[2] >= 0).all()
