@@ -3,7 +3,7 @@ import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from bayesrul_b200 import Engine, Noise
-from oracle.bnn_oracle import init_params
+from bayesrul_b200.compat.nets import init_flat_params as init_params
 
 dev = "cuda:0"
 B, S = 10000, 8

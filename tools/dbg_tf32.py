@@ -1,8 +1,17 @@
 import sys, math, torch
 sys.path.insert(0, '/root/repo')
 from bayesrul_b200 import Engine, Noise
-from oracle import bnn_oracle as O
-from tests.helpers import synth
+from bayesrul_b200.compat.nets import init_flat_params
+
+
+def synth(net, B, seed=0, sigma=0.05):  # (the oracle is test infrastructure: tools build their inputs from the package)
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, 30, 18, generator=g)
+    y = torch.rand(B, generator=g) * 100
+    mu = init_flat_params(net, seed + 1)
+    return x, y, mu, torch.full_like(mu, sigma)
+
+
 DEV = "cuda:0"
 for net in ("linear", "inception"):
     e = Engine(net, DEV)

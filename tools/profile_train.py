@@ -3,7 +3,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from bayesrul_b200 import Engine, Noise
-from oracle.bnn_oracle import init_params
+from bayesrul_b200.compat.nets import init_flat_params as init_params
 
 mode = sys.argv[1] if len(sys.argv) > 1 else "lrt"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3

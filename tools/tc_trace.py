@@ -6,7 +6,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from bayesrul_b200 import Engine, Noise
-from oracle.bnn_oracle import init_params
+from bayesrul_b200.compat.nets import init_flat_params as init_params
 
 dev = "cuda:0"
 e = Engine("inception", dev)
